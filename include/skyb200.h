@@ -1,0 +1,224 @@
+/*
+ * skyb200 — C ABI of the B200-native policy-update hot path (libskyb200.so).
+ *
+ * The reference (SkyRL / skyrl_train) has no FFI for this path: its boundary is the Python plugin API
+ * (AdvantageEstimatorRegistry / PolicyLossRegistry, logprobs_from_logits, chunked_entropy_from_logits).
+ * The Python shims in skyrl_b200/ present exactly that API and call the entry points below; each entry
+ * point names the reference function (file:line under skyrl-train/skyrl_train/) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; the caller owns and sizes every buffer;
+ *   - `stream` is a cudaStream_t passed as void*; no call synchronises the device;
+ *   - return value 0 = success, otherwise a SKYB200_E* code; skyb200_last_error() gives the text
+ *     (thread-local);
+ *   - matrices are row-major; [B, A] = sequences x response positions; N = tokens, H = hidden, V = vocab.
+ */
+#ifndef SKYB200_H
+#define SKYB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKYB200_OK 0
+#define SKYB200_EINVAL 1 /* bad argument (null pointer, bad enum, misaligned leading dimension) */
+#define SKYB200_ECUDA 2  /* a CUDA runtime / driver call failed */
+#define SKYB200_EARCH 3  /* device is not compute capability 10.x */
+#define SKYB200_EWORKSPACE 4
+
+/* mask element types accepted by the advantage kernels (reference masks are int64 or fp32) */
+#define SKYB200_MASK_F32 0
+#define SKYB200_MASK_I64 1
+#define SKYB200_MASK_NONE 2
+
+/* policy_loss_type (ppo_utils.py:463-508) */
+#define SKYB200_LOSS_REGULAR 0
+#define SKYB200_LOSS_DUAL_CLIP 1
+#define SKYB200_LOSS_GSPO 2
+
+/* loss_reduction (ppo_utils.py:984-1009) */
+#define SKYB200_REDUCE_TOKEN_MEAN 0
+#define SKYB200_REDUCE_SEQUENCE_MEAN 1
+#define SKYB200_REDUCE_SEQ_MEAN_TOKEN_SUM_NORM 2
+
+/* kl_estimator_type (ppo_utils.py:88-124) */
+#define SKYB200_KL_K1 0
+#define SKYB200_KL_ABS 1
+#define SKYB200_KL_K2 2
+#define SKYB200_KL_K3 3
+
+int skyb200_abi_version(void);
+const char* skyb200_last_error(void);
+/* 0 if the current device is sm_10x and the library can run, else SKYB200_EARCH / SKYB200_ECUDA */
+int skyb200_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Policy loss, fused forward + backward (+ KL-loss and entropy terms of the worker's loss assembly).
+ * Replaces ppo_policy_loss (ppo_utils.py:548-586), gspo_policy_loss (:661-725), reduce_loss (:984-1009),
+ * compute_approx_kl (:88-124) as used at worker.py:864-874, the entropy masked_mean (worker.py:852-861)
+ * and loss = policy + kl*coef - entropy*coef (worker.py:876).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct skyb200_loss_params {
+    int32_t loss_type;   /* SKYB200_LOSS_* */
+    int32_t reduction;   /* SKYB200_REDUCE_* */
+    int32_t kl_type;     /* SKYB200_KL_*; used iff base_log_probs != NULL */
+    int32_t kl_has_grad; /* 0 = reference behaviour (compute_approx_kl is @torch.no_grad) */
+    int32_t use_entropy_loss; /* 1: final loss -= entropy*coef and d_entropy carries its gradient */
+    int32_t reserved0;
+    float eps_clip_low;
+    float eps_clip_high;
+    float clip_ratio_c;
+    float max_seq_len; /* for SEQ_MEAN_TOKEN_SUM_NORM */
+    float kl_loss_coef;
+    float entropy_loss_coef;
+} skyb200_loss_params;
+
+/* indices into the fp32 stats vector written by skyb200_policy_loss (SKYB200_LOSS_NSTATS floats) */
+#define SKYB200_STAT_POLICY_LOSS 0
+#define SKYB200_STAT_CLIP_RATIO 1
+#define SKYB200_STAT_KL_LOSS 2      /* mean_b(masked_mean_t(kl)) ; 0 if no base_log_probs */
+#define SKYB200_STAT_ENTROPY 3      /* masked_mean(entropy, loss_mask); 0 if no entropy */
+#define SKYB200_STAT_FINAL_LOSS 4   /* policy + kl*kl_coef - entropy*ent_coef (ent term iff use_entropy_loss) */
+#define SKYB200_STAT_MASK_SUM 5     /* sum(loss_mask) (B*A if mask is NULL) */
+#define SKYB200_STAT_RATIO_MEAN 6   /* masked mean of the importance ratio (diagnostic) */
+#define SKYB200_STAT_RATIO_MAX 7
+#define SKYB200_STAT_RATIO_MIN 8
+#define SKYB200_LOSS_NSTATS 16
+
+/* bytes of scratch the call needs */
+size_t skyb200_policy_loss_workspace(int64_t B, int64_t A);
+
+/*
+ * log_probs, old_log_probs, advantages: [B, A] fp32.  loss_mask: [B, A] fp32 or NULL (= all ones).
+ * base_log_probs: [B, A] fp32 or NULL (no KL term).  entropy: [B, A] fp32 or NULL.
+ * d_log_probs: [B, A] fp32 out, = d final_loss / d log_probs (NULL = forward only).
+ * d_entropy:   [B, A] fp32 out or NULL; zeros unless params->use_entropy_loss.
+ * stats: SKYB200_LOSS_NSTATS floats out.
+ */
+int skyb200_policy_loss(const float* log_probs, const float* old_log_probs, const float* advantages,
+                        const float* loss_mask, const float* base_log_probs, const float* entropy,
+                        float* d_log_probs, float* d_entropy, float* stats, void* workspace, size_t workspace_bytes,
+                        int64_t B, int64_t A, const skyb200_loss_params* params, void* stream);
+
+/* x[i] *= *scale_dev  (applies an upstream autograd gradient that lives on the device) */
+int skyb200_scale_inplace(float* x, const float* scale_dev, int64_t n, void* stream);
+
+/* masked_mean(x, mask) over everything (torch_utils.py:180-184); out: 1 float.  mask may be NULL. */
+int skyb200_masked_mean(const float* x, const float* mask, float* out, void* workspace, size_t workspace_bytes,
+                        int64_t n, void* stream);
+
+/* compute_approx_kl (ppo_utils.py:88-124): out = estimator(lp, base) [* mask] */
+int skyb200_approx_kl(const float* log_probs, const float* base_log_probs, const float* loss_mask, float* out,
+                      int64_t n, int32_t kl_type, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Advantage estimation.
+ * ------------------------------------------------------------------------------------------------ */
+
+/*
+ * GRPO (compute_grpo_outcome_advantage, ppo_utils.py:1132-1182) and RLOO
+ * (compute_rloo_outcome_advantage, :1048-1098).  The uid -> dense group id map is built on the host
+ * (bit-exact group assignment); groups are passed in CSR form:
+ *   group_of_row[B]  int32  dense group id of each row
+ *   group_start[G+1] int32  offsets into group_rows
+ *   group_rows[B]    int32  row indices sorted by group (original order inside a group)
+ * mode: 0 = GRPO with std normalisation, 1 = GRPO mean only (grpo_norm_by_std=False), 2 = RLOO.
+ * rewards [B, A] fp32; mask [B, A] of mask_type; out [B, A] fp32 (advantages == returns, one buffer).
+ * scores_ws: B floats of scratch.
+ */
+int skyb200_group_advantage(const float* rewards, const void* response_mask, int32_t mask_type,
+                            const int32_t* group_of_row, const int32_t* group_start, const int32_t* group_rows,
+                            float* out, float* scores_ws, int64_t B, int64_t A, int32_t num_groups, int32_t mode,
+                            float epsilon, void* stream);
+
+/*
+ * GAE (compute_gae_advantage_return, ppo_utils.py:1101-1129) + masked_whiten (:163-172).
+ * One segment per ROW, no reset on mask (the reference does not reset).
+ * rewards, values [B, A] fp32; mask of mask_type; advantages, returns [B, A] fp32 out.
+ * stats_out: 4 floats {mask_sum, mean, var (Bessel), rstd}; the caller must raise if mask_sum is 0 or 1
+ * (masked_var, ppo_utils.py:148-160).  workspace: skyb200_gae_workspace(B) bytes.
+ */
+size_t skyb200_gae_workspace(int64_t B);
+int skyb200_gae_advantage(const float* rewards, const float* values, const void* response_mask, int32_t mask_type,
+                          float* advantages, float* returns, float* stats_out, void* workspace,
+                          size_t workspace_bytes, int64_t B, int64_t A, float gamma, float lambd, void* stream);
+
+/*
+ * KL-in-reward (RayPPOTrainer.apply_reward_kl_penalty, trainer.py:981-1035):
+ *   kl = compute_approx_kl(lp, base, loss_mask); rewards_out = rewards - kl * max(0, kl_coef)
+ *   metrics_out[0] = mean_b(masked_mean_t(kl)), metrics_out[1] = mean_b(max_t |kl|)
+ * row_ws: 2*B floats scratch.
+ */
+int skyb200_reward_kl_penalty(const float* log_probs, const float* base_log_probs, const float* loss_mask,
+                              const float* rewards, float* rewards_out, float* metrics_out, float* row_ws, int64_t B,
+                              int64_t A, int32_t kl_type, float kl_coef, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused LM head: projection + online log-softmax + label gather + entropy, never materialising
+ * [tokens x vocab].  Replaces lm_head GEMM + logits.div_(T) + logprobs_from_logits + chunked entropy
+ * (model_wrapper.py:309-363, torch_utils.py:59-177).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* scratch bytes for forward / backward with token chunks of `chunk` rows (0 = library default) */
+size_t skyb200_head_forward_workspace(int64_t N, int64_t H, int64_t V, int64_t chunk);
+size_t skyb200_head_backward_workspace(int64_t N, int64_t H, int64_t V, int64_t chunk);
+
+/*
+ * hidden [N, H] bf16, weight [V, H] bf16 (nn.Linear layout), labels [N] int64.
+ * logprobs [N] fp32 out; entropy [N] fp32 out (NULL to skip); lse2 [N] fp32 out = log2-sum-exp of
+ * logits*log2(e)/T, saved for backward.  entropy_mask [N] fp32 or NULL multiplies the entropy
+ * (attention_mask semantics of chunked_entropy_from_logits).
+ */
+int skyb200_head_forward(const void* hidden, const void* weight, const int64_t* labels, const float* entropy_mask,
+                         float* logprobs, float* entropy, float* lse2, void* workspace, size_t workspace_bytes,
+                         int64_t N, int64_t H, int64_t V, float temperature, int64_t chunk, void* stream);
+
+/*
+ * Backward: given g_logprobs [N] and optional g_entropy [N] (upstream grads w.r.t. the forward outputs,
+ * g_entropy already multiplied by entropy_mask by the caller if one was used) produce
+ *   d_hidden [N, H] bf16   and   d_weight [V, H] fp32 (+= if accumulate != 0, else overwritten).
+ * `entropy` is the UNMASKED per-token entropy from forward (needed iff g_entropy != NULL).
+ */
+int skyb200_head_backward(const void* hidden, const void* weight, const int64_t* labels, const float* lse2,
+                          const float* entropy, const float* g_logprobs, const float* g_entropy, void* d_hidden,
+                          float* d_weight, int32_t accumulate, void* workspace, size_t workspace_bytes, int64_t N,
+                          int64_t H, int64_t V, float temperature, int64_t chunk, void* stream);
+
+/*
+ * logprobs_from_logits (torch_utils.py:115-177) and chunked_entropy_from_logits (:59-111) on materialised
+ * logits [N, V] (bf16 or fp32), for callers that still hold logits.  logits_dtype: 0 = fp32, 1 = bf16.
+ * Any output pointer may be NULL.  entropy_mask [N] fp32 or NULL.  lse [N] = natural-log sum-exp (saved for
+ * backward).
+ */
+int skyb200_logits_logprob_entropy(const void* logits, int32_t logits_dtype, const int64_t* labels,
+                                   const float* entropy_mask, float* logprobs, float* entropy, float* lse, int64_t N,
+                                   int64_t V, void* stream);
+
+/*
+ * Backward of the materialised-logits path.  d_logits (same dtype as logits; may alias `logits`, which is the
+ * inplace_backward=True behaviour of the reference's flash-attn cross-entropy, model_wrapper.py:317-321):
+ *   d_j = g_lp * (1[j == label] - p_j) - g_ent * p_j * (log p_j + H)
+ * g_lp / g_ent [N] fp32, either may be NULL (treated as 0); entropy [N] = UNMASKED forward entropy (iff g_ent).
+ */
+int skyb200_logits_backward(const void* logits, int32_t logits_dtype, const int64_t* labels, const float* lse,
+                            const float* entropy, const float* g_lp, const float* g_ent, void* d_logits, int64_t N,
+                            int64_t V, void* stream);
+
+/*
+ * Self-test hook: C[M,N] (fp32) = A * B^T through the same tcgen05 mainloop the head uses.
+ * a_mn / b_mn: 0 = K-major ([M,K] / [N,K] row-major), 1 = MN-major ([K,M] / [K,N] row-major).
+ * ctas: 1 or 2 (cta_group).  bn: 128 or 256.
+ */
+int skyb200_gemm_selftest(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int32_t a_mn,
+                          int32_t b_mn, int32_t ctas, int32_t bn, int32_t accumulate, void* stream);
+
+/* host pointer to the last GEMM watchdog record (8 uint32: flag, role, which, stage, parity, tile, block, pad) */
+const uint32_t* skyb200_gemm_debug_record(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKYB200_H */

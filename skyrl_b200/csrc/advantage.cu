@@ -1,0 +1,435 @@
+// Advantage estimation for the policy update: GRPO / RLOO group statistics, the GAE reverse scan with
+// global whitening, and the KL-in-reward penalty.  All HBM-bound; rows are [B, A] fp32, row-major.
+//
+// Reference arithmetic (skyrl-train/skyrl_train/):
+//   compute_grpo_outcome_advantage   utils/ppo_utils.py:1132-1182
+//   compute_rloo_outcome_advantage   utils/ppo_utils.py:1048-1098
+//   compute_gae_advantage_return     utils/ppo_utils.py:1101-1129  (no reset on mask!)
+//   masked_whiten / masked_var       utils/ppo_utils.py:148-172
+//   apply_reward_kl_penalty          trainer.py:981-1035
+#include "common.cuh"
+
+namespace skyb200 {
+
+template <int kMaskType>
+__device__ __forceinline__ float mask_at(const void* mask, int64_t i) {
+    if constexpr (kMaskType == SKYB200_MASK_F32) return static_cast<const float*>(mask)[i];
+    if constexpr (kMaskType == SKYB200_MASK_I64) return static_cast<float>(static_cast<const long long*>(mask)[i]);
+    return 1.f;
+}
+
+// ------------------------------------------------------------------------------------------ GRPO / RLOO
+
+// scores[row] = sum_t rewards[row, t]   (unmasked, as the reference)
+__global__ void __launch_bounds__(256) row_sum_kernel(const float* __restrict__ x, float* __restrict__ scores,
+                                                      int64_t A) {
+    __shared__ float sh[34];
+    const int64_t base = static_cast<int64_t>(blockIdx.x) * A;
+    float s = 0.f;
+    const bool vec = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+    if (vec) {
+        const float4* x4 = reinterpret_cast<const float4*>(x + base);
+        const int64_t n4 = A / 4;
+        for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+            const float4 v = ldg_stream(x4 + i);
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < A; i += blockDim.x) s += x[base + i];
+    }
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) scores[blockIdx.x] = s;
+}
+
+constexpr int kBcastTile = 4096;  // elements per block of the broadcast pass
+
+// Per row: group mean / unbiased std from the (tiny) group, then out[row, t] = normalised_score * mask[row, t].
+template <int kMaskType>
+__global__ void __launch_bounds__(256)
+group_broadcast_kernel(const float* __restrict__ scores, const void* __restrict__ mask,
+                       const int32_t* __restrict__ group_of_row, const int32_t* __restrict__ group_start,
+                       const int32_t* __restrict__ group_rows, float* __restrict__ out, int64_t A, int mode,
+                       float eps) {
+    __shared__ float sh[34];
+    const int row = blockIdx.y;
+    const int g = group_of_row[row];
+    const int beg = group_start[g], end = group_start[g + 1];
+    const int n = end - beg;
+    float value;
+    {
+        float s = 0.f;
+        for (int i = beg + threadIdx.x; i < end; i += blockDim.x) s += scores[group_rows[i]];
+        s = block_sum(s, sh);
+        const float mean = s / static_cast<float>(n);
+        const float sc = scores[row];
+        if (mode == 2) {  // RLOO: (score - mean) * n / (n - 1); singleton -> 0
+            value = (n > 1) ? (sc - mean) * (static_cast<float>(n) / static_cast<float>(n - 1)) : 0.f;
+        } else if (n == 1) {  // GRPO singleton: mean 0, std 1
+            value = (mode == 0) ? sc / (1.f + eps) : sc;
+        } else if (mode == 1) {
+            value = sc - mean;
+        } else {
+            float q = 0.f;
+            for (int i = beg + threadIdx.x; i < end; i += blockDim.x) {
+                const float d = scores[group_rows[i]] - mean;
+                q = fmaf(d, d, q);
+            }
+            q = block_sum(q, sh);
+            const float sd = sqrtf(q / static_cast<float>(n - 1));
+            value = (sc - mean) / (sd + eps);
+        }
+    }
+    const int64_t base = static_cast<int64_t>(row) * A;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * kBcastTile;
+    const int64_t t1 = min(A, t0 + kBcastTile);
+    const bool vec = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0) && kMaskType != SKYB200_MASK_NONE;
+    if (vec) {
+        for (int64_t t = t0 + threadIdx.x * 4; t < t1; t += blockDim.x * 4) {
+            float4 m;
+            if constexpr (kMaskType == SKYB200_MASK_F32) {
+                m = ldg_stream(reinterpret_cast<const float4*>(static_cast<const float*>(mask) + base + t));
+            } else {
+                const longlong2* mp = reinterpret_cast<const longlong2*>(static_cast<const long long*>(mask) + base + t);
+                const longlong2 a = mp[0], b = mp[1];
+                m = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+            }
+            *reinterpret_cast<float4*>(out + base + t) = make_float4(value * m.x, value * m.y, value * m.z, value * m.w);
+        }
+    } else {
+        for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x)
+            out[base + t] = value * mask_at<kMaskType>(mask, base + t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ GAE
+
+constexpr int kGaeThreads = 256;
+constexpr int kGaePer = 16;                       // contiguous positions per thread
+constexpr int kGaeTile = kGaeThreads * kGaePer;   // 4096 positions per tile
+constexpr int kGaePitch = kGaePer + 1;            // +1 float of padding per thread segment: no bank conflicts
+
+// The recurrence  adv_t = delta_t + c * adv_{t+1}  (c = gamma*lambda) is an affine map per position; a thread's
+// 16-position segment composes to  carry_out = mul * carry_in + add.  Segments combine right-to-left.
+struct Affine {
+    double mul, add;
+};
+__device__ __forceinline__ Affine compose_left_of(const Affine& left, const Affine& right) {
+    // apply `right` first (it is further right in the row), then `left`
+    Affine r;
+    r.mul = left.mul * right.mul;
+    r.add = left.mul * right.add + left.add;
+    return r;
+}
+
+template <int kMaskType>
+__global__ void __launch_bounds__(kGaeThreads)
+gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const void* __restrict__ mask,
+                float* __restrict__ adv_raw, float* __restrict__ returns, double* __restrict__ row_stats, int64_t A,
+                float gamma, float lambd) {
+    __shared__ float s_delta[kGaeThreads * kGaePitch];
+    __shared__ double s_wmul[kGaeThreads / 32], s_wadd[kGaeThreads / 32];
+    __shared__ double s_carry;
+    __shared__ double sh_d[34];
+    const int row = blockIdx.x;
+    const int64_t base = static_cast<int64_t>(row) * A;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double c = static_cast<double>(gamma) * static_cast<double>(lambd);
+    double cpow[kGaePer + 1];
+    cpow[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j <= kGaePer; ++j) cpow[j] = cpow[j - 1] * c;
+
+    double sum_m = 0.0, sum_mx = 0.0, sum_mxx = 0.0;
+    if (tid == 0) s_carry = 0.0;
+    const int64_t num_tiles = (A + kGaeTile - 1) / kGaeTile;
+    for (int64_t tile = num_tiles - 1; tile >= 0; --tile) {
+        const int64_t t0 = tile * kGaeTile;
+        __syncthreads();
+        // coalesced load: delta_t = r_t + gamma * V_{t+1} - V_t   (V_A = 0); positions >= A contribute delta = 0
+#pragma unroll 4
+        for (int k = 0; k < kGaePer; ++k) {
+            const int p = k * kGaeThreads + tid;
+            const int64_t t = t0 + p;
+            float d = 0.f;
+            if (t < A) {
+                const float v = values[base + t];
+                const float vn = (t + 1 < A) ? values[base + t + 1] : 0.f;
+                d = rewards[base + t] + gamma * vn - v;
+            }
+            s_delta[(p / kGaePer) * kGaePitch + (p % kGaePer)] = d;
+        }
+        __syncthreads();
+        // local right-to-left scan of this thread's 16 positions with zero carry-in
+        double x[kGaePer];
+        {
+            double run = 0.0;
+#pragma unroll
+            for (int j = kGaePer - 1; j >= 0; --j) {
+                run = static_cast<double>(s_delta[tid * kGaePitch + j]) + c * run;
+                x[j] = run;
+            }
+        }
+        // suffix-compose the per-thread affine maps: carry_in(tid) = maps of all threads to the right applied to
+        // the tile carry.  Inclusive suffix scan inside the warp, then across the 8 warps.
+        Affine incl;
+        incl.mul = cpow[kGaePer];
+        incl.add = x[0];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double om = __shfl_down_sync(0xffffffffu, incl.mul, o);
+            const double oa = __shfl_down_sync(0xffffffffu, incl.add, o);
+            if (lane + o < 32) {
+                Affine right;
+                right.mul = om;
+                right.add = oa;
+                incl = compose_left_of(incl, right);
+            }
+        }
+        if (lane == 0) {
+            s_wmul[warp] = incl.mul;
+            s_wadd[warp] = incl.add;
+        }
+        __syncthreads();
+        // carry entering this warp from the right = warps (warp+1 .. 7) applied to the tile carry
+        double cin = s_carry;
+        for (int w = kGaeThreads / 32 - 1; w > warp; --w) cin = s_wmul[w] * cin + s_wadd[w];
+        // carry entering this thread: lanes to the right inside the warp = exclusive suffix = incl of lane+1
+        const double nm = __shfl_down_sync(0xffffffffu, incl.mul, 1);
+        const double na = __shfl_down_sync(0xffffffffu, incl.add, 1);
+        const double my_cin = (lane == 31) ? cin : (nm * cin + na);
+        __syncthreads();
+        if (tid == 0) s_carry = s_wmul[0] * cin + s_wadd[0];  // warp == 0 here: carry into the next (left) tile
+        // final values, staged through shared memory for coalesced stores
+#pragma unroll
+        for (int j = 0; j < kGaePer; ++j)
+            s_delta[tid * kGaePitch + j] = static_cast<float>(x[j] + cpow[kGaePer - j] * my_cin);
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < kGaePer; ++k) {
+            const int p = k * kGaeThreads + tid;
+            const int64_t t = t0 + p;
+            if (t < A) {
+                const float a = s_delta[(p / kGaePer) * kGaePitch + (p % kGaePer)];
+                adv_raw[base + t] = a;
+                returns[base + t] = a + values[base + t];
+                const double m = static_cast<double>(mask_at<kMaskType>(mask, base + t));
+                const double ad = static_cast<double>(a);
+                sum_m += m;
+                sum_mx += m * ad;
+                sum_mxx += m * ad * ad;
+            }
+        }
+    }
+    sum_m = block_sum(sum_m, sh_d);
+    sum_mx = block_sum(sum_mx, sh_d);
+    sum_mxx = block_sum(sum_mxx, sh_d);
+    if (tid == 0) {
+        row_stats[3 * row + 0] = sum_m;
+        row_stats[3 * row + 1] = sum_mx;
+        row_stats[3 * row + 2] = sum_mxx;
+    }
+}
+
+// One block: fold the per-row moments (fixed order) -> {n, mean, var (Bessel), rstd}
+__global__ void __launch_bounds__(256) whiten_stats_kernel(const double* __restrict__ row_stats, int B,
+                                                           float* __restrict__ stats_out) {
+    __shared__ double sh_d[34];
+    double n = 0.0, sx = 0.0, sxx = 0.0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        n += row_stats[3 * i + 0];
+        sx += row_stats[3 * i + 1];
+        sxx += row_stats[3 * i + 2];
+    }
+    n = block_sum(n, sh_d);
+    sx = block_sum(sx, sh_d);
+    sxx = block_sum(sxx, sh_d);
+    if (threadIdx.x == 0) {
+        const double den = fmax(n, 1.0);                   // masked_mean clamps the denominator to >= 1
+        const double mean = sx / den;
+        double var = (sxx - 2.0 * mean * sx + mean * mean * n) / den;  // masked_mean((x - mean)^2, mask)
+        if (n > 1.0) var *= n / (n - 1.0);                 // Bessel (the host raises for n in {0, 1})
+        stats_out[0] = static_cast<float>(n);
+        stats_out[1] = static_cast<float>(mean);
+        stats_out[2] = static_cast<float>(var);
+        stats_out[3] = static_cast<float>(1.0 / sqrt(static_cast<double>(static_cast<float>(var)) + 1e-8));
+    }
+}
+
+__global__ void __launch_bounds__(256) whiten_apply_kernel(float* __restrict__ x, const float* __restrict__ stats,
+                                                           int64_t n) {
+    const float mean = stats[1], rstd = stats[3];
+    const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (vec) {
+        float4* x4 = reinterpret_cast<float4*>(x);
+        for (int64_t i = tid; i < n / 4; i += stride) {
+            float4 v = x4[i];
+            v.x = (v.x - mean) * rstd;
+            v.y = (v.y - mean) * rstd;
+            v.z = (v.z - mean) * rstd;
+            v.w = (v.w - mean) * rstd;
+            x4[i] = v;
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += stride) x[i] = (x[i] - mean) * rstd;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ KL in reward
+
+__device__ __forceinline__ float kl_value(float lp, float base, int type) {
+    const float d = lp - base;
+    switch (type) {
+        case SKYB200_KL_K1:
+            return d;
+        case SKYB200_KL_ABS:
+            return fabsf(d);
+        case SKYB200_KL_K2:
+            return 0.5f * d * d;
+        default: {
+            const float x = fminf(fmaxf(base - lp, -20.f), 20.f);
+            const float k = expf(x) - x - 1.f;
+            return fminf(fmaxf(k, -10.f), 10.f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+reward_kl_kernel(const float* __restrict__ lp, const float* __restrict__ base_lp, const float* __restrict__ mask,
+                 const float* __restrict__ rewards, float* __restrict__ rewards_out, float* __restrict__ row_mean,
+                 float* __restrict__ row_max, int64_t A, int kl_type, float coef) {
+    __shared__ float sh[34];
+    const int row = blockIdx.x;
+    const int64_t base = static_cast<int64_t>(row) * A;
+    float s_km = 0.f, s_m = 0.f, mx = 0.f;
+    for (int64_t t = threadIdx.x; t < A; t += blockDim.x) {
+        const int64_t i = base + t;
+        const float m = mask ? mask[i] : 1.f;
+        float kl = kl_value(lp[i], base_lp[i], kl_type);
+        if (mask) kl *= m;
+        rewards_out[i] = rewards[i] - kl * coef;
+        mx = fmaxf(mx, fabsf(kl));
+        s_km = fmaf(kl, m, s_km);
+        s_m += m;
+    }
+    s_km = block_sum(s_km, sh);
+    s_m = block_sum(s_m, sh);
+    mx = block_max(mx, sh);
+    if (threadIdx.x == 0) {
+        row_mean[row] = mask ? s_km / fmaxf(s_m, 1.f) : s_km / static_cast<float>(A);
+        row_max[row] = mx;
+    }
+}
+
+__global__ void __launch_bounds__(256) row_means_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                        int B, float* __restrict__ out) {
+    __shared__ float sh[34];
+    float sa = 0.f, sb = 0.f;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        sa += a[i];
+        sb += b[i];
+    }
+    sa = block_sum(sa, sh);
+    sb = block_sum(sb, sh);
+    if (threadIdx.x == 0) {
+        out[0] = sa / static_cast<float>(B);
+        out[1] = sb / static_cast<float>(B);
+    }
+}
+
+}  // namespace skyb200
+
+using namespace skyb200;
+
+extern "C" int skyb200_group_advantage(const float* rewards, const void* response_mask, int32_t mask_type,
+                                       const int32_t* group_of_row, const int32_t* group_start,
+                                       const int32_t* group_rows, float* out, float* scores_ws, int64_t B, int64_t A,
+                                       int32_t num_groups, int32_t mode, float epsilon, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (B == 0 || A == 0) return SKYB200_OK;
+    SKYB200_REQUIRE(rewards && group_of_row && group_start && group_rows && out && scores_ws, "null pointer");
+    SKYB200_REQUIRE(mask_type == SKYB200_MASK_NONE || response_mask != nullptr, "mask pointer missing");
+    SKYB200_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (grpo), 1 (grpo no std) or 2 (rloo)");
+    SKYB200_REQUIRE(B < 65536 && num_groups > 0, "need B < 65536 and num_groups > 0");
+    row_sum_kernel<<<(unsigned)B, 256, 0, stream>>>(rewards, scores_ws, A);
+    int rc = check_launch("row_sum_kernel");
+    if (rc) return rc;
+    const dim3 grid((unsigned)((A + kBcastTile - 1) / kBcastTile), (unsigned)B);
+    switch (mask_type) {
+        case SKYB200_MASK_F32:
+            group_broadcast_kernel<SKYB200_MASK_F32><<<grid, 256, 0, stream>>>(
+                scores_ws, response_mask, group_of_row, group_start, group_rows, out, A, mode, epsilon);
+            break;
+        case SKYB200_MASK_I64:
+            group_broadcast_kernel<SKYB200_MASK_I64><<<grid, 256, 0, stream>>>(
+                scores_ws, response_mask, group_of_row, group_start, group_rows, out, A, mode, epsilon);
+            break;
+        case SKYB200_MASK_NONE:
+            group_broadcast_kernel<SKYB200_MASK_NONE><<<grid, 256, 0, stream>>>(
+                scores_ws, response_mask, group_of_row, group_start, group_rows, out, A, mode, epsilon);
+            break;
+        default:
+            return fail(SKYB200_EINVAL, "bad mask_type %d", mask_type);
+    }
+    return check_launch("group_broadcast_kernel");
+}
+
+extern "C" size_t skyb200_gae_workspace(int64_t B) { return (size_t)(B * 3 * sizeof(double) + 256); }
+
+extern "C" int skyb200_gae_advantage(const float* rewards, const float* values, const void* response_mask,
+                                     int32_t mask_type, float* advantages, float* returns, float* stats_out,
+                                     void* workspace, size_t workspace_bytes, int64_t B, int64_t A, float gamma,
+                                     float lambd, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(rewards && values && advantages && returns && stats_out && workspace, "null pointer");
+    SKYB200_REQUIRE(mask_type == SKYB200_MASK_NONE || response_mask != nullptr, "mask pointer missing");
+    SKYB200_REQUIRE(B > 0 && A > 0 && B < (1ll << 31), "bad shape");
+    if (workspace_bytes < skyb200_gae_workspace(B)) return fail(SKYB200_EWORKSPACE, "gae workspace too small");
+    double* row_stats = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    switch (mask_type) {
+        case SKYB200_MASK_F32:
+            gae_scan_kernel<SKYB200_MASK_F32><<<(unsigned)B, kGaeThreads, 0, stream>>>(
+                rewards, values, response_mask, advantages, returns, row_stats, A, gamma, lambd);
+            break;
+        case SKYB200_MASK_I64:
+            gae_scan_kernel<SKYB200_MASK_I64><<<(unsigned)B, kGaeThreads, 0, stream>>>(
+                rewards, values, response_mask, advantages, returns, row_stats, A, gamma, lambd);
+            break;
+        case SKYB200_MASK_NONE:
+            gae_scan_kernel<SKYB200_MASK_NONE><<<(unsigned)B, kGaeThreads, 0, stream>>>(
+                rewards, values, response_mask, advantages, returns, row_stats, A, gamma, lambd);
+            break;
+        default:
+            return fail(SKYB200_EINVAL, "bad mask_type %d", mask_type);
+    }
+    int rc = check_launch("gae_scan_kernel");
+    if (rc) return rc;
+    whiten_stats_kernel<<<1, 256, 0, stream>>>(row_stats, (int)B, stats_out);
+    rc = check_launch("whiten_stats_kernel");
+    if (rc) return rc;
+    const int64_t n = B * A;
+    int64_t blocks = (n / 4 + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    whiten_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(advantages, stats_out, n);
+    return check_launch("whiten_apply_kernel");
+}
+
+extern "C" int skyb200_reward_kl_penalty(const float* log_probs, const float* base_log_probs, const float* loss_mask,
+                                         const float* rewards, float* rewards_out, float* metrics_out, float* row_ws,
+                                         int64_t B, int64_t A, int32_t kl_type, float kl_coef, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(log_probs && base_log_probs && rewards && rewards_out && metrics_out && row_ws, "null pointer");
+    SKYB200_REQUIRE(kl_type >= 0 && kl_type <= SKYB200_KL_K3, "Invalid KL estimator type");
+    SKYB200_REQUIRE(B > 0 && A > 0 && B < (1ll << 31), "bad shape");
+    const float coef = kl_coef > 0.f ? kl_coef : 0.f;  // max(0, kl_loss_coef)
+    reward_kl_kernel<<<(unsigned)B, 256, 0, stream>>>(log_probs, base_log_probs, loss_mask, rewards, rewards_out,
+                                                      row_ws, row_ws + B, A, kl_type, coef);
+    int rc = check_launch("reward_kl_kernel");
+    if (rc) return rc;
+    row_means_kernel<<<1, 256, 0, stream>>>(row_ws, row_ws + B, (int)B, metrics_out);
+    return check_launch("row_means_kernel");
+}

@@ -1,0 +1,528 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a with pluggable TMEM epilogues.
+//
+//   C[M,N] = A[M,K] * B[N,K]^T        (fp32 accumulation in tensor memory)
+//
+// Operands are staged by TMA into 128B-swizzled shared memory, multiplied by tcgen05.mma (one issuing
+// thread), accumulated in TMEM (double-buffered, 2 x BN columns) and drained by four epilogue warps
+// (thread i <-> accumulator row i) through tcgen05.ld.  kCtas == 2 pairs two SMs on one 256-row tile
+// (cta_group::2): each CTA loads its own 128 A rows and half of the B tile.
+//
+// Either operand may be K-major (rows of K contiguous elements) or MN-major (stored [K, MN] with MN
+// contiguous); the backward GEMMs of the fused LM head use the MN-major forms so no transposed copies of
+// the weight / hidden / dlogits matrices are ever made.
+//
+// Warp roles (256 threads):  warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (leader CTA only),
+// warp 2 = TMEM allocator, warps 4..7 = epilogue.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "ptx.cuh"
+
+namespace skyb200 {
+
+constexpr int kBM = 128;  // accumulator rows per CTA (= TMEM lanes)
+constexpr int kBK = 64;   // bf16 elements per 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+// Debug record written to mapped host memory when a barrier wait times out (so a protocol bug shows up
+// as a failed launch with a readable reason instead of a hung GPU).
+struct GemmDebug {
+    unsigned int flag;
+    unsigned int role;
+    unsigned int which;
+    unsigned int stage;
+    unsigned int parity;
+    unsigned int tile;
+    unsigned int block;
+    unsigned int pad;
+};
+
+__device__ __forceinline__ void bounded_wait(uint64_t* bar, uint32_t parity, GemmDebug* dbg, uint32_t role,
+                                             uint32_t which, uint32_t stage, uint32_t tile) {
+    uint32_t spins = 0;
+    while (!ptx::mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) {  // try_wait itself blocks for a HW-defined slice; this is seconds
+            if (dbg != nullptr && atomicExch(&dbg->flag, 1u) == 0u) {
+                dbg->role = role;
+                dbg->which = which;
+                dbg->stage = stage;
+                dbg->parity = parity;
+                dbg->tile = tile;
+                dbg->block = blockIdx.x;
+                __threadfence_system();
+            }
+            __trap();
+        }
+    }
+}
+
+struct TileCoord {
+    int m_tile;
+    int n_tile;
+};
+
+// Tile order: groups of `group_m` M-tiles sweep all N-tiles with the M index fastest, so concurrently
+// resident CTAs share the same B tile (L2 hits) while the A group stays L2-resident.
+__device__ __forceinline__ TileCoord decode_tile(int t, int num_m_tiles, int num_n_tiles, int group_m) {
+    const int tiles_per_group = group_m * num_n_tiles;
+    const int g = t / tiles_per_group;
+    const int first_m = g * group_m;
+    const int gm = min(group_m, num_m_tiles - first_m);
+    const int r = t - g * tiles_per_group;
+    TileCoord c;
+    c.n_tile = r / gm;
+    c.m_tile = first_m + (r - c.n_tile * gm);
+    return c;
+}
+
+template <int kCtas, int BN, int kStages>
+struct GemmSmem {
+    static constexpr uint32_t kABytes = kBM * kBK * 2;
+    static constexpr uint32_t kLoadN = BN / kCtas;
+    static constexpr uint32_t kBBytes = kLoadN * kBK * 2;
+    static constexpr uint32_t kBarBytes = (2 * kStages + 4) * 8 + 16;
+    static constexpr uint32_t kTotal = 1024 + kStages * (kABytes + kBBytes) + kBarBytes;
+};
+
+template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
+                  int N, int K, int group_m, typename Epi::Params ep, GemmDebug* dbg) {
+    using S = GemmSmem<kCtas, BN, kStages>;
+    constexpr int TILE_M = kBM * kCtas;
+    constexpr uint32_t kTmemCols = 2 * BN;
+    static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
+    static_assert(kTmemCols <= 512, "TMEM overflow");
+
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment (required by the 128B swizzle atoms); identical in both CTAs of a pair.
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * S::kABytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kStages * S::kBBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (kCtas == 2) ? ptx::cluster_ctarank() : 0u;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmap_a);
+        ptx::prefetch_tensormap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], kCtas * 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc<kCtas>(tmem_slot, kTmemCols);
+    }
+    ptx::tcgen05_fence_before();
+    if constexpr (kCtas == 2) {
+        ptx::cluster_sync();
+    } else {
+        __syncthreads();
+    }
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    const int num_m_tiles = (M + TILE_M - 1) / TILE_M;
+    const int num_n_tiles = (N + BN - 1) / BN;
+    const int total_tiles = num_m_tiles * num_n_tiles;
+    const int num_kb = (K + kBK - 1) / kBK;
+    const int cluster_id = blockIdx.x / kCtas;
+    const int num_clusters = gridDim.x / kCtas;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (one lane)
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+                const TileCoord tc = decode_tile(t, num_m_tiles, num_n_tiles, group_m);
+                const int m0 = tc.m_tile * TILE_M + static_cast<int>(cta_rank) * kBM;
+                const int n0 = tc.n_tile * BN + static_cast<int>(cta_rank * S::kLoadN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    bounded_wait(&empty_bar[stage], phase ^ 1u, dbg, 0, 0, stage, t);
+                    if (cta_rank == 0) {
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], (S::kABytes + S::kBBytes) * kCtas);
+                    }
+                    uint8_t* a_dst = smem_a + stage * S::kABytes;
+                    uint8_t* b_dst = smem_b + stage * S::kBBytes;
+                    const int k0 = kb * kBK;
+                    if constexpr (kAMn) {
+#pragma unroll
+                        for (int j = 0; j < kBM / 64; ++j) {
+                            if constexpr (kCtas == 2)
+                                ptx::tma_load_2d_2sm(&tmap_a, &full_bar[stage], a_dst + j * 8192, m0 + j * 64, k0);
+                            else
+                                ptx::tma_load_2d(&tmap_a, &full_bar[stage], a_dst + j * 8192, m0 + j * 64, k0);
+                        }
+                    } else {
+                        if constexpr (kCtas == 2)
+                            ptx::tma_load_2d_2sm(&tmap_a, &full_bar[stage], a_dst, k0, m0);
+                        else
+                            ptx::tma_load_2d(&tmap_a, &full_bar[stage], a_dst, k0, m0);
+                    }
+                    if constexpr (kBMn) {
+#pragma unroll
+                        for (int j = 0; j < static_cast<int>(S::kLoadN) / 64; ++j) {
+                            if constexpr (kCtas == 2)
+                                ptx::tma_load_2d_2sm(&tmap_b, &full_bar[stage], b_dst + j * 8192, n0 + j * 64, k0);
+                            else
+                                ptx::tma_load_2d(&tmap_b, &full_bar[stage], b_dst + j * 8192, n0 + j * 64, k0);
+                        }
+                    } else {
+                        if constexpr (kCtas == 2)
+                            ptx::tma_load_2d_2sm(&tmap_b, &full_bar[stage], b_dst, k0, n0);
+                        else
+                            ptx::tma_load_2d(&tmap_b, &full_bar[stage], b_dst, k0, n0);
+                    }
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one lane, leader CTA)
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BN, kAMn ? 1u : 0u, kBMn ? 1u : 0u);
+            // K-major: 8-row groups are 1024 B apart, K advances 32 B inside the swizzle atom.
+            // MN-major: 64-element MN groups are one [64 x 64] box (8192 B) apart, 8-row K groups 1024 B.
+            constexpr uint32_t a_lbo = kAMn ? 8192u : 16u, a_sbo = 1024u, a_kstep = kAMn ? 2048u : 32u;
+            constexpr uint32_t b_lbo = kBMn ? 8192u : 16u, b_sbo = 1024u, b_kstep = kBMn ? 2048u : 32u;
+            uint32_t stage = 0, phase = 0, accum = 0, aphase = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+                bounded_wait(&tempty_bar[accum], aphase ^ 1u, dbg, 1, 1, accum, t);
+                ptx::tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + accum * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    bounded_wait(&full_bar[stage], phase, dbg, 1, 0, stage, t);
+                    ptx::tcgen05_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem_a + stage * S::kABytes);
+                    const uint32_t b_addr = ptx::smem_u32(smem_b + stage * S::kBBytes);
+#pragma unroll
+                    for (int j = 0; j < kBK / kUmmaK; ++j) {
+                        const uint64_t da = ptx::make_smem_desc_sw128(a_addr + j * a_kstep, a_lbo, a_sbo);
+                        const uint64_t db = ptx::make_smem_desc_sw128(b_addr + j * b_kstep, b_lbo, b_sbo);
+                        ptx::umma_bf16<kCtas>(tmem_d, da, db, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                    }
+                    ptx::umma_commit<kCtas>(&empty_bar[stage]);
+                    if (kb == num_kb - 1) ptx::umma_commit<kCtas>(&tfull_bar[accum]);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (++accum == 2) {
+                    accum = 0;
+                    aphase ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ------------------------------------------------------------ epilogue (4 warps, row per thread)
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        uint32_t accum = 0, aphase = 0;
+        for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+            const TileCoord tc = decode_tile(t, num_m_tiles, num_n_tiles, group_m);
+            bounded_wait(&tfull_bar[accum], aphase, dbg, 2, 2, accum, t);
+            ptx::tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + accum * BN;
+            const int row = tc.m_tile * TILE_M + static_cast<int>(cta_rank) * kBM + q * 32 + lane;
+            Epi::template run<BN>(ep, taddr, row, tc.n_tile, M, N);
+            ptx::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (kCtas == 2)
+                    ptx::mbar_arrive_cluster(&tempty_bar[accum], 0);
+                else
+                    ptx::mbar_arrive(&tempty_bar[accum]);
+            }
+            if (++accum == 2) {
+                accum = 0;
+                aphase ^= 1u;
+            }
+        }
+    }
+
+    ptx::tcgen05_fence_before();
+    if constexpr (kCtas == 2) {
+        ptx::cluster_sync();
+    } else {
+        __syncthreads();
+    }
+    if (warp == 2) {
+        ptx::tcgen05_fence_after();
+        ptx::tmem_dealloc<kCtas>(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ epilogues
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// C (fp32, row-major, leading dim ldc) = or += accumulator.   Used for dW and for GEMM self-tests.
+struct EpiStoreF32 {
+    struct Params {
+        float* C;
+        int64_t ldc;
+        int accumulate;
+    };
+    template <int BN>
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+        const int n0 = n_tile * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            __syncwarp();
+            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            const int col0 = n0 + c * 32;
+            if (row < M && col0 < N) {
+                float* dst = p.C + static_cast<int64_t>(row) * p.ldc + col0;
+                if (col0 + 32 <= N && (p.ldc & 3) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 o = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                               __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                        float4* d4 = reinterpret_cast<float4*>(dst) + i;
+                        if (p.accumulate) {
+                            const float4 old = *d4;
+                            o.x += old.x;
+                            o.y += old.y;
+                            o.z += old.z;
+                            o.w += old.w;
+                        }
+                        *d4 = o;
+                    }
+                } else {
+                    for (int i = 0; i < 32 && col0 + i < N; ++i) {
+                        const float a = __uint_as_float(v[i]);
+                        dst[i] = p.accumulate ? dst[i] + a : a;
+                    }
+                }
+            }
+        }
+    }
+};
+
+// C (bf16, row-major) = accumulator.   Used for d_hidden.
+struct EpiStoreBF16 {
+    struct Params {
+        __nv_bfloat16* C;
+        int64_t ldc;
+    };
+    template <int BN>
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+        const int n0 = n_tile * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            __syncwarp();
+            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            const int col0 = n0 + c * 32;
+            if (row < M && col0 < N) {
+                __nv_bfloat16* dst = p.C + static_cast<int64_t>(row) * p.ldc + col0;
+                if (col0 + 32 <= N && (p.ldc & 7) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 o;
+                        o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+                        o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+                        o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+                        o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+                        reinterpret_cast<uint4*>(dst)[i] = o;
+                    }
+                } else {
+                    for (int i = 0; i < 32 && col0 + i < N; ++i) dst[i] = __float2bfloat16_rn(__uint_as_float(v[i]));
+                }
+            }
+        }
+    }
+};
+
+// Forward LM-head epilogue: per (row, vocab-slab) online-softmax partials in log2 units.
+//   y = acc * scale_log2  (scale_log2 = log2(e) / temperature)
+//   part_m = max_j y_j ; part_s = sum_j 2^(y_j - part_m) ; part_t = sum_j 2^(y_j - part_m) * acc_j
+// and the raw accumulator at the label column (written by the one slab that contains it).
+struct EpiLsePartials {
+    struct Params {
+        float scale_log2;
+        float* part_m;  // [num_n_tiles][ld]
+        float* part_s;
+        float* part_t;
+        int64_t ld;
+        const int64_t* labels;  // [M]
+        float* label_acc;       // [M]
+    };
+    template <int BN>
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+        const int n0 = n_tile * BN;
+        const bool row_ok = row < M;
+        const int lab = row_ok ? static_cast<int>(p.labels[row]) : -1;
+        float m2 = -INFINITY, s = 0.f, tt = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            __syncwarp();
+            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            const int col0 = n0 + c * 32;
+            if (col0 >= N) continue;  // uniform across the whole warp
+            const int nvalid = min(32, N - col0);
+            float cm = -INFINITY;
+            if (nvalid == 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < nvalid) cm = fmaxf(cm, __uint_as_float(v[i]));
+            }
+            const float m_new = fmaxf(m2, cm * p.scale_log2);
+            const float corr = ex2_approx(m2 - m_new);  // 0 on the first chunk (m2 = -inf)
+            s *= corr;
+            tt *= corr;
+            m2 = m_new;
+            if (nvalid == 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float a = __uint_as_float(v[i]);
+                    const float e = ex2_approx(fmaf(a, p.scale_log2, -m2));
+                    s += e;
+                    tt = fmaf(e, a, tt);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i < nvalid) {
+                        const float a = __uint_as_float(v[i]);
+                        const float e = ex2_approx(fmaf(a, p.scale_log2, -m2));
+                        s += e;
+                        tt = fmaf(e, a, tt);
+                    }
+                }
+            }
+            if (lab >= col0 && lab < col0 + nvalid) {
+                float z = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (col0 + i == lab) z = __uint_as_float(v[i]);
+                p.label_acc[row] = z;
+            }
+        }
+        if (row_ok) {
+            const int64_t o = static_cast<int64_t>(n_tile) * p.ld + row;
+            p.part_m[o] = m2;
+            p.part_s[o] = s;
+            p.part_t[o] = tt;
+        }
+    }
+};
+
+// Backward LM-head epilogue: recompute the logits tile and turn it into d(raw logits) in bf16:
+//   u = acc*scale_log2 - lse2[row]         (log2 p)
+//   p = 2^u
+//   d = inv_T * ( g_lp * 1[j == label] - p * (g_lp + g_ent * (u*ln2 + H)) )
+struct EpiDLogits {
+    struct Params {
+        float scale_log2;
+        float inv_temperature;
+        const float* lse2;     // [M] log2-sum-exp of y
+        const float* g_lp;     // [M]
+        const float* g_ent;    // [M] or nullptr
+        const float* entropy;  // [M] (needed iff g_ent)
+        const int64_t* labels;
+        __nv_bfloat16* dS;  // [M, ld]
+        int64_t ld;
+    };
+    template <int BN>
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+        const int n0 = n_tile * BN;
+        const bool row_ok = row < M;
+        float lse2 = 0.f, glp = 0.f, gent = 0.f, H = 0.f;
+        int lab = -1;
+        if (row_ok) {
+            lse2 = p.lse2[row];
+            glp = p.g_lp[row];
+            lab = static_cast<int>(p.labels[row]);
+            if (p.g_ent != nullptr) {
+                gent = p.g_ent[row];
+                H = p.entropy[row];
+            }
+        }
+        const float a0 = (glp + gent * H) * (-p.inv_temperature);
+        const float b0 = gent * 0.6931471805599453f * (-p.inv_temperature);
+        const float lab_add = glp * p.inv_temperature;
+        const bool all_zero = (glp == 0.f && gent == 0.f);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            __syncwarp();
+            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            const int col0 = n0 + c * 32;
+            if (col0 >= N || !row_ok) continue;  // lanes reconverge at the __syncwarp above
+            float d[32];
+            if (all_zero) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) d[i] = 0.f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float u = fmaf(__uint_as_float(v[i]), p.scale_log2, -lse2);
+                    const float pr = ex2_approx(u);
+                    d[i] = pr * fmaf(u, b0, a0);
+                }
+                if (lab >= col0 && lab < col0 + 32) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (col0 + i == lab) d[i] += lab_add;
+                }
+            }
+            __nv_bfloat16* dst = p.dS + static_cast<int64_t>(row) * p.ld + col0;
+            if (col0 + 32 <= N && (p.ld & 7) == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 o;
+                    o.x = pack_bf16x2(d[8 * i + 0], d[8 * i + 1]);
+                    o.y = pack_bf16x2(d[8 * i + 2], d[8 * i + 3]);
+                    o.z = pack_bf16x2(d[8 * i + 4], d[8 * i + 5]);
+                    o.w = pack_bf16x2(d[8 * i + 6], d[8 * i + 7]);
+                    reinterpret_cast<uint4*>(dst)[i] = o;
+                }
+            } else {
+                for (int i = 0; i < 32 && col0 + i < N; ++i) dst[i] = __float2bfloat16_rn(d[i]);
+            }
+        }
+    }
+};
+
+}  // namespace skyb200

@@ -1,0 +1,478 @@
+// Fused LM head for the policy update: hidden[N,H] x weight[V,H]^T -> per-token log-prob of the label and
+// entropy, forward and backward, without ever holding [N, V] logits.
+//
+// Forward  (per token chunk):  tcgen05 GEMM whose epilogue reduces each 128x256 logits tile (still in TMEM)
+//                              to online-softmax partials, then a merge kernel over the vocab slabs.
+// Backward (per token chunk):  (1) the same GEMM again, epilogue = d(logits) in bf16 into a bounded scratch
+//                              [chunk, V]; (2) d_hidden = dS * W (B operand MN-major straight from the
+//                              nn.Linear weight); (3) d_weight += dS^T * hidden (both operands MN-major).
+//
+// Replaces model_wrapper.py:309-363 + torch_utils.py:59-177 of the reference (lm_head GEMM, logits.div_(T),
+// flash-attn cross-entropy, chunked entropy) — see include/skyb200.h.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+
+namespace skyb200 {
+
+// ------------------------------------------------------------------------------------------ host utils
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
+}
+
+// 2D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch in elements.
+static int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                          uint32_t box_inner, uint32_t box_outer) {
+    auto enc = get_encode_fn();
+    if (enc == nullptr) return fail(SKYB200_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return fail(SKYB200_EINVAL, "TMA base not 16B aligned");
+    if ((pitch_elems * 2) % 16 != 0) return fail(SKYB200_EINVAL, "row pitch must be a multiple of 8 bf16");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SKYB200_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SKYB200_OK;
+}
+
+static GemmDebug* g_dbg_host = nullptr;  // mapped pinned memory
+static GemmDebug* g_dbg_dev = nullptr;
+
+static GemmDebug* debug_record_dev() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = nullptr;
+        if (cudaHostAlloc(&h, sizeof(GemmDebug), cudaHostAllocMapped) == cudaSuccess) {
+            memset(h, 0, sizeof(GemmDebug));
+            void* d = nullptr;
+            if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+                g_dbg_host = static_cast<GemmDebug*>(h);
+                g_dbg_dev = static_cast<GemmDebug*>(d);
+            }
+        }
+    });
+    return g_dbg_dev;
+}
+
+// A: K-major -> [M, K] with pitch lda; MN-major -> [K, M] with pitch lda.  Same for B with N.
+template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
+static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int group_m,
+                       const typename Epi::Params& ep, cudaStream_t stream) {
+    using S = GemmSmem<kCtas, BN, kStages>;
+    if (M <= 0 || N <= 0 || K <= 0) return SKYB200_OK;
+    CUtensorMap ta, tb;
+    int rc;
+    if (kAMn)
+        rc = make_tmap_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, 64);
+    else
+        rc = make_tmap_bf16(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, kBM);
+    if (rc) return rc;
+    if (kBMn)
+        rc = make_tmap_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64);
+    else
+        rc = make_tmap_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, S::kLoadN);
+    if (rc) return rc;
+
+    auto kern = gemm_sm100_kernel<kCtas, BN, kStages, kAMn, kBMn, Epi>;
+    static bool attr_set = false;  // per template instantiation
+    if (!attr_set) {
+        SKYB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kTotal));
+        attr_set = true;
+    }
+    const int tile_m = kBM * kCtas;
+    const int64_t tiles = (int64_t)((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
+    const int clusters = (int)std::min<int64_t>(tiles, num_sms() / kCtas);
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * kCtas);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = S::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GemmDebug* dbg = debug_record_dev();
+    if (group_m < 1) group_m = 1;
+    SKYB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group_m, ep, dbg));
+    return SKYB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ configuration
+
+// The production configuration: CTA pairs (cta_group::2) on 256x256 tiles, 6-stage TMA ring.
+constexpr int kHeadCtas = 2;
+constexpr int kHeadBN = 256;
+constexpr int kHeadStages = 6;
+constexpr int kTileM = kBM * kHeadCtas;
+
+// Token chunk = 37 pair-tiles: 37 * n_tiles is a multiple of the 74 resident CTA pairs, so every GEMM of the
+// chunk runs in whole waves on the 148 SMs.
+constexpr int64_t kDefaultChunk = 37 * kTileM;  // 9472 tokens
+
+static int64_t pick_chunk(int64_t N, int64_t chunk) {
+    if (chunk <= 0) chunk = kDefaultChunk;
+    chunk = std::min<int64_t>(chunk, ((N + kTileM - 1) / kTileM) * kTileM);
+    chunk = ((chunk + kTileM - 1) / kTileM) * kTileM;
+    return std::max<int64_t>(chunk, kTileM);
+}
+static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static int64_t num_slabs(int64_t V) { return (V + kHeadBN - 1) / kHeadBN; }
+
+// ------------------------------------------------------------------------------------------ merge kernel
+
+// Combine the per-slab online-softmax partials of one token chunk.
+//   lse2 = M + log2(S);  logprob = acc_label/T - ln2*lse2;  entropy = ln2*lse2 - (T_sum/S)/T
+__global__ void __launch_bounds__(256) head_merge_kernel(const float* __restrict__ part_m,
+                                                         const float* __restrict__ part_s,
+                                                         const float* __restrict__ part_t, int64_t ld, int slabs,
+                                                         const float* __restrict__ label_acc,
+                                                         const float* __restrict__ entropy_mask, float inv_T,
+                                                         float* __restrict__ logprobs, float* __restrict__ entropy,
+                                                         float* __restrict__ lse2_out, int rows) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float M = -INFINITY;
+    for (int s = 0; s < slabs; ++s) M = fmaxf(M, part_m[(int64_t)s * ld + r]);
+    float S = 0.f, T = 0.f;
+    for (int s = 0; s < slabs; ++s) {
+        const int64_t o = (int64_t)s * ld + r;
+        const float w = exp2f(part_m[o] - M);
+        S = fmaf(part_s[o], w, S);
+        T = fmaf(part_t[o], w, T);
+    }
+    const float lse2 = M + log2f(S);
+    const float lse = lse2 * 0.6931471805599453f;
+    lse2_out[r] = lse2;
+    logprobs[r] = label_acc[r] * inv_T - lse;
+    if (entropy != nullptr) {
+        float h = lse - (T / S) * inv_T;
+        if (entropy_mask != nullptr) h *= entropy_mask[r];
+        entropy[r] = h;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ logits path
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) {
+    return v;
+}
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) {
+    return __bfloat162float(v);
+}
+
+// One block per row of materialised logits: online (max, sum exp, sum exp*z) + label gather.
+template <typename T>
+__global__ void __launch_bounds__(512) logits_row_kernel(const T* __restrict__ logits,
+                                                         const int64_t* __restrict__ labels,
+                                                         const float* __restrict__ entropy_mask,
+                                                         float* __restrict__ logprobs, float* __restrict__ entropy,
+                                                         float* __restrict__ lse_out, int64_t V) {
+    __shared__ float sh[34];
+    const int64_t row = blockIdx.x;
+    const T* z = logits + row * V;
+    float m = -INFINITY, s = 0.f, t = 0.f;
+    for (int64_t j = threadIdx.x; j < V; j += blockDim.x) {
+        const float x = to_f32<T>(z[j]);
+        if (x > m) {
+            const float c = __expf(m - x);
+            s *= c;
+            t *= c;
+            m = x;
+        }
+        const float e = __expf(x - m);
+        s += e;
+        t = fmaf(e, x, t);
+    }
+    const float M = block_max(m, sh);
+    const float w = (m == -INFINITY) ? 0.f : __expf(m - M);
+    const float S = block_sum(s * w, sh);
+    const float Tt = block_sum(t * w, sh);
+    if (threadIdx.x == 0) {
+        const float lse = M + logf(S);
+        if (lse_out != nullptr) lse_out[row] = lse;
+        if (logprobs != nullptr) logprobs[row] = to_f32<T>(z[labels[row]]) - lse;
+        if (entropy != nullptr) {
+            float h = lse - Tt / S;
+            if (entropy_mask != nullptr) h *= entropy_mask[row];
+            entropy[row] = h;
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) {
+    return v;
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+    return __float2bfloat16_rn(v);
+}
+
+// One block per row: d_j = g_lp*(onehot - p_j) - g_ent*p_j*(log p_j + H); may run in place over the logits.
+template <typename T>
+__global__ void __launch_bounds__(512) logits_backward_kernel(const T* __restrict__ logits,
+                                                              const int64_t* __restrict__ labels,
+                                                              const float* __restrict__ lse,
+                                                              const float* __restrict__ entropy,
+                                                              const float* __restrict__ g_lp,
+                                                              const float* __restrict__ g_ent, T* d_logits,
+                                                              int64_t V) {
+    const int64_t row = blockIdx.x;
+    const T* z = logits + row * V;
+    T* d = d_logits + row * V;
+    const float l = lse[row];
+    const float glp = g_lp ? g_lp[row] : 0.f;
+    const float ge = g_ent ? g_ent[row] : 0.f;
+    const float H = g_ent ? entropy[row] : 0.f;
+    const int64_t lab = labels ? labels[row] : -1;
+    for (int64_t j = threadIdx.x; j < V; j += blockDim.x) {
+        const float lpj = to_f32<T>(z[j]) - l;
+        const float p = __expf(lpj);
+        float g = -p * (glp + ge * (lpj + H));
+        if (j == lab) g += glp;
+        d[j] = from_f32<T>(g);
+    }
+}
+
+}  // namespace skyb200
+
+using namespace skyb200;
+
+// ================================================================================================ C ABI
+
+extern "C" size_t skyb200_head_forward_workspace(int64_t N, int64_t H, int64_t V, int64_t chunk) {
+    (void)H;
+    const int64_t c = pick_chunk(N, chunk);
+    // 3 partial arrays [slabs][c] + label_acc [c]
+    return (size_t)((3 * num_slabs(V) + 1) * c * sizeof(float) + 256);
+}
+
+extern "C" size_t skyb200_head_backward_workspace(int64_t N, int64_t H, int64_t V, int64_t chunk) {
+    (void)H;
+    const int64_t c = pick_chunk(N, chunk);
+    return (size_t)(c * round_up(V, 64) * 2 + 1024);  // dS scratch, bf16
+}
+
+extern "C" int skyb200_head_forward(const void* hidden, const void* weight, const int64_t* labels,
+                                    const float* entropy_mask, float* logprobs, float* entropy, float* lse2,
+                                    void* workspace, size_t workspace_bytes, int64_t N, int64_t H, int64_t V,
+                                    float temperature, int64_t chunk, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (N == 0) return SKYB200_OK;
+    SKYB200_REQUIRE(hidden && weight && labels && logprobs && lse2 && workspace, "null pointer");
+    SKYB200_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
+    SKYB200_REQUIRE(temperature > 0.f, "temperature must be > 0");
+    SKYB200_REQUIRE(N < (1ll << 31) && V < (1ll << 31) && H < (1ll << 31), "dimension too large");
+    if (workspace_bytes < skyb200_head_forward_workspace(N, H, V, chunk))
+        return fail(SKYB200_EWORKSPACE, "head_forward workspace too small");
+    int rc = skyb200_check_device();
+    if (rc) return rc;
+
+    const int64_t c = pick_chunk(N, chunk);
+    const int slabs = (int)num_slabs(V);
+    float* part_m = static_cast<float*>(workspace);
+    float* part_s = part_m + (int64_t)slabs * c;
+    float* part_t = part_s + (int64_t)slabs * c;
+    float* label_acc = part_t + (int64_t)slabs * c;
+    const float inv_T = 1.0f / temperature;
+    const __nv_bfloat16* hid = static_cast<const __nv_bfloat16*>(hidden);
+
+    for (int64_t r0 = 0; r0 < N; r0 += c) {
+        const int rows = (int)std::min<int64_t>(c, N - r0);
+        EpiLsePartials::Params ep;
+        ep.scale_log2 = 1.4426950408889634f * inv_T;
+        ep.part_m = part_m;
+        ep.part_s = part_s;
+        ep.part_t = part_t;
+        ep.ld = c;
+        ep.labels = labels + r0;
+        ep.label_acc = label_acc;
+        // a label outside [0, V) never matches a slab: give it a defined (zero) logit
+        SKYB200_CUDA_CHECK(cudaMemsetAsync(label_acc, 0, (size_t)rows * sizeof(float), stream));
+        rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
+            hid + r0 * H, H, weight, H, rows, (int)V, (int)H, 16, ep, stream);
+        if (rc) return rc;
+        head_merge_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(
+            part_m, part_s, part_t, c, slabs, label_acc, entropy_mask ? entropy_mask + r0 : nullptr, inv_T,
+            logprobs + r0, entropy ? entropy + r0 : nullptr, lse2 + r0, rows);
+        rc = check_launch("head_merge_kernel");
+        if (rc) return rc;
+    }
+    return SKYB200_OK;
+}
+
+extern "C" int skyb200_head_backward(const void* hidden, const void* weight, const int64_t* labels,
+                                     const float* lse2, const float* entropy, const float* g_logprobs,
+                                     const float* g_entropy, void* d_hidden, float* d_weight, int32_t accumulate,
+                                     void* workspace, size_t workspace_bytes, int64_t N, int64_t H, int64_t V,
+                                     float temperature, int64_t chunk, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(hidden && weight && labels && lse2 && g_logprobs && workspace, "null pointer");
+    SKYB200_REQUIRE(d_hidden || d_weight, "nothing to compute");
+    SKYB200_REQUIRE(g_entropy == nullptr || entropy != nullptr, "g_entropy needs the forward entropy");
+    SKYB200_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
+    SKYB200_REQUIRE(temperature > 0.f, "temperature must be > 0");
+    SKYB200_REQUIRE(N < (1ll << 31) && V < (1ll << 31) && H < (1ll << 31), "dimension too large");
+    if (workspace_bytes < skyb200_head_backward_workspace(N, H, V, chunk))
+        return fail(SKYB200_EWORKSPACE, "head_backward workspace too small");
+    int rc = skyb200_check_device();
+    if (rc) return rc;
+    if (N == 0) {
+        if (d_weight && !accumulate) SKYB200_CUDA_CHECK(cudaMemsetAsync(d_weight, 0, (size_t)V * H * 4, stream));
+        return SKYB200_OK;
+    }
+
+    const int64_t c = pick_chunk(N, chunk);
+    const int64_t ldS = round_up(V, 64);
+    __nv_bfloat16* dS = static_cast<__nv_bfloat16*>(workspace);
+    const float inv_T = 1.0f / temperature;
+    const __nv_bfloat16* hid = static_cast<const __nv_bfloat16*>(hidden);
+    __nv_bfloat16* dhid = static_cast<__nv_bfloat16*>(d_hidden);
+
+    for (int64_t r0 = 0; r0 < N; r0 += c) {
+        const int rows = (int)std::min<int64_t>(c, N - r0);
+        // (1) recompute logits tile by tile -> d(logits) bf16
+        EpiDLogits::Params ed;
+        ed.scale_log2 = 1.4426950408889634f * inv_T;
+        ed.inv_temperature = inv_T;
+        ed.lse2 = lse2 + r0;
+        ed.g_lp = g_logprobs + r0;
+        ed.g_ent = g_entropy ? g_entropy + r0 : nullptr;
+        ed.entropy = entropy ? entropy + r0 : nullptr;
+        ed.labels = labels + r0;
+        ed.dS = dS;
+        ed.ld = ldS;
+        rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiDLogits>(
+            hid + r0 * H, H, weight, H, rows, (int)V, (int)H, 16, ed, stream);
+        if (rc) return rc;
+        // (2) d_hidden[rows, H] = dS[rows, V] * W[V, H]      (A K-major, B MN-major)
+        if (dhid != nullptr) {
+            EpiStoreBF16::Params eh;
+            eh.C = dhid + r0 * H;
+            eh.ldc = H;
+            rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
+                dS, ldS, weight, H, rows, (int)H, (int)V, 5, eh, stream);
+            if (rc) return rc;
+        }
+        // (3) d_weight[V, H] (+)= dS^T[V, rows] * hidden[rows, H]   (both MN-major)
+        if (d_weight != nullptr) {
+            EpiStoreF32::Params ew;
+            ew.C = d_weight;
+            ew.ldc = H;
+            ew.accumulate = (accumulate != 0 || r0 > 0) ? 1 : 0;
+            rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
+                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, 5, ew, stream);
+            if (rc) return rc;
+        }
+    }
+    return SKYB200_OK;
+}
+
+extern "C" int skyb200_logits_logprob_entropy(const void* logits, int32_t logits_dtype, const int64_t* labels,
+                                              const float* entropy_mask, float* logprobs, float* entropy,
+                                              float* lse, int64_t N, int64_t V, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (N == 0) return SKYB200_OK;
+    SKYB200_REQUIRE(logits != nullptr, "null logits");
+    SKYB200_REQUIRE(logprobs == nullptr || labels != nullptr, "labels required for logprobs");
+    SKYB200_REQUIRE(V > 0 && N < (1ll << 31), "bad shape");
+    if (logits_dtype == 0)
+        logits_row_kernel<float><<<(unsigned)N, 512, 0, stream>>>(static_cast<const float*>(logits), labels,
+                                                                  entropy_mask, logprobs, entropy, lse, V);
+    else if (logits_dtype == 1)
+        logits_row_kernel<__nv_bfloat16><<<(unsigned)N, 512, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(logits), labels, entropy_mask, logprobs, entropy, lse, V);
+    else
+        return fail(SKYB200_EINVAL, "logits_dtype must be 0 (fp32) or 1 (bf16)");
+    return check_launch("logits_row_kernel");
+}
+
+extern "C" int skyb200_logits_backward(const void* logits, int32_t logits_dtype, const int64_t* labels,
+                                       const float* lse, const float* entropy, const float* g_lp, const float* g_ent,
+                                       void* d_logits, int64_t N, int64_t V, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (N == 0) return SKYB200_OK;
+    SKYB200_REQUIRE(logits && lse && d_logits, "null pointer");
+    SKYB200_REQUIRE(g_ent == nullptr || entropy != nullptr, "g_ent needs the forward entropy");
+    SKYB200_REQUIRE(g_lp == nullptr || labels != nullptr, "g_lp needs labels");
+    SKYB200_REQUIRE(V > 0 && N < (1ll << 31), "bad shape");
+    if (logits_dtype == 0)
+        logits_backward_kernel<float><<<(unsigned)N, 512, 0, stream>>>(
+            static_cast<const float*>(logits), labels, lse, entropy, g_lp, g_ent, static_cast<float*>(d_logits), V);
+    else if (logits_dtype == 1)
+        logits_backward_kernel<__nv_bfloat16><<<(unsigned)N, 512, 0, stream>>>(
+            static_cast<const __nv_bfloat16*>(logits), labels, lse, entropy, g_lp, g_ent,
+            static_cast<__nv_bfloat16*>(d_logits), V);
+    else
+        return fail(SKYB200_EINVAL, "logits_dtype must be 0 (fp32) or 1 (bf16)");
+    return check_launch("logits_backward_kernel");
+}
+
+template <int kCtas, int BN, int kStages>
+static int selftest_dispatch(const void* A, const void* B, float* C, int M, int N, int K, int a_mn, int b_mn,
+                             int accumulate, cudaStream_t stream) {
+    EpiStoreF32::Params ep;
+    ep.C = C;
+    ep.ldc = N;
+    ep.accumulate = accumulate;
+    const int64_t lda = a_mn ? M : K, ldb = b_mn ? N : K;
+    if (!a_mn && !b_mn)
+        return launch_gemm<kCtas, BN, kStages, false, false, EpiStoreF32>(A, lda, B, ldb, M, N, K, 4, ep, stream);
+    if (!a_mn && b_mn)
+        return launch_gemm<kCtas, BN, kStages, false, true, EpiStoreF32>(A, lda, B, ldb, M, N, K, 4, ep, stream);
+    if (a_mn && !b_mn)
+        return launch_gemm<kCtas, BN, kStages, true, false, EpiStoreF32>(A, lda, B, ldb, M, N, K, 4, ep, stream);
+    return launch_gemm<kCtas, BN, kStages, true, true, EpiStoreF32>(A, lda, B, ldb, M, N, K, 4, ep, stream);
+}
+
+extern "C" int skyb200_gemm_selftest(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K,
+                                     int32_t a_mn, int32_t b_mn, int32_t ctas, int32_t bn, int32_t accumulate,
+                                     void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(A && B && C, "null pointer");
+    int rc = skyb200_check_device();
+    if (rc) return rc;
+    if (ctas == 1 && bn == 256)
+        return selftest_dispatch<1, 256, 4>(A, B, C, (int)M, (int)N, (int)K, a_mn, b_mn, accumulate, stream);
+    if (ctas == 1 && bn == 128)
+        return selftest_dispatch<1, 128, 6>(A, B, C, (int)M, (int)N, (int)K, a_mn, b_mn, accumulate, stream);
+    if (ctas == 2 && bn == 256)
+        return selftest_dispatch<2, 256, 6>(A, B, C, (int)M, (int)N, (int)K, a_mn, b_mn, accumulate, stream);
+    if (ctas == 2 && bn == 128)
+        return selftest_dispatch<2, 128, 6>(A, B, C, (int)M, (int)N, (int)K, a_mn, b_mn, accumulate, stream);
+    return fail(SKYB200_EINVAL, "unsupported selftest configuration ctas=%d bn=%d", ctas, bn);
+}
+
+extern "C" const uint32_t* skyb200_gemm_debug_record(void) {
+    debug_record_dev();
+    return reinterpret_cast<const uint32_t*>(g_dbg_host);
+}

@@ -1,0 +1,494 @@
+// Policy loss of the PPO/GRPO/GSPO update, forward and backward fused in one memory-bound pass.
+//
+// Reference arithmetic (skyrl-train/skyrl_train/):
+//   ppo_policy_loss            utils/ppo_utils.py:548-586   ("regular", "dual_clip")
+//   gspo_policy_loss           utils/ppo_utils.py:661-725
+//   reduce_loss                utils/ppo_utils.py:984-1009
+//   compute_approx_kl          utils/ppo_utils.py:88-124    (under @torch.no_grad -> no gradient by default)
+//   masked_mean                utils/torch_utils.py:180-184 (denominator clamp(min=1))
+//   loss assembly              workers/worker.py:852-876
+//
+// Two launches: (1) per-row mask sums (+ the GSPO sequence log-ratio) and the global mask sum;
+// (2) the per-token pass that writes d_log_probs / d_entropy and reduces every scalar the worker reports.
+// All reductions are order-deterministic (per-block partials, last block folds them in index order).
+#include "common.cuh"
+
+namespace skyb200 {
+
+constexpr int kLossThreads = 256;
+constexpr int kLossVec = 4;
+constexpr int kLossIters = 4;  // elements per block = 256 * 4 * 4 = 4096
+constexpr int kLossTile = kLossThreads * kLossVec * kLossIters;
+constexpr int kNumPartials = 8;
+
+struct LossWs {
+    float* row_msum;          // [B]
+    float* row_lw;            // [B]  GSPO: masked mean of (lp - olp)
+    float* total_msum;        // [1]
+    unsigned int* counters;   // [2]
+    float* partials;          // [num_blocks][kNumPartials]
+};
+
+static size_t loss_ws_layout(int64_t B, int64_t A, LossWs* ws, void* base) {
+    const int64_t chunks = (A + kLossTile - 1) / kLossTile;
+    const int64_t blocks = B * chunks;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    size_t o_rm = take(B * 4), o_lw = take(B * 4), o_tot = take(16), o_cnt = take(16),
+           o_part = take(blocks * kNumPartials * 4);
+    if (ws != nullptr) {
+        char* b = static_cast<char*>(base);
+        ws->row_msum = reinterpret_cast<float*>(b + o_rm);
+        ws->row_lw = reinterpret_cast<float*>(b + o_lw);
+        ws->total_msum = reinterpret_cast<float*>(b + o_tot);
+        ws->counters = reinterpret_cast<unsigned int*>(b + o_cnt);
+        ws->partials = reinterpret_cast<float*>(b + o_part);
+    }
+    return off;
+}
+
+// ---------------------------------------------------------------------------- (1) row statistics
+__global__ void __launch_bounds__(kLossThreads)
+loss_rowstats_kernel(const float* __restrict__ lp, const float* __restrict__ olp, const float* __restrict__ mask,
+                     float* __restrict__ row_msum, float* __restrict__ row_lw, float* __restrict__ total_msum,
+                     unsigned int* __restrict__ counter, int B, int64_t A, int need_lw) {
+    __shared__ float sh[34];
+    __shared__ bool is_last;
+    const int row = blockIdx.x;
+    const int64_t base = static_cast<int64_t>(row) * A;
+    float ms = 0.f, lw = 0.f;
+    for (int64_t t = threadIdx.x; t < A; t += blockDim.x) {
+        const float m = mask ? mask[base + t] : 1.f;
+        ms += m;
+        if (need_lw) lw += (lp[base + t] - olp[base + t]) * m;
+    }
+    ms = block_sum(ms, sh);
+    if (need_lw) lw = block_sum(lw, sh);
+    if (threadIdx.x == 0) {
+        row_msum[row] = ms;
+        row_lw[row] = need_lw ? lw / fmaxf(ms, 1.f) : 0.f;
+        __threadfence();
+        const unsigned int prev = atomicAdd(counter, 1u);
+        is_last = (prev == static_cast<unsigned int>(B) - 1u);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        float tot = 0.f;
+        for (int i = threadIdx.x; i < B; i += blockDim.x) tot += __ldcg(&row_msum[i]);
+        tot = block_sum(tot, sh);
+        if (threadIdx.x == 0) {
+            *total_msum = tot;
+            *counter = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- (2) per-token pass
+struct LossArgs {
+    const float* lp;
+    const float* olp;
+    const float* adv;
+    const float* mask;
+    const float* base;
+    const float* ent;
+    float* d_lp;
+    float* d_ent;
+    float* stats;
+    LossWs ws;
+    int B;
+    int vec4;
+    int64_t A;
+    skyb200_loss_params p;
+};
+
+__device__ __forceinline__ float kl_estimate(float lp, float base, int type, float* dkl_dlp) {
+    const float d = lp - base;
+    switch (type) {
+        case SKYB200_KL_K1:
+            *dkl_dlp = 1.f;
+            return d;
+        case SKYB200_KL_ABS:
+            *dkl_dlp = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+            return fabsf(d);
+        case SKYB200_KL_K2:
+            *dkl_dlp = d;
+            return 0.5f * d * d;
+        default: {  // k3
+            const float xr = base - lp;
+            const float x = fminf(fmaxf(xr, -20.f), 20.f);
+            const float r = expf(x);
+            const float k = r - x - 1.f;
+            const float kc = fminf(fmaxf(k, -10.f), 10.f);
+            const bool pass = (xr >= -20.f && xr <= 20.f) && (k >= -10.f && k <= 10.f);
+            *dkl_dlp = pass ? (1.f - r) : 0.f;
+            return kc;
+        }
+    }
+}
+
+struct LossAcc {
+    float s_loss = 0.f, s_clip = 0.f, s_kl = 0.f, s_ent = 0.f, s_ratio = 0.f;
+    float r_max = -INFINITY, r_min = INFINITY;
+};
+struct TokenCtx {
+    bool gspo, dual, has_mask, has_base;
+    float lo, hi, seq_ratio, seq_pass, w_scale, kl_scale, clip_c, kl_grad_scale, d_ent_val;
+    int kl_type;
+};
+
+// One response token: accumulates the reductions, returns d final_loss / d log_prob.
+__device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, float lp, float olp, float adv, float m,
+                                            float base) {
+    float ratio, dr_dlp;
+    if (cx.gspo) {
+        ratio = cx.seq_ratio;
+        dr_dlp = cx.seq_ratio * cx.seq_pass;
+    } else {
+        const float delta = lp - olp;
+        ratio = expf(fminf(fmaxf(delta, -20.f), 20.f));
+        dr_dlp = (delta >= -20.f && delta <= 20.f) ? ratio : 0.f;
+    }
+    const float rc = fminf(fmaxf(ratio, cx.lo), cx.hi);
+    const float in_rng = (ratio >= cx.lo && ratio <= cx.hi) ? 1.f : 0.f;
+    const float s1 = ratio * adv, s2 = rc * adv;
+    float loss = -fminf(s1, s2);
+    // d loss / d ratio: torch.min splits ties 50/50 between its two arguments
+    float dl_dr = (s1 < s2) ? -adv : ((s1 > s2) ? -adv * in_rng : -adv * (0.5f + 0.5f * in_rng));
+    const float clipped = (s2 < s1) ? 1.f : 0.f;  // (-surr2 > -surr1), before dual clip
+    if (cx.dual && adv < 0.f) {
+        const float l3 = -adv * cx.clip_c;
+        if (l3 < loss) {
+            loss = l3;
+            dl_dr = 0.f;
+        } else if (l3 == loss) {
+            dl_dr *= 0.5f;
+        }
+    }
+    const float w = m * cx.w_scale;
+    acc.s_loss = fmaf(loss, w, acc.s_loss);
+    acc.s_clip = fmaf(clipped, m, acc.s_clip);
+    acc.s_ratio = fmaf(ratio, m, acc.s_ratio);
+    if (m != 0.f) {
+        acc.r_max = fmaxf(acc.r_max, ratio);
+        acc.r_min = fminf(acc.r_min, ratio);
+    }
+    float g = w * dl_dr * dr_dlp;
+    if (cx.has_base) {
+        float dk;
+        const float kl = kl_estimate(lp, base, cx.kl_type, &dk);
+        const float km = cx.has_mask ? kl * m : kl;  // compute_approx_kl multiplies by the mask ...
+        acc.s_kl = fmaf(km * m, cx.kl_scale, acc.s_kl);  // ... and masked_mean multiplies again
+        g = fmaf(cx.kl_grad_scale * m * (cx.has_mask ? m : 1.f), dk, g);
+    }
+    return g;
+}
+
+__global__ void __launch_bounds__(kLossThreads) loss_main_kernel(LossArgs a) {
+    __shared__ float sh[34];
+    __shared__ bool is_last;
+    const int row = blockIdx.y;
+    const int64_t A = a.A;
+    const int64_t rbase = static_cast<int64_t>(row) * A;
+    const float total_m = __ldcg(a.ws.total_msum);
+    const float row_m = __ldcg(&a.ws.row_msum[row]);
+    const float Bf = static_cast<float>(a.B);
+    const float inv_total = 1.f / fmaxf(total_m, 1.f);
+    const float inv_row = 1.f / fmaxf(row_m, 1.f);
+    float w_scale;
+    if (a.p.reduction == SKYB200_REDUCE_TOKEN_MEAN)
+        w_scale = inv_total;
+    else if (a.p.reduction == SKYB200_REDUCE_SEQUENCE_MEAN)
+        w_scale = inv_row / Bf;
+    else
+        w_scale = 1.f / (a.p.max_seq_len * Bf);
+    const float kl_scale = inv_row / Bf;
+    const bool gspo = (a.p.loss_type == SKYB200_LOSS_GSPO);
+    const bool dual = (a.p.loss_type == SKYB200_LOSS_DUAL_CLIP);
+    const float lo = 1.f - a.p.eps_clip_low, hi = 1.f + a.p.eps_clip_high;
+    float seq_ratio = 1.f, seq_pass = 1.f;
+    if (gspo) {
+        const float lw = __ldcg(&a.ws.row_lw[row]);
+        seq_ratio = expf(fminf(lw, 10.f));
+        seq_pass = (lw <= 10.f) ? 1.f : 0.f;
+    }
+    const bool use_ent_loss = (a.p.use_entropy_loss != 0);
+
+    LossAcc acc;
+    TokenCtx cx;
+    cx.gspo = gspo;
+    cx.dual = dual;
+    cx.lo = lo;
+    cx.hi = hi;
+    cx.seq_ratio = seq_ratio;
+    cx.seq_pass = seq_pass;
+    cx.w_scale = w_scale;
+    cx.kl_scale = kl_scale;
+    cx.clip_c = a.p.clip_ratio_c;
+    cx.kl_type = a.p.kl_type;
+    cx.kl_grad_scale = a.p.kl_has_grad ? a.p.kl_loss_coef * kl_scale : 0.f;
+    cx.has_mask = (a.mask != nullptr);
+    cx.has_base = (a.base != nullptr);
+    cx.d_ent_val = use_ent_loss ? -a.p.entropy_loss_coef * inv_total : 0.f;
+
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * kLossTile;
+    if (a.vec4) {
+        // 128-bit path: every array is 16-byte aligned and A % 4 == 0, so rows start on 16-byte boundaries
+#pragma unroll
+        for (int it = 0; it < kLossIters; ++it) {
+            const int64_t t = t0 + (static_cast<int64_t>(it) * kLossThreads + threadIdx.x) * 4;
+            if (t < A) {
+                const int64_t i = rbase + t;
+                const float4 lp = ldg_stream(reinterpret_cast<const float4*>(a.lp + i));
+                const float4 olp = ldg_stream(reinterpret_cast<const float4*>(a.olp + i));
+                const float4 adv = ldg_stream(reinterpret_cast<const float4*>(a.adv + i));
+                float4 m = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f), en = bs;
+                if (a.mask) m = ldg_stream(reinterpret_cast<const float4*>(a.mask + i));
+                if (a.base) bs = ldg_stream(reinterpret_cast<const float4*>(a.base + i));
+                if (a.ent) en = ldg_stream(reinterpret_cast<const float4*>(a.ent + i));
+                float4 g;
+                g.x = loss_token(cx, acc, lp.x, olp.x, adv.x, m.x, bs.x);
+                g.y = loss_token(cx, acc, lp.y, olp.y, adv.y, m.y, bs.y);
+                g.z = loss_token(cx, acc, lp.z, olp.z, adv.z, m.z, bs.z);
+                g.w = loss_token(cx, acc, lp.w, olp.w, adv.w, m.w, bs.w);
+                if (a.d_lp) *reinterpret_cast<float4*>(a.d_lp + i) = g;
+                if (a.ent) {
+                    acc.s_ent = fmaf(en.x, m.x, acc.s_ent);
+                    acc.s_ent = fmaf(en.y, m.y, acc.s_ent);
+                    acc.s_ent = fmaf(en.z, m.z, acc.s_ent);
+                    acc.s_ent = fmaf(en.w, m.w, acc.s_ent);
+                    if (a.d_ent)
+                        *reinterpret_cast<float4*>(a.d_ent + i) =
+                            make_float4(cx.d_ent_val * m.x, cx.d_ent_val * m.y, cx.d_ent_val * m.z, cx.d_ent_val * m.w);
+                }
+            }
+        }
+    } else {
+#pragma unroll 4
+        for (int it = 0; it < kLossIters * kLossVec; ++it) {
+            const int64_t t = t0 + static_cast<int64_t>(it) * kLossThreads + threadIdx.x;
+            if (t < A) {
+                const int64_t i = rbase + t;
+                const float m = a.mask ? a.mask[i] : 1.f;
+                const float g = loss_token(cx, acc, a.lp[i], a.olp[i], a.adv[i], m, a.base ? a.base[i] : 0.f);
+                if (a.d_lp) a.d_lp[i] = g;
+                if (a.ent) {
+                    acc.s_ent = fmaf(a.ent[i], m, acc.s_ent);
+                    if (a.d_ent) a.d_ent[i] = cx.d_ent_val * m;
+                }
+            }
+        }
+    }
+    float s_loss = acc.s_loss, s_clip = acc.s_clip, s_kl = acc.s_kl, s_ent = acc.s_ent, s_ratio = acc.s_ratio;
+    float r_max = acc.r_max, r_min = acc.r_min;
+
+    // block partials -> workspace, last block folds them in a fixed order
+    const int nblk = gridDim.x * gridDim.y;
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    s_loss = block_sum(s_loss, sh);
+    s_clip = block_sum(s_clip, sh);
+    s_kl = block_sum(s_kl, sh);
+    s_ent = block_sum(s_ent, sh);
+    s_ratio = block_sum(s_ratio, sh);
+    r_max = block_max(r_max, sh);
+    r_min = block_min(r_min, sh);
+    if (threadIdx.x == 0) {
+        float* p = a.ws.partials + static_cast<int64_t>(blk) * kNumPartials;
+        p[0] = s_loss;
+        p[1] = s_clip;
+        p[2] = s_kl;
+        p[3] = s_ent;
+        p[4] = s_ratio;
+        p[5] = r_max;
+        p[6] = r_min;
+        __threadfence();
+        const unsigned int prev = atomicAdd(a.ws.counters + 1, 1u);
+        is_last = (prev == static_cast<unsigned int>(nblk) - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    float f_loss = 0.f, f_clip = 0.f, f_kl = 0.f, f_ent = 0.f, f_ratio = 0.f, f_max = -INFINITY, f_min = INFINITY;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+        const float* p = a.ws.partials + static_cast<int64_t>(b) * kNumPartials;
+        f_loss += __ldcg(p + 0);
+        f_clip += __ldcg(p + 1);
+        f_kl += __ldcg(p + 2);
+        f_ent += __ldcg(p + 3);
+        f_ratio += __ldcg(p + 4);
+        f_max = fmaxf(f_max, __ldcg(p + 5));
+        f_min = fminf(f_min, __ldcg(p + 6));
+    }
+    f_loss = block_sum(f_loss, sh);
+    f_clip = block_sum(f_clip, sh);
+    f_kl = block_sum(f_kl, sh);
+    f_ent = block_sum(f_ent, sh);
+    f_ratio = block_sum(f_ratio, sh);
+    f_max = block_max(f_max, sh);
+    f_min = block_min(f_min, sh);
+    if (threadIdx.x == 0) {
+        const float clip_ratio = f_clip * inv_total;
+        const float ent_mean = f_ent * inv_total;
+        float final_loss = f_loss + f_kl * a.p.kl_loss_coef;
+        if (use_ent_loss && a.ent != nullptr) final_loss -= ent_mean * a.p.entropy_loss_coef;
+        a.stats[SKYB200_STAT_POLICY_LOSS] = f_loss;
+        a.stats[SKYB200_STAT_CLIP_RATIO] = clip_ratio;
+        a.stats[SKYB200_STAT_KL_LOSS] = f_kl;
+        a.stats[SKYB200_STAT_ENTROPY] = ent_mean;
+        a.stats[SKYB200_STAT_FINAL_LOSS] = final_loss;
+        a.stats[SKYB200_STAT_MASK_SUM] = total_m;
+        a.stats[SKYB200_STAT_RATIO_MEAN] = f_ratio * inv_total;
+        a.stats[SKYB200_STAT_RATIO_MAX] = f_max;
+        a.stats[SKYB200_STAT_RATIO_MIN] = f_min;
+        for (int i = SKYB200_STAT_RATIO_MIN + 1; i < SKYB200_LOSS_NSTATS; ++i) a.stats[i] = 0.f;
+        a.ws.counters[1] = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------- small helpers
+__global__ void scale_inplace_kernel(float* __restrict__ x, const float* __restrict__ s, int64_t n) {
+    const float k = __ldg(s);
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        x[i] *= k;
+}
+
+__global__ void __launch_bounds__(256) masked_sum_kernel(const float* __restrict__ x, const float* __restrict__ m,
+                                                         float* __restrict__ partials, int64_t n) {
+    __shared__ float sh[34];
+    float sx = 0.f, sm = 0.f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float mm = m ? m[i] : 1.f;
+        sx = fmaf(x[i], mm, sx);
+        sm += mm;
+    }
+    sx = block_sum(sx, sh);
+    sm = block_sum(sm, sh);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = sx;
+        partials[2 * blockIdx.x + 1] = sm;
+    }
+}
+__global__ void __launch_bounds__(256) masked_mean_final_kernel(const float* __restrict__ partials, int nblk,
+                                                                float* __restrict__ out) {
+    __shared__ float sh[34];
+    float sx = 0.f, sm = 0.f;
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+        sx += partials[2 * i];
+        sm += partials[2 * i + 1];
+    }
+    sx = block_sum(sx, sh);
+    sm = block_sum(sm, sh);
+    if (threadIdx.x == 0) *out = sx / fmaxf(sm, 1.f);
+}
+
+__global__ void approx_kl_kernel(const float* __restrict__ lp, const float* __restrict__ base,
+                                 const float* __restrict__ mask, float* __restrict__ out, int64_t n, int type) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float dk;
+        float k = kl_estimate(lp[i], base[i], type, &dk);
+        if (mask) k *= mask[i];
+        out[i] = k;
+    }
+}
+
+static int grid_for(int64_t n, int threads, int per_sm) {
+    int64_t b = (n + threads - 1) / threads;
+    int64_t cap = static_cast<int64_t>(num_sms()) * per_sm;
+    return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace skyb200
+
+using namespace skyb200;
+
+extern "C" size_t skyb200_policy_loss_workspace(int64_t B, int64_t A) {
+    return loss_ws_layout(B, A, nullptr, nullptr) + 256;
+}
+
+extern "C" int skyb200_policy_loss(const float* log_probs, const float* old_log_probs, const float* advantages,
+                                   const float* loss_mask, const float* base_log_probs, const float* entropy,
+                                   float* d_log_probs, float* d_entropy, float* stats, void* workspace,
+                                   size_t workspace_bytes, int64_t B, int64_t A, const skyb200_loss_params* params,
+                                   void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(log_probs && old_log_probs && advantages && stats && workspace && params, "null pointer");
+    SKYB200_REQUIRE(B > 0 && A > 0 && B < 65536, "need 0 < B < 65536 and A > 0");
+    SKYB200_REQUIRE(params->loss_type >= 0 && params->loss_type <= SKYB200_LOSS_GSPO, "bad loss_type");
+    SKYB200_REQUIRE(params->reduction >= 0 && params->reduction <= SKYB200_REDUCE_SEQ_MEAN_TOKEN_SUM_NORM,
+                    "bad reduction");
+    SKYB200_REQUIRE(params->kl_type >= 0 && params->kl_type <= SKYB200_KL_K3, "bad kl_type");
+    SKYB200_REQUIRE(params->reduction != SKYB200_REDUCE_SEQ_MEAN_TOKEN_SUM_NORM || params->max_seq_len > 0.f,
+                    "max_seq_len must be provided for seq_mean_token_sum_norm");
+    if (workspace_bytes < skyb200_policy_loss_workspace(B, A))
+        return fail(SKYB200_EWORKSPACE, "policy_loss workspace too small");
+    LossWs ws;
+    // 256-byte align the workspace base
+    char* wbase = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    loss_ws_layout(B, A, &ws, wbase);
+    SKYB200_CUDA_CHECK(cudaMemsetAsync(ws.counters, 0, 16, stream));
+    const int need_lw = params->loss_type == SKYB200_LOSS_GSPO;
+    loss_rowstats_kernel<<<(unsigned)B, kLossThreads, 0, stream>>>(log_probs, old_log_probs, loss_mask, ws.row_msum,
+                                                                   ws.row_lw, ws.total_msum, ws.counters, (int)B, A,
+                                                                   need_lw);
+    int rc = check_launch("loss_rowstats_kernel");
+    if (rc) return rc;
+    LossArgs a;
+    a.lp = log_probs;
+    a.olp = old_log_probs;
+    a.adv = advantages;
+    a.mask = loss_mask;
+    a.base = base_log_probs;
+    a.ent = entropy;
+    a.d_lp = d_log_probs;
+    a.d_ent = d_entropy;
+    a.stats = stats;
+    a.ws = ws;
+    a.B = (int)B;
+    a.A = A;
+    a.p = *params;
+    auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    a.vec4 = (A % 4 == 0) && al16(log_probs) && al16(old_log_probs) && al16(advantages) && al16(loss_mask) &&
+             al16(base_log_probs) && al16(entropy) && al16(d_log_probs) && al16(d_entropy);
+    const unsigned chunks = (unsigned)((A + kLossTile - 1) / kLossTile);
+    loss_main_kernel<<<dim3(chunks, (unsigned)B), kLossThreads, 0, stream>>>(a);
+    return check_launch("loss_main_kernel");
+}
+
+extern "C" int skyb200_scale_inplace(float* x, const float* scale_dev, int64_t n, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n == 0) return SKYB200_OK;
+    SKYB200_REQUIRE(x && scale_dev, "null pointer");
+    scale_inplace_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(x, scale_dev, n);
+    return check_launch("scale_inplace_kernel");
+}
+
+extern "C" int skyb200_masked_mean(const float* x, const float* mask, float* out, void* workspace,
+                                   size_t workspace_bytes, int64_t n, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(x && out && workspace, "null pointer");
+    const int nblk = grid_for(n, 256, 4);
+    if (workspace_bytes < (size_t)nblk * 8) return fail(SKYB200_EWORKSPACE, "masked_mean workspace too small");
+    float* partials = static_cast<float*>(workspace);
+    masked_sum_kernel<<<nblk, 256, 0, stream>>>(x, mask, partials, n);
+    int rc = check_launch("masked_sum_kernel");
+    if (rc) return rc;
+    masked_mean_final_kernel<<<1, 256, 0, stream>>>(partials, nblk, out);
+    return check_launch("masked_mean_final_kernel");
+}
+
+extern "C" int skyb200_approx_kl(const float* log_probs, const float* base_log_probs, const float* loss_mask,
+                                 float* out, int64_t n, int32_t kl_type, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n == 0) return SKYB200_OK;
+    SKYB200_REQUIRE(log_probs && base_log_probs && out, "null pointer");
+    SKYB200_REQUIRE(kl_type >= 0 && kl_type <= SKYB200_KL_K3, "Invalid KL estimator type");
+    approx_kl_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(log_probs, base_log_probs, loss_mask, out, n, kl_type);
+    return check_launch("approx_kl_kernel");
+}
