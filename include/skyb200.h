@@ -147,6 +147,16 @@ int skyb200_gae_advantage(const float* rewards, const float* values, const void*
                           size_t workspace_bytes, int64_t B, int64_t A, float gamma, float lambd, void* stream);
 
 /*
+ * The two halves of skyb200_gae_advantage, for batches sharded over several GPUs (whitening needs GLOBAL
+ * moments, trainer.py:268-276): scan locally, all-reduce `moments` (3 doubles: sum m, sum m*x, sum m*x^2),
+ * then whiten.  moments is a device pointer, 8-byte aligned.
+ */
+int skyb200_gae_scan(const float* rewards, const float* values, const void* response_mask, int32_t mask_type,
+                     float* adv_raw, float* returns, double* moments, void* workspace, size_t workspace_bytes,
+                     int64_t B, int64_t A, float gamma, float lambd, void* stream);
+int skyb200_whiten_from_moments(float* x, const double* moments, float* stats_out, int64_t n, void* stream);
+
+/*
  * KL-in-reward (RayPPOTrainer.apply_reward_kl_penalty, trainer.py:981-1035):
  *   kl = compute_approx_kl(lp, base, loss_mask); rewards_out = rewards - kl * max(0, kl_coef)
  *   metrics_out[0] = mean_b(masked_mean_t(kl)), metrics_out[1] = mean_b(max_t |kl|)

@@ -1,0 +1,219 @@
+"""CPU (torch fp32) restatement of the reference's policy-update hot path.  TEST INFRASTRUCTURE — see
+``oracle/__init__.py``.  Each function names the reference lines it restates (paths relative to
+``skyrl-train/skyrl_train/``).  Written vectorised where the reference loops in Python; the sequential fp32
+accumulation order of the reference is kept where it matters for parity (the GAE recurrence).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# ---------------------------------------------------------------------------------------- small helpers
+def masked_mean(x: torch.Tensor, mask: Optional[torch.Tensor], dim=None) -> torch.Tensor:
+    """utils/torch_utils.py:180-184 — denominator clamped to >= 1."""
+    if mask is None:
+        return x.mean(dim) if dim is not None else x.mean()
+    num = (x * mask).sum(dim) if dim is not None else (x * mask).sum()
+    den = mask.sum(dim) if dim is not None else mask.sum()
+    return num / den.clamp(min=1.0)
+
+
+def masked_var(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """utils/ppo_utils.py:148-160 — Bessel-corrected; raises when the mask sums to 0 or 1."""
+    mu = masked_mean(x, mask)
+    var = masked_mean((x - mu) ** 2, mask)
+    n = mask.sum()
+    if n == 0:
+        raise ValueError("At least one element in the mask has to be 1.")
+    if n == 1:
+        raise ValueError("The sum of the mask is one, which can cause a division by zero.")
+    return var * (n / (n - 1))
+
+
+def masked_whiten(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """utils/ppo_utils.py:163-172 (shift_mean=True)."""
+    mu, var = masked_mean(x, mask), masked_var(x, mask)
+    return (x - mu) * torch.rsqrt(var + 1e-8)
+
+
+def approx_kl(lp: torch.Tensor, base: torch.Tensor, mask: Optional[torch.Tensor], kind: str = "k3") -> torch.Tensor:
+    """utils/ppo_utils.py:88-124 (no gradient)."""
+    with torch.no_grad():
+        d = lp - base
+        if kind == "k1":
+            out = d
+        elif kind == "abs":
+            out = d.abs()
+        elif kind == "k2":
+            out = 0.5 * d * d
+        elif kind == "k3":
+            x = (-d).clamp(-20.0, 20.0)
+            out = (x.exp() - x - 1.0).clamp(-10.0, 10.0)
+        else:
+            raise ValueError(f"Invalid KL estimator type: {kind}")
+        return out * mask if mask is not None else out
+
+
+# ---------------------------------------------------------------------------------------- advantages
+def _group_ids(index: Sequence) -> Tuple[torch.Tensor, int]:
+    table: Dict = {}
+    ids = []
+    for u in index:
+        u = u.item() if isinstance(u, np.generic) else u
+        ids.append(table.setdefault(u, len(table)))
+    return torch.tensor(ids, dtype=torch.int64), len(table)
+
+
+def grpo_advantage(rewards, response_mask, index, eps: float = 1e-6, norm_by_std: bool = True):
+    """utils/ppo_utils.py:1132-1182 — unmasked row sums, per-uid mean / unbiased std, eps on std,
+    singleton -> mean 0 std 1, result * mask; (adv, returns) are the same tensor."""
+    scores = rewards.float().sum(-1)
+    gid, ng = _group_ids(index)
+    cnt = torch.zeros(ng).index_add_(0, gid, torch.ones_like(scores))
+    mean = torch.zeros(ng).index_add_(0, gid, scores) / cnt
+    dev2 = torch.zeros(ng).index_add_(0, gid, (scores - mean[gid]) ** 2)
+    std = torch.sqrt(dev2 / (cnt - 1).clamp(min=1.0))
+    single = cnt == 1
+    mean = torch.where(single, torch.zeros_like(mean), mean)
+    std = torch.where(single, torch.ones_like(std), std)
+    out = (scores - mean[gid]) / (std[gid] + eps) if norm_by_std else scores - mean[gid]
+    adv = out.unsqueeze(-1) * response_mask
+    return adv, adv
+
+
+def rloo_advantage(rewards, response_mask, index):
+    """utils/ppo_utils.py:1048-1098 — (score - group mean) * n/(n-1); singleton -> 0."""
+    scores = rewards.float().sum(-1)
+    gid, ng = _group_ids(index)
+    cnt = torch.zeros(ng).index_add_(0, gid, torch.ones_like(scores))
+    mean = torch.zeros(ng).index_add_(0, gid, scores) / cnt
+    n = cnt[gid]
+    out = torch.where(n > 1, (scores - mean[gid]) * (n / (n - 1).clamp(min=1.0)), torch.zeros_like(scores))
+    adv = out.unsqueeze(-1) * response_mask
+    return adv, adv
+
+
+def gae_advantage_return(rewards, values, response_mask, gamma: float, lambd: float):
+    """utils/ppo_utils.py:1101-1129 — sequential fp32 recurrence over ALL positions (no mask reset),
+    returns = raw advantages + values, advantages whitened over the whole batch, not re-masked."""
+    r = rewards.float().numpy()
+    v = values.float().numpy()
+    B, A = r.shape
+    adv = np.zeros((B, A), dtype=np.float32)
+    last = np.zeros(B, dtype=np.float32)
+    g = np.float32(gamma)
+    gl = np.float32(gamma * lambd)
+    for t in range(A - 1, -1, -1):
+        nxt = v[:, t + 1] if t + 1 < A else np.zeros(B, dtype=np.float32)
+        delta = r[:, t] + g * nxt - v[:, t]
+        last = (delta + gl * last).astype(np.float32)
+        adv[:, t] = last
+    adv_t = torch.from_numpy(adv)
+    returns = adv_t + values.float()
+    return masked_whiten(adv_t, response_mask), returns
+
+
+def reward_kl_penalty(rewards, lp, base, loss_mask, kind: str = "k3", coef: float = 1e-3):
+    """trainer.py:981-1035 — rewards - kl*max(0, coef); avg_kl = mean_b masked_mean_t kl; avg_kl_max = mean_b max_t|kl|."""
+    kl = approx_kl(lp, base, loss_mask, kind)
+    kl_max = kl.abs().max(dim=-1)[0]
+    kl_mean = masked_mean(kl, loss_mask, dim=-1)
+    out = rewards - kl * max(0, coef)
+    return out, {"avg_kl": kl_mean.mean().item(), "avg_kl_max": kl_max.mean().item()}
+
+
+# ---------------------------------------------------------------------------------------- policy loss
+def reduce_loss(loss, mask, reduction: str, max_seq_len=None):
+    """utils/ppo_utils.py:984-1009."""
+    if reduction == "token_mean":
+        return masked_mean(loss, mask)
+    if reduction == "sequence_mean":
+        return masked_mean(loss, mask, dim=-1).mean()
+    if reduction == "seq_mean_token_sum_norm":
+        assert max_seq_len is not None
+        tot = (loss * mask).sum(-1) if mask is not None else loss.sum(-1)
+        return (tot / max_seq_len).mean()
+    raise ValueError(f"Invalid loss reduction type: {reduction}")
+
+
+def policy_loss(lp, olp, adv, cfg, mask=None):
+    """"regular"/"dual_clip": utils/ppo_utils.py:548-586; "gspo": :661-725.  Returns (loss, clip_ratio)."""
+    kind = cfg.policy_loss_type
+    if kind == "gspo":
+        seq = masked_mean(lp - olp, mask, dim=-1).unsqueeze(-1)
+        log_w = (lp - lp.detach() + seq.detach()).clamp(max=10.0)
+        ratio = log_w.exp()
+    else:
+        ratio = (lp - olp).float().clamp(-20.0, 20.0).exp()
+    s1 = ratio * adv
+    s2 = ratio.clamp(1 - cfg.eps_clip_low, 1 + cfg.eps_clip_high) * adv
+    loss = -torch.min(s1, s2)
+    clip_ratio = masked_mean((-s2 > -s1).float(), mask).mean().item()
+    if kind == "dual_clip":
+        capped = torch.min(-adv * cfg.clip_ratio_c, loss)
+        loss = torch.where(adv < 0, capped, loss)
+    return reduce_loss(loss, mask, cfg.loss_reduction, getattr(cfg, "max_seq_len", None)), clip_ratio
+
+
+def loss_assembly(lp, olp, adv, cfg, mask=None, base=None, entropy=None):
+    """workers/worker.py:852-889 — final = policy + kl*coef - entropy*coef; returns (final_loss, status)."""
+    pl, clip_ratio = policy_loss(lp, olp, adv, cfg, mask)
+    status = {"policy_loss": pl.item(), "loss_metrics/clip_ratio": clip_ratio}
+    ent_term = torch.tensor(0.0)
+    if entropy is not None:
+        with torch.set_grad_enabled(bool(cfg.use_entropy_loss)):
+            ent = masked_mean(entropy, mask)
+        status["policy_entropy"] = ent.item()
+        if cfg.use_entropy_loss:
+            ent_term = ent * cfg.entropy_loss_coef
+    kl = torch.tensor(0.0)
+    if cfg.use_kl_loss and base is not None:
+        kl = masked_mean(approx_kl(lp, base, mask, cfg.kl_estimator_type), mask, dim=-1).mean()
+        status["policy_kl"] = kl.item()
+    final = pl + kl * cfg.kl_loss_coef - ent_term
+    status["final_loss"] = final.item()
+    return final, status
+
+
+# ---------------------------------------------------------------------------------------- logits / head
+def logprobs_from_logits(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """utils/torch_utils.py:158-168 (fp32 branch): gather - logsumexp."""
+    z = logits.float()
+    return z.gather(-1, labels.unsqueeze(-1)).squeeze(-1) - torch.logsumexp(z, dim=-1)
+
+
+def entropy_from_logits(logits: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """utils/torch_utils.py:59-111: -(p * log p).sum(-1) [* mask]."""
+    logp = F.log_softmax(logits.float(), dim=-1)
+    ent = -(logp.exp() * logp).sum(-1)
+    return ent * attention_mask if attention_mask is not None else ent
+
+
+def head_logprobs_entropy(hidden_bf16, weight_bf16, labels, temperature: float = 1.0, chunk: int = 512):
+    """model_wrapper.py:309-363 in fp32: logits = hidden @ W^T / T (fp32 math on the bf16-rounded inputs),
+    then the two helpers above.  Differentiable w.r.t. hidden/weight when they are fp32 leaves."""
+    h = hidden_bf16.float() if hidden_bf16.dtype != torch.float32 else hidden_bf16
+    w = weight_bf16.float() if weight_bf16.dtype != torch.float32 else weight_bf16
+    lps, ents = [], []
+    for s in range(0, h.shape[0], chunk):
+        z = (h[s:s + chunk] @ w.t()) / temperature
+        lps.append(logprobs_from_logits(z, labels[s:s + chunk]))
+        ents.append(entropy_from_logits(z))
+    return torch.cat(lps), torch.cat(ents)
+
+
+def make_cfg(**kw) -> SimpleNamespace:
+    """AlgorithmConfig defaults (config/config.py:273-303) as a plain namespace."""
+    base = dict(
+        policy_loss_type="regular", loss_reduction="token_mean", eps_clip_low=0.2, eps_clip_high=0.2,
+        clip_ratio_c=3.0, max_seq_len=None, use_kl_loss=True, kl_estimator_type="k3", kl_loss_coef=1e-3,
+        use_entropy_loss=False, entropy_loss_coef=0.01, gamma=1.0, lambd=1.0, grpo_norm_by_std=True,
+        off_policy_correction=SimpleNamespace(tis_ratio_type=None, sequence_mask_metric=None),
+    )
+    base.update(kw)
+    return SimpleNamespace(**base)

@@ -58,6 +58,8 @@ SIGNATURES = {
     "skyb200_group_advantage": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _P]),
     "skyb200_gae_workspace": (_SZ, [_I64]),
     "skyb200_gae_advantage": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _SZ, _I64, _I64, _F, _F, _P]),
+    "skyb200_gae_scan": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _SZ, _I64, _I64, _F, _F, _P]),
+    "skyb200_whiten_from_moments": (C.c_int, [_P, _P, _P, _I64, _P]),
     "skyb200_reward_kl_penalty": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _F, _P]),
     "skyb200_head_forward_workspace": (_SZ, [_I64, _I64, _I64, _I64]),
     "skyb200_head_backward_workspace": (_SZ, [_I64, _I64, _I64, _I64]),

@@ -231,9 +231,9 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     }
 }
 
-// One block: fold the per-row moments (fixed order) -> {n, mean, var (Bessel), rstd}
-__global__ void __launch_bounds__(256) whiten_stats_kernel(const double* __restrict__ row_stats, int B,
-                                                           float* __restrict__ stats_out) {
+// One block: fold the per-row moments in a fixed order -> moments[3] = {sum m, sum m*x, sum m*x*x} (double)
+__global__ void __launch_bounds__(256) fold_moments_kernel(const double* __restrict__ row_stats, int B,
+                                                           double* __restrict__ moments) {
     __shared__ double sh_d[34];
     double n = 0.0, sx = 0.0, sxx = 0.0;
     for (int i = threadIdx.x; i < B; i += blockDim.x) {
@@ -245,15 +245,24 @@ __global__ void __launch_bounds__(256) whiten_stats_kernel(const double* __restr
     sx = block_sum(sx, sh_d);
     sxx = block_sum(sxx, sh_d);
     if (threadIdx.x == 0) {
-        const double den = fmax(n, 1.0);                   // masked_mean clamps the denominator to >= 1
-        const double mean = sx / den;
-        double var = (sxx - 2.0 * mean * sx + mean * mean * n) / den;  // masked_mean((x - mean)^2, mask)
-        if (n > 1.0) var *= n / (n - 1.0);                 // Bessel (the host raises for n in {0, 1})
-        stats_out[0] = static_cast<float>(n);
-        stats_out[1] = static_cast<float>(mean);
-        stats_out[2] = static_cast<float>(var);
-        stats_out[3] = static_cast<float>(1.0 / sqrt(static_cast<double>(static_cast<float>(var)) + 1e-8));
+        moments[0] = n;
+        moments[1] = sx;
+        moments[2] = sxx;
     }
+}
+
+// moments -> stats {n, mean, var (Bessel), rstd}; masked_mean clamps its denominator to >= 1
+__global__ void whiten_stats_kernel(const double* __restrict__ moments, float* __restrict__ stats_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double n = moments[0], sx = moments[1], sxx = moments[2];
+    const double den = fmax(n, 1.0);
+    const double mean = sx / den;
+    double var = (sxx - 2.0 * mean * sx + mean * mean * n) / den;  // masked_mean((x - mean)^2, mask)
+    if (n > 1.0) var *= n / (n - 1.0);                             // Bessel (the host raises for n in {0, 1})
+    stats_out[0] = static_cast<float>(n);
+    stats_out[1] = static_cast<float>(mean);
+    stats_out[2] = static_cast<float>(var);
+    stats_out[3] = static_cast<float>(1.0 / sqrt(static_cast<double>(static_cast<float>(var)) + 1e-8));
 }
 
 __global__ void __launch_bounds__(256) whiten_apply_kernel(float* __restrict__ x, const float* __restrict__ stats,
@@ -376,46 +385,70 @@ extern "C" int skyb200_group_advantage(const float* rewards, const void* respons
     return check_launch("group_broadcast_kernel");
 }
 
-extern "C" size_t skyb200_gae_workspace(int64_t B) { return (size_t)(B * 3 * sizeof(double) + 256); }
+extern "C" size_t skyb200_gae_workspace(int64_t B) { return (size_t)((B * 3 + 3) * sizeof(double) + 512); }
 
-extern "C" int skyb200_gae_advantage(const float* rewards, const float* values, const void* response_mask,
-                                     int32_t mask_type, float* advantages, float* returns, float* stats_out,
-                                     void* workspace, size_t workspace_bytes, int64_t B, int64_t A, float gamma,
-                                     float lambd, void* stream_) {
+extern "C" int skyb200_gae_scan(const float* rewards, const float* values, const void* response_mask,
+                                int32_t mask_type, float* adv_raw, float* returns, double* moments, void* workspace,
+                                size_t workspace_bytes, int64_t B, int64_t A, float gamma, float lambd,
+                                void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    SKYB200_REQUIRE(rewards && values && advantages && returns && stats_out && workspace, "null pointer");
+    SKYB200_REQUIRE(rewards && values && adv_raw && returns && moments && workspace, "null pointer");
     SKYB200_REQUIRE(mask_type == SKYB200_MASK_NONE || response_mask != nullptr, "mask pointer missing");
     SKYB200_REQUIRE(B > 0 && A > 0 && B < (1ll << 31), "bad shape");
+    SKYB200_REQUIRE((reinterpret_cast<uintptr_t>(moments) & 7u) == 0, "moments must be 8-byte aligned");
     if (workspace_bytes < skyb200_gae_workspace(B)) return fail(SKYB200_EWORKSPACE, "gae workspace too small");
     double* row_stats = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     switch (mask_type) {
         case SKYB200_MASK_F32:
             gae_scan_kernel<SKYB200_MASK_F32><<<(unsigned)B, kGaeThreads, 0, stream>>>(
-                rewards, values, response_mask, advantages, returns, row_stats, A, gamma, lambd);
+                rewards, values, response_mask, adv_raw, returns, row_stats, A, gamma, lambd);
             break;
         case SKYB200_MASK_I64:
             gae_scan_kernel<SKYB200_MASK_I64><<<(unsigned)B, kGaeThreads, 0, stream>>>(
-                rewards, values, response_mask, advantages, returns, row_stats, A, gamma, lambd);
+                rewards, values, response_mask, adv_raw, returns, row_stats, A, gamma, lambd);
             break;
         case SKYB200_MASK_NONE:
             gae_scan_kernel<SKYB200_MASK_NONE><<<(unsigned)B, kGaeThreads, 0, stream>>>(
-                rewards, values, response_mask, advantages, returns, row_stats, A, gamma, lambd);
+                rewards, values, response_mask, adv_raw, returns, row_stats, A, gamma, lambd);
             break;
         default:
             return fail(SKYB200_EINVAL, "bad mask_type %d", mask_type);
     }
     int rc = check_launch("gae_scan_kernel");
     if (rc) return rc;
-    whiten_stats_kernel<<<1, 256, 0, stream>>>(row_stats, (int)B, stats_out);
-    rc = check_launch("whiten_stats_kernel");
+    fold_moments_kernel<<<1, 256, 0, stream>>>(row_stats, (int)B, moments);
+    return check_launch("fold_moments_kernel");
+}
+
+extern "C" int skyb200_whiten_from_moments(float* x, const double* moments, float* stats_out, int64_t n,
+                                           void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(x && moments && stats_out, "null pointer");
+    whiten_stats_kernel<<<1, 32, 0, stream>>>(moments, stats_out);
+    int rc = check_launch("whiten_stats_kernel");
     if (rc) return rc;
-    const int64_t n = B * A;
+    if (n == 0) return SKYB200_OK;
     int64_t blocks = (n / 4 + 255) / 256;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    whiten_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(advantages, stats_out, n);
+    whiten_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, stats_out, n);
     return check_launch("whiten_apply_kernel");
+}
+
+extern "C" int skyb200_gae_advantage(const float* rewards, const float* values, const void* response_mask,
+                                     int32_t mask_type, float* advantages, float* returns, float* stats_out,
+                                     void* workspace, size_t workspace_bytes, int64_t B, int64_t A, float gamma,
+                                     float lambd, void* stream_) {
+    SKYB200_REQUIRE(stats_out && workspace, "null pointer");
+    if (workspace_bytes < skyb200_gae_workspace(B)) return fail(SKYB200_EWORKSPACE, "gae workspace too small");
+    // moments live at the (8-byte aligned) tail of the workspace
+    uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+    double* moments = reinterpret_cast<double*>(base) + 3 * B;
+    int rc = skyb200_gae_scan(rewards, values, response_mask, mask_type, advantages, returns, moments, workspace,
+                              workspace_bytes, B, A, gamma, lambd, stream_);
+    if (rc) return rc;
+    return skyb200_whiten_from_moments(advantages, moments, stats_out, B * A, stream_);
 }
 
 extern "C" int skyb200_reward_kl_penalty(const float* log_probs, const float* base_log_probs, const float* loss_mask,

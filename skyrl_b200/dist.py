@@ -1,0 +1,137 @@
+"""Multi-GPU plumbing of the policy update: one process per GPU, data parallel over whole prompt groups.
+
+What shards: rollout batches split by *whole prompt groups* (all samples of a uid on one rank), so
+GRPO / RLOO statistics stay local and the per-token loss needs no exchange.  What crosses NVLink:
+
+1. ``all_reduce_metrics`` — the status dict of a micro-batch, all keys in ONE collective (the reference issues
+   one NCCL all-reduce + H2D + D2H per scalar: workers/worker_utils.py:25-35, distributed/strategy.py:70-95).
+   Same semantics: mean across ranks, ``*_min`` -> min, ``*_max`` -> max.
+2. ``all_reduce_d_weight`` — lm_head weight-gradient all-reduce (mean, fp32: FSDP ``reduce_dtype=fp32``,
+   fsdp_strategy.py:218-226), once per optimizer step, on a side stream.
+3. ``gae_advantage_sharded`` — GAE whitening needs global moments (trainer.py:268-276): 3 doubles all-reduced
+   between the scan and the whiten kernels.
+
+Works with the ``nccl`` backend on GPUs and with ``gloo`` on CPU tensors (used by the CPU tests for the host logic).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_prompt_groups(index: Sequence, valid_tokens: Sequence[int], world_size: int) -> List[List[int]]:
+    """Assign whole uid groups to ranks, balancing valid-token counts (longest-processing-time first).
+
+    Returns ``rows_per_rank[r]`` = sorted row indices for rank r.  Deterministic: ties break on first
+    appearance of the uid, so every rank computes the same partition from the same inputs.
+    """
+    groups: Dict = {}
+    order: List = []
+    for i, u in enumerate(index):
+        u = u.item() if isinstance(u, np.generic) else u
+        if u not in groups:
+            groups[u] = []
+            order.append(u)
+        groups[u].append(i)
+    weights = [(sum(int(valid_tokens[i]) for i in groups[u]), k, u) for k, u in enumerate(order)]
+    weights.sort(key=lambda x: (-x[0], x[1]))
+    load = [0] * world_size
+    rows: List[List[int]] = [[] for _ in range(world_size)]
+    for wgt, _, u in weights:
+        r = min(range(world_size), key=lambda j: (load[j], j))
+        load[r] += wgt
+        rows[r].extend(groups[u])
+    return [sorted(r) for r in rows]
+
+
+def _world(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def all_reduce_metrics(status: Dict[str, float], device: Optional[torch.device] = None, group=None) -> Dict[str, float]:
+    """Reference semantics of ``all_reduce_metrics`` (worker_utils.py:25-35) in a single collective.
+
+    Every rank contributes one packed fp32 vector; one ``all_gather`` moves it; mean / min / max are folded
+    locally in rank order (deterministic).  Non-numeric entries are passed through untouched.
+    """
+    keys = [k for k, v in status.items() if isinstance(v, (int, float))]
+    ws = _world(group)
+    if ws == 1 or not keys:
+        return dict(status)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    vec = torch.tensor([float(status[k]) for k in keys], dtype=torch.float32, device=device)
+    gathered = torch.empty(ws * len(keys), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(gathered, vec, group=group)
+    table = gathered.view(ws, len(keys)).cpu()
+    out = dict(status)
+    for j, k in enumerate(keys):
+        col = table[:, j]
+        if k.endswith("_max"):
+            out[k] = float(col.max())
+        elif k.endswith("_min"):
+            out[k] = float(col.min())
+        else:
+            # the reference divides each rank's value by world_size and SUM-reduces
+            out[k] = float((col / ws).sum())
+    return out
+
+
+def all_reduce_packed_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """Mean-of-local-means of a packed device stats vector (one NCCL all-reduce, no host round trip)."""
+    ws = _world(group)
+    if ws == 1:
+        return stats
+    out = stats / ws
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+def all_reduce_d_weight(d_weight: torch.Tensor, group=None, async_op: bool = False):
+    """Mean all-reduce of the fp32 lm_head weight gradient over NVLink (FSDP averages gradients over DP ranks)."""
+    ws = _world(group)
+    if ws == 1:
+        return None
+    d_weight.div_(ws)
+    return dist.all_reduce(d_weight, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def gae_advantage_sharded(token_level_rewards, values, response_mask, gamma: float, lambd: float, group=None):
+    """GAE on this rank's rows with GLOBAL whitening statistics (3 doubles all-reduced).
+
+    Equals ``compute_gae_advantage_return`` on the concatenated batch (trainer.py:268-276 computes advantages
+    over the whole batch before sharding).
+    """
+    from . import _lib
+    from .advantages import _f32, _mask_arg
+
+    lib = _lib.load()
+    dev = token_level_rewards.device
+    if not token_level_rewards.is_cuda:
+        raise RuntimeError("gae_advantage_sharded needs CUDA tensors")
+    B, A = token_level_rewards.shape
+    with torch.cuda.device(dev):
+        r, v = _f32(token_level_rewards, dev), _f32(values, dev)
+        m, mtype = _mask_arg(response_mask, dev)
+        adv = torch.empty((B, A), dtype=torch.float32, device=dev)
+        ret = torch.empty((B, A), dtype=torch.float32, device=dev)
+        moments = torch.zeros(3, dtype=torch.float64, device=dev)
+        stats = torch.empty(4, dtype=torch.float32, device=dev)
+        wsb = lib.skyb200_gae_workspace(B)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        _lib.check(lib.skyb200_gae_scan(_lib.ptr(r), _lib.ptr(v), _lib.ptr(m), mtype, _lib.ptr(adv), _lib.ptr(ret),
+                                        _lib.ptr(moments), _lib.ptr(ws), wsb, B, A, float(gamma), float(lambd),
+                                        _lib.stream_ptr()), "skyb200_gae_scan")
+        if _world(group) > 1:
+            dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
+        _lib.check(lib.skyb200_whiten_from_moments(_lib.ptr(adv), _lib.ptr(moments), _lib.ptr(stats), B * A,
+                                                   _lib.stream_ptr()), "skyb200_whiten_from_moments")
+        n = float(stats[0].item())
+    if n == 0:
+        raise ValueError("At least one element in the mask has to be 1.")
+    if n == 1:
+        raise ValueError("The sum of the mask is one, which can cause a division by zero.")
+    return adv, ret

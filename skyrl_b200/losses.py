@@ -1,0 +1,256 @@
+"""Policy losses on the fused B200 loss kernel, behind the reference's ``PolicyLossRegistry`` signature.
+
+    fn(log_probs, old_log_probs, advantages, config, loss_mask=None, rollout_logprobs=None)
+        -> (loss: 0-d tensor with a grad path to log_probs, metrics: dict[str, float])
+
+(reference: skyrl-train/skyrl_train/utils/ppo_utils.py:548-586 ``ppo_policy_loss`` for "regular"/"dual_clip",
+:661-725 ``gspo_policy_loss``, :984-1009 ``reduce_loss``.)  One kernel pass computes the loss value, the
+``clip_ratio`` metric and ``d loss / d log_probs``; backward only rescales by the upstream gradient.
+
+:func:`policy_update_loss` additionally folds in the worker's loss assembly (worker.py:852-889): KL-loss term
+(no gradient, like ``compute_approx_kl`` under ``@torch.no_grad``), entropy ``masked_mean`` and
+``loss = policy + kl*coef - entropy*coef`` — still a single pass, one packed stats vector, one host sync.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_VALID_REDUCTIONS = ("token_mean", "sequence_mean", "seq_mean_token_sum_norm")
+
+
+def _cfg(config, name, default=None):
+    """Attribute or mapping access (AlgorithmConfig dataclass, DictConfig, SimpleNamespace, dict)."""
+    if isinstance(config, dict):
+        return config.get(name, default)
+    return getattr(config, name, default)
+
+
+def _off_policy_enabled(config, rollout_logprobs) -> bool:
+    if rollout_logprobs is None:
+        return False
+    opc = _cfg(config, "off_policy_correction", None)
+    if opc is None:
+        return False
+    return _cfg(opc, "tis_ratio_type", None) is not None or _cfg(opc, "sequence_mask_metric", None) is not None
+
+
+def _make_params(loss_type: str, reduction: str, config, *, kl_type: str = "k3", kl_coef: float = 0.0,
+                 use_entropy_loss: bool = False, entropy_coef: float = 0.0,
+                 kl_has_grad: bool = False) -> _lib.LossParams:
+    if reduction not in _VALID_REDUCTIONS:
+        raise ValueError(f"Invalid loss reduction type: {reduction}")
+    max_seq_len = _cfg(config, "max_seq_len", None)
+    if reduction == "seq_mean_token_sum_norm":
+        assert max_seq_len is not None, "max_seq_len must be provided for seq_mean_token_sum_norm loss reduction"
+    if kl_type not in _lib.KL_TYPES:
+        raise ValueError(f"Invalid KL estimator type: {kl_type}")
+    p = _lib.LossParams()
+    p.loss_type = _lib.LOSS_TYPES[loss_type]
+    p.reduction = _lib.REDUCTIONS[reduction]
+    p.kl_type = _lib.KL_TYPES[kl_type]
+    p.kl_has_grad = int(kl_has_grad)
+    p.use_entropy_loss = int(use_entropy_loss)
+    p.eps_clip_low = float(_cfg(config, "eps_clip_low", 0.2))
+    p.eps_clip_high = float(_cfg(config, "eps_clip_high", 0.2))
+    p.clip_ratio_c = float(_cfg(config, "clip_ratio_c", 3.0))
+    p.max_seq_len = float(max_seq_len) if max_seq_len is not None else 0.0
+    p.kl_loss_coef = float(kl_coef)
+    p.entropy_loss_coef = float(entropy_coef)
+    return p
+
+
+def _prep(t: Optional[torch.Tensor], ref: torch.Tensor) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    t = t.detach()
+    if t.device != ref.device or t.dtype != torch.float32:
+        t = t.to(device=ref.device, dtype=torch.float32)
+    return t.contiguous()
+
+
+def _run_kernel(lp, olp, adv, mask, base, ent, params, want_d_ent):
+    """Launch skyb200_policy_loss. Returns (stats[16] device tensor, d_lp, d_ent or None)."""
+    lib = _lib.load()
+    B, A = lp.shape
+    with torch.cuda.device(lp.device):
+        stats = torch.empty(_lib.LOSS_NSTATS, dtype=torch.float32, device=lp.device)
+        d_lp = torch.empty_like(lp)
+        d_ent = torch.empty_like(lp) if want_d_ent else None
+        ws_bytes = lib.skyb200_policy_loss_workspace(B, A)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=lp.device)
+        _lib.check(
+            lib.skyb200_policy_loss(_lib.ptr(lp), _lib.ptr(olp), _lib.ptr(adv), _lib.ptr(mask), _lib.ptr(base),
+                                    _lib.ptr(ent), _lib.ptr(d_lp), _lib.ptr(d_ent), _lib.ptr(stats), _lib.ptr(ws),
+                                    ws_bytes, B, A, C.byref(params), _lib.stream_ptr()),
+            "skyb200_policy_loss",
+        )
+    return stats, d_lp, d_ent
+
+
+def _scale_by_upstream(grad: torch.Tensor, upstream: torch.Tensor) -> torch.Tensor:
+    """grad *= upstream (0-d device tensor) without a host sync."""
+    lib = _lib.load()
+    up = upstream.detach().to(device=grad.device, dtype=torch.float32).reshape(1).contiguous()
+    with torch.cuda.device(grad.device):
+        _lib.check(lib.skyb200_scale_inplace(_lib.ptr(grad), _lib.ptr(up), grad.numel(), _lib.stream_ptr()),
+                   "skyb200_scale_inplace")
+    return grad
+
+
+class _PolicyLossFn(torch.autograd.Function):
+    """loss, stats = f(log_probs [, entropy]); gradients were produced by the forward kernel."""
+
+    @staticmethod
+    def forward(ctx, log_probs, entropy, old_log_probs, advantages, loss_mask, base_log_probs, params, stat_index):
+        if not log_probs.is_cuda:
+            raise RuntimeError("skyrl_b200 policy losses need CUDA tensors (no CPU fallback)")
+        if log_probs.dim() != 2:
+            raise ValueError(f"log_probs must be [batch, actions], got {tuple(log_probs.shape)}")
+        lp = _prep(log_probs, log_probs)
+        olp = _prep(old_log_probs, lp)
+        adv = _prep(advantages, lp)
+        mask = _prep(loss_mask, lp)
+        base = _prep(base_log_probs, lp)
+        ent = _prep(entropy, lp)
+        want_d_ent = ent is not None and entropy.requires_grad and bool(params.use_entropy_loss)
+        stats, d_lp, d_ent = _run_kernel(lp, olp, adv, mask, base, ent, params, want_d_ent)
+        ctx.save_for_backward(d_lp, d_ent if d_ent is not None else torch.empty(0, device=lp.device))
+        ctx.has_d_ent = d_ent is not None
+        ctx.in_dtype = log_probs.dtype
+        ctx.ent_dtype = entropy.dtype if entropy is not None else None
+        ctx.mark_non_differentiable(stats)
+        loss = stats[stat_index].clone()
+        return loss, stats
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_stats):
+        d_lp, d_ent = ctx.saved_tensors
+        g_lp = _scale_by_upstream(d_lp.clone(), g_loss)
+        if g_lp.dtype != ctx.in_dtype:
+            g_lp = g_lp.to(ctx.in_dtype)
+        g_ent = None
+        if ctx.has_d_ent:
+            g_ent = _scale_by_upstream(d_ent.clone(), g_loss)
+            if g_ent.dtype != ctx.ent_dtype:
+                g_ent = g_ent.to(ctx.ent_dtype)
+        return g_lp, g_ent, None, None, None, None, None, None
+
+
+def _registry_loss(loss_type, log_probs, old_log_probs, advantages, config, loss_mask, rollout_logprobs):
+    if _off_policy_enabled(config, rollout_logprobs):
+        raise NotImplementedError(
+            "off_policy_correction (tis_ratio_type / sequence_mask_metric) is not fused into the B200 loss kernel "
+            "yet; disable it or use the reference loss for this configuration"
+        )
+    params = _make_params(loss_type, _cfg(config, "loss_reduction"), config)
+    loss, stats = _PolicyLossFn.apply(log_probs, None, old_log_probs, advantages, loss_mask, None, params,
+                                      _lib.STAT_POLICY_LOSS)
+    clip_ratio = float(stats[_lib.STAT_CLIP_RATIO].item())  # the single host sync of this call
+    return loss, {"clip_ratio": clip_ratio}
+
+
+def ppo_policy_loss(
+    log_probs: torch.Tensor,
+    old_log_probs: torch.Tensor,
+    advantages: torch.Tensor,
+    config,
+    loss_mask: Optional[torch.Tensor] = None,
+    rollout_logprobs: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, Dict[str, float]]:
+    """"regular" and "dual_clip" PPO losses (reference: ppo_utils.py:548-586)."""
+    loss_type = _cfg(config, "policy_loss_type")
+    assert loss_type in ["regular", "dual_clip"], "loss_type must be either 'regular' or 'dual_clip'"
+    assert _cfg(config, "loss_reduction") in _VALID_REDUCTIONS, (
+        "loss_reduction must be either 'token_mean', 'sequence_mean', or 'seq_mean_token_sum_norm'"
+    )
+    return _registry_loss(loss_type, log_probs, old_log_probs, advantages, config, loss_mask, rollout_logprobs)
+
+
+def gspo_policy_loss(
+    log_probs: torch.Tensor,
+    old_log_probs: torch.Tensor,
+    advantages: torch.Tensor,
+    config,
+    loss_mask: Optional[torch.Tensor] = None,
+    rollout_logprobs: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, Dict[str, float]]:
+    """GSPO sequence-level importance ratio loss (reference: ppo_utils.py:661-725)."""
+    if _cfg(config, "loss_reduction") != "sequence_mean":
+        import logging
+
+        logging.getLogger("skyrl_b200").warning(
+            "With GSPO it's recommended to use 'sequence_mean' loss reduction; got %s", _cfg(config, "loss_reduction")
+        )
+    return _registry_loss("gspo", log_probs, old_log_probs, advantages, config, loss_mask, rollout_logprobs)
+
+
+def policy_update_loss(
+    log_probs: torch.Tensor,
+    old_log_probs: torch.Tensor,
+    advantages: torch.Tensor,
+    config,
+    loss_mask: Optional[torch.Tensor] = None,
+    base_log_probs: Optional[torch.Tensor] = None,
+    entropy: Optional[torch.Tensor] = None,
+    policy_loss_type: Optional[str] = None,
+    kl_has_grad: bool = False,
+    sync: bool = True,
+):
+    """The worker's whole loss assembly in one kernel pass (reference: worker.py:787-889).
+
+    ``loss = policy_loss + kl_loss * kl_loss_coef - entropy * entropy_loss_coef`` with
+    ``kl_loss = mean_b masked_mean_t compute_approx_kl(...)`` (iff ``use_kl_loss``; contributes to the value,
+    not to the gradient, exactly like the reference) and ``entropy = masked_mean(entropy, loss_mask)`` (gradient
+    iff ``use_entropy_loss``).
+
+    Returns ``(final_loss, status)``; ``status`` has the reference's metric names (``final_loss``,
+    ``policy_loss``, ``policy_entropy``, ``policy_kl``, ``loss_metrics/clip_ratio``).  With ``sync=False`` the
+    status values stay on the device as a packed fp32 vector (key ``"packed"``) for a later single all-reduce.
+    """
+    loss_type = policy_loss_type or _cfg(config, "policy_loss_type", "regular")
+    if loss_type not in _lib.LOSS_TYPES:
+        raise ValueError(f"policy loss '{loss_type}' has no fused B200 kernel; available: {list(_lib.LOSS_TYPES)}")
+    use_kl = bool(_cfg(config, "use_kl_loss", False)) and base_log_probs is not None
+    use_ent = bool(_cfg(config, "use_entropy_loss", False))
+    params = _make_params(
+        loss_type,
+        _cfg(config, "loss_reduction", "token_mean"),
+        config,
+        kl_type=_cfg(config, "kl_estimator_type", "k3"),
+        kl_coef=float(_cfg(config, "kl_loss_coef", 0.0)) if use_kl else 0.0,
+        use_entropy_loss=use_ent,
+        entropy_coef=float(_cfg(config, "entropy_loss_coef", 0.0)),
+        kl_has_grad=kl_has_grad,
+    )
+    loss, stats = _PolicyLossFn.apply(log_probs, entropy, old_log_probs, advantages, loss_mask,
+                                      base_log_probs if use_kl else None, params, _lib.STAT_FINAL_LOSS)
+    if not sync:
+        return loss, {"packed": stats}
+    s = stats.tolist()  # one D2H copy for every metric
+    status = {
+        "final_loss": s[_lib.STAT_FINAL_LOSS],
+        "policy_loss": s[_lib.STAT_POLICY_LOSS],
+        "policy_entropy": s[_lib.STAT_ENTROPY],
+        "loss_metrics/clip_ratio": s[_lib.STAT_CLIP_RATIO],
+    }
+    if use_kl:
+        status["policy_kl"] = s[_lib.STAT_KL_LOSS]
+    return loss, status
+
+
+def status_from_packed(stats_host, use_kl: bool) -> Dict[str, float]:
+    """Decode a packed stats vector (list of floats) into the reference's status dict."""
+    status = {
+        "final_loss": stats_host[_lib.STAT_FINAL_LOSS],
+        "policy_loss": stats_host[_lib.STAT_POLICY_LOSS],
+        "policy_entropy": stats_host[_lib.STAT_ENTROPY],
+        "loss_metrics/clip_ratio": stats_host[_lib.STAT_CLIP_RATIO],
+    }
+    if use_kl:
+        status["policy_kl"] = stats_host[_lib.STAT_KL_LOSS]
+    return status

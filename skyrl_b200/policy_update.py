@@ -1,0 +1,171 @@
+"""One policy-update step of the hot path: fused LM head forward -> loss assembly -> fused LM head backward.
+
+This is the B200 replacement for the body of ``PolicyWorkerBase._forward_backward_micro``
+(skyrl-train/skyrl_train/workers/worker.py:787-900) *after* the transformer trunk has produced the last hidden
+states: it consumes ``hidden`` instead of logits, never builds ``[tokens x vocab]``, and returns the same status
+dict the reference reports (``final_loss, policy_loss, policy_entropy, policy_kl, loss_metrics/clip_ratio``) plus
+the gradients that continue into the trunk (``d_hidden``) and the lm_head (``d_weight``, fp32).
+
+The three C-ABI calls run back to back on the current stream with no host synchronisation in between; the only
+sync is the single D2H copy of the packed stats vector (skipped with ``sync=False``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .losses import _cfg, _make_params, status_from_packed
+
+
+@dataclass
+class PolicyUpdateOutput:
+    status: Dict[str, float]           # python floats (or {"packed": tensor} when sync=False)
+    stats: torch.Tensor                # packed fp32 stats vector on the device (SKYB200_STAT_* layout)
+    log_probs: torch.Tensor            # [B, A] fp32
+    entropy: torch.Tensor              # [B, A] fp32 (masked by entropy_mask if one was given)
+    d_hidden: Optional[torch.Tensor]   # [B*A, H] bf16
+    d_weight: Optional[torch.Tensor]   # [V, H] fp32 (the buffer passed in, or a new one)
+
+
+class _Workspace:
+    """Grow-only per-device scratch so steady-state steps do not touch the allocator."""
+
+    def __init__(self):
+        self.bufs: Dict[tuple, torch.Tensor] = {}
+
+    def get(self, key: str, nbytes: int, dev: torch.device) -> torch.Tensor:
+        k = (key, dev.index)
+        b = self.bufs.get(k)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.bufs[k] = b
+        return b
+
+
+_WS = _Workspace()
+
+
+def policy_update_step(
+    hidden: torch.Tensor,
+    weight: torch.Tensor,
+    labels: torch.Tensor,
+    old_log_probs: torch.Tensor,
+    advantages: torch.Tensor,
+    config,
+    loss_mask: Optional[torch.Tensor] = None,
+    base_log_probs: Optional[torch.Tensor] = None,
+    temperature: float = 1.0,
+    entropy_mask: Optional[torch.Tensor] = None,
+    d_weight: Optional[torch.Tensor] = None,
+    accumulate_d_weight: bool = False,
+    need_d_hidden: bool = True,
+    need_d_weight: bool = True,
+    chunk: int = 0,
+    sync: bool = True,
+) -> PolicyUpdateOutput:
+    """``hidden`` [B, A, H] (or [B*A, H]) bf16, ``weight`` [V, H] bf16, ``labels`` [B, A] int64,
+    ``old_log_probs`` / ``advantages`` / ``loss_mask`` / ``base_log_probs`` [B, A] fp32.
+
+    ``config`` carries the reference's ``AlgorithmConfig`` fields (policy_loss_type, loss_reduction, eps_clip_*,
+    clip_ratio_c, use_kl_loss, kl_estimator_type, kl_loss_coef, use_entropy_loss, entropy_loss_coef,
+    max_seq_len).  Gradients are those of ``final_loss`` (upstream gradient 1), i.e. what ``loss.backward()``
+    delivers in the reference (worker.py:876-877).
+    """
+    lib = _lib.load()
+    if not hidden.is_cuda:
+        raise RuntimeError("policy_update_step needs CUDA tensors (no CPU fallback)")
+    B, A = old_log_probs.shape
+    H = hidden.shape[-1]
+    V = weight.shape[0]
+    N = B * A
+    dev = hidden.device
+    h = hidden.reshape(N, H)
+    if h.dtype != torch.bfloat16 or not h.is_contiguous():
+        h = h.to(torch.bfloat16).contiguous()
+    w = weight if (weight.dtype == torch.bfloat16 and weight.is_contiguous()) else weight.to(torch.bfloat16).contiguous()
+    lab = labels.reshape(N).to(device=dev, dtype=torch.int64).contiguous()
+
+    def f32(t):
+        if t is None:
+            return None
+        t = t.detach()
+        if t.dtype != torch.float32 or t.device != dev:
+            t = t.to(device=dev, dtype=torch.float32)
+        return t.contiguous()
+
+    olp, adv, mask, base = f32(old_log_probs), f32(advantages), f32(loss_mask), f32(base_log_probs)
+    emask = None if entropy_mask is None else f32(entropy_mask).reshape(N)
+    loss_type = _cfg(config, "policy_loss_type", "regular")
+    if loss_type not in _lib.LOSS_TYPES:
+        raise ValueError(f"policy loss '{loss_type}' has no fused B200 kernel; available: {list(_lib.LOSS_TYPES)}")
+    use_kl = bool(_cfg(config, "use_kl_loss", False)) and base is not None
+    use_ent = bool(_cfg(config, "use_entropy_loss", False))
+    params = _make_params(
+        loss_type, _cfg(config, "loss_reduction", "token_mean"), config,
+        kl_type=_cfg(config, "kl_estimator_type", "k3"),
+        kl_coef=float(_cfg(config, "kl_loss_coef", 0.0)) if use_kl else 0.0,
+        use_entropy_loss=use_ent, entropy_coef=float(_cfg(config, "entropy_loss_coef", 0.0)),
+    )
+    T = float(temperature)
+    stream = _lib.stream_ptr()
+    with torch.cuda.device(dev):
+        logprobs = torch.empty(N, dtype=torch.float32, device=dev)
+        ent_raw = torch.empty(N, dtype=torch.float32, device=dev)
+        lse2 = torch.empty(N, dtype=torch.float32, device=dev)
+        fb = lib.skyb200_head_forward_workspace(N, H, V, chunk)
+        ws_f = _WS.get("head_fwd", fb, dev)
+        _lib.check(
+            lib.skyb200_head_forward(_lib.ptr(h), _lib.ptr(w), _lib.ptr(lab), None, _lib.ptr(logprobs),
+                                     _lib.ptr(ent_raw), _lib.ptr(lse2), _lib.ptr(ws_f), fb, N, H, V, T, int(chunk),
+                                     stream),
+            "skyb200_head_forward",
+        )
+        ent = ent_raw * emask if emask is not None else ent_raw
+
+        stats = torch.empty(_lib.LOSS_NSTATS, dtype=torch.float32, device=dev)
+        d_lp = torch.empty(N, dtype=torch.float32, device=dev)
+        d_ent = torch.empty(N, dtype=torch.float32, device=dev) if use_ent else None
+        lb = lib.skyb200_policy_loss_workspace(B, A)
+        ws_l = _WS.get("loss", lb, dev)
+        _lib.check(
+            lib.skyb200_policy_loss(_lib.ptr(logprobs), _lib.ptr(olp), _lib.ptr(adv), _lib.ptr(mask),
+                                    _lib.ptr(base) if use_kl else None, _lib.ptr(ent), _lib.ptr(d_lp),
+                                    _lib.ptr(d_ent), _lib.ptr(stats), _lib.ptr(ws_l), lb, B, A, C.byref(params),
+                                    stream),
+            "skyb200_policy_loss",
+        )
+        d_hidden = None
+        if need_d_hidden or need_d_weight:
+            g_ent = None
+            if use_ent:
+                g_ent = d_ent * emask if emask is not None else d_ent
+            d_hidden = torch.empty((N, H), dtype=torch.bfloat16, device=dev) if need_d_hidden else None
+            acc = 0
+            if need_d_weight:
+                if d_weight is None:
+                    d_weight = torch.empty((V, H), dtype=torch.float32, device=dev)
+                else:
+                    if d_weight.dtype != torch.float32 or tuple(d_weight.shape) != (V, H) or not d_weight.is_contiguous():
+                        raise ValueError("d_weight must be a contiguous fp32 [V, H] tensor")
+                    acc = 1 if accumulate_d_weight else 0
+            bb = lib.skyb200_head_backward_workspace(N, H, V, chunk)
+            ws_b = _WS.get("head_bwd", bb, dev)
+            _lib.check(
+                lib.skyb200_head_backward(_lib.ptr(h), _lib.ptr(w), _lib.ptr(lab), _lib.ptr(lse2),
+                                          _lib.ptr(ent_raw) if g_ent is not None else None, _lib.ptr(d_lp),
+                                          _lib.ptr(g_ent), _lib.ptr(d_hidden),
+                                          _lib.ptr(d_weight) if need_d_weight else None, acc, _lib.ptr(ws_b), bb, N,
+                                          H, V, T, int(chunk), stream),
+                "skyb200_head_backward",
+            )
+        if sync:
+            status = status_from_packed(stats.tolist(), use_kl)  # the single host sync of the step
+            status["response_length"] = A
+        else:
+            status = {"packed": stats}
+    return PolicyUpdateOutput(status=status, stats=stats, log_probs=logprobs.view(B, A), entropy=ent.view(B, A),
+                              d_hidden=d_hidden, d_weight=d_weight if need_d_weight else None)

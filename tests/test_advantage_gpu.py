@@ -1,0 +1,150 @@
+"""CUDA advantage kernels (GRPO / RLOO / GAE / KL) vs the golden reference outputs and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import skyrl_b200
+from skyrl_b200 import advantages
+from oracle import policy_oracle as O
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def test_grpo_rloo_match_reference_golden(golden_adv):
+    g = golden_adv
+    r, dense = _t(g["rewards"]), _t(g["dense_rewards"])
+    im = _t(g["mask_i64"])
+    fm = im.float()
+    uids = g["uids"]
+    est = skyrl_b200.AdvantageEstimatorRegistry.get
+    # CPU tensors in (as the reference's driver passes them), int64 mask consumed natively
+    adv, ret = est("grpo")(token_level_rewards=r, response_mask=im, index=uids, values=None, grpo_norm_by_std=True,
+                           gamma=1.0, lambd=1.0, config=None)
+    assert adv is ret and adv.device.type == "cpu" and adv.dtype == torch.float32
+    assert_close(adv, g["grpo_std"], what="grpo_std")
+    assert torch.equal(adv == 0, _t(g["grpo_std"]) == 0), "mask zeros must be bit-exact"
+    adv, _ = est("grpo")(token_level_rewards=r.to(DEV), response_mask=fm.to(DEV), index=list(uids),
+                         grpo_norm_by_std=False)
+    assert adv.is_cuda
+    assert_close(adv, g["grpo_nostd"], what="grpo_nostd")
+    assert_close(est("grpo")(token_level_rewards=dense, response_mask=fm, index=uids)[0], g["grpo_dense"])
+    assert_close(est("rloo")(token_level_rewards=r, response_mask=fm, index=uids)[0], g["rloo"], what="rloo")
+    assert_close(est("rloo")(token_level_rewards=dense.to(DEV), response_mask=im.to(DEV), index=uids)[0],
+                 g["rloo_dense"], what="rloo dense")
+
+
+def test_gae_matches_reference_golden(golden_adv):
+    g = golden_adv
+    dense, v, fm = _t(g["dense_rewards"]), _t(g["values"]), _t(g["mask_i64"]).float()
+    for name, (gm, lm) in {"gae_1_095": (1.0, 0.95), "gae_099_1": (0.99, 1.0), "gae_1_1": (1.0, 1.0)}.items():
+        adv, ret = skyrl_b200.compute_advantages_and_returns(dense.to(DEV), fm.to(DEV), None, "gae", None,
+                                                             values=v.to(DEV), gamma=gm, lambd=lm)
+        assert_close(adv, g[name + "_adv"], what=name + " adv")
+        assert_close(ret, g[name + "_ret"], what=name + " ret")
+
+
+def test_gae_known_answers():  # reference: tests/cpu/utils/test_ppo_utils.py:175-242
+    r, v = torch.tensor([[1.0, 2.0, 3.0]]), torch.tensor([[0.5, 1.0, 1.5]])
+    adv, ret = advantages.compute_gae_advantage_return(r, v, torch.tensor([[1.0, 0.0, 1.0]]), 1.0, 1.0)
+    assert torch.allclose(ret, torch.tensor([[6.0, 5.0, 3.0]]), atol=1e-5)
+    assert torch.allclose(adv, torch.tensor([[0.7071, 0.1768, -0.7071]]), atol=1e-4)  # no reset on the mask
+    _, ret = advantages.compute_gae_advantage_return(r, v, torch.ones(1, 3), 0.5, 1.0)
+    assert torch.allclose(ret, torch.tensor([[2.75, 3.5, 3.0]]), atol=1e-5)
+    _, ret = advantages.compute_gae_advantage_return(r, v, torch.ones(1, 3), 1.0, 0.5)
+    assert torch.allclose(ret, torch.tensor([[3.625, 4.25, 3.0]]), atol=1e-5)
+
+
+def test_gae_mask_errors_like_masked_var():
+    r = torch.zeros(2, 3)
+    with pytest.raises(ValueError, match="At least one element"):
+        advantages.compute_gae_advantage_return(r, r, torch.zeros(2, 3), 1.0, 1.0)
+    m = torch.zeros(2, 3)
+    m[0, 0] = 1
+    with pytest.raises(ValueError, match="sum of the mask is one"):
+        advantages.compute_gae_advantage_return(r, r, m, 1.0, 1.0)
+
+
+@pytest.mark.parametrize("B,A", [(1, 1), (3, 17), (4, 4096), (5, 4097), (2, 9000), (16, 8192)])
+@pytest.mark.parametrize("gamma,lambd", [(1.0, 0.95), (1.0, 1.0), (0.99, 0.9)])
+def test_gae_random_vs_oracle(B, A, gamma, lambd):
+    if B * A < 2:
+        pytest.skip("masked_var needs two elements")
+    g = torch.Generator().manual_seed(A * 7 + B)
+    lens = torch.randint(max(1, A // 2), A + 1, (B,), generator=g)
+    mask = (torch.arange(A)[None] < lens[:, None]).float()
+    r = torch.zeros(B, A)
+    r[torch.arange(B), lens - 1] = torch.randn(B, generator=g)
+    r = r - 0.01 * torch.rand(B, A, generator=g) * mask
+    v = torch.randn(B, A, generator=g)
+    a_ref, r_ref = O.gae_advantage_return(r, v, mask, gamma, lambd)
+    a, ret = advantages.compute_gae_advantage_return(r.to(DEV), v.to(DEV), mask.to(DEV), gamma, lambd)
+    assert_close(ret, r_ref, what="returns")
+    assert_close(a, a_ref, what="advantages")
+
+
+@pytest.mark.parametrize("B,A,G", [(8, 5, 4), (64, 1024, 8), (48, 1000, 16), (6, 4100, 1)])
+def test_group_random_vs_oracle(B, A, G):
+    g = torch.Generator().manual_seed(B + A)
+    uids = np.array([f"uid-{i // G}" for i in range(B)])
+    uids = uids[torch.randperm(B, generator=g).numpy()]  # non-contiguous groups
+    lens = torch.randint(1, A + 1, (B,), generator=g)
+    mask = (torch.arange(A)[None] < lens[:, None]).long()
+    r = torch.zeros(B, A)
+    r[torch.arange(B), lens - 1] = (torch.rand(B, generator=g) < 0.3).float()
+    for mode, fn, kw in (("grpo", O.grpo_advantage, {}), ("grpo", O.grpo_advantage, {"norm_by_std": False}),
+                         ("rloo", O.rloo_advantage, {})):
+        want, _ = fn(r, mask, uids, **kw)
+        got, _ = skyrl_b200.AdvantageEstimatorRegistry.get(mode)(
+            token_level_rewards=r.to(DEV), response_mask=mask.to(DEV), index=uids,
+            grpo_norm_by_std=kw.get("norm_by_std", True))
+        assert_close(got, want, what=f"{mode} {kw}")
+        assert torch.equal(got.cpu() == 0, want == 0)
+
+
+def test_kl_estimators_and_reward_penalty_match_reference_golden(golden_adv):
+    g = golden_adv
+    lp, base, fm, r = _t(g["lp"]), _t(g["base"]), _t(g["mask_i64"]).float(), _t(g["rewards"])
+    for kind in ("k1", "abs", "k2", "k3"):
+        assert_close(skyrl_b200.compute_approx_kl(lp.to(DEV), base.to(DEV), fm.to(DEV), kind), g["kl_" + kind])
+        assert_close(skyrl_b200.compute_approx_kl(lp, base, None, kind), g["kl_nomask_" + kind])
+        out, met = skyrl_b200.apply_reward_kl_penalty(r.to(DEV), lp.to(DEV), base.to(DEV), fm.to(DEV), kind, 0.05)
+        assert_close(out, g["klrew_" + kind], what="klrew " + kind)
+        assert_close([met["avg_kl"], met["avg_kl_max"]], g["klrew_metrics_" + kind], what="klrew metrics")
+    out, _ = skyrl_b200.apply_reward_kl_penalty(r.to(DEV), lp.to(DEV), base.to(DEV), fm.to(DEV), "k3", -1.0)
+    assert torch.equal(out.cpu(), r), "negative coefficient is clamped to 0 (max(0, coef))"
+
+
+def test_kl_in_reward_known_answer():  # reference: tests/cpu/test_trainer.py:66-133 (k3): 0.1249 / 0.3143
+    probs = torch.tensor([[0.1, 0.2, 0.3, 0.2, 0.2], [0.25, 0.25, 0.25, 0.15, 0.10]])
+    base = torch.tensor([[0.15, 0.15, 0.25, 0.25, 0.2], [0.2, 0.3, 0.2, 0.2, 0.10]])
+    lp, bp = probs.log(), base.log()
+    mask = torch.ones(2, 5)
+    want_out, want = O.reward_kl_penalty(torch.zeros(2, 5), lp, bp, mask, "k3", 0.1)
+    out, met = skyrl_b200.apply_reward_kl_penalty(torch.zeros(2, 5), lp, bp, mask, "k3", 0.1)
+    assert_close(out, want_out)
+    assert met["avg_kl"] == pytest.approx(want["avg_kl"], rel=1e-5)
+    assert met["avg_kl_max"] == pytest.approx(want["avg_kl_max"], rel=1e-5)
+
+
+def test_full_size_properties_c3_shape():
+    """C3 per-GPU shard (64 x 8192 here x8 = 512 x 8192): size-independent checks of GAE + GRPO."""
+    B, A = 512, 8192
+    g = torch.Generator(device=DEV).manual_seed(5)
+    v = torch.randn(B, A, device=DEV, generator=g)
+    r = torch.zeros(B, A, device=DEV)
+    r[:, -1] = 1.0
+    mask = torch.ones(B, A, device=DEV)
+    adv, ret = advantages.compute_gae_advantage_return(r, v, mask, 1.0, 1.0)
+    # gamma = lambda = 1: returns_t = sum_{s>=t} r_s = 1 (telescoping), independent of the values
+    assert_close(ret, torch.ones(B, A), rel=1e-5)
+    # whitening: zero mean, unit (Bessel) variance over the mask
+    assert abs(adv.mean().item()) < 1e-4 and abs(adv.var().item() - 1.0) < 1e-3
+    uids = [i // 8 for i in range(B)]
+    a, _ = advantages.compute_grpo_outcome_advantage(r, mask, uids)  # every group has equal scores -> 0
+    assert torch.count_nonzero(a) == 0

@@ -1,0 +1,139 @@
+"""Host-side logic that needs no GPU: registries (same behaviour as the reference's), uid grouping, sharding,
+config validation, and the loud failure when no CUDA device / library is present."""
+import numpy as np
+import pytest
+import torch
+
+import skyrl_b200
+from skyrl_b200 import advantages, dist as sdist, losses
+from skyrl_b200.registry import (AdvantageEstimator, AdvantageEstimatorRegistry, PolicyLossRegistry,
+                                 register_advantage_estimator, register_policy_loss)
+from oracle import policy_oracle as O
+
+
+def test_builtin_names_registered():
+    assert set(AdvantageEstimatorRegistry.list_available()) >= {"grpo", "rloo", "gae"}
+    assert set(PolicyLossRegistry.list_available()) >= {"regular", "dual_clip", "gspo"}
+    assert PolicyLossRegistry.get("regular") is losses.ppo_policy_loss
+    assert PolicyLossRegistry.get("dual_clip") is losses.ppo_policy_loss
+    assert AdvantageEstimatorRegistry.get(AdvantageEstimator.GRPO) is advantages.compute_grpo_outcome_advantage
+
+
+def test_register_get_unregister_roundtrip():  # reference: tests/cpu/utils/test_ppo_utils.py:287-403
+    def fn(**kw):
+        return 1
+
+    AdvantageEstimatorRegistry.register("unit_test_est", fn)
+    try:
+        assert AdvantageEstimatorRegistry.get("unit_test_est") is fn
+        assert "unit_test_est" in AdvantageEstimatorRegistry.list_available()
+        with pytest.raises(ValueError, match="already registered"):
+            AdvantageEstimatorRegistry.register("unit_test_est", fn)
+    finally:
+        AdvantageEstimatorRegistry.unregister("unit_test_est")
+    with pytest.raises(ValueError, match="Unknown advantage estimator"):
+        AdvantageEstimatorRegistry.get("unit_test_est")
+    with pytest.raises(ValueError, match="not registered"):
+        AdvantageEstimatorRegistry.unregister("unit_test_est")
+    with pytest.raises(ValueError, match="Unknown policy loss"):
+        PolicyLossRegistry.get("nope")
+
+
+def test_decorators_register():
+    @register_policy_loss("unit_test_loss")
+    def my_loss(log_probs, old_log_probs, advantages, config, loss_mask=None, rollout_logprobs=None):
+        return log_probs.sum(), {}
+
+    @register_advantage_estimator("unit_test_adv")
+    def my_adv(**kw):
+        return 0, 0
+
+    try:
+        assert PolicyLossRegistry.get("unit_test_loss").__name__ == "my_loss"
+        assert AdvantageEstimatorRegistry.get("unit_test_adv")() == (0, 0)
+    finally:
+        PolicyLossRegistry.unregister("unit_test_loss")
+        AdvantageEstimatorRegistry.unregister("unit_test_adv")
+
+
+def test_repopulate_is_idempotent():
+    before = list(PolicyLossRegistry.list_available())
+    skyrl_b200.repopulate_all_registries()
+    assert list(PolicyLossRegistry.list_available()) == before
+
+
+def test_registered_functions_pickle_by_reference():
+    import pickle
+
+    for fn in (losses.ppo_policy_loss, losses.gspo_policy_loss, advantages.compute_grpo_outcome_advantage,
+               advantages.compute_gae_advantage_return):
+        assert pickle.loads(pickle.dumps(fn)) is fn
+
+
+def test_group_index_matches_dict_semantics():
+    uids = np.array(["b", "a", "b", "c", "a", "b"])
+    gor, gstart, grows, ng = advantages.build_group_index(uids)
+    assert ng == 3
+    assert gor.tolist() == [0, 1, 0, 2, 1, 0]  # dense ids in order of first appearance
+    assert gstart.tolist() == [0, 3, 5, 6]
+    assert grows.tolist() == [0, 2, 5, 1, 4, 3]  # stable inside a group
+    # arbitrary hashables, python list input, numpy ints equal to python ints
+    gor2, _, _, ng2 = advantages.build_group_index([np.int64(7), 7, (1, 2), (1, 2), "7"])
+    assert ng2 == 3 and gor2.tolist() == [0, 0, 1, 1, 2]
+    # group assignment agrees bit-exactly with the oracle's
+    gid, n = O._group_ids(uids)
+    assert n == ng and gid.tolist() == gor.tolist()
+
+
+def test_shard_prompt_groups_keeps_groups_whole_and_balanced():
+    rng = np.random.default_rng(0)
+    uids = np.repeat([f"p{i}" for i in range(32)], 16)
+    rng.shuffle(uids)
+    lens = rng.integers(128, 16384, size=len(uids))
+    for ws in (2, 4, 8):
+        rows = sdist.shard_prompt_groups(uids, lens, ws)
+        flat = sorted(i for r in rows for i in r)
+        assert flat == list(range(len(uids)))
+        owner = {}
+        for r, rr in enumerate(rows):
+            for i in rr:
+                assert owner.setdefault(uids[i], r) == r, "a prompt group was split across ranks"
+        loads = [int(lens[r].sum()) for r in rows]
+        assert max(loads) <= 1.15 * (sum(loads) / ws)
+
+
+def test_config_validation_matches_reference_messages():
+    lp = torch.zeros(2, 3)
+    with pytest.raises(AssertionError, match="loss_type must be either"):
+        losses.ppo_policy_loss(lp, lp, lp, O.make_cfg(policy_loss_type="gspo"))
+    with pytest.raises(AssertionError, match="loss_reduction must be either"):
+        losses.ppo_policy_loss(lp, lp, lp, O.make_cfg(loss_reduction="bogus"))
+    with pytest.raises(AssertionError, match="max_seq_len must be provided"):
+        losses.ppo_policy_loss(lp, lp, lp, O.make_cfg(loss_reduction="seq_mean_token_sum_norm", max_seq_len=None))
+    with pytest.raises(ValueError, match="Invalid KL estimator type"):
+        advantages.compute_approx_kl(lp, lp, None, "k9")
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_ops_fail_loudly_without_cuda():
+    lp = torch.zeros(2, 4, requires_grad=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        losses.ppo_policy_loss(lp, lp.detach(), lp.detach(), O.make_cfg())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        advantages.compute_grpo_outcome_advantage(torch.zeros(2, 4), torch.ones(2, 4), ["a", "a"])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        skyrl_b200.fused_lm_head(torch.zeros(4, 8, dtype=torch.bfloat16), torch.zeros(16, 8, dtype=torch.bfloat16),
+                                 torch.zeros(4, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        skyrl_b200.logprobs_from_logits(torch.zeros(2, 3, 5), torch.zeros(2, 3, dtype=torch.long))
+
+
+def test_product_code_never_imports_the_oracle():
+    import os
+    import re
+
+    pkg = os.path.dirname(skyrl_b200.__file__)
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            src = open(os.path.join(pkg, name)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{name} imports the oracle"

@@ -1,0 +1,196 @@
+"""The oracle (oracle/policy_oracle.py) against (1) the golden fixtures generated from the unmodified reference,
+(2) the known-answer vectors of the reference's own unit tests, (3) the live reference when /root/reference exists."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import policy_oracle as O
+from oracle import ref_loader
+from conftest import assert_close
+
+T = torch.tensor
+
+
+def _t(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+# ---------------------------------------------------------------- golden fixtures (reference outputs)
+def test_golden_advantages(golden_adv):
+    g = golden_adv
+    r, dense, v = _t(g["rewards"]), _t(g["dense_rewards"]), _t(g["values"])
+    im = _t(g["mask_i64"])
+    fm = im.float()
+    uids = g["uids"]
+    assert_close(O.grpo_advantage(r, im, uids)[0], g["grpo_std"], what="grpo_std")
+    assert_close(O.grpo_advantage(r, fm, uids, norm_by_std=False)[0], g["grpo_nostd"], what="grpo_nostd")
+    assert_close(O.grpo_advantage(dense, fm, uids)[0], g["grpo_dense"], what="grpo_dense")
+    assert_close(O.rloo_advantage(r, fm, uids)[0], g["rloo"], what="rloo")
+    assert_close(O.rloo_advantage(dense, im, uids)[0], g["rloo_dense"], what="rloo_dense")
+    for name, (gm, lm) in {"gae_1_095": (1.0, 0.95), "gae_099_1": (0.99, 1.0), "gae_1_1": (1.0, 1.0)}.items():
+        adv, ret = O.gae_advantage_return(dense, v, fm, gm, lm)
+        assert_close(adv, g[name + "_adv"], what=name + " adv")
+        assert_close(ret, g[name + "_ret"], what=name + " ret")
+
+
+def test_golden_kl(golden_adv):
+    g = golden_adv
+    lp, base, fm, r = _t(g["lp"]), _t(g["base"]), _t(g["mask_i64"]).float(), _t(g["rewards"])
+    for kind in ("k1", "abs", "k2", "k3"):
+        assert_close(O.approx_kl(lp, base, fm, kind), g["kl_" + kind], what="kl " + kind)
+        assert_close(O.approx_kl(lp, base, None, kind), g["kl_nomask_" + kind], what="kl nomask " + kind)
+        out, met = O.reward_kl_penalty(r, lp, base, fm, kind, 0.05)
+        assert_close(out, g["klrew_" + kind], what="klrew " + kind)
+        assert_close([met["avg_kl"], met["avg_kl_max"]], g["klrew_metrics_" + kind], what="klrew metrics " + kind)
+
+
+@pytest.mark.parametrize("kind", ["regular", "dual_clip", "gspo"])
+@pytest.mark.parametrize("red", ["token_mean", "sequence_mean", "seq_mean_token_sum_norm"])
+@pytest.mark.parametrize("mname", ["mask", "nomask"])
+def test_golden_losses(golden_loss, kind, red, mname):
+    g = golden_loss
+    lp, olp, adv, fm = _t(g["lp"]), _t(g["olp"]), _t(g["adv"]), _t(g["mask"])
+    cfg = O.make_cfg(policy_loss_type=kind, loss_reduction=red, max_seq_len=64,
+                     eps_clip_high=0.28 if kind == "dual_clip" else 0.2)
+    x = lp.clone().requires_grad_(True)
+    loss, clip = O.policy_loss(x, olp, adv, cfg, fm if mname == "mask" else None)
+    loss.backward()
+    key = f"{kind}__{red}__{mname}"
+    assert_close(loss, g[key + "__loss"], what=key + " loss")
+    assert_close(clip, g[key + "__clip"], what=key + " clip")
+    assert_close(x.grad, g[key + "__grad"], what=key + " grad")
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("asm_grpo_kl", dict(policy_loss_type="regular", use_kl_loss=True, use_entropy_loss=False)),
+    ("asm_ent", dict(policy_loss_type="dual_clip", use_kl_loss=False, use_entropy_loss=True)),
+    ("asm_gspo_all", dict(policy_loss_type="gspo", loss_reduction="sequence_mean", use_kl_loss=True,
+                          use_entropy_loss=True, kl_estimator_type="k2")),
+])
+def test_golden_loss_assembly(golden_loss, name, kw):
+    g = golden_loss
+    lp, olp, adv, fm, base, ent = (_t(g[k]) for k in ("lp", "olp", "adv", "mask", "base", "ent"))
+    cfg = O.make_cfg(max_seq_len=64, **kw)
+    x = lp.clone().requires_grad_(True)
+    e = ent.clone().requires_grad_(True)
+    final, st = O.loss_assembly(x, olp, adv, cfg, fm, base, e)
+    final.backward()
+    want = g[name + "__stats"]
+    assert_close(st["final_loss"], want[0], what="final")
+    assert_close(st["policy_loss"], want[1], what="policy")
+    assert_close(st["policy_entropy"], want[2], what="entropy")
+    assert_close(st.get("policy_kl", 0.0), want[3], what="kl")
+    assert_close(st["loss_metrics/clip_ratio"], want[4], what="clip")
+    assert_close(x.grad, g[name + "__dlp"], what="d_lp")
+    assert_close(e.grad if e.grad is not None else torch.zeros_like(e), g[name + "__dent"], what="d_ent")
+
+
+def test_golden_head(golden_head):
+    g = golden_head
+    hidden, weight, labels = _t(g["hidden"]), _t(g["weight"]), _t(g["labels"])
+    for Tm in (1.0, 0.6):
+        k = f"T{Tm}"
+        h = hidden.clone().requires_grad_(True)
+        w = weight.clone().requires_grad_(True)
+        lp, ent = O.head_logprobs_entropy(h, w, labels, Tm)
+        assert_close(lp, g[k + "_lp"], rel=1e-5, what=k + " lp")
+        assert_close(ent, g[k + "_ent"], rel=1e-5, what=k + " ent")
+        g_lp, g_ent = _t(g[k + "_g_lp"]), _t(g[k + "_g_ent"])
+        if Tm == 1.0:
+            (lp * g_lp).sum().backward()
+            assert_close(h.grad, g[k + "_dh_lp"], rel=1e-4, what="dh")
+            assert_close(w.grad, g[k + "_dw_lp"], rel=1e-4, what="dw")
+        else:
+            ((lp * g_lp).sum() + (ent * g_ent).sum()).backward()
+            assert_close(h.grad, g[k + "_dh_both"], rel=1e-4, what="dh")
+            assert_close(w.grad, g[k + "_dw_both"], rel=1e-4, what="dw")
+    assert_close(O.logprobs_from_logits(_t(g["logits"]), _t(g["labels2"])), g["logits_lp"], what="logits lp")
+    assert_close(O.entropy_from_logits(_t(g["logits"]), _t(g["amask"])), g["logits_ent"], what="logits ent")
+
+
+# ---------------------------------------------------------------- known-answer vectors of the reference's tests
+def test_kat_kl_estimators():  # tests/cpu/utils/test_ppo_utils.py:27-62
+    lp, base, m = T([[0.2, 0.3, 0.5]]), T([[0.1, 0.2, 0.4]]), T([[1.0, 1.0, 0.0]])
+    d = lp - base
+    assert torch.allclose(O.approx_kl(lp, base, m, "k1"), d * m, atol=1e-4)
+    assert torch.allclose(O.approx_kl(lp, base, m, "abs"), d.abs() * m, atol=1e-4)
+    assert torch.allclose(O.approx_kl(lp, base, m, "k2"), 0.5 * d * d * m, atol=1e-4)
+    x = -d
+    assert torch.allclose(O.approx_kl(lp, base, m, "k3"), (x.exp() - 1 - x) * m, atol=1e-4)
+
+
+def test_kat_gae():  # tests/cpu/utils/test_ppo_utils.py:175-242
+    r, v = T([[1.0, 2.0, 3.0]]), T([[0.5, 1.0, 1.5]])
+    ones = torch.ones(1, 3)
+    _, ret = O.gae_advantage_return(r, v, ones, 1.0, 1.0)
+    assert torch.allclose(ret, T([[6.0, 5.0, 3.0]]), atol=1e-5)
+    adv, ret = O.gae_advantage_return(r, v, T([[1.0, 0.0, 1.0]]), 1.0, 1.0)  # mask does NOT reset the scan
+    assert torch.allclose(ret, T([[6.0, 5.0, 3.0]]), atol=1e-5)
+    assert torch.allclose(adv, T([[0.7071, 0.1768, -0.7071]]), atol=1e-4)
+    _, ret = O.gae_advantage_return(r, v, ones, 0.5, 1.0)
+    assert torch.allclose(ret, T([[2.75, 3.5, 3.0]]), atol=1e-5)
+    _, ret = O.gae_advantage_return(r, v, ones, 1.0, 0.5)
+    assert torch.allclose(ret, T([[3.625, 4.25, 3.0]]), atol=1e-5)
+
+
+def test_kat_grpo_rloo():  # tests/cpu/utils/test_ppo_utils.py:103-172
+    r = T([[1.0, 2.0, 3.0], [1.0, 1.0, 1.0], [2.0, 3.0, 4.0], [3.0, 4.0, 5.0]])  # sums 6, 3, 9, 12
+    m = torch.ones(4, 3)
+    adv, ret = O.grpo_advantage(r, m, np.array([0, 0, 1, 1]), norm_by_std=False)
+    assert torch.allclose(adv, T([1.5, -1.5, -1.5, 1.5]).unsqueeze(-1) * m, atol=1e-5)
+    assert adv is ret
+    r5 = torch.cat([r, T([[1.0, 0.0, 0.0]])])
+    adv, _ = O.rloo_advantage(r5, torch.ones(5, 3), np.array([0, 0, 1, 1, 2]))
+    assert torch.allclose(adv, T([3.0, -3.0, -3.0, 3.0, 0.0]).unsqueeze(-1) * torch.ones(5, 3), atol=1e-5)
+
+
+def test_kat_reduce_loss():  # tests/cpu/utils/test_ppo_utils.py:245-268
+    loss, mask = T([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]]), T([[1.0, 1.0, 1.0], [1.0, 0.0, 0.0]])
+    assert math.isclose(O.reduce_loss(loss, mask, "token_mean").item(), 2.5, rel_tol=1e-6)
+    assert math.isclose(O.reduce_loss(loss, mask, "sequence_mean").item(), 3.0, rel_tol=1e-6)
+    assert math.isclose(O.reduce_loss(loss, mask, "seq_mean_token_sum_norm", 4).item(), 1.25, rel_tol=1e-6)
+
+
+def test_kat_dual_clip():  # tests/cpu/algorithms/test_losses.py:32-82 -> 4.1667
+    adv, olp, lp = T([[1.0, -1.0, -4.0]]), T([[-1.0, -1.0, -3.0]]), T([[-1.69315, -1.0, -0.69741]])
+    cfg = O.make_cfg(policy_loss_type="dual_clip", clip_ratio_c=3.0)
+    loss, _ = O.policy_loss(lp, olp, adv, cfg, None)
+    assert abs(loss.item() - 4.1667) < 1e-4
+
+
+def test_kat_entropy_uniform():  # tests/cpu/utils/test_torch_utils.py:33-55
+    ent = O.entropy_from_logits(torch.zeros(2, 3, 4))
+    assert torch.allclose(ent, torch.full((2, 3), math.log(4.0)), atol=1e-4)
+    mask = T([[1.0, 0.0, 1.0], [0.0, 1.0, 1.0]])
+    assert torch.equal(O.entropy_from_logits(torch.zeros(2, 3, 4), mask) == 0, mask == 0)
+
+
+def test_masked_var_errors():  # utils/ppo_utils.py:155-160
+    with pytest.raises(ValueError):
+        O.masked_var(torch.ones(2, 2), torch.zeros(2, 2))
+    with pytest.raises(ValueError):
+        O.masked_var(torch.ones(2, 2), T([[1.0, 0.0], [0.0, 0.0]]))
+
+
+# ---------------------------------------------------------------- live reference (build container only)
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_vs_live_reference_random():
+    pu, tu = ref_loader.load()
+    g = torch.Generator().manual_seed(7)
+    B, A = 10, 33
+    lens = torch.randint(2, A + 1, (B,), generator=g)
+    mask = (torch.arange(A)[None] < lens[:, None]).float()
+    r = torch.randn(B, A, generator=g) * mask
+    v = torch.randn(B, A, generator=g)
+    idx = np.array([f"u{i // 3}" for i in range(B)])
+    assert_close(O.grpo_advantage(r, mask, idx)[0], pu.compute_grpo_outcome_advantage(r.clone(), mask, idx)[0])
+    a1, r1 = pu.compute_gae_advantage_return(r, v, mask, gamma=0.97, lambd=0.9)
+    a2, r2 = O.gae_advantage_return(r, v, mask, 0.97, 0.9)
+    assert_close(a2, a1)
+    assert_close(r2, r1)
+    z = torch.randn(5, 7, 50, generator=g)
+    lab = torch.randint(0, 50, (5, 7), generator=g)
+    assert_close(O.logprobs_from_logits(z, lab), tu.logprobs_from_logits_v2(z, lab))
+    assert_close(O.entropy_from_logits(z), tu.chunked_entropy_from_logits(z))
