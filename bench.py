@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""Benchmark of the policy-update hot path (BASELINE.json metric: policy-update tokens/sec/GPU for
+loss head + advantage + loss, fwd/bwd, and % of roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|tiny]
+
+One "step" = one pass of the hot path over one synthetic rollout batch:
+    GRPO advantages -> fused LM head forward (log-probs + entropy) -> policy loss fwd/bwd (+KL term)
+    -> fused LM head backward (d_hidden, d_weight).
+Default workload = BASELINE config 2 (Qwen2.5-7B head: hidden 3584, vocab 152064; 256 seqs x 4096 tokens, group 8,
+bf16) per GPU.  N > 1 (launched by torchrun, one rank per GPU) is weak scaling: every rank owns its own
+prompt-group shard of that size; per step the packed stats vector and the fp32 lm_head weight gradient are
+all-reduced over NCCL.  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the CPU restatement of the reference's torch path (oracle/, "port": the Python reference
+cannot travel to the GPU box) on a bounded token sample with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    # name: (B, A, H, V, group)
+    "c2": dict(B=256, A=4096, H=3584, V=152064, G=8, model="Qwen2.5-7B head"),
+    "c1": dict(B=64, A=1024, H=896, V=151936, G=8, model="Qwen2.5-0.5B head"),
+    "c2s": dict(B=8, A=4096, H=3584, V=152064, G=8, model="Qwen2.5-7B head (8-sequence slice, profiling)"),
+    "tiny": dict(B=16, A=256, H=256, V=4096, G=8, model="tiny"),
+}
+METRIC = "policy-update tokens/sec/GPU (loss head+adv+loss fwd/bwd)"
+TEMPERATURE = 1.0
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d["bf16_tflops_sustained"]), tflops_burst=float(d["bf16_tflops"]),
+                    hbm=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def make_cfg():
+    from types import SimpleNamespace
+
+    return SimpleNamespace(
+        policy_loss_type="regular", loss_reduction="token_mean", eps_clip_low=0.2, eps_clip_high=0.2,
+        clip_ratio_c=3.0, max_seq_len=None, use_kl_loss=True, kl_estimator_type="k3", kl_loss_coef=1e-3,
+        use_entropy_loss=False, entropy_loss_coef=0.01,
+        off_policy_correction=SimpleNamespace(tis_ratio_type=None, sequence_mask_metric=None),
+    )
+
+
+def host_batch(w, seed, pinned, tokens=None):
+    """Synthetic rollout batch on the host.  Dense: every response position is valid."""
+    B, A, H, V, G = w["B"], w["A"], w["H"], w["V"], w["G"]
+    g = torch.Generator().manual_seed(seed)
+    pin = dict(pin_memory=True) if pinned else {}
+    hidden = torch.empty((B, A, H), dtype=torch.bfloat16, **pin)
+    # fill in slabs to bound the fp32 temporary
+    rows = max(1, (1 << 24) // (A * H))
+    for b0 in range(0, B, rows):
+        hidden[b0:b0 + rows] = torch.randn((min(rows, B - b0), A, H), generator=g).to(torch.bfloat16)
+    labels = torch.empty((B, A), dtype=torch.int64, **pin).copy_(torch.randint(0, V, (B, A), generator=g))
+    olp = torch.empty((B, A), dtype=torch.float32, **pin).copy_(-12.0 + 0.05 * torch.randn(B, A, generator=g))
+    base = torch.empty((B, A), dtype=torch.float32, **pin).copy_(-12.0 + 0.1 * torch.randn(B, A, generator=g))
+    mask = torch.ones((B, A), dtype=torch.float32, **pin)
+    rewards = torch.zeros((B, A), dtype=torch.float32, **pin)
+    rewards[:, -1] = (torch.rand(B, generator=g) < 0.3).float()
+    uids = np.array([f"prompt-{seed}-{i // G}" for i in range(B)])
+    return dict(hidden=hidden, labels=labels, olp=olp, base=base, mask=mask, rewards=rewards, uids=uids)
+
+
+def make_weight(w, device):
+    g = torch.Generator(device=device).manual_seed(99)
+    V, H = w["V"], w["H"]
+    out = torch.empty((V, H), dtype=torch.bfloat16, device=device)
+    step = 16384
+    for v0 in range(0, V, step):
+        n = min(step, V - v0)
+        out[v0:v0 + n] = (torch.randn((n, H), device=device, generator=g) / H ** 0.5).to(torch.bfloat16)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_port_step(w, sample_tokens, threads, seed=1234):
+    """The reference's torch CPU path (restated in oracle/): GRPO advantages on the full [B, A] batch + head and
+    loss fwd/bwd (fp32) on `sample_tokens` tokens.  Returns seconds for the sample."""
+    from oracle import policy_oracle as O
+
+    torch.set_num_threads(threads)
+    B, A, H, V, G = w["B"], w["A"], w["H"], w["V"], w["G"]
+    g = torch.Generator().manual_seed(seed)
+    rows = max(1, sample_tokens // A) if sample_tokens >= A else 1
+    a_len = A if sample_tokens >= A else sample_tokens
+    hidden = torch.randn(rows * a_len, H, generator=g).to(torch.bfloat16).float()
+    weight = (torch.randn(V, H, generator=g) / H ** 0.5).to(torch.bfloat16).float()
+    labels = torch.randint(0, V, (rows * a_len,), generator=g)
+    olp = -12.0 + 0.05 * torch.randn(rows, a_len, generator=g)
+    base = -12.0 + 0.1 * torch.randn(rows, a_len, generator=g)
+    mask = torch.ones(rows, a_len)
+    rewards = torch.zeros(B, A)
+    rewards[:, -1] = (torch.rand(B, generator=g) < 0.3).float()
+    uids = np.array([f"p{i // G}" for i in range(B)])
+    cfg = make_cfg()
+    t0 = time.perf_counter()
+    adv_full, _ = O.grpo_advantage(rewards, torch.ones(B, A), uids)
+    t_adv = time.perf_counter() - t0
+    adv = adv_full[:rows, :a_len]
+    h = hidden.requires_grad_(True)
+    wt = weight.requires_grad_(True)
+    t0 = time.perf_counter()
+    lp, ent = O.head_logprobs_entropy(h, wt, labels, TEMPERATURE, chunk=256)
+    final, _ = O.loss_assembly(lp.view(rows, a_len), olp, adv, cfg, mask, base, ent.view(rows, a_len))
+    final.backward()
+    t_head = time.perf_counter() - t0
+    n_tok = rows * a_len
+    # advantages are O(B*A) for the whole batch; scale them to the sample so the figure is per-token consistent
+    return t_head + t_adv * (n_tok / (B * A)), n_tok
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 1024 if w["V"] > 100000 else 4096
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, n_tok = cpu_port_step(w, sample, threads, seed=1234 + i)
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    value = n_tok / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{w['model']}: GRPO, {w['B']} seqs x {w['A']} tokens, H={w['H']}, V={w['V']}, "
+                               f"group {w['G']}; CPU path timed on a {n_tok}-token sample per step"},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_tok} tokens/step of the same workload (head+loss fwd/bwd fp32, GRPO advantages "
+                                   f"pro-rated); oracle/policy_oracle.py = restatement of the reference torch path"},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args, w):
+    import torch.distributed as dist
+
+    import skyrl_b200
+    from skyrl_b200 import dist as sdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the policy-update kernels have no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = measured_peaks()
+    B, A, H, V = w["B"], w["A"], w["H"], w["V"]
+    N = B * A
+    cfg = make_cfg()
+
+    hb = host_batch(w, 1234 + rank, pinned=True)
+    weight = make_weight(w, dev)
+    d_weight = torch.zeros((V, H), dtype=torch.float32, device=dev)
+    db = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
+    torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    phase_ms = {"adv": [], "step": []}
+
+    def device_step(record):
+        """Inputs already resident in HBM."""
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        adv, _ = skyrl_b200.compute_grpo_outcome_advantage(db["rewards"], db["mask"], db["uids"])
+        e1.record()
+        out = skyrl_b200.policy_update_step(db["hidden"], weight, db["labels"], db["olp"], adv, cfg,
+                                            loss_mask=db["mask"], base_log_probs=db["base"], temperature=TEMPERATURE,
+                                            d_weight=d_weight, accumulate_d_weight=False, sync=False)
+        e2.record()
+        if world > 1:
+            sdist.all_reduce_packed_stats(out.stats)
+            sdist.all_reduce_d_weight(out.d_weight)
+        if record:
+            phase_ms["_ev"].append((e0, e1, e2))
+        return out
+
+    def e2e_step():
+        """Host buffers in, python-float status out: what a user of the plugin API pays per step."""
+        d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
+        adv, _ = skyrl_b200.compute_grpo_outcome_advantage(d["rewards"], d["mask"], d["uids"])
+        out = skyrl_b200.policy_update_step(d["hidden"], weight, d["labels"], d["olp"], adv, cfg,
+                                            loss_mask=d["mask"], base_log_probs=d["base"], temperature=TEMPERATURE,
+                                            d_weight=d_weight, accumulate_d_weight=False, sync=(world == 1))
+        if world > 1:
+            st = sdist.all_reduce_packed_stats(out.stats)
+            sdist.all_reduce_d_weight(out.d_weight)
+            return st.tolist()
+        return out.status
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, record=False):
+        for _ in range(warmup):
+            fn(False) if record else fn()
+        barrier()
+        phase_ms["_ev"] = []
+        s, e = ev(), ev()
+        s.record()
+        for _ in range(steps):
+            fn(True) if record else fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    # isolated timing of the dominant kernel family (forward GEMM + epilogue) with CUDA events on the launch stream
+    from skyrl_b200 import _lib
+
+    lib = _lib.load()
+    lp_buf = torch.empty(N, dtype=torch.float32, device=dev)
+    ent_buf = torch.empty(N, dtype=torch.float32, device=dev)
+    lse_buf = torch.empty(N, dtype=torch.float32, device=dev)
+    fws = lib.skyb200_head_forward_workspace(N, H, V, 0)
+    fws_buf = torch.empty(fws, dtype=torch.uint8, device=dev)
+    hid2d = db["hidden"].view(N, H)
+    lab1d = db["labels"].view(N)
+
+    def fwd_only():
+        _lib.check(lib.skyb200_head_forward(_lib.ptr(hid2d), _lib.ptr(weight), _lib.ptr(lab1d), None, _lib.ptr(lp_buf),
+                                            _lib.ptr(ent_buf), _lib.ptr(lse_buf), _lib.ptr(fws_buf), fws, N, H, V,
+                                            TEMPERATURE, 0, _lib.stream_ptr()))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_step = timed(device_step, args.steps, args.warmup, record=True)
+    evs = phase_ms["_ev"]
+    adv_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in evs])) if evs else None
+    upd_ms = float(np.mean([b.elapsed_time(c) for _, b, c in evs])) if evs else None
+    clocks = sampler.stop() if rank == 0 else None
+    ms_fwd = timed(fwd_only, max(1, min(args.steps, 3)), 1)
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e = timed(e2e_step, e2e_steps, 1)
+
+    chunk = 37 * 256
+    n_chunks = (N + chunk - 1) // chunk
+    launches_per_step = 2 + 2 * n_chunks + 2 + 3 * n_chunks  # GRPO(2) + fwd(GEMM+merge) + loss(2) + bwd(3 GEMMs)
+    tok_s = world * N / (ms_step * 1e-3)
+    tok_s_e2e = world * N / (ms_e2e * 1e-3)
+    flops_fwd_launch = 2.0 * min(chunk, N) * H * V
+    fwd_launch_ms = ms_fwd / n_chunks
+    achieved = flops_fwd_launch / (fwd_launch_ms * 1e-3) / 1e12
+    step_tflops_alg = 6.0 * N * H * V / (ms_step * 1e-3) / 1e12
+    h2d = sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
+
+    if rank == 0:
+        threads = os.cpu_count() or 1
+        sample = 4096 if V > 100000 else 16384  # ~10-20 s of host work
+        dt, n_tok = cpu_port_step(w, sample, threads)
+        line = {
+            "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {
+                "workload": f"{w['model']}: GRPO + regular loss (token_mean, k3 KL loss), {B} seqs x {A} tokens per GPU, "
+                            f"H={H}, V={V}, group {w['G']}",
+                "per_gpu_tokens": N, "l2": "inputs exceed L2 (hidden is %.1f GB per GPU)" % (N * H * 2 / 1e9),
+                "parallelism": f"dp{world} by whole prompt groups",
+            },
+            "tokens_per_s_per_gpu": tok_s / world,
+            "phases_ms": {"advantages": adv_ms, "head_fwd+loss+head_bwd": upd_ms, "head_fwd_alone": ms_fwd},
+            "step_roofline": {"bound": "tensor", "algorithmic_flops_per_token": 6.0 * H * V,
+                              "achieved": step_tflops_alg, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                              "frac": step_tflops_alg / peaks["tflops"],
+                              "note": "6*H*V*N algorithmic flops / step time; the backward re-computes the logits "
+                                      "tile (8*H*V*N executed); peak = " + peaks["source"]},
+            "roofline": {"kernel": "gemm_sm100_kernel<2,256,6,K-major,K-major,EpiLsePartials> (head forward)",
+                         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["tflops"], "traffic": None,
+                         "flops_per_launch": flops_fwd_launch, "ms_per_launch": fwd_launch_ms,
+                         "note": "per-launch = head_forward call / %d chunks (includes the <1%% merge kernel); peak = %s"
+                                 % (n_chunks, peaks["source"])},
+            "cpu_baseline": {"value": n_tok / dt, "unit": "tokens/s", "cores": threads, "kind": "port",
+                             "sample": f"{n_tok} tokens of the same workload, fp32 torch CPU path restated in oracle/"},
+            "e2e": {"value": tok_s_e2e, "unit": "tokens/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": 64, "ms_per_step": ms_e2e, "steps": e2e_steps,
+                    "api": "compute_grpo_outcome_advantage + policy_update_step on pinned host tensors"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -201,17 +201,17 @@ __global__ void __launch_bounds__(512) logits_row_kernel(const T* __restrict__ l
     for (int64_t j = threadIdx.x; j < V; j += blockDim.x) {
         const float x = to_f32<T>(z[j]);
         if (x > m) {
-            const float c = __expf(m - x);
+            const float c = expf(m - x);
             s *= c;
             t *= c;
             m = x;
         }
-        const float e = __expf(x - m);
+        const float e = expf(x - m);
         s += e;
         t = fmaf(e, x, t);
     }
     const float M = block_max(m, sh);
-    const float w = (m == -INFINITY) ? 0.f : __expf(m - M);
+    const float w = (m == -INFINITY) ? 0.f : expf(m - M);
     const float S = block_sum(s * w, sh);
     const float Tt = block_sum(t * w, sh);
     if (threadIdx.x == 0) {
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(512) logits_backward_kernel(const T* __restric
     const int64_t lab = labels ? labels[row] : -1;
     for (int64_t j = threadIdx.x; j < V; j += blockDim.x) {
         const float lpj = to_f32<T>(z[j]) - l;
-        const float p = __expf(lpj);
+        const float p = expf(lpj);
         float g = -p * (glp + ge * (lpj + H));
         if (j == lab) g += glp;
         d[j] = from_f32<T>(g);

@@ -141,8 +141,9 @@ def test_full_size_properties_c3_shape():
     r[:, -1] = 1.0
     mask = torch.ones(B, A, device=DEV)
     adv, ret = advantages.compute_gae_advantage_return(r, v, mask, 1.0, 1.0)
-    # gamma = lambda = 1: returns_t = sum_{s>=t} r_s = 1 (telescoping), independent of the values
-    assert_close(ret, torch.ones(B, A), rel=1e-5)
+    # gamma = lambda = 1: returns_t = sum_{s>=t} r_s = 1 (telescoping), independent of the values.  delta_t is
+    # formed in fp32 exactly as the reference forms it, so 8192 rounded deltas leave ~1e-5 of noise around 1.
+    assert_close(ret, torch.ones(B, A), rel=1e-4)
     # whitening: zero mean, unit (Bessel) variance over the mask
     assert abs(adv.mean().item()) < 1e-4 and abs(adv.var().item() - 1.0) < 1e-3
     uids = [i // 8 for i in range(B)]
