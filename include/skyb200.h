@@ -198,6 +198,26 @@ int skyb200_head_backward(const void* hidden, const void* weight, const int64_t*
                           int64_t H, int64_t V, float temperature, int64_t chunk, void* stream);
 
 /*
+ * The whole step in one call: head forward -> loss assembly -> head backward, chunk by chunk over the tokens
+ * (replaces worker.py:787-877 after the trunk).  Because the loss gradient of a chunk is available as soon as its
+ * log-probs are (normalisers come from a mask-only pre-pass), the forward GEMM keeps a bf16 copy of its logits
+ * tiles in a bounded [chunk, V] store and the backward reads it instead of recomputing the projection:
+ * 6*H*V executed flop per token instead of 8*H*V.  GSPO uses row-aligned chunks (needs A*k tokens per chunk).
+ *
+ * old_log_probs / advantages / loss_mask / base_log_probs: [B, A] fp32 (mask / base may be NULL);
+ * entropy_mask [B*A] fp32 or NULL; log_probs / entropy: [B*A] fp32 out (entropy already * entropy_mask);
+ * d_hidden [B*A, H] bf16 and d_weight [V, H] fp32 may be NULL (both NULL = evaluate the loss only);
+ * gradients are those of stats[SKYB200_STAT_FINAL_LOSS] with upstream gradient 1.
+ */
+size_t skyb200_policy_step_workspace(int64_t B, int64_t A, int64_t H, int64_t V, int32_t loss_type,
+                                     int32_t need_grad);
+int skyb200_policy_step(const void* hidden, const void* weight, const int64_t* labels, const float* old_log_probs,
+                        const float* advantages, const float* loss_mask, const float* base_log_probs,
+                        const float* entropy_mask, float* log_probs, float* entropy, void* d_hidden, float* d_weight,
+                        int32_t accumulate, float* stats, void* workspace, size_t workspace_bytes, int64_t B, int64_t A,
+                        int64_t H, int64_t V, float temperature, const skyb200_loss_params* params, void* stream);
+
+/*
  * logprobs_from_logits (torch_utils.py:115-177) and chunked_entropy_from_logits (:59-111) on materialised
  * logits [N, V] (bf16 or fp32), for callers that still hold logits.  logits_dtype: 0 = fp32, 1 = bf16.
  * Any output pointer may be NULL.  entropy_mask [N] fp32 or NULL.  lse [N] = natural-log sum-exp (saved for

@@ -287,6 +287,31 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// 256-bit global accesses (sm_100): one instruction covers a full 32-byte sector, so partial-sector
+// read-for-fill traffic at L2 disappears for row-per-thread epilogue stores.
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                              uint32_t a5, uint32_t a6, uint32_t a7) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2),
+                 "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p)
+                 : "memory");
+}
+// 32 fp32 values -> 32 bf16 -> two 32-byte stores (dst must be 32-byte aligned)
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float (&d)[32]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        st_global_256(dst + 16 * h, pack_bf16x2(d[16 * h + 0], d[16 * h + 1]), pack_bf16x2(d[16 * h + 2], d[16 * h + 3]),
+                      pack_bf16x2(d[16 * h + 4], d[16 * h + 5]), pack_bf16x2(d[16 * h + 6], d[16 * h + 7]),
+                      pack_bf16x2(d[16 * h + 8], d[16 * h + 9]), pack_bf16x2(d[16 * h + 10], d[16 * h + 11]),
+                      pack_bf16x2(d[16 * h + 12], d[16 * h + 13]), pack_bf16x2(d[16 * h + 14], d[16 * h + 15]));
+    }
+}
+
 // C (fp32, row-major, leading dim ldc) = or += accumulator.   Used for dW and for GEMM self-tests.
 struct EpiStoreF32 {
     struct Params {
@@ -306,20 +331,20 @@ struct EpiStoreF32 {
             const int col0 = n0 + c * 32;
             if (row < M && col0 < N) {
                 float* dst = p.C + static_cast<int64_t>(row) * p.ldc + col0;
-                if (col0 + 32 <= N && (p.ldc & 3) == 0) {
+                if (col0 + 32 <= N && (p.ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 31u) == 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float4 o = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                               __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-                        float4* d4 = reinterpret_cast<float4*>(dst) + i;
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t o[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o[k] = v[8 * i + k];
                         if (p.accumulate) {
-                            const float4 old = *d4;
-                            o.x += old.x;
-                            o.y += old.y;
-                            o.z += old.z;
-                            o.w += old.w;
+                            uint32_t old[8];
+                            ld_global_256(dst + 8 * i, old);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                o[k] = __float_as_uint(__uint_as_float(o[k]) + __uint_as_float(old[k]));
                         }
-                        *d4 = o;
+                        st_global_256(dst + 8 * i, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
                     }
                 } else {
                     for (int i = 0; i < 32 && col0 + i < N; ++i) {
@@ -350,16 +375,11 @@ struct EpiStoreBF16 {
             const int col0 = n0 + c * 32;
             if (row < M && col0 < N) {
                 __nv_bfloat16* dst = p.C + static_cast<int64_t>(row) * p.ldc + col0;
-                if (col0 + 32 <= N && (p.ldc & 7) == 0) {
+                if (col0 + 32 <= N && (p.ldc & 15) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 31u) == 0) {
+                    float d[32];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 o;
-                        o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
-                        o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
-                        o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
-                        o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
-                        reinterpret_cast<uint4*>(dst)[i] = o;
-                    }
+                    for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(v[i]);
+                    store_row32_bf16(dst, d);
                 } else {
                     for (int i = 0; i < 32 && col0 + i < N; ++i) dst[i] = __float2bfloat16_rn(__uint_as_float(v[i]));
                 }
@@ -381,6 +401,8 @@ struct EpiLsePartials {
         int64_t ld;
         const int64_t* labels;  // [M]
         float* label_acc;       // [M]
+        __nv_bfloat16* logits;  // [M, ld_logits] bf16 copy of the raw accumulators, or nullptr
+        int64_t ld_logits;
     };
     template <int BN>
     __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
@@ -436,6 +458,17 @@ struct EpiLsePartials {
                 for (int i = 0; i < 32; ++i)
                     if (col0 + i == lab) z = __uint_as_float(v[i]);
                 p.label_acc[row] = z;
+            }
+            if (p.logits != nullptr && row_ok) {
+                __nv_bfloat16* dst = p.logits + static_cast<int64_t>(row) * p.ld_logits + col0;
+                if (nvalid == 32 && (p.ld_logits & 15) == 0 && (reinterpret_cast<uintptr_t>(p.logits) & 31u) == 0) {
+                    float d[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(v[i]);
+                    store_row32_bf16(dst, d);
+                } else {
+                    for (int i = 0; i < nvalid; ++i) dst[i] = __float2bfloat16_rn(__uint_as_float(v[i]));
+                }
             }
         }
         if (row_ok) {
@@ -508,16 +541,8 @@ struct EpiDLogits {
                 }
             }
             __nv_bfloat16* dst = p.dS + static_cast<int64_t>(row) * p.ld + col0;
-            if (col0 + 32 <= N && (p.ld & 7) == 0) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint4 o;
-                    o.x = pack_bf16x2(d[8 * i + 0], d[8 * i + 1]);
-                    o.y = pack_bf16x2(d[8 * i + 2], d[8 * i + 3]);
-                    o.z = pack_bf16x2(d[8 * i + 4], d[8 * i + 5]);
-                    o.w = pack_bf16x2(d[8 * i + 6], d[8 * i + 7]);
-                    reinterpret_cast<uint4*>(dst)[i] = o;
-                }
+            if (col0 + 32 <= N && (p.ld & 15) == 0 && (reinterpret_cast<uintptr_t>(p.dS) & 31u) == 0) {
+                store_row32_bf16(dst, d);
             } else {
                 for (int i = 0; i < 32 && col0 + i < N; ++i) dst[i] = __float2bfloat16_rn(d[i]);
             }

@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "gemm_sm100.cuh"
+#include "internal.h"
 
 namespace skyb200 {
 
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float* __restrict
                                                          const float* __restrict__ label_acc,
                                                          const float* __restrict__ entropy_mask, float inv_T,
                                                          float* __restrict__ logprobs, float* __restrict__ entropy,
+                                                         float* __restrict__ entropy_raw,
                                                          float* __restrict__ lse2_out, int rows) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
@@ -167,10 +169,69 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float* __restrict
     const float lse = lse2 * 0.6931471805599453f;
     lse2_out[r] = lse2;
     logprobs[r] = label_acc[r] * inv_T - lse;
-    if (entropy != nullptr) {
+    if (entropy != nullptr || entropy_raw != nullptr) {
         float h = lse - (T / S) * inv_T;
+        if (entropy_raw != nullptr) entropy_raw[r] = h;
         if (entropy_mask != nullptr) h *= entropy_mask[r];
-        entropy[r] = h;
+        if (entropy != nullptr) entropy[r] = h;
+    }
+}
+
+// In-place turn of a stored bf16 logits tile store [rows, ld] into d(logits) (fused step, no recompute):
+//   u = z*scale_log2 - lse2 ; p = 2^u ; d = inv_T * ( g_lp*1[j == label] - p*(g_lp + g_ent*(u*ln2 + H)) )
+// One block row per token; each thread owns 16 consecutive vocab entries (one 32-byte access each way).
+__global__ void __launch_bounds__(256)
+dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const float* __restrict__ lse2,
+                         const float* __restrict__ g_lp, const float* __restrict__ g_ent,
+                         const float* __restrict__ g_ent_mask, const float* __restrict__ entropy_raw,
+                         const int64_t* __restrict__ labels, float scale_log2, float inv_T) {
+    const int row = blockIdx.y;
+    const int col0 = (blockIdx.x * 256 + threadIdx.x) * 16;
+    if (col0 >= V) return;
+    const float l2 = lse2[row];
+    const float glp = g_lp[row];
+    float ge = 0.f, H = 0.f;
+    if (g_ent != nullptr) {
+        ge = g_ent[row];
+        if (g_ent_mask != nullptr) ge *= g_ent_mask[row];
+        H = entropy_raw[row];
+    }
+    const int lab = static_cast<int>(labels[row]);
+    const float a0 = (glp + ge * H) * (-inv_T);
+    const float b0 = ge * 0.6931471805599453f * (-inv_T);
+    const float lab_add = glp * inv_T;
+    const bool all_zero = (glp == 0.f && ge == 0.f);
+    __nv_bfloat16* ptr = S + static_cast<int64_t>(row) * ld + col0;
+    if (col0 + 16 <= V && (ld & 15) == 0) {
+        uint32_t r[8];
+        if (all_zero) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = 0u;
+        } else {
+            ld_global_256(ptr, r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&r[k]);
+                float2 z = __bfloat1622float2(z2);
+                const float u0 = fmaf(z.x, scale_log2, -l2), u1 = fmaf(z.y, scale_log2, -l2);
+                float d0 = ex2_approx(u0) * fmaf(u0, b0, a0);
+                float d1 = ex2_approx(u1) * fmaf(u1, b0, a0);
+                if (col0 + 2 * k == lab) d0 += lab_add;
+                if (col0 + 2 * k + 1 == lab) d1 += lab_add;
+                r[k] = pack_bf16x2(d0, d1);
+            }
+        }
+        st_global_256(ptr, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+    } else {
+        for (int k = 0; k < 16 && col0 + k < V; ++k) {
+            float d = 0.f;
+            if (!all_zero) {
+                const float u = fmaf(__bfloat162float(ptr[k]), scale_log2, -l2);
+                d = ex2_approx(u) * fmaf(u, b0, a0);
+                if (col0 + k == lab) d += lab_add;
+            }
+            ptr[k] = __float2bfloat16_rn(d);
+        }
     }
 }
 
@@ -316,6 +377,8 @@ extern "C" int skyb200_head_forward(const void* hidden, const void* weight, cons
         ep.ld = c;
         ep.labels = labels + r0;
         ep.label_acc = label_acc;
+        ep.logits = nullptr;
+        ep.ld_logits = 0;
         // a label outside [0, V) never matches a slab: give it a defined (zero) logit
         SKYB200_CUDA_CHECK(cudaMemsetAsync(label_acc, 0, (size_t)rows * sizeof(float), stream));
         rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
@@ -323,7 +386,7 @@ extern "C" int skyb200_head_forward(const void* hidden, const void* weight, cons
         if (rc) return rc;
         head_merge_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(
             part_m, part_s, part_t, c, slabs, label_acc, entropy_mask ? entropy_mask + r0 : nullptr, inv_T,
-            logprobs + r0, entropy ? entropy + r0 : nullptr, lse2 + r0, rows);
+            logprobs + r0, entropy ? entropy + r0 : nullptr, nullptr, lse2 + r0, rows);
         rc = check_launch("head_merge_kernel");
         if (rc) return rc;
     }
@@ -395,6 +458,173 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
         }
     }
     return SKYB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ fused step
+namespace {
+
+struct StepPlan {
+    int64_t chunk;     // tokens per chunk (multiple of 256)
+    int64_t ldS;       // pitch of the bf16 logits / d_logits store
+    int slabs;
+    size_t off_part, off_label, off_lse2, off_entraw, off_dlp, off_dent, off_S, off_loss, total;
+};
+
+int64_t gcd64(int64_t a, int64_t b) { return b == 0 ? a : gcd64(b, a % b); }
+
+// Chunks are flat token ranges; GSPO needs whole sequences per chunk (its ratio is a per-sequence mean).
+StepPlan plan_step(int64_t B, int64_t A, int64_t H, int64_t V, int loss_type, bool need_grad) {
+    StepPlan p;
+    const int64_t N = B * A;
+    int64_t chunk = kDefaultChunk;
+    if (loss_type == SKYB200_LOSS_GSPO) {
+        // smallest multiple of A that is also a multiple of 256 tokens, repeated up to ~24K tokens
+        const int64_t unit = A / gcd64(A, kTileM) * kTileM;  // lcm(A, 256)
+        chunk = unit * std::max<int64_t>(1, (3 * kDefaultChunk / 2) / unit);
+    }
+    chunk = std::min<int64_t>(chunk, round_up(N, kTileM));
+    p.chunk = chunk;
+    p.ldS = round_up(V, 64);
+    p.slabs = (int)num_slabs(V);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) / 256 * 256;
+        return o;
+    };
+    p.off_part = take((size_t)3 * p.slabs * chunk * 4);
+    p.off_label = take((size_t)chunk * 4);
+    p.off_lse2 = take((size_t)chunk * 4);
+    p.off_entraw = take((size_t)chunk * 4);
+    p.off_dlp = take((size_t)chunk * 4);
+    p.off_dent = take((size_t)chunk * 4);
+    p.off_S = take(need_grad ? (size_t)chunk * p.ldS * 2 : 0);
+    p.off_loss = take(loss_chunk_ws_bytes(B, A) + (size_t)(N / chunk + 2) * 8 * 4 * 4);
+    p.total = off + 512;
+    (void)H;
+    return p;
+}
+
+}  // namespace
+
+extern "C" size_t skyb200_policy_step_workspace(int64_t B, int64_t A, int64_t H, int64_t V, int32_t loss_type,
+                                                int32_t need_grad) {
+    return plan_step(B, A, H, V, loss_type, need_grad != 0).total;
+}
+
+extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const int64_t* labels,
+                                   const float* old_log_probs, const float* advantages, const float* loss_mask,
+                                   const float* base_log_probs, const float* entropy_mask, float* log_probs,
+                                   float* entropy, void* d_hidden, float* d_weight, int32_t accumulate, float* stats,
+                                   void* workspace, size_t workspace_bytes, int64_t B, int64_t A, int64_t H, int64_t V,
+                                   float temperature, const skyb200_loss_params* params, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(hidden && weight && labels && old_log_probs && advantages && log_probs && entropy && stats &&
+                        workspace && params,
+                    "null pointer");
+    SKYB200_REQUIRE(B > 0 && A > 0 && B < 65536, "need 0 < B < 65536 and A > 0");
+    SKYB200_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
+    SKYB200_REQUIRE(temperature > 0.f, "temperature must be > 0");
+    SKYB200_REQUIRE(params->loss_type >= 0 && params->loss_type <= SKYB200_LOSS_GSPO, "bad loss_type");
+    SKYB200_REQUIRE(params->reduction >= 0 && params->reduction <= SKYB200_REDUCE_SEQ_MEAN_TOKEN_SUM_NORM,
+                    "bad reduction");
+    SKYB200_REQUIRE(params->kl_type >= 0 && params->kl_type <= SKYB200_KL_K3, "bad kl_type");
+    SKYB200_REQUIRE(params->reduction != SKYB200_REDUCE_SEQ_MEAN_TOKEN_SUM_NORM || params->max_seq_len > 0.f,
+                    "max_seq_len must be provided for seq_mean_token_sum_norm");
+    const int64_t N = B * A;
+    SKYB200_REQUIRE(N < (1ll << 31) && V < (1ll << 31) && H < (1ll << 31), "dimension too large");
+    const bool need_grad = (d_hidden != nullptr) || (d_weight != nullptr);
+    const StepPlan plan = plan_step(B, A, H, V, params->loss_type, need_grad);
+    if (workspace_bytes < plan.total) return fail(SKYB200_EWORKSPACE, "policy_step workspace too small");
+    int rc = skyb200_check_device();
+    if (rc) return rc;
+
+    char* wb = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    const int64_t c = plan.chunk;
+    float* part_m = reinterpret_cast<float*>(wb + plan.off_part);
+    float* part_s = part_m + (int64_t)plan.slabs * c;
+    float* part_t = part_s + (int64_t)plan.slabs * c;
+    float* label_acc = reinterpret_cast<float*>(wb + plan.off_label);
+    float* lse2 = reinterpret_cast<float*>(wb + plan.off_lse2);
+    float* ent_raw = reinterpret_cast<float*>(wb + plan.off_entraw);
+    float* d_lp = reinterpret_cast<float*>(wb + plan.off_dlp);
+    float* d_ent = reinterpret_cast<float*>(wb + plan.off_dent);
+    __nv_bfloat16* S = reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S);
+    LossChunkWs lws;
+    loss_chunk_ws_carve(wb + plan.off_loss, B, A, &lws);
+
+    const float inv_T = 1.0f / temperature;
+    const float scale_log2 = 1.4426950408889634f * inv_T;
+    const __nv_bfloat16* hid = static_cast<const __nv_bfloat16*>(hidden);
+    __nv_bfloat16* dhid = static_cast<__nv_bfloat16*>(d_hidden);
+    const bool use_ent_grad = need_grad && params->use_entropy_loss != 0;
+
+    rc = loss_prepass(loss_mask, lws, B, A, stream);
+    if (rc) return rc;
+
+    int64_t slot = 0;
+    for (int64_t t0 = 0; t0 < N; t0 += c) {
+        const int rows = (int)std::min<int64_t>(c, N - t0);
+        // (1) logits tiles -> online-softmax partials (+ bf16 copy of the tile when a backward follows)
+        EpiLsePartials::Params ep;
+        ep.scale_log2 = scale_log2;
+        ep.part_m = part_m;
+        ep.part_s = part_s;
+        ep.part_t = part_t;
+        ep.ld = c;
+        ep.labels = labels + t0;
+        ep.label_acc = label_acc;
+        ep.logits = need_grad ? S : nullptr;
+        ep.ld_logits = plan.ldS;
+        SKYB200_CUDA_CHECK(cudaMemsetAsync(label_acc, 0, (size_t)rows * sizeof(float), stream));
+        rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
+            hid + t0 * H, H, weight, H, rows, (int)V, (int)H, 16, ep, stream);
+        if (rc) return rc;
+        head_merge_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(
+            part_m, part_s, part_t, c, plan.slabs, label_acc, entropy_mask ? entropy_mask + t0 : nullptr, inv_T,
+            log_probs + t0, entropy + t0, ent_raw, lse2, rows);
+        rc = check_launch("head_merge_kernel");
+        if (rc) return rc;
+        // (2) loss of this token range (normalisers come from the mask-only pre-pass)
+        if (params->loss_type == SKYB200_LOSS_GSPO) {
+            rc = loss_row_logratio(log_probs, old_log_probs, loss_mask, lws, t0 / A, rows / A, A, stream);
+            if (rc) return rc;
+        }
+        rc = loss_flat_range(log_probs, old_log_probs, advantages, loss_mask, base_log_probs, entropy,
+                             need_grad ? d_lp - t0 : nullptr, use_ent_grad ? d_ent - t0 : nullptr, lws, B, A, t0,
+                             t0 + rows, slot, *params, stream);
+        if (rc) return rc;
+        slot += loss_chunk_blocks(rows);
+        if (!need_grad) continue;
+        // (3) stored logits -> d(logits), in place
+        {
+            const dim3 grid((unsigned)((V + 4095) / 4096), (unsigned)rows);
+            dlogits_transform_kernel<<<grid, 256, 0, stream>>>(
+                S, plan.ldS, (int)V, lse2, d_lp, use_ent_grad ? d_ent : nullptr,
+                (use_ent_grad && entropy_mask) ? entropy_mask + t0 : nullptr, ent_raw, labels + t0, scale_log2, inv_T);
+            rc = check_launch("dlogits_transform_kernel");
+            if (rc) return rc;
+        }
+        // (4) d_hidden = dS * W ; (5) d_weight (+)= dS^T * hidden
+        if (dhid != nullptr) {
+            EpiStoreBF16::Params eh;
+            eh.C = dhid + t0 * H;
+            eh.ldc = H;
+            rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
+                S, plan.ldS, weight, H, rows, (int)H, (int)V, 5, eh, stream);
+            if (rc) return rc;
+        }
+        if (d_weight != nullptr) {
+            EpiStoreF32::Params ew;
+            ew.C = d_weight;
+            ew.ldc = H;
+            ew.accumulate = (accumulate != 0 || t0 > 0) ? 1 : 0;
+            rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
+                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, 5, ew, stream);
+            if (rc) return rc;
+        }
+    }
+    return loss_finalize(lws, slot, true, stats, *params, stream);
 }
 
 extern "C" int skyb200_logits_logprob_entropy(const void* logits, int32_t logits_dtype, const int64_t* labels,

@@ -12,6 +12,7 @@
 // (2) the per-token pass that writes d_log_probs / d_entropy and reduces every scalar the worker reports.
 // All reductions are order-deterministic (per-block partials, last block folds them in index order).
 #include "common.cuh"
+#include "internal.h"
 
 namespace skyb200 {
 
@@ -71,9 +72,12 @@ loss_rowstats_kernel(const float* __restrict__ lp, const float* __restrict__ olp
     if (threadIdx.x == 0) {
         row_msum[row] = ms;
         row_lw[row] = need_lw ? lw / fmaxf(ms, 1.f) : 0.f;
-        __threadfence();
-        const unsigned int prev = atomicAdd(counter, 1u);
-        is_last = (prev == static_cast<unsigned int>(B) - 1u);
+        is_last = false;
+        if (total_msum != nullptr) {
+            __threadfence();
+            const unsigned int prev = atomicAdd(counter, 1u);
+            is_last = (prev == static_cast<unsigned int>(B) - 1u);
+        }
     }
     __syncthreads();
     if (is_last) {
@@ -347,6 +351,242 @@ __global__ void __launch_bounds__(kLossThreads) loss_main_kernel(LossArgs a) {
         for (int i = SKYB200_STAT_RATIO_MIN + 1; i < SKYB200_LOSS_NSTATS; ++i) a.stats[i] = 0.f;
         a.ws.counters[1] = 0u;
     }
+}
+
+// ---------------------------------------------------------------------------- chunked (flat token range) variant
+// Used by the fused step: the loss of a [B, A] batch is evaluated chunk by chunk as the head produces log-probs.
+// Normalisers come from a mask-only pre-pass, so a chunk never needs another chunk's log-probs
+// (GSPO needs whole sequences per chunk; the caller aligns its chunks to rows for it).
+constexpr int kFlatTile = kLossThreads * 4 * 2;  // 2048 tokens per block
+
+struct FlatArgs {
+    const float* lp;
+    const float* olp;
+    const float* adv;
+    const float* mask;
+    const float* base;
+    const float* ent;
+    float* d_lp;
+    float* d_ent;
+    LossChunkWs ws;
+    int B;
+    int vec4;
+    int64_t A;
+    int64_t t0, t1;
+    int64_t slot0;
+    skyb200_loss_params p;
+};
+
+__global__ void __launch_bounds__(kLossThreads) loss_flat_kernel(FlatArgs a) {
+    __shared__ float sh[34];
+    const int64_t A = a.A;
+    const float total_m = __ldcg(a.ws.total_msum);
+    const float Bf = static_cast<float>(a.B);
+    const float inv_total = 1.f / fmaxf(total_m, 1.f);
+    const bool gspo = (a.p.loss_type == SKYB200_LOSS_GSPO);
+    const bool use_ent_loss = (a.p.use_entropy_loss != 0);
+    LossAcc acc;
+    TokenCtx cx;
+    cx.gspo = gspo;
+    cx.dual = (a.p.loss_type == SKYB200_LOSS_DUAL_CLIP);
+    cx.lo = 1.f - a.p.eps_clip_low;
+    cx.hi = 1.f + a.p.eps_clip_high;
+    cx.seq_ratio = 1.f;
+    cx.seq_pass = 1.f;
+    cx.clip_c = a.p.clip_ratio_c;
+    cx.kl_type = a.p.kl_type;
+    cx.has_mask = (a.mask != nullptr);
+    cx.has_base = (a.base != nullptr);
+    cx.d_ent_val = use_ent_loss ? -a.p.entropy_loss_coef * inv_total : 0.f;
+
+    auto set_row = [&](int64_t row) {
+        const float row_m = a.mask ? __ldcg(&a.ws.row_msum[row]) : static_cast<float>(A);
+        const float inv_row = 1.f / fmaxf(row_m, 1.f);
+        if (a.p.reduction == SKYB200_REDUCE_TOKEN_MEAN)
+            cx.w_scale = inv_total;
+        else if (a.p.reduction == SKYB200_REDUCE_SEQUENCE_MEAN)
+            cx.w_scale = inv_row / Bf;
+        else
+            cx.w_scale = 1.f / (a.p.max_seq_len * Bf);
+        cx.kl_scale = inv_row / Bf;
+        cx.kl_grad_scale = a.p.kl_has_grad ? a.p.kl_loss_coef * cx.kl_scale : 0.f;
+        if (gspo) {
+            const float lw = __ldcg(&a.ws.row_lw[row]);
+            cx.seq_ratio = expf(fminf(lw, 10.f));
+            cx.seq_pass = (lw <= 10.f) ? 1.f : 0.f;
+        }
+    };
+
+    const int64_t base_t = a.t0 + static_cast<int64_t>(blockIdx.x) * kFlatTile;
+    if (a.vec4) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int64_t i = base_t + (static_cast<int64_t>(it) * kLossThreads + threadIdx.x) * 4;
+            if (i < a.t1) {
+                set_row(i / A);  // A % 4 == 0: the four tokens share a row
+                const float4 lp = ldg_stream(reinterpret_cast<const float4*>(a.lp + i));
+                const float4 olp = ldg_stream(reinterpret_cast<const float4*>(a.olp + i));
+                const float4 adv = ldg_stream(reinterpret_cast<const float4*>(a.adv + i));
+                float4 m = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f), en = bs;
+                if (a.mask) m = ldg_stream(reinterpret_cast<const float4*>(a.mask + i));
+                if (a.base) bs = ldg_stream(reinterpret_cast<const float4*>(a.base + i));
+                if (a.ent) en = ldg_stream(reinterpret_cast<const float4*>(a.ent + i));
+                float4 g;
+                g.x = loss_token(cx, acc, lp.x, olp.x, adv.x, m.x, bs.x);
+                g.y = loss_token(cx, acc, lp.y, olp.y, adv.y, m.y, bs.y);
+                g.z = loss_token(cx, acc, lp.z, olp.z, adv.z, m.z, bs.z);
+                g.w = loss_token(cx, acc, lp.w, olp.w, adv.w, m.w, bs.w);
+                if (a.d_lp) *reinterpret_cast<float4*>(a.d_lp + i) = g;
+                if (a.ent) {
+                    acc.s_ent = fmaf(en.x, m.x, acc.s_ent);
+                    acc.s_ent = fmaf(en.y, m.y, acc.s_ent);
+                    acc.s_ent = fmaf(en.z, m.z, acc.s_ent);
+                    acc.s_ent = fmaf(en.w, m.w, acc.s_ent);
+                    if (a.d_ent)
+                        *reinterpret_cast<float4*>(a.d_ent + i) =
+                            make_float4(cx.d_ent_val * m.x, cx.d_ent_val * m.y, cx.d_ent_val * m.z, cx.d_ent_val * m.w);
+                }
+            }
+        }
+    } else {
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+            const int64_t i = base_t + static_cast<int64_t>(it) * kLossThreads + threadIdx.x;
+            if (i < a.t1) {
+                set_row(i / A);
+                const float m = a.mask ? a.mask[i] : 1.f;
+                const float g = loss_token(cx, acc, a.lp[i], a.olp[i], a.adv[i], m, a.base ? a.base[i] : 0.f);
+                if (a.d_lp) a.d_lp[i] = g;
+                if (a.ent) {
+                    acc.s_ent = fmaf(a.ent[i], m, acc.s_ent);
+                    if (a.d_ent) a.d_ent[i] = cx.d_ent_val * m;
+                }
+            }
+        }
+    }
+    const float s_loss = block_sum(acc.s_loss, sh);
+    const float s_clip = block_sum(acc.s_clip, sh);
+    const float s_kl = block_sum(acc.s_kl, sh);
+    const float s_ent = block_sum(acc.s_ent, sh);
+    const float s_ratio = block_sum(acc.s_ratio, sh);
+    const float r_max = block_max(acc.r_max, sh);
+    const float r_min = block_min(acc.r_min, sh);
+    if (threadIdx.x == 0) {
+        float* p = a.ws.partials + (a.slot0 + blockIdx.x) * kNumPartials;
+        p[0] = s_loss;
+        p[1] = s_clip;
+        p[2] = s_kl;
+        p[3] = s_ent;
+        p[4] = s_ratio;
+        p[5] = r_max;
+        p[6] = r_min;
+    }
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+loss_finalize_kernel(LossChunkWs ws, int64_t nslots, int has_entropy, float* __restrict__ stats,
+                     skyb200_loss_params p) {
+    __shared__ float sh[34];
+    float f_loss = 0.f, f_clip = 0.f, f_kl = 0.f, f_ent = 0.f, f_ratio = 0.f, f_max = -INFINITY, f_min = INFINITY;
+    for (int64_t b = threadIdx.x; b < nslots; b += blockDim.x) {
+        const float* q = ws.partials + b * kNumPartials;
+        f_loss += q[0];
+        f_clip += q[1];
+        f_kl += q[2];
+        f_ent += q[3];
+        f_ratio += q[4];
+        f_max = fmaxf(f_max, q[5]);
+        f_min = fminf(f_min, q[6]);
+    }
+    f_loss = block_sum(f_loss, sh);
+    f_clip = block_sum(f_clip, sh);
+    f_kl = block_sum(f_kl, sh);
+    f_ent = block_sum(f_ent, sh);
+    f_ratio = block_sum(f_ratio, sh);
+    f_max = block_max(f_max, sh);
+    f_min = block_min(f_min, sh);
+    if (threadIdx.x == 0) {
+        const float total_m = *ws.total_msum;
+        const float inv_total = 1.f / fmaxf(total_m, 1.f);
+        const float ent_mean = f_ent * inv_total;
+        float final_loss = f_loss + f_kl * p.kl_loss_coef;
+        if (p.use_entropy_loss && has_entropy) final_loss -= ent_mean * p.entropy_loss_coef;
+        stats[SKYB200_STAT_POLICY_LOSS] = f_loss;
+        stats[SKYB200_STAT_CLIP_RATIO] = f_clip * inv_total;
+        stats[SKYB200_STAT_KL_LOSS] = f_kl;
+        stats[SKYB200_STAT_ENTROPY] = ent_mean;
+        stats[SKYB200_STAT_FINAL_LOSS] = final_loss;
+        stats[SKYB200_STAT_MASK_SUM] = total_m;
+        stats[SKYB200_STAT_RATIO_MEAN] = f_ratio * inv_total;
+        stats[SKYB200_STAT_RATIO_MAX] = f_max;
+        stats[SKYB200_STAT_RATIO_MIN] = f_min;
+        for (int i = SKYB200_STAT_RATIO_MIN + 1; i < SKYB200_LOSS_NSTATS; ++i) stats[i] = 0.f;
+    }
+}
+
+size_t loss_chunk_ws_bytes(int64_t B, int64_t A) {
+    const int64_t slots = loss_chunk_blocks(B * A) + 4 * 64;  // every chunk rounds its block count up
+    return static_cast<size_t>(2 * ((B * 4 + 255) / 256 * 256) + 512 + (slots + B) * kNumPartials * 4 + 512);
+}
+int64_t loss_chunk_blocks(int64_t n_tokens) { return (n_tokens + kFlatTile - 1) / kFlatTile; }
+
+void loss_chunk_ws_carve(void* base, int64_t B, int64_t A, LossChunkWs* ws) {
+    (void)A;
+    char* b = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(base) + 255) & ~uintptr_t(255));
+    const size_t rb = static_cast<size_t>((B * 4 + 255) / 256 * 256);
+    ws->row_msum = reinterpret_cast<float*>(b);
+    ws->row_lw = reinterpret_cast<float*>(b + rb);
+    ws->total_msum = reinterpret_cast<float*>(b + 2 * rb);
+    ws->counters = reinterpret_cast<unsigned int*>(b + 2 * rb + 64);
+    ws->partials = reinterpret_cast<float*>(b + 2 * rb + 256);
+}
+
+int loss_prepass(const float* loss_mask, const LossChunkWs& ws, int64_t B, int64_t A, cudaStream_t stream) {
+    SKYB200_CUDA_CHECK(cudaMemsetAsync(ws.counters, 0, 16, stream));
+    loss_rowstats_kernel<<<(unsigned)B, kLossThreads, 0, stream>>>(nullptr, nullptr, loss_mask, ws.row_msum, ws.row_lw,
+                                                                   ws.total_msum, ws.counters, (int)B, A, 0);
+    return check_launch("loss_rowstats_kernel(prepass)");
+}
+
+int loss_row_logratio(const float* lp, const float* olp, const float* loss_mask, const LossChunkWs& ws, int64_t row0,
+                      int64_t rows, int64_t A, cudaStream_t stream) {
+    loss_rowstats_kernel<<<(unsigned)rows, kLossThreads, 0, stream>>>(
+        lp + row0 * A, olp + row0 * A, loss_mask ? loss_mask + row0 * A : nullptr, ws.row_msum + row0, ws.row_lw + row0,
+        nullptr, ws.counters, (int)rows, A, 1);
+    return check_launch("loss_rowstats_kernel(gspo)");
+}
+
+int loss_flat_range(const float* lp, const float* olp, const float* adv, const float* loss_mask, const float* base,
+                    const float* ent, float* d_lp, float* d_ent, const LossChunkWs& ws, int64_t B, int64_t A,
+                    int64_t t0, int64_t t1, int64_t slot0, const skyb200_loss_params& p, cudaStream_t stream) {
+    if (t1 <= t0) return SKYB200_OK;
+    FlatArgs a;
+    a.lp = lp;
+    a.olp = olp;
+    a.adv = adv;
+    a.mask = loss_mask;
+    a.base = base;
+    a.ent = ent;
+    a.d_lp = d_lp;
+    a.d_ent = d_ent;
+    a.ws = ws;
+    a.B = (int)B;
+    a.A = A;
+    a.t0 = t0;
+    a.t1 = t1;
+    a.slot0 = slot0;
+    a.p = p;
+    auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    a.vec4 = (A % 4 == 0) && (t0 % 4 == 0) && al16(lp) && al16(olp) && al16(adv) && al16(loss_mask) && al16(base) &&
+             al16(ent) && al16(d_lp) && al16(d_ent);
+    loss_flat_kernel<<<(unsigned)loss_chunk_blocks(t1 - t0), kLossThreads, 0, stream>>>(a);
+    return check_launch("loss_flat_kernel");
+}
+
+int loss_finalize(const LossChunkWs& ws, int64_t nslots, bool has_entropy, float* stats, const skyb200_loss_params& p,
+                  cudaStream_t stream) {
+    loss_finalize_kernel<<<1, kLossThreads, 0, stream>>>(ws, nslots, has_entropy ? 1 : 0, stats, p);
+    return check_launch("loss_finalize_kernel");
 }
 
 // ---------------------------------------------------------------------------- small helpers

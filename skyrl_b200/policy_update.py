@@ -66,6 +66,7 @@ def policy_update_step(
     need_d_weight: bool = True,
     chunk: int = 0,
     sync: bool = True,
+    fused: bool = True,
 ) -> PolicyUpdateOutput:
     """``hidden`` [B, A, H] (or [B*A, H]) bf16, ``weight`` [V, H] bf16, ``labels`` [B, A] int64,
     ``old_log_probs`` / ``advantages`` / ``loss_mask`` / ``base_log_probs`` [B, A] fp32.
@@ -74,6 +75,11 @@ def policy_update_step(
     clip_ratio_c, use_kl_loss, kl_estimator_type, kl_loss_coef, use_entropy_loss, entropy_loss_coef,
     max_seq_len).  Gradients are those of ``final_loss`` (upstream gradient 1), i.e. what ``loss.backward()``
     delivers in the reference (worker.py:876-877).
+
+    ``fused=True`` (default) runs ``skyb200_policy_step``: per token chunk forward GEMM -> loss -> backward GEMMs,
+    the forward keeping a bf16 copy of its logits tiles in a bounded [chunk, V] store so the backward does not
+    recompute the projection (6*H*V executed flop per token).  ``fused=False`` runs the three C-ABI calls
+    (``head_forward`` / ``policy_loss`` / ``head_backward``) the autograd path uses (8*H*V, fp32 logits in backward).
     """
     lib = _lib.load()
     if not hidden.is_cuda:
@@ -112,6 +118,38 @@ def policy_update_step(
     )
     T = float(temperature)
     stream = _lib.stream_ptr()
+    if fused:
+        with torch.cuda.device(dev):
+            logprobs = torch.empty(N, dtype=torch.float32, device=dev)
+            ent = torch.empty(N, dtype=torch.float32, device=dev)
+            stats = torch.empty(_lib.LOSS_NSTATS, dtype=torch.float32, device=dev)
+            need_grad = need_d_hidden or need_d_weight
+            d_hidden = torch.empty((N, H), dtype=torch.bfloat16, device=dev) if need_d_hidden else None
+            acc = 0
+            if need_d_weight:
+                if d_weight is None:
+                    d_weight = torch.empty((V, H), dtype=torch.float32, device=dev)
+                else:
+                    if d_weight.dtype != torch.float32 or tuple(d_weight.shape) != (V, H) or not d_weight.is_contiguous():
+                        raise ValueError("d_weight must be a contiguous fp32 [V, H] tensor")
+                    acc = 1 if accumulate_d_weight else 0
+            wsb = lib.skyb200_policy_step_workspace(B, A, H, V, params.loss_type, int(need_grad))
+            ws = _WS.get("step", wsb, dev)
+            _lib.check(
+                lib.skyb200_policy_step(_lib.ptr(h), _lib.ptr(w), _lib.ptr(lab), _lib.ptr(olp), _lib.ptr(adv),
+                                        _lib.ptr(mask), _lib.ptr(base) if use_kl else None, _lib.ptr(emask),
+                                        _lib.ptr(logprobs), _lib.ptr(ent), _lib.ptr(d_hidden),
+                                        _lib.ptr(d_weight) if need_d_weight else None, acc, _lib.ptr(stats),
+                                        _lib.ptr(ws), wsb, B, A, H, V, T, C.byref(params), stream),
+                "skyb200_policy_step",
+            )
+            if sync:
+                status = status_from_packed(stats.tolist(), use_kl)  # the single host sync of the step
+                status["response_length"] = A
+            else:
+                status = {"packed": stats}
+        return PolicyUpdateOutput(status=status, stats=stats, log_probs=logprobs.view(B, A), entropy=ent.view(B, A),
+                                  d_hidden=d_hidden, d_weight=d_weight if need_d_weight else None)
     with torch.cuda.device(dev):
         logprobs = torch.empty(N, dtype=torch.float32, device=dev)
         ent_raw = torch.empty(N, dtype=torch.float32, device=dev)

@@ -29,8 +29,11 @@ def _batch(B, A, H, V, seed):
     dict(policy_loss_type="gspo", loss_reduction="sequence_mean", use_kl_loss=True, use_entropy_loss=True,
          eps_clip_low=0.05, eps_clip_high=0.05),
 ])
-def test_step_matches_oracle(kw):
-    B, A, H, V, T = 8, 96, 128, 2000, 0.9
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("shape", [(8, 96, 128, 2000), (5, 1000, 64, 1500)])
+def test_step_matches_oracle(kw, fused, shape):
+    B, A, H, V = shape
+    T = 0.9
     g, hidden, weight, labels, mask = _batch(B, A, H, V, 42)
     cfg = O.make_cfg(**kw)
     h = hidden.float().reshape(B * A, H).requires_grad_(True)
@@ -44,7 +47,8 @@ def test_step_matches_oracle(kw):
     final_ref.backward()
 
     out = skyrl_b200.policy_update_step(hidden.to(DEV), weight.to(DEV), labels.to(DEV), olp.to(DEV), adv.to(DEV),
-                                        cfg, loss_mask=mask.to(DEV), base_log_probs=base.to(DEV), temperature=T)
+                                        cfg, loss_mask=mask.to(DEV), base_log_probs=base.to(DEV), temperature=T,
+                                        fused=fused)
     assert (out.log_probs.cpu() - lp_ref.detach()).abs().max().item() < 1e-3
     for k in ("final_loss", "policy_loss", "policy_entropy", "loss_metrics/clip_ratio"):
         assert out.status[k] == pytest.approx(st_ref[k], rel=2e-3, abs=2e-4), k
@@ -61,8 +65,41 @@ def test_step_matches_oracle(kw):
     loss, st = skyrl_b200.policy_update_loss(lp.view(B, A), olp.to(DEV), adv.to(DEV), cfg, loss_mask=mask.to(DEV),
                                              base_log_probs=base.to(DEV), entropy=ent.view(B, A))
     loss.backward()
-    assert st["final_loss"] == pytest.approx(out.status["final_loss"], rel=1e-6, abs=1e-7)
-    assert rel(hd.grad.float(), out.d_hidden.float().cpu()) < 1e-3
+    assert st["final_loss"] == pytest.approx(out.status["final_loss"], rel=1e-5, abs=1e-6)
+    # fused keeps bf16 logits for the backward, the autograd path recomputes them in fp32: both within tolerance
+    assert rel(hd.grad.float(), out.d_hidden.float().cpu()) < (1e-2 if fused else 1e-3)
+
+
+def test_fused_step_multi_chunk_entropy_mask_and_accumulate():
+    """Several chunks (ragged last one), an entropy mask, entropy gradient and d_weight accumulation."""
+    B, A, H, V, T = 3, 4096, 64, 1024, 1.0
+    g, hidden, weight, labels, mask = _batch(B, A, H, V, 5)
+    emask = (torch.rand(B, A, generator=g) > 0.1).float()
+    cfg = O.make_cfg(policy_loss_type="regular", loss_reduction="sequence_mean", use_kl_loss=True,
+                     use_entropy_loss=True, entropy_loss_coef=0.05)
+    h = hidden.float().reshape(B * A, H).requires_grad_(True)
+    w = weight.float().requires_grad_(True)
+    lp_ref, ent_ref = O.head_logprobs_entropy(h, w, labels.reshape(-1), T)
+    lp_ref, ent_ref = lp_ref.view(B, A), ent_ref.view(B, A) * emask
+    olp = lp_ref.detach() + 0.05 * torch.randn(B, A, generator=g)
+    base = lp_ref.detach() + 0.1 * torch.randn(B, A, generator=g)
+    adv = torch.randn(B, A, generator=g)
+    final_ref, st_ref = O.loss_assembly(lp_ref, olp, adv, cfg, mask, base, ent_ref)
+    final_ref.backward()
+    dw = torch.ones(V, H, device=DEV)
+    args = (hidden.to(DEV), weight.to(DEV), labels.to(DEV), olp.to(DEV), adv.to(DEV), cfg)
+    kw = dict(loss_mask=mask.to(DEV), base_log_probs=base.to(DEV), temperature=T, entropy_mask=emask.to(DEV))
+    out = skyrl_b200.policy_update_step(*args, d_weight=dw, accumulate_d_weight=True, **kw)
+    rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+    for k in ("final_loss", "policy_loss", "policy_entropy", "policy_kl", "loss_metrics/clip_ratio"):
+        assert out.status[k] == pytest.approx(st_ref[k], rel=2e-3, abs=2e-4), k
+    assert torch.equal(out.entropy.cpu() == 0, ent_ref.detach() == 0)
+    assert rel(out.d_hidden.float(), h.grad) < 2e-2
+    assert rel(out.d_weight - 1.0, w.grad) < 2e-2  # accumulated on top of the ones
+    # loss-only evaluation (no gradients requested) gives the same status
+    out2 = skyrl_b200.policy_update_step(*args, need_d_hidden=False, need_d_weight=False, **kw)
+    assert out2.d_hidden is None and out2.d_weight is None
+    assert out2.status["final_loss"] == pytest.approx(out.status["final_loss"], rel=1e-6)
 
 
 def test_grpo_config1_slice_end_to_end():
