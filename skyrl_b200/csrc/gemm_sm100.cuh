@@ -66,17 +66,29 @@ struct TileCoord {
     int n_tile;
 };
 
-// Tile order: groups of `group_m` M-tiles sweep all N-tiles with the M index fastest, so concurrently
-// resident CTAs share the same B tile (L2 hits) while the A group stays L2-resident.
-__device__ __forceinline__ TileCoord decode_tile(int t, int num_m_tiles, int num_n_tiles, int group_m) {
-    const int tiles_per_group = group_m * num_n_tiles;
-    const int g = t / tiles_per_group;
-    const int first_m = g * group_m;
-    const int gm = min(group_m, num_m_tiles - first_m);
-    const int r = t - g * tiles_per_group;
+// Tile order.  order 0: groups of `group` M-tiles sweep all N-tiles with the M index fastest, so concurrently
+// resident CTAs share the same B tile (L2 hits) while the A group stays L2-resident.  order 1: the transpose -
+// groups of `group` N-tiles sweep all M-tiles with the N index fastest (the B panels of the group stay hot while
+// the A panels stream through once per group); used when N is small and K is short (d_weight GEMM).
+__device__ __forceinline__ TileCoord decode_tile(int t, int num_m_tiles, int num_n_tiles, int group, int order) {
     TileCoord c;
-    c.n_tile = r / gm;
-    c.m_tile = first_m + (r - c.n_tile * gm);
+    if (order == 0) {
+        const int tiles_per_group = group * num_n_tiles;
+        const int g = t / tiles_per_group;
+        const int first_m = g * group;
+        const int gm = min(group, num_m_tiles - first_m);
+        const int r = t - g * tiles_per_group;
+        c.n_tile = r / gm;
+        c.m_tile = first_m + (r - c.n_tile * gm);
+    } else {
+        const int tiles_per_group = group * num_m_tiles;
+        const int g = t / tiles_per_group;
+        const int first_n = g * group;
+        const int gn = min(group, num_n_tiles - first_n);
+        const int r = t - g * tiles_per_group;
+        c.m_tile = r / gn;
+        c.n_tile = first_n + (r - c.m_tile * gn);
+    }
     return c;
 }
 
@@ -92,7 +104,7 @@ struct GemmSmem {
 template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
-                  int N, int K, int group_m, typename Epi::Params ep, GemmDebug* dbg) {
+                  int N, int K, int group_m, int tile_order, typename Epi::Params ep, GemmDebug* dbg) {
     using S = GemmSmem<kCtas, BN, kStages>;
     constexpr int TILE_M = kBM * kCtas;
     constexpr uint32_t kTmemCols = 2 * BN;
@@ -154,7 +166,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-                const TileCoord tc = decode_tile(t, num_m_tiles, num_n_tiles, group_m);
+                const TileCoord tc = decode_tile(t, num_m_tiles, num_n_tiles, group_m, tile_order);
                 const int m0 = tc.m_tile * TILE_M + static_cast<int>(cta_rank) * kBM;
                 const int n0 = tc.n_tile * BN + static_cast<int>(cta_rank * S::kLoadN);
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -242,7 +254,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         uint32_t accum = 0, aphase = 0;
         for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-            const TileCoord tc = decode_tile(t, num_m_tiles, num_n_tiles, group_m);
+            const TileCoord tc = decode_tile(t, num_m_tiles, num_n_tiles, group_m, tile_order);
             bounded_wait(&tfull_bar[accum], aphase, dbg, 2, 2, accum, t);
             ptx::tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + accum * BN;

@@ -77,7 +77,7 @@ static GemmDebug* debug_record_dev() {
 // A: K-major -> [M, K] with pitch lda; MN-major -> [K, M] with pitch lda.  Same for B with N.
 template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
 static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int group_m,
-                       const typename Epi::Params& ep, cudaStream_t stream) {
+                       const typename Epi::Params& ep, cudaStream_t stream, int tile_order = 0) {
     using S = GemmSmem<kCtas, BN, kStages>;
     if (M <= 0 || N <= 0 || K <= 0) return SKYB200_OK;
     CUtensorMap ta, tb;
@@ -117,7 +117,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
     cfg.numAttrs = 1;
     GemmDebug* dbg = debug_record_dev();
     if (group_m < 1) group_m = 1;
-    SKYB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group_m, ep, dbg));
+    SKYB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group_m, tile_order, ep, dbg));
     return SKYB200_OK;
 }
 
@@ -453,7 +453,7 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
             ew.ldc = H;
             ew.accumulate = (accumulate != 0 || r0 > 0) ? 1 : 0;
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
-                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, 5, ew, stream);
+                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, 7, ew, stream, 1);
             if (rc) return rc;
         }
     }
@@ -620,7 +620,7 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
             ew.ldc = H;
             ew.accumulate = (accumulate != 0 || t0 > 0) ? 1 : 0;
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
-                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, 5, ew, stream);
+                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, 7, ew, stream, 1);
             if (rc) return rc;
         }
     }

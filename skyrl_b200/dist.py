@@ -47,6 +47,21 @@ def shard_prompt_groups(index: Sequence, valid_tokens: Sequence[int], world_size
     return [sorted(r) for r in rows]
 
 
+def reduce_metrics(metrics: Dict[str, List[float]]) -> Dict[str, float]:
+    """Fold per-micro-batch metric lists: mean, ``*_max`` -> max, ``*_min`` -> min (worker_utils.py:8-22)."""
+    out = {}
+    for k, v in metrics.items():
+        assert len(v) > 0, f"No metrics for key {k}"
+        assert all(isinstance(x, (int, float)) for x in v), f"Metrics for key {k} are not all numbers"
+        if k.endswith("_max"):
+            out[k] = max(v)
+        elif k.endswith("_min"):
+            out[k] = min(v)
+        else:
+            out[k] = sum(v) / len(v)
+    return out
+
+
 def _world(group=None) -> int:
     return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
