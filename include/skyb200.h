@@ -103,6 +103,17 @@ int skyb200_policy_loss(const float* log_probs, const float* old_log_probs, cons
                         float* d_log_probs, float* d_entropy, float* stats, void* workspace, size_t workspace_bytes,
                         int64_t B, int64_t A, const skyb200_loss_params* params, void* stream);
 
+/*
+ * Critic (value) loss, forward + backward (ppo_critic_loss, ppo_utils.py:175-193):
+ *   loss = 0.5 * mean_b masked_mean_t max((old + clamp(v - old, +-clip) - R)^2, (v - R)^2)   (use_clip != 0)
+ *        = 0.5 * mean_b masked_mean_t (v - R)^2                                               (use_clip == 0)
+ * stats[0] = loss, stats[1] = clipfrac = masked_mean(1[surr1 > surr2]), stats[2] = sum(mask); 4 floats.
+ * d_values [B, A] out (NULL = forward only).  workspace: skyb200_policy_loss_workspace(B, A) bytes.
+ */
+int skyb200_critic_loss(const float* values, const float* old_values, const float* returns, const float* loss_mask,
+                        float* d_values, float* stats, void* workspace, size_t workspace_bytes, int64_t B, int64_t A,
+                        float value_clip, int32_t use_clip, void* stream);
+
 /* x[i] *= *scale_dev  (applies an upstream autograd gradient that lives on the device) */
 int skyb200_scale_inplace(float* x, const float* scale_dev, int64_t n, void* stream);
 
@@ -155,6 +166,23 @@ int skyb200_gae_scan(const float* rewards, const float* values, const void* resp
                      float* adv_raw, float* returns, double* moments, void* workspace, size_t workspace_bytes,
                      int64_t B, int64_t A, float gamma, float lambd, void* stream);
 int skyb200_whiten_from_moments(float* x, const double* moments, float* stats_out, int64_t n, void* stream);
+
+/*
+ * REINFORCE++ (compute_reinforce_plus_plus_outcome_advantage, ppo_utils.py:1013-1045):
+ *   returns_t = r_t + gamma * returns_{t+1} * mask_{t+1} (reset after EOS); advantages = masked_whiten(returns) * mask.
+ * stats_out: 4 floats {mask_sum, mean, var, rstd} (raise for mask_sum in {0, 1}); workspace: skyb200_gae_workspace(B).
+ */
+int skyb200_reinforce_pp_advantage(const float* rewards, const void* response_mask, int32_t mask_type,
+                                   float* advantages, float* returns, float* stats_out, void* workspace,
+                                   size_t workspace_bytes, int64_t B, int64_t A, float gamma, void* stream);
+
+/*
+ * normalize_advantages_dict (ppo_utils.py:127-145): mean over ALL n positions (unmasked), variance over the mask:
+ *   out = (adv - mean) * rsqrt(max(sum(m * (adv - mean)^2) / sum(m), 1e-8)).   stats_out: {sum m, mean, var, rstd}.
+ */
+size_t skyb200_normalize_advantages_workspace(void);
+int skyb200_normalize_advantages(const float* advantages, const void* response_mask, int32_t mask_type, float* out,
+                                 float* stats_out, void* workspace, size_t workspace_bytes, int64_t n, void* stream);
 
 /*
  * KL-in-reward (RayPPOTrainer.apply_reward_kl_penalty, trainer.py:981-1035):

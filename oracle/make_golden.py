@@ -65,6 +65,16 @@ def gen_advantages(pu):
     for name, (gm, lm) in {"gae_1_095": (1.0, 0.95), "gae_099_1": (0.99, 1.0), "gae_1_1": (1.0, 1.0)}.items():
         adv, ret = pu.compute_gae_advantage_return(dense, values, fm, gamma=gm, lambd=lm)
         out[name + "_adv"], out[name + "_ret"] = adv.numpy(), ret.numpy()
+    for gm in (1.0, 0.9):
+        adv, ret = pu.compute_reinforce_plus_plus_outcome_advantage(dense, fm, gamma=gm)
+        out[f"rpp_{gm}_adv"], out[f"rpp_{gm}_ret"] = adv.numpy(), ret.numpy()
+    hole = fm.clone()
+    hole[2, 3:6] = 0.0  # a hole inside the response: the running return resets there
+    adv, ret = pu.compute_reinforce_plus_plus_outcome_advantage(dense, hole, gamma=0.95)
+    out["rpp_hole_mask"], out["rpp_hole_adv"], out["rpp_hole_ret"] = hole.numpy(), adv.numpy(), ret.numpy()
+    batch = {"advantages": torch.from_numpy(out["gae_1_095_adv"]).clone() * 3 + 0.5, "response_mask": fm}
+    out["norm_in"] = batch["advantages"].numpy().copy()
+    out["norm_out"] = pu.normalize_advantages_dict(batch)["advantages"].numpy()
     # KL in reward: trainer.py:992-1011 composed from the reference primitives
     lp = -torch.rand(B, A, generator=g) * 2
     base = lp + 0.1 * torch.randn(B, A, generator=g)
@@ -113,6 +123,21 @@ def gen_losses(pu):
                 out[key + "__loss"] = np.float32(loss.item())
                 out[key + "__clip"] = np.float32(met["clip_ratio"])
                 out[key + "__grad"] = x.grad.numpy()
+    # critic loss (ppo_utils.py:175-193)
+    vals = torch.randn(B, A, generator=g)
+    old_vals = vals + 0.3 * torch.randn(B, A, generator=g)
+    old_vals[0, :4] = vals[0, :4]  # exact ties surr1 == surr2
+    rets = torch.randn(B, A, generator=g)
+    out.update(values=vals.numpy(), old_values=old_vals.numpy(), returns=rets.numpy())
+    for cname, clip in (("clip02", 0.2), ("noclip", None)):
+        for mname, m in (("mask", fm), ("nomask", None)):
+            v = vals.clone().requires_grad_(True)
+            loss, clipfrac = pu.ppo_critic_loss(v, old_vals, rets, SimpleNamespace(value_clip=clip), loss_mask=m)
+            loss.backward()
+            key = f"critic__{cname}__{mname}"
+            out[key + "__loss"] = np.float32(loss.item())
+            out[key + "__clipfrac"] = np.float32(-1.0 if clipfrac is None else clipfrac)
+            out[key + "__grad"] = v.grad.numpy()
     # worker.py:787-889 loss assembly from the reference primitives, same order of operations
     for name, kw in {
         "asm_grpo_kl": dict(policy_loss_type="regular", use_kl_loss=True, use_entropy_loss=False),

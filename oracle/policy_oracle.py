@@ -118,6 +118,44 @@ def gae_advantage_return(rewards, values, response_mask, gamma: float, lambd: fl
     return masked_whiten(adv_t, response_mask), returns
 
 
+def reinforce_pp_advantage(rewards, response_mask, gamma: float):
+    """utils/ppo_utils.py:1013-1045 — discounted returns, running return reset after EOS (running *= mask[t]),
+    advantages = masked_whiten(returns, mask) * mask."""
+    r = rewards.float().numpy()
+    m = response_mask.float().numpy()
+    B, A = r.shape
+    ret = np.zeros((B, A), dtype=np.float32)
+    run = np.zeros(B, dtype=np.float32)
+    g = np.float32(gamma)
+    for t in range(A - 1, -1, -1):
+        run = (r[:, t] + g * run).astype(np.float32)
+        ret[:, t] = run
+        run = run * m[:, t]
+    ret_t = torch.from_numpy(ret)
+    mask = response_mask.float()
+    return masked_whiten(ret_t, mask) * mask, ret_t
+
+
+def normalize_advantages(adv, response_mask):
+    """utils/ppo_utils.py:127-145 — mean over all positions, variance over the mask, rsqrt(clamp(var, 1e-8))."""
+    mask = response_mask.float()
+    mean = adv.mean()
+    var = ((adv - mean).pow(2) * mask).sum() / mask.sum()
+    return (adv - mean) * var.clamp(min=1e-8).rsqrt()
+
+
+def critic_loss(values, old_values, returns, value_clip, mask=None):
+    """utils/ppo_utils.py:175-193 — returns (0.5 * loss, clipfrac or None)."""
+    if value_clip is not None:
+        clipped = old_values + (values - old_values).clamp(-value_clip, value_clip)
+        s1, s2 = (clipped - returns) ** 2, (values - returns) ** 2
+        loss = torch.max(s1, s2)
+        clipfrac = masked_mean((s1 > s2).float(), mask).mean().item()
+    else:
+        loss, clipfrac = (values - returns) ** 2, None
+    return 0.5 * masked_mean(loss, mask, dim=-1).mean(), clipfrac
+
+
 def reward_kl_penalty(rewards, lp, base, loss_mask, kind: str = "k3", coef: float = 1e-3):
     """trainer.py:981-1035 — rewards - kl*max(0, coef); avg_kl = mean_b masked_mean_t kl; avg_kl_max = mean_b max_t|kl|."""
     kl = approx_kl(lp, base, loss_mask, kind)

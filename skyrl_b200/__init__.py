@@ -21,10 +21,13 @@ from .advantages import (  # noqa: F401
     compute_approx_kl,
     compute_gae_advantage_return,
     compute_grpo_outcome_advantage,
+    compute_reinforce_plus_plus_outcome_advantage,
+    normalize_advantages,
+    normalize_advantages_dict,
     compute_rloo_outcome_advantage,
 )
 from .fused_head import fused_lm_head, fused_lm_head_logprobs  # noqa: F401
-from .losses import gspo_policy_loss, policy_update_loss, ppo_policy_loss  # noqa: F401
+from .losses import gspo_policy_loss, policy_update_loss, ppo_critic_loss, ppo_policy_loss  # noqa: F401
 from .model_wrapper import action_log_probs_from_hidden  # noqa: F401
 from .policy_update import PolicyUpdateOutput, policy_update_step  # noqa: F401
 from .registry import (  # noqa: F401

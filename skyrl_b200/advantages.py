@@ -178,6 +178,70 @@ def compute_gae_advantage_return(
     return adv, ret
 
 
+def compute_reinforce_plus_plus_outcome_advantage(
+    token_level_rewards: torch.Tensor,
+    response_mask: torch.Tensor,
+    gamma: float,
+    **kwargs,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """REINFORCE++ (reference: ppo_utils.py:1013-1045): discounted returns with a reset after EOS
+    (``running *= mask[t]``), advantages = ``masked_whiten(returns, mask) * mask``."""
+    lib = _lib.load()
+    dev = _device_for(token_level_rewards)
+    out_dev = token_level_rewards.device
+    B, A = token_level_rewards.shape
+    with torch.cuda.device(dev):
+        r = _f32(token_level_rewards, dev)
+        m, mtype = _mask_arg(response_mask, dev)
+        adv = torch.empty((B, A), dtype=torch.float32, device=dev)
+        ret = torch.empty((B, A), dtype=torch.float32, device=dev)
+        stats = torch.empty(4, dtype=torch.float32, device=dev)
+        ws_bytes = lib.skyb200_gae_workspace(B)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(
+            lib.skyb200_reinforce_pp_advantage(_lib.ptr(r), _lib.ptr(m), mtype, _lib.ptr(adv), _lib.ptr(ret),
+                                               _lib.ptr(stats), _lib.ptr(ws), ws_bytes, B, A, float(gamma),
+                                               _lib.stream_ptr()),
+            "skyb200_reinforce_pp_advantage",
+        )
+        mask_sum = float(stats[0].item())
+    if mask_sum == 0:
+        raise ValueError("At least one element in the mask has to be 1.")
+    if mask_sum == 1:
+        raise ValueError("The sum of the mask is one, which can cause a division by zero.")
+    if out_dev != dev:
+        adv, ret = adv.to(out_dev), ret.to(out_dev)
+    return adv, ret
+
+
+@torch.no_grad()
+def normalize_advantages(advantages: torch.Tensor, response_mask: torch.Tensor) -> torch.Tensor:
+    """Batch normalisation of advantages (reference: ``normalize_advantages_dict``, ppo_utils.py:127-145):
+    mean over ALL positions, variance over the mask, ``(adv - mean) * rsqrt(clamp(var, 1e-8))``."""
+    lib = _lib.load()
+    dev = _device_for(advantages)
+    out_dev = advantages.device
+    with torch.cuda.device(dev):
+        a = _f32(advantages, dev)
+        m, mtype = _mask_arg(response_mask, dev)
+        out = torch.empty_like(a)
+        stats = torch.empty(4, dtype=torch.float32, device=dev)
+        wsb = lib.skyb200_normalize_advantages_workspace()
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        _lib.check(
+            lib.skyb200_normalize_advantages(_lib.ptr(a), _lib.ptr(m), mtype, _lib.ptr(out), _lib.ptr(stats),
+                                             _lib.ptr(ws), wsb, a.numel(), _lib.stream_ptr()),
+            "skyb200_normalize_advantages",
+        )
+    return out if out_dev == dev else out.to(out_dev)
+
+
+def normalize_advantages_dict(data):
+    """Dict / TrainingInputBatch form of :func:`normalize_advantages` (same keys as the reference)."""
+    data["advantages"] = normalize_advantages(data["advantages"], data["response_mask"])
+    return data
+
+
 _KL_NAMES = ("k1", "abs", "k2", "k3")
 
 

@@ -286,6 +286,180 @@ __global__ void __launch_bounds__(256) whiten_apply_kernel(float* __restrict__ x
     }
 }
 
+// ------------------------------------------------------------------------------------------ REINFORCE++
+// returns_t = r_t + gamma * (returns_{t+1} * mask_{t+1})   (reset after EOS; ppo_utils.py:1036-1040)
+// Same affine suffix scan as GAE, with a position-dependent multiplier c_t = gamma * mask_{t+1}.
+template <int kMaskType>
+__global__ void __launch_bounds__(kGaeThreads)
+rpp_scan_kernel(const float* __restrict__ rewards, const void* __restrict__ mask, float* __restrict__ returns,
+                double* __restrict__ row_stats, int64_t A, float gamma) {
+    __shared__ float s_val[kGaeThreads * kGaePitch];
+    __shared__ float s_mul[kGaeThreads * kGaePitch];
+    __shared__ double s_wmul[kGaeThreads / 32], s_wadd[kGaeThreads / 32];
+    __shared__ double s_carry;
+    __shared__ double sh_d[34];
+    const int row = blockIdx.x;
+    const int64_t base = static_cast<int64_t>(row) * A;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double sum_m = 0.0, sum_mx = 0.0, sum_mxx = 0.0;
+    if (tid == 0) s_carry = 0.0;
+    const int64_t num_tiles = (A + kGaeTile - 1) / kGaeTile;
+    for (int64_t tile = num_tiles - 1; tile >= 0; --tile) {
+        const int64_t t0 = tile * kGaeTile;
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < kGaePer; ++k) {
+            const int p = k * kGaeThreads + tid;
+            const int64_t t = t0 + p;
+            float d = 0.f, c = 0.f;
+            if (t < A) {
+                d = rewards[base + t];
+                c = (t + 1 < A) ? gamma * mask_at<kMaskType>(mask, base + t + 1) : 0.f;
+            }
+            const int o = (p / kGaePer) * kGaePitch + (p % kGaePer);
+            s_val[o] = d;
+            s_mul[o] = c;
+        }
+        __syncthreads();
+        double x[kGaePer], pr[kGaePer];  // local scan and the product of multipliers from j to the segment end
+        {
+            double run = 0.0, prod = 1.0;
+#pragma unroll
+            for (int j = kGaePer - 1; j >= 0; --j) {
+                const double c = static_cast<double>(s_mul[tid * kGaePitch + j]);
+                run = static_cast<double>(s_val[tid * kGaePitch + j]) + c * run;
+                prod *= c;
+                x[j] = run;
+                pr[j] = prod;
+            }
+        }
+        Affine incl;
+        incl.mul = pr[0];
+        incl.add = x[0];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double om = __shfl_down_sync(0xffffffffu, incl.mul, o);
+            const double oa = __shfl_down_sync(0xffffffffu, incl.add, o);
+            if (lane + o < 32) {
+                Affine right;
+                right.mul = om;
+                right.add = oa;
+                incl = compose_left_of(incl, right);
+            }
+        }
+        if (lane == 0) {
+            s_wmul[warp] = incl.mul;
+            s_wadd[warp] = incl.add;
+        }
+        __syncthreads();
+        double cin = s_carry;
+        for (int w = kGaeThreads / 32 - 1; w > warp; --w) cin = s_wmul[w] * cin + s_wadd[w];
+        const double nm = __shfl_down_sync(0xffffffffu, incl.mul, 1);
+        const double na = __shfl_down_sync(0xffffffffu, incl.add, 1);
+        const double my_cin = (lane == 31) ? cin : (nm * cin + na);
+        __syncthreads();
+        if (tid == 0) s_carry = s_wmul[0] * cin + s_wadd[0];
+#pragma unroll
+        for (int j = 0; j < kGaePer; ++j) s_val[tid * kGaePitch + j] = static_cast<float>(x[j] + pr[j] * my_cin);
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < kGaePer; ++k) {
+            const int p = k * kGaeThreads + tid;
+            const int64_t t = t0 + p;
+            if (t < A) {
+                const float a = s_val[(p / kGaePer) * kGaePitch + (p % kGaePer)];
+                returns[base + t] = a;
+                const double m = static_cast<double>(mask_at<kMaskType>(mask, base + t));
+                const double ad = static_cast<double>(a);
+                sum_m += m;
+                sum_mx += m * ad;
+                sum_mxx += m * ad * ad;
+            }
+        }
+    }
+    sum_m = block_sum(sum_m, sh_d);
+    sum_mx = block_sum(sum_mx, sh_d);
+    sum_mxx = block_sum(sum_mxx, sh_d);
+    if (tid == 0) {
+        row_stats[3 * row + 0] = sum_m;
+        row_stats[3 * row + 1] = sum_mx;
+        row_stats[3 * row + 2] = sum_mxx;
+    }
+}
+
+// out = (x - mean) * rstd * mask      (REINFORCE++: whitened returns re-masked, ppo_utils.py:1042-1043)
+template <int kMaskType>
+__global__ void __launch_bounds__(256)
+whiten_masked_kernel(const float* __restrict__ x, const void* __restrict__ mask, const float* __restrict__ stats,
+                     float* __restrict__ out, int64_t n) {
+    const float mean = stats[1], rstd = stats[3];
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        out[i] = (x[i] - mean) * rstd * mask_at<kMaskType>(mask, i);
+}
+
+// ------------------------------------------------------------------------------------------ batch normalisation
+// normalize_advantages_dict (ppo_utils.py:127-145): mean over ALL positions (unmasked), variance over the mask.
+// moments: {sum x, sum m, sum m*x, sum m*x*x}
+template <int kMaskType>
+__global__ void __launch_bounds__(256)
+adv_moments_kernel(const float* __restrict__ x, const void* __restrict__ mask, double* __restrict__ partials,
+                   int64_t n) {
+    __shared__ double sh_d[34];
+    double sx = 0.0, sm = 0.0, smx = 0.0, smxx = 0.0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const double v = static_cast<double>(x[i]);
+        const double m = static_cast<double>(mask_at<kMaskType>(mask, i));
+        sx += v;
+        sm += m;
+        smx += m * v;
+        smxx += m * v * v;
+    }
+    sx = block_sum(sx, sh_d);
+    sm = block_sum(sm, sh_d);
+    smx = block_sum(smx, sh_d);
+    smxx = block_sum(smxx, sh_d);
+    if (threadIdx.x == 0) {
+        partials[4 * blockIdx.x + 0] = sx;
+        partials[4 * blockIdx.x + 1] = sm;
+        partials[4 * blockIdx.x + 2] = smx;
+        partials[4 * blockIdx.x + 3] = smxx;
+    }
+}
+__global__ void __launch_bounds__(256) adv_norm_stats_kernel(const double* __restrict__ partials, int nblk, int64_t n,
+                                                             float* __restrict__ stats_out) {
+    __shared__ double sh_d[34];
+    double sx = 0.0, sm = 0.0, smx = 0.0, smxx = 0.0;
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+        sx += partials[4 * i + 0];
+        sm += partials[4 * i + 1];
+        smx += partials[4 * i + 2];
+        smxx += partials[4 * i + 3];
+    }
+    sx = block_sum(sx, sh_d);
+    sm = block_sum(sm, sh_d);
+    smx = block_sum(smx, sh_d);
+    smxx = block_sum(smxx, sh_d);
+    if (threadIdx.x == 0) {
+        const double mean = sx / static_cast<double>(n);
+        const double ss = smxx - 2.0 * mean * smx + mean * mean * sm;  // sum m*(x - mean)^2
+        const float var = static_cast<float>(ss) / static_cast<float>(sm);  // no clamp on the count (reference)
+        const float rstd = rsqrtf(fmaxf(var, 1e-8f));
+        stats_out[0] = static_cast<float>(sm);
+        stats_out[1] = static_cast<float>(mean);
+        stats_out[2] = var;
+        stats_out[3] = rstd;
+    }
+}
+__global__ void __launch_bounds__(256) affine_out_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                                         float* __restrict__ out, int64_t n) {
+    const float mean = stats[1], rstd = stats[3];
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        out[i] = (x[i] - mean) * rstd;
+}
+
 // ------------------------------------------------------------------------------------------ KL in reward
 
 __device__ __forceinline__ float kl_value(float lp, float base, int type) {
@@ -465,4 +639,75 @@ extern "C" int skyb200_reward_kl_penalty(const float* log_probs, const float* ba
     if (rc) return rc;
     row_means_kernel<<<1, 256, 0, stream>>>(row_ws, row_ws + B, (int)B, metrics_out);
     return check_launch("row_means_kernel");
+}
+
+static int grid_cap(int64_t n, int per_sm) {
+    int64_t b = (n + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+extern "C" int skyb200_reinforce_pp_advantage(const float* rewards, const void* response_mask, int32_t mask_type,
+                                              float* advantages, float* returns, float* stats_out, void* workspace,
+                                              size_t workspace_bytes, int64_t B, int64_t A, float gamma,
+                                              void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(rewards && response_mask && advantages && returns && stats_out && workspace, "null pointer");
+    SKYB200_REQUIRE(mask_type == SKYB200_MASK_F32 || mask_type == SKYB200_MASK_I64, "bad mask_type");
+    SKYB200_REQUIRE(B > 0 && A > 0 && B < (1ll << 31), "bad shape");
+    if (workspace_bytes < skyb200_gae_workspace(B)) return fail(SKYB200_EWORKSPACE, "workspace too small");
+    uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+    double* row_stats = reinterpret_cast<double*>(base);
+    double* moments = row_stats + 3 * B;
+    const int64_t n = B * A;
+    if (mask_type == SKYB200_MASK_F32)
+        rpp_scan_kernel<SKYB200_MASK_F32><<<(unsigned)B, kGaeThreads, 0, stream>>>(rewards, response_mask, returns,
+                                                                                  row_stats, A, gamma);
+    else
+        rpp_scan_kernel<SKYB200_MASK_I64><<<(unsigned)B, kGaeThreads, 0, stream>>>(rewards, response_mask, returns,
+                                                                                  row_stats, A, gamma);
+    int rc = check_launch("rpp_scan_kernel");
+    if (rc) return rc;
+    fold_moments_kernel<<<1, 256, 0, stream>>>(row_stats, (int)B, moments);
+    rc = check_launch("fold_moments_kernel");
+    if (rc) return rc;
+    whiten_stats_kernel<<<1, 32, 0, stream>>>(moments, stats_out);
+    rc = check_launch("whiten_stats_kernel");
+    if (rc) return rc;
+    if (mask_type == SKYB200_MASK_F32)
+        whiten_masked_kernel<SKYB200_MASK_F32><<<grid_cap(n, 8), 256, 0, stream>>>(returns, response_mask, stats_out,
+                                                                                  advantages, n);
+    else
+        whiten_masked_kernel<SKYB200_MASK_I64><<<grid_cap(n, 8), 256, 0, stream>>>(returns, response_mask, stats_out,
+                                                                                  advantages, n);
+    return check_launch("whiten_masked_kernel");
+}
+
+extern "C" size_t skyb200_normalize_advantages_workspace(void) { return (size_t)(148 * 8 * 4 * sizeof(double) * 2 + 512); }
+
+extern "C" int skyb200_normalize_advantages(const float* advantages, const void* response_mask, int32_t mask_type,
+                                            float* out, float* stats_out, void* workspace, size_t workspace_bytes,
+                                            int64_t n, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(advantages && response_mask && out && stats_out && workspace, "null pointer");
+    SKYB200_REQUIRE(mask_type == SKYB200_MASK_F32 || mask_type == SKYB200_MASK_I64, "bad mask_type");
+    SKYB200_REQUIRE(n > 0, "empty input");
+    if (workspace_bytes < skyb200_normalize_advantages_workspace())
+        return fail(SKYB200_EWORKSPACE, "workspace too small");
+    double* partials = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    int nblk = grid_cap(n, 8);
+    if (nblk > 148 * 8) nblk = 148 * 8;
+    if (mask_type == SKYB200_MASK_F32)
+        adv_moments_kernel<SKYB200_MASK_F32><<<nblk, 256, 0, stream>>>(advantages, response_mask, partials, n);
+    else
+        adv_moments_kernel<SKYB200_MASK_I64><<<nblk, 256, 0, stream>>>(advantages, response_mask, partials, n);
+    int rc = check_launch("adv_moments_kernel");
+    if (rc) return rc;
+    adv_norm_stats_kernel<<<1, 256, 0, stream>>>(partials, nblk, n, stats_out);
+    rc = check_launch("adv_norm_stats_kernel");
+    if (rc) return rc;
+    affine_out_kernel<<<grid_cap(n, 8), 256, 0, stream>>>(advantages, stats_out, out, n);
+    return check_launch("affine_out_kernel");
 }

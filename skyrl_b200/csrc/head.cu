@@ -13,8 +13,10 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "gemm_sm100.cuh"
@@ -140,6 +142,19 @@ static int64_t pick_chunk(int64_t N, int64_t chunk) {
     return std::max<int64_t>(chunk, kTileM);
 }
 static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    if (v == nullptr || *v == 0) return dflt;
+    const int x = atoi(v);
+    return x > 0 ? x : dflt;
+}
+// tile-order group sizes (tunable for experiments; defaults measured on the 7B head)
+static int fwd_group_m() { static int v = env_int("SKYB200_FWD_GROUP_M", 16); return v; }
+static int dh_group_m() { static int v = env_int("SKYB200_DH_GROUP_M", 5); return v; }
+static int dw_group_n() { static int v = env_int("SKYB200_DW_GROUP_N", 7); return v; }
+
+
 static int64_t num_slabs(int64_t V) { return (V + kHeadBN - 1) / kHeadBN; }
 
 // ------------------------------------------------------------------------------------------ merge kernel
@@ -382,7 +397,7 @@ extern "C" int skyb200_head_forward(const void* hidden, const void* weight, cons
         // a label outside [0, V) never matches a slab: give it a defined (zero) logit
         SKYB200_CUDA_CHECK(cudaMemsetAsync(label_acc, 0, (size_t)rows * sizeof(float), stream));
         rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
-            hid + r0 * H, H, weight, H, rows, (int)V, (int)H, 16, ep, stream);
+            hid + r0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream);
         if (rc) return rc;
         head_merge_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(
             part_m, part_s, part_t, c, slabs, label_acc, entropy_mask ? entropy_mask + r0 : nullptr, inv_T,
@@ -435,7 +450,7 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
         ed.dS = dS;
         ed.ld = ldS;
         rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiDLogits>(
-            hid + r0 * H, H, weight, H, rows, (int)V, (int)H, 16, ed, stream);
+            hid + r0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ed, stream);
         if (rc) return rc;
         // (2) d_hidden[rows, H] = dS[rows, V] * W[V, H]      (A K-major, B MN-major)
         if (dhid != nullptr) {
@@ -443,7 +458,7 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
             eh.C = dhid + r0 * H;
             eh.ldc = H;
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
-                dS, ldS, weight, H, rows, (int)H, (int)V, 5, eh, stream);
+                dS, ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream);
             if (rc) return rc;
         }
         // (3) d_weight[V, H] (+)= dS^T[V, rows] * hidden[rows, H]   (both MN-major)
@@ -453,7 +468,7 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
             ew.ldc = H;
             ew.accumulate = (accumulate != 0 || r0 > 0) ? 1 : 0;
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
-                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, 7, ew, stream, 1);
+                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1);
             if (rc) return rc;
         }
     }
@@ -464,10 +479,13 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
 namespace {
 
 struct StepPlan {
-    int64_t chunk;     // tokens per chunk (multiple of 256)
-    int64_t ldS;       // pitch of the bf16 logits / d_logits store
+    int64_t chunk;  // tokens per chunk (multiple of 256)
+    int64_t ldS;    // pitch of the bf16 logits / d_logits store
     int slabs;
-    size_t off_part, off_label, off_lse2, off_entraw, off_dlp, off_dent, off_S, off_loss, total;
+    // everything below exists twice (parity of the chunk index): the small kernels of chunk c+1 run on the
+    // auxiliary stream while the backward GEMMs of chunk c run on the caller's stream
+    size_t off_part[2], off_label[2], off_lse2[2], off_entraw[2], off_dlp[2], off_dent[2], off_S[2];
+    size_t off_loss, total;
 };
 
 int64_t gcd64(int64_t a, int64_t b) { return b == 0 ? a : gcd64(b, a % b); }
@@ -478,7 +496,6 @@ StepPlan plan_step(int64_t B, int64_t A, int64_t H, int64_t V, int loss_type, bo
     const int64_t N = B * A;
     int64_t chunk = kDefaultChunk;
     if (loss_type == SKYB200_LOSS_GSPO) {
-        // smallest multiple of A that is also a multiple of 256 tokens, repeated up to ~24K tokens
         const int64_t unit = A / gcd64(A, kTileM) * kTileM;  // lcm(A, 256)
         chunk = unit * std::max<int64_t>(1, (3 * kDefaultChunk / 2) / unit);
     }
@@ -492,17 +509,40 @@ StepPlan plan_step(int64_t B, int64_t A, int64_t H, int64_t V, int loss_type, bo
         off += (bytes + 255) / 256 * 256;
         return o;
     };
-    p.off_part = take((size_t)3 * p.slabs * chunk * 4);
-    p.off_label = take((size_t)chunk * 4);
-    p.off_lse2 = take((size_t)chunk * 4);
-    p.off_entraw = take((size_t)chunk * 4);
-    p.off_dlp = take((size_t)chunk * 4);
-    p.off_dent = take((size_t)chunk * 4);
-    p.off_S = take(need_grad ? (size_t)chunk * p.ldS * 2 : 0);
+    for (int i = 0; i < 2; ++i) {
+        p.off_part[i] = take((size_t)3 * p.slabs * chunk * 4);
+        p.off_label[i] = take((size_t)chunk * 4);
+        p.off_lse2[i] = take((size_t)chunk * 4);
+        p.off_entraw[i] = take((size_t)chunk * 4);
+        p.off_dlp[i] = take((size_t)chunk * 4);
+        p.off_dent[i] = take((size_t)chunk * 4);
+        p.off_S[i] = take(need_grad ? (size_t)chunk * p.ldS * 2 : 0);
+    }
     p.off_loss = take(loss_chunk_ws_bytes(B, A) + (size_t)(N / chunk + 2) * 8 * 4 * 4);
     p.total = off + 512;
     (void)H;
     return p;
+}
+
+// One auxiliary stream + a few events per device, created on first use.
+struct StepStreams {
+    cudaStream_t aux = nullptr;
+    cudaEvent_t start = nullptr, fwd[2] = {nullptr, nullptr}, mid[2] = {nullptr, nullptr};
+    bool ok = false;
+};
+StepStreams* step_streams() {
+    static StepStreams per_dev[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    StepStreams& s = per_dev[dev];
+    if (!s.ok) {
+        if (cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEvent_t* evs[5] = {&s.start, &s.fwd[0], &s.fwd[1], &s.mid[0], &s.mid[1]};
+        for (auto* e : evs)
+            if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        s.ok = true;
+    }
+    return &s;
 }
 
 }  // namespace
@@ -538,93 +578,147 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
     if (workspace_bytes < plan.total) return fail(SKYB200_EWORKSPACE, "policy_step workspace too small");
     int rc = skyb200_check_device();
     if (rc) return rc;
+    StepStreams* ss = step_streams();
+    if (ss == nullptr) return fail(SKYB200_ECUDA, "could not create the auxiliary stream / events");
+    cudaStream_t aux = ss->aux;
 
     char* wb = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     const int64_t c = plan.chunk;
-    float* part_m = reinterpret_cast<float*>(wb + plan.off_part);
-    float* part_s = part_m + (int64_t)plan.slabs * c;
-    float* part_t = part_s + (int64_t)plan.slabs * c;
-    float* label_acc = reinterpret_cast<float*>(wb + plan.off_label);
-    float* lse2 = reinterpret_cast<float*>(wb + plan.off_lse2);
-    float* ent_raw = reinterpret_cast<float*>(wb + plan.off_entraw);
-    float* d_lp = reinterpret_cast<float*>(wb + plan.off_dlp);
-    float* d_ent = reinterpret_cast<float*>(wb + plan.off_dent);
-    __nv_bfloat16* S = reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S);
     LossChunkWs lws;
     loss_chunk_ws_carve(wb + plan.off_loss, B, A, &lws);
-
     const float inv_T = 1.0f / temperature;
     const float scale_log2 = 1.4426950408889634f * inv_T;
     const __nv_bfloat16* hid = static_cast<const __nv_bfloat16*>(hidden);
     __nv_bfloat16* dhid = static_cast<__nv_bfloat16*>(d_hidden);
     const bool use_ent_grad = need_grad && params->use_entropy_loss != 0;
+    const int64_t n_chunks = (N + c - 1) / c;
 
-    rc = loss_prepass(loss_mask, lws, B, A, stream);
-    if (rc) return rc;
+    auto fptr = [&](size_t off) { return reinterpret_cast<float*>(wb + off); };
 
-    int64_t slot = 0;
-    for (int64_t t0 = 0; t0 < N; t0 += c) {
+    // ---- stage A (caller's stream): logits tiles -> online-softmax partials (+ bf16 copy of the tile)
+    auto issue_fwd = [&](int64_t ci) -> int {
+        const int p = (int)(ci & 1);
+        const int64_t t0 = ci * c;
         const int rows = (int)std::min<int64_t>(c, N - t0);
-        // (1) logits tiles -> online-softmax partials (+ bf16 copy of the tile when a backward follows)
+        float* part_m = fptr(plan.off_part[p]);
         EpiLsePartials::Params ep;
         ep.scale_log2 = scale_log2;
         ep.part_m = part_m;
-        ep.part_s = part_s;
-        ep.part_t = part_t;
+        ep.part_s = part_m + (int64_t)plan.slabs * c;
+        ep.part_t = part_m + 2 * (int64_t)plan.slabs * c;
         ep.ld = c;
         ep.labels = labels + t0;
-        ep.label_acc = label_acc;
-        ep.logits = need_grad ? S : nullptr;
+        ep.label_acc = fptr(plan.off_label[p]);
+        ep.logits = need_grad ? reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]) : nullptr;
         ep.ld_logits = plan.ldS;
-        SKYB200_CUDA_CHECK(cudaMemsetAsync(label_acc, 0, (size_t)rows * sizeof(float), stream));
-        rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
-            hid + t0 * H, H, weight, H, rows, (int)V, (int)H, 16, ep, stream);
-        if (rc) return rc;
-        head_merge_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(
-            part_m, part_s, part_t, c, plan.slabs, label_acc, entropy_mask ? entropy_mask + t0 : nullptr, inv_T,
-            log_probs + t0, entropy + t0, ent_raw, lse2, rows);
-        rc = check_launch("head_merge_kernel");
-        if (rc) return rc;
-        // (2) loss of this token range (normalisers come from the mask-only pre-pass)
+        // the parity buffers were last read by the auxiliary-stream kernels of chunk ci - 2
+        if (ci >= 2) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[p], 0));
+        SKYB200_CUDA_CHECK(cudaMemsetAsync(ep.label_acc, 0, (size_t)rows * sizeof(float), stream));
+        int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
+            hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream);
+        if (r) return r;
+        SKYB200_CUDA_CHECK(cudaEventRecord(ss->fwd[p], stream));
+        return SKYB200_OK;
+    };
+    // ---- stage B (auxiliary stream, overlaps the GEMMs): merge -> loss of the token range -> d(logits) in place
+    auto issue_mid = [&](int64_t ci, int64_t slot) -> int {
+        const int p = (int)(ci & 1);
+        const int64_t t0 = ci * c;
+        const int rows = (int)std::min<int64_t>(c, N - t0);
+        float* part_m = fptr(plan.off_part[p]);
+        float* lse2 = fptr(plan.off_lse2[p]);
+        float* ent_raw = fptr(plan.off_entraw[p]);
+        float* d_lp = fptr(plan.off_dlp[p]);
+        float* d_ent = fptr(plan.off_dent[p]);
+        SKYB200_CUDA_CHECK(cudaStreamWaitEvent(aux, ss->fwd[p], 0));
+        head_merge_kernel<<<(rows + 255) / 256, 256, 0, aux>>>(
+            part_m, part_m + (int64_t)plan.slabs * c, part_m + 2 * (int64_t)plan.slabs * c, c, plan.slabs,
+            fptr(plan.off_label[p]), entropy_mask ? entropy_mask + t0 : nullptr, inv_T, log_probs + t0, entropy + t0,
+            ent_raw, lse2, rows);
+        int r = check_launch("head_merge_kernel");
+        if (r) return r;
         if (params->loss_type == SKYB200_LOSS_GSPO) {
-            rc = loss_row_logratio(log_probs, old_log_probs, loss_mask, lws, t0 / A, rows / A, A, stream);
-            if (rc) return rc;
+            r = loss_row_logratio(log_probs, old_log_probs, loss_mask, lws, t0 / A, rows / A, A, aux);
+            if (r) return r;
         }
-        rc = loss_flat_range(log_probs, old_log_probs, advantages, loss_mask, base_log_probs, entropy,
-                             need_grad ? d_lp - t0 : nullptr, use_ent_grad ? d_ent - t0 : nullptr, lws, B, A, t0,
-                             t0 + rows, slot, *params, stream);
-        if (rc) return rc;
-        slot += loss_chunk_blocks(rows);
-        if (!need_grad) continue;
-        // (3) stored logits -> d(logits), in place
-        {
+        r = loss_flat_range(log_probs, old_log_probs, advantages, loss_mask, base_log_probs, entropy,
+                            need_grad ? d_lp - t0 : nullptr, use_ent_grad ? d_ent - t0 : nullptr, lws, B, A, t0,
+                            t0 + rows, slot, *params, aux);
+        if (r) return r;
+        if (need_grad) {
             const dim3 grid((unsigned)((V + 4095) / 4096), (unsigned)rows);
-            dlogits_transform_kernel<<<grid, 256, 0, stream>>>(
-                S, plan.ldS, (int)V, lse2, d_lp, use_ent_grad ? d_ent : nullptr,
-                (use_ent_grad && entropy_mask) ? entropy_mask + t0 : nullptr, ent_raw, labels + t0, scale_log2, inv_T);
-            rc = check_launch("dlogits_transform_kernel");
-            if (rc) return rc;
+            dlogits_transform_kernel<<<grid, 256, 0, aux>>>(
+                reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]), plan.ldS, (int)V, lse2, d_lp,
+                use_ent_grad ? d_ent : nullptr, (use_ent_grad && entropy_mask) ? entropy_mask + t0 : nullptr, ent_raw,
+                labels + t0, scale_log2, inv_T);
+            r = check_launch("dlogits_transform_kernel");
+            if (r) return r;
         }
-        // (4) d_hidden = dS * W ; (5) d_weight (+)= dS^T * hidden
+        SKYB200_CUDA_CHECK(cudaEventRecord(ss->mid[p], aux));
+        return SKYB200_OK;
+    };
+    // ---- stage C (caller's stream): d_hidden = dS * W ; d_weight (+)= dS^T * hidden
+    auto issue_bwd = [&](int64_t ci) -> int {
+        const int p = (int)(ci & 1);
+        const int64_t t0 = ci * c;
+        const int rows = (int)std::min<int64_t>(c, N - t0);
+        __nv_bfloat16* S = reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]);
+        SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[p], 0));
         if (dhid != nullptr) {
             EpiStoreBF16::Params eh;
             eh.C = dhid + t0 * H;
             eh.ldc = H;
-            rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
-                S, plan.ldS, weight, H, rows, (int)H, (int)V, 5, eh, stream);
-            if (rc) return rc;
+            int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
+                S, plan.ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream);
+            if (r) return r;
         }
         if (d_weight != nullptr) {
             EpiStoreF32::Params ew;
             ew.C = d_weight;
             ew.ldc = H;
             ew.accumulate = (accumulate != 0 || t0 > 0) ? 1 : 0;
-            rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
-                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, 7, ew, stream, 1);
+            int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
+                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1);
+            if (r) return r;
+        }
+        return SKYB200_OK;
+    };
+
+    // the auxiliary stream starts after everything already queued on the caller's stream (inputs are ready)
+    rc = loss_prepass(loss_mask, lws, B, A, stream);
+    if (rc) return rc;
+    SKYB200_CUDA_CHECK(cudaEventRecord(ss->start, stream));
+    SKYB200_CUDA_CHECK(cudaStreamWaitEvent(aux, ss->start, 0));
+
+    std::vector<int64_t> slot_of(n_chunks);
+    {
+        int64_t slot = 0;
+        for (int64_t ci = 0; ci < n_chunks; ++ci) {
+            slot_of[ci] = slot;
+            slot += loss_chunk_blocks(std::min<int64_t>(c, N - ci * c));
+        }
+    }
+    rc = issue_fwd(0);
+    if (rc) return rc;
+    rc = issue_mid(0, slot_of[0]);
+    if (rc) return rc;
+    for (int64_t ci = 0; ci < n_chunks; ++ci) {
+        if (ci + 1 < n_chunks) {
+            rc = issue_fwd(ci + 1);
+            if (rc) return rc;
+            rc = issue_mid(ci + 1, slot_of[ci + 1]);
+            if (rc) return rc;
+        }
+        if (need_grad) {
+            rc = issue_bwd(ci);
             if (rc) return rc;
         }
     }
-    return loss_finalize(lws, slot, true, stats, *params, stream);
+    // join: the caller's stream continues only after the last auxiliary-stream work
+    SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[(n_chunks - 1) & 1], 0));
+    if (n_chunks > 1) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[(n_chunks - 2) & 1], 0));
+    const int64_t total_slots = slot_of[n_chunks - 1] + loss_chunk_blocks(std::min<int64_t>(c, N - (n_chunks - 1) * c));
+    return loss_finalize(lws, total_slots, true, stats, *params, stream);
 }
 
 extern "C" int skyb200_logits_logprob_entropy(const void* logits, int32_t logits_dtype, const int64_t* labels,

@@ -589,6 +589,92 @@ int loss_finalize(const LossChunkWs& ws, int64_t nslots, bool has_entropy, float
     return check_launch("loss_finalize_kernel");
 }
 
+// ---------------------------------------------------------------------------- critic (value) loss
+// ppo_critic_loss (ppo_utils.py:175-193): 0.5 * mean_b masked_mean_t max((clip(v) - R)^2, (v - R)^2),
+// clipfrac = masked_mean(1[surr1 > surr2]) over the whole batch.  Forward + d loss / d values in one pass.
+struct CriticArgs {
+    const float* values;
+    const float* old_values;
+    const float* returns;
+    const float* mask;
+    float* d_values;
+    float* stats;  // [0] loss, [1] clipfrac, [2] mask_sum
+    LossWs ws;
+    int B;
+    int64_t A;
+    float value_clip;
+    int use_clip;
+};
+
+__global__ void __launch_bounds__(kLossThreads) critic_main_kernel(CriticArgs a) {
+    __shared__ float sh[34];
+    __shared__ bool is_last;
+    const int row = blockIdx.y;
+    const int64_t rbase = static_cast<int64_t>(row) * a.A;
+    const float total_m = __ldcg(a.ws.total_msum);
+    const float row_m = a.mask ? __ldcg(&a.ws.row_msum[row]) : static_cast<float>(a.A);
+    const float w_row = 0.5f / (fmaxf(row_m, 1.f) * static_cast<float>(a.B));
+    float s_loss = 0.f, s_clip = 0.f;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * kLossTile;
+#pragma unroll 4
+    for (int it = 0; it < kLossIters * kLossVec; ++it) {
+        const int64_t t = t0 + static_cast<int64_t>(it) * kLossThreads + threadIdx.x;
+        if (t < a.A) {
+            const int64_t i = rbase + t;
+            const float v = a.values[i], R = a.returns[i];
+            const float m = a.mask ? a.mask[i] : 1.f;
+            const float e2 = v - R;
+            float loss = e2 * e2, g = 2.f * e2;
+            if (a.use_clip) {
+                const float ov = a.old_values[i];
+                const float dv = v - ov;
+                const float vc = ov + fminf(fmaxf(dv, -a.value_clip), a.value_clip);
+                const float pass = (dv >= -a.value_clip && dv <= a.value_clip) ? 1.f : 0.f;
+                const float e1 = vc - R;
+                const float s1 = e1 * e1, s2 = e2 * e2;
+                const float g1 = 2.f * e1 * pass, g2 = 2.f * e2;
+                loss = fmaxf(s1, s2);
+                g = (s1 > s2) ? g1 : ((s1 < s2) ? g2 : 0.5f * (g1 + g2));  // torch.max splits ties 50/50
+                s_clip = fmaf((s1 > s2) ? 1.f : 0.f, m, s_clip);
+            }
+            const float w = m * w_row;
+            s_loss = fmaf(loss, w, s_loss);
+            if (a.d_values) a.d_values[i] = g * w;
+        }
+    }
+    const int nblk = gridDim.x * gridDim.y;
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    s_loss = block_sum(s_loss, sh);
+    s_clip = block_sum(s_clip, sh);
+    if (threadIdx.x == 0) {
+        float* p = a.ws.partials + static_cast<int64_t>(blk) * kNumPartials;
+        p[0] = s_loss;
+        p[1] = s_clip;
+        __threadfence();
+        const unsigned int prev = atomicAdd(a.ws.counters + 1, 1u);
+        is_last = (prev == static_cast<unsigned int>(nblk) - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    float f_loss = 0.f, f_clip = 0.f;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+        const float* p = a.ws.partials + static_cast<int64_t>(b) * kNumPartials;
+        f_loss += __ldcg(p + 0);
+        f_clip += __ldcg(p + 1);
+    }
+    f_loss = block_sum(f_loss, sh);
+    f_clip = block_sum(f_clip, sh);
+    if (threadIdx.x == 0) {
+        const float denom = a.mask ? fmaxf(total_m, 1.f) : static_cast<float>(a.B) * static_cast<float>(a.A);
+        a.stats[0] = f_loss;
+        a.stats[1] = f_clip / denom;
+        a.stats[2] = total_m;
+        a.stats[3] = 0.f;
+        a.ws.counters[1] = 0u;
+    }
+}
+
 // ---------------------------------------------------------------------------- small helpers
 __global__ void scale_inplace_kernel(float* __restrict__ x, const float* __restrict__ s, int64_t n) {
     const float k = __ldg(s);
@@ -731,4 +817,39 @@ extern "C" int skyb200_approx_kl(const float* log_probs, const float* base_log_p
     SKYB200_REQUIRE(kl_type >= 0 && kl_type <= SKYB200_KL_K3, "Invalid KL estimator type");
     approx_kl_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(log_probs, base_log_probs, loss_mask, out, n, kl_type);
     return check_launch("approx_kl_kernel");
+}
+
+extern "C" int skyb200_critic_loss(const float* values, const float* old_values, const float* returns,
+                                   const float* loss_mask, float* d_values, float* stats, void* workspace,
+                                   size_t workspace_bytes, int64_t B, int64_t A, float value_clip, int32_t use_clip,
+                                   void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(values && returns && stats && workspace, "null pointer");
+    SKYB200_REQUIRE(!use_clip || old_values != nullptr, "value clipping needs old_values");
+    SKYB200_REQUIRE(B > 0 && A > 0 && B < 65536, "need 0 < B < 65536 and A > 0");
+    if (workspace_bytes < skyb200_policy_loss_workspace(B, A))
+        return fail(SKYB200_EWORKSPACE, "critic_loss workspace too small");
+    LossWs ws;
+    char* wbase = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    loss_ws_layout(B, A, &ws, wbase);
+    SKYB200_CUDA_CHECK(cudaMemsetAsync(ws.counters, 0, 16, stream));
+    loss_rowstats_kernel<<<(unsigned)B, kLossThreads, 0, stream>>>(nullptr, nullptr, loss_mask, ws.row_msum, ws.row_lw,
+                                                                   ws.total_msum, ws.counters, (int)B, A, 0);
+    int rc = check_launch("loss_rowstats_kernel");
+    if (rc) return rc;
+    CriticArgs a;
+    a.values = values;
+    a.old_values = old_values;
+    a.returns = returns;
+    a.mask = loss_mask;
+    a.d_values = d_values;
+    a.stats = stats;
+    a.ws = ws;
+    a.B = (int)B;
+    a.A = A;
+    a.value_clip = value_clip;
+    a.use_clip = use_clip;
+    const unsigned chunks = (unsigned)((A + kLossTile - 1) / kLossTile);
+    critic_main_kernel<<<dim3(chunks, (unsigned)B), kLossThreads, 0, stream>>>(a);
+    return check_launch("critic_main_kernel");
 }

@@ -189,6 +189,55 @@ def gspo_policy_loss(
     return _registry_loss("gspo", log_probs, old_log_probs, advantages, config, loss_mask, rollout_logprobs)
 
 
+class _CriticLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, values, old_values, returns, loss_mask, value_clip):
+        if not values.is_cuda:
+            raise RuntimeError("skyrl_b200 critic loss needs CUDA tensors (no CPU fallback)")
+        lib = _lib.load()
+        v = _prep(values, values)
+        ov = _prep(old_values, v)
+        ret = _prep(returns, v)
+        mask = _prep(loss_mask, v)
+        B, A = v.shape
+        with torch.cuda.device(v.device):
+            stats = torch.empty(4, dtype=torch.float32, device=v.device)
+            d_v = torch.empty_like(v)
+            ws_bytes = lib.skyb200_policy_loss_workspace(B, A)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device)
+            use_clip = value_clip is not None
+            _lib.check(
+                lib.skyb200_critic_loss(_lib.ptr(v), _lib.ptr(ov), _lib.ptr(ret), _lib.ptr(mask), _lib.ptr(d_v),
+                                        _lib.ptr(stats), _lib.ptr(ws), ws_bytes, B, A,
+                                        float(value_clip) if use_clip else 0.0, int(use_clip), _lib.stream_ptr()),
+                "skyb200_critic_loss",
+            )
+        ctx.save_for_backward(d_v)
+        ctx.in_dtype = values.dtype
+        ctx.mark_non_differentiable(stats)
+        return stats[0].clone(), stats
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_stats):
+        (d_v,) = ctx.saved_tensors
+        g = _scale_by_upstream(d_v.clone(), g_loss)
+        return (g if g.dtype == ctx.in_dtype else g.to(ctx.in_dtype)), None, None, None, None
+
+
+def ppo_critic_loss(
+    values: torch.Tensor,
+    old_values: torch.Tensor,
+    returns: torch.Tensor,
+    config,
+    loss_mask: Optional[torch.Tensor] = None,
+):
+    """Clipped value loss (reference: ppo_utils.py:175-193). Returns ``(0.5 * loss, clipfrac or None)``."""
+    value_clip = _cfg(config, "value_clip", None)
+    loss, stats = _CriticLossFn.apply(values, old_values, returns, loss_mask, value_clip)
+    clipfrac = float(stats[1].item()) if value_clip is not None else None
+    return loss, clipfrac
+
+
 def policy_update_loss(
     log_probs: torch.Tensor,
     old_log_probs: torch.Tensor,

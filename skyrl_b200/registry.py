@@ -182,7 +182,7 @@ class PolicyLossType(StrEnum):
 
 
 class AdvantageEstimatorRegistry(BaseFunctionRegistry):
-    """B200 estimators: ``grpo``, ``rloo``, ``gae`` (ppo_utils.py:425-460 registers the same names)."""
+    """B200 estimators: ``grpo``, ``rloo``, ``gae``, ``reinforce++`` (the names ppo_utils.py:425-460 registers)."""
 
     _actor_name = "advantage_estimator_registry"
     _function_type = "advantage estimator"
@@ -196,6 +196,7 @@ class AdvantageEstimatorRegistry(BaseFunctionRegistry):
             ("grpo", adv.compute_grpo_outcome_advantage),
             ("gae", adv.compute_gae_advantage_return),
             ("rloo", adv.compute_rloo_outcome_advantage),
+            ("reinforce++", adv.compute_reinforce_plus_plus_outcome_advantage),
         ):
             if name not in have:
                 cls.register(name, fn)
@@ -279,7 +280,8 @@ def install_into_skyrl_train(patch_model_wrapper: bool = True) -> List[str]:
     for reg, table in (
         (pu.AdvantageEstimatorRegistry, {"grpo": adv.compute_grpo_outcome_advantage,
                                          "rloo": adv.compute_rloo_outcome_advantage,
-                                         "gae": adv.compute_gae_advantage_return}),
+                                         "gae": adv.compute_gae_advantage_return,
+                                         "reinforce++": adv.compute_reinforce_plus_plus_outcome_advantage}),
         (pu.PolicyLossRegistry, {"regular": losses.ppo_policy_loss, "dual_clip": losses.ppo_policy_loss,
                                  "gspo": losses.gspo_policy_loss}),
     ):

@@ -149,3 +149,36 @@ def test_full_size_properties_c3_shape():
     uids = [i // 8 for i in range(B)]
     a, _ = advantages.compute_grpo_outcome_advantage(r, mask, uids)  # every group has equal scores -> 0
     assert torch.count_nonzero(a) == 0
+
+
+def test_reinforce_pp_and_normalize_match_reference_golden(golden_adv):
+    g = golden_adv
+    dense, fm = _t(g["dense_rewards"]), _t(g["mask_i64"]).float()
+    est = skyrl_b200.AdvantageEstimatorRegistry.get("reinforce++")
+    for gm in (1.0, 0.9):
+        adv, ret = est(token_level_rewards=dense.to(DEV), response_mask=fm.to(DEV), index=None, values=None,
+                       gamma=gm, lambd=1.0, config=None)
+        assert_close(ret, g[f"rpp_{gm}_ret"], what="rpp ret")
+        assert_close(adv, g[f"rpp_{gm}_adv"], what="rpp adv")
+    adv, ret = est(token_level_rewards=dense, response_mask=_t(g["rpp_hole_mask"]), gamma=0.95)
+    assert_close(ret, g["rpp_hole_ret"], what="rpp hole ret")  # running return resets inside the hole
+    assert_close(adv, g["rpp_hole_adv"], what="rpp hole adv")
+    assert torch.equal(adv == 0, _t(g["rpp_hole_adv"]) == 0)
+    assert_close(skyrl_b200.normalize_advantages(_t(g["norm_in"]).to(DEV), fm.to(DEV)), g["norm_out"])
+    assert_close(skyrl_b200.normalize_advantages(_t(g["norm_in"]), _t(g["mask_i64"])), g["norm_out"])
+
+
+def test_reinforce_pp_known_answers_and_long_rows():  # reference: tests/cpu/utils/test_ppo_utils.py:65-100
+    r = torch.tensor([[1.0, 2.0, 3.0]])
+    _, ret = advantages.compute_reinforce_plus_plus_outcome_advantage(r, torch.tensor([[1.0, 1.0, 0.0]]), 1.0)
+    assert torch.allclose(ret, torch.tensor([[3.0, 2.0, 3.0]]), atol=1e-5)
+    _, ret = advantages.compute_reinforce_plus_plus_outcome_advantage(r, torch.ones(1, 3), 0.5)
+    assert torch.allclose(ret, torch.tensor([[2.75, 3.5, 3.0]]), atol=1e-5)
+    g = torch.Generator().manual_seed(9)
+    B, A = 6, 9001  # several 4096-position tiles with carries across them, holes in the mask
+    mask = (torch.rand(B, A, generator=g) > 0.01).float()
+    rew = torch.randn(B, A, generator=g) * 0.1
+    a_ref, r_ref = O.reinforce_pp_advantage(rew, mask, 0.999)
+    a, ret = advantages.compute_reinforce_plus_plus_outcome_advantage(rew.to(DEV), mask.to(DEV), 0.999)
+    assert_close(ret, r_ref, what="ret")
+    assert_close(a, a_ref, what="adv")

@@ -141,3 +141,22 @@ def test_full_size_properties_c2_shape():
     # linearity in the advantages
     loss2, _ = losses.ppo_policy_loss(lp.clone().requires_grad_(True), lp, 3 * adv, cfg, loss_mask=mask)
     assert_close(loss2, 3 * loss.detach(), rel=1e-5)
+
+
+@pytest.mark.parametrize("cname,clip", [("clip02", 0.2), ("noclip", None)])
+@pytest.mark.parametrize("mname", ["mask", "nomask"])
+def test_critic_loss_matches_reference_golden(golden_loss, cname, clip, mname):
+    from types import SimpleNamespace
+
+    g = golden_loss
+    v = _t(g["values"]).to(DEV).requires_grad_(True)
+    mask = _t(g["mask"]).to(DEV) if mname == "mask" else None
+    loss, clipfrac = skyrl_b200.ppo_critic_loss(v, _t(g["old_values"]).to(DEV), _t(g["returns"]).to(DEV),
+                                                SimpleNamespace(value_clip=clip), loss_mask=mask)
+    loss.backward()
+    key = f"critic__{cname}__{mname}"
+    assert_close(loss, g[key + "__loss"], what="loss")
+    assert (clipfrac is None) == (clip is None)
+    if clip is not None:
+        assert_close(clipfrac, g[key + "__clipfrac"], what="clipfrac")
+    assert_close(v.grad, g[key + "__grad"], what="grad")

@@ -194,3 +194,39 @@ def test_oracle_vs_live_reference_random():
     lab = torch.randint(0, 50, (5, 7), generator=g)
     assert_close(O.logprobs_from_logits(z, lab), tu.logprobs_from_logits_v2(z, lab))
     assert_close(O.entropy_from_logits(z), tu.chunked_entropy_from_logits(z))
+
+
+# ---------------------------------------------------------------- "next" rows
+def test_golden_reinforce_pp_and_normalize(golden_adv):
+    g = golden_adv
+    dense, fm = _t(g["dense_rewards"]), _t(g["mask_i64"]).float()
+    for gm in (1.0, 0.9):
+        adv, ret = O.reinforce_pp_advantage(dense, fm, gm)
+        assert_close(ret, g[f"rpp_{gm}_ret"], what="rpp ret")
+        assert_close(adv, g[f"rpp_{gm}_adv"], what="rpp adv")
+    adv, ret = O.reinforce_pp_advantage(dense, _t(g["rpp_hole_mask"]), 0.95)
+    assert_close(ret, g["rpp_hole_ret"])
+    assert_close(adv, g["rpp_hole_adv"])
+    assert_close(O.normalize_advantages(_t(g["norm_in"]), fm), g["norm_out"])
+
+
+def test_kat_reinforce_pp():  # tests/cpu/utils/test_ppo_utils.py:65-100
+    r = T([[1.0, 2.0, 3.0]])
+    _, ret = O.reinforce_pp_advantage(r, T([[1.0, 1.0, 0.0]]), 1.0)
+    assert torch.allclose(ret, T([[3.0, 2.0, 3.0]]), atol=1e-5)  # reset after EOS
+    _, ret = O.reinforce_pp_advantage(r, torch.ones(1, 3), 0.5)
+    assert torch.allclose(ret, T([[2.75, 3.5, 3.0]]), atol=1e-5)
+
+
+@pytest.mark.parametrize("cname,clip", [("clip02", 0.2), ("noclip", None)])
+@pytest.mark.parametrize("mname", ["mask", "nomask"])
+def test_golden_critic_loss(golden_loss, cname, clip, mname):
+    g = golden_loss
+    v = _t(g["values"]).clone().requires_grad_(True)
+    loss, clipfrac = O.critic_loss(v, _t(g["old_values"]), _t(g["returns"]), clip,
+                                   _t(g["mask"]) if mname == "mask" else None)
+    loss.backward()
+    key = f"critic__{cname}__{mname}"
+    assert_close(loss, g[key + "__loss"])
+    assert_close(-1.0 if clipfrac is None else clipfrac, g[key + "__clipfrac"])
+    assert_close(v.grad, g[key + "__grad"])
