@@ -52,6 +52,18 @@ def measured_peaks():
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def config_dict(w, world):
+    """The `config` object both arms print (same workload, same string)."""
+    N = w["B"] * w["A"]
+    return {
+        "workload": f"{w['model']}: GRPO + regular loss (token_mean, k3 KL loss), {w['B']} seqs x {w['A']} tokens per GPU, "
+                    f"H={w['H']}, V={w['V']}, group {w['G']}",
+        "per_gpu_tokens": N,
+        "l2": "inputs exceed L2 (hidden is %.1f GB per GPU)" % (N * w["H"] * 2 / 1e9),
+        "parallelism": f"dp{world} by whole prompt groups",
+    }
+
+
 def make_cfg():
     from types import SimpleNamespace
 
@@ -203,8 +215,7 @@ def run_reference(args, w):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{w['model']}: GRPO, {w['B']} seqs x {w['A']} tokens, H={w['H']}, V={w['V']}, "
-                               f"group {w['G']}; CPU path timed on a {n_tok}-token sample per step"},
+        "config": config_dict(w, args.gpus),
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port",
                          "sample": f"{n_tok} tokens/step of the same workload (head+loss fwd/bwd fp32, GRPO advantages "
                                    f"pro-rated); oracle/policy_oracle.py = restatement of the reference torch path"},
@@ -367,12 +378,7 @@ def run_ours(args, w):
             "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {
-                "workload": f"{w['model']}: GRPO + regular loss (token_mean, k3 KL loss), {B} seqs x {A} tokens per GPU, "
-                            f"H={H}, V={V}, group {w['G']}",
-                "per_gpu_tokens": N, "l2": "inputs exceed L2 (hidden is %.1f GB per GPU)" % (N * H * 2 / 1e9),
-                "parallelism": f"dp{world} by whole prompt groups",
-            },
+            "config": config_dict(w, world),
             "tokens_per_s_per_gpu": tok_s / world,
             "phases_ms": {"advantages": adv_ms, "head_fwd+loss+head_bwd": upd_ms, "head_fwd_alone": ms_fwd},
             "cublas_same_shape_tflops": cublas_tflops,

@@ -273,6 +273,15 @@ int skyb200_logits_backward(const void* logits, int32_t logits_dtype, const int6
 int skyb200_gemm_selftest(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int32_t a_mn,
                           int32_t b_mn, int32_t ctas, int32_t bn, int32_t accumulate, void* stream);
 
+/*
+ * Tuning hook (scripts/gemm_tune.py): the production GEMM configuration with a chosen epilogue and tile order,
+ * K-major operands A [M, K], B [N, K].  epi: 0 = fp32 C [M, N], 1 = bf16 C [M, N], 2 = discard (C may be NULL),
+ * 3 = head-forward LSE partials (scratch = (3*ceil(N/256)+1)*M floats followed by M int64 labels; C = optional
+ * bf16 logits store with pitch round_up(N, 64)).  order / group: see gemm_sm100.cuh decode_tile.
+ */
+int skyb200_gemm_bench(const void* A, const void* B, void* C, void* scratch, int64_t M, int64_t N, int64_t K,
+                       int32_t epi, int32_t group, int32_t order, void* stream);
+
 /* host pointer to the last GEMM watchdog record (8 uint32: flag, role, which, stage, parity, tile, block, pad) */
 const uint32_t* skyb200_gemm_debug_record(void);
 

@@ -1,0 +1,87 @@
+"""Sustained-regime comparison of the tcgen05 mainloop against cuBLAS on the head-forward shape, per epilogue and
+tile order.  Each variant runs back to back for ~1.5 s (power-capped clocks), like MEASURED_PEAKS' sustained figure.
+
+    python scripts/gemm_tune.py [M N K]
+"""
+import json
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from skyrl_b200 import _lib  # noqa: E402
+
+
+def sustained(fn, seconds=1.5):
+    from bench import ClockSampler
+
+    cs = ClockSampler(0)
+    cs.start()
+    ms = _sustained(fn, seconds)
+    c = cs.stop()
+    return ms, c.get("sm_mhz")
+
+
+def _sustained(fn, seconds=1.5):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 0
+    s.record()
+    t_end = time.perf_counter() + seconds
+    while time.perf_counter() < t_end:
+        for _ in range(10):
+            fn()
+        reps += 10
+        torch.cuda.synchronize()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / reps
+
+
+def main():
+    M, N, K = (int(x) for x in sys.argv[1:4]) if len(sys.argv) >= 4 else (9472, 152064, 3584)
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(0)
+    A = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    B = (torch.randn(N, K, device=dev, generator=g) / K ** 0.5).bfloat16()
+    C = torch.empty(M, ((N + 63) // 64) * 64, dtype=torch.bfloat16, device=dev)
+    slabs = (N + 255) // 256
+    scratch = torch.zeros((3 * slabs + 1) * M + 2 * M, dtype=torch.float32, device=dev)
+    flops = 2.0 * M * N * K
+    out = {}
+    Cc = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    ms, mhz = sustained(lambda: torch.matmul(A, B.t(), out=Cc))
+    out["cublas_bf16_out"] = (round(flops / ms / 1e9, 1), mhz)
+    st = _lib.stream_ptr()
+
+    def ours(epi, group, order, c_ptr):
+        def f():
+            _lib.check(lib.skyb200_gemm_bench(_lib.ptr(A), _lib.ptr(B), c_ptr, _lib.ptr(scratch), M, N, K, epi, group,
+                                              order, st))
+        return f
+
+    for name, epi, group, order, cp in [
+        ("null_epilogue_g16", 2, 16, 0, None),
+        ("bf16_store_g16", 1, 16, 0, _lib.ptr(Cc)),
+        ("lse_g16", 3, 16, 0, None),
+        ("lse_store_g16", 3, 16, 0, _lib.ptr(C)),
+        ("lse_g37", 3, 37, 0, None),
+        ("f32_store_g16", 0, 16, 0, "f32"),
+    ]:
+        if epi == 1 and N % 16:
+            continue
+        if cp == "f32":
+            if M * N * 4 > 8e9:
+                continue
+            cp = _lib.ptr(torch.empty(M, N, dtype=torch.float32, device=dev))
+        ms, mhz = sustained(ours(epi, group, order, cp))
+        out[name] = (round(flops / ms / 1e9, 1), mhz)
+    print(json.dumps({"shape": [M, N, K], "tflops_sustained": out}))
+
+
+if __name__ == "__main__":
+    main()

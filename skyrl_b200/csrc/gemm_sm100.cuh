@@ -11,8 +11,8 @@
 // contiguous); the backward GEMMs of the fused LM head use the MN-major forms so no transposed copies of
 // the weight / hidden / dlogits matrices are ever made.
 //
-// Warp roles (256 threads):  warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (leader CTA only),
-// warp 2 = TMEM allocator, warps 4..7 = epilogue.
+// Warp roles (256 threads):  warps 0..3 = epilogue, warp 4 lane 0 = TMA producer, warp 5 lane 0 = MMA issuer
+// (leader CTA only), warp 6 = TMEM allocator.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -27,7 +27,17 @@ constexpr int kBM = 128;  // accumulator rows per CTA (= TMEM lanes)
 constexpr int kBK = 64;   // bf16 elements per 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 256;
-constexpr int kEpiWarp0 = 4;
+// Warp roles.  The control warps get the HIGHER warp ids: the SM's warp arbiter favours higher ids among
+// eligible warps, so the single TMA lane and the single MMA lane are never starved of issue slots by an
+// epilogue warp that shares their scheduler and is in the middle of a long ALU burst.
+#ifndef SKYB200_EPI_FIRST
+#define SKYB200_EPI_FIRST 1
+#endif
+#if SKYB200_EPI_FIRST
+constexpr int kEpiWarp0 = 0, kTmaWarp = 4, kMmaWarp = 5, kAllocWarp = 6;
+#else
+constexpr int kEpiWarp0 = 4, kTmaWarp = 0, kMmaWarp = 1, kAllocWarp = 2;
+#endif
 
 // Debug record written to mapped host memory when a barrier wait times out (so a protocol bug shows up
 // as a failed launch with a readable reason instead of a hung GPU).
@@ -45,8 +55,10 @@ struct GemmDebug {
 __device__ __forceinline__ void bounded_wait(uint64_t* bar, uint32_t parity, GemmDebug* dbg, uint32_t role,
                                              uint32_t which, uint32_t stage, uint32_t tile) {
     uint32_t spins = 0;
-    while (!ptx::mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) {  // try_wait itself blocks for a HW-defined slice; this is seconds
+    // fast path first (the barrier is usually already complete for the MMA lane), then sleep-waits
+    if (ptx::mbar_try_wait(bar, parity)) return;
+    while (!ptx::mbar_try_wait_hint(bar, parity, 2000u)) {
+        if (++spins > (1u << 22)) {  // each try is a hardware sleep of up to 2 us: this is seconds
             if (dbg != nullptr && atomicExch(&dbg->flag, 1u) == 0u) {
                 dbg->role = role;
                 dbg->which = which;
@@ -127,11 +139,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int lane = threadIdx.x & 31;
     const uint32_t cta_rank = (kCtas == 2) ? ptx::cluster_ctarank() : 0u;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == kTmaWarp && lane == 0) {
         ptx::prefetch_tensormap(&tmap_a);
         ptx::prefetch_tensormap(&tmap_b);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == kMmaWarp && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
             ptx::mbar_init(&empty_bar[i], 1);
@@ -142,7 +154,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         ptx::tmem_alloc<kCtas>(tmem_slot, kTmemCols);
     }
     ptx::tcgen05_fence_before();
@@ -161,7 +173,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int cluster_id = blockIdx.x / kCtas;
     const int num_clusters = gridDim.x / kCtas;
 
-    if (warp == 0) {
+    if (warp == kTmaWarp) {
         // ------------------------------------------------------------ TMA producer (one lane)
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -212,7 +224,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------ MMA issuer (one lane, leader CTA)
         if (lane == 0 && cta_rank == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BN, kAMn ? 1u : 0u, kBMn ? 1u : 0u);
@@ -249,7 +261,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
             }
         }
-    } else if (warp >= kEpiWarp0) {
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
         // ------------------------------------------------------------ epilogue (4 warps, row per thread)
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         uint32_t accum = 0, aphase = 0;
@@ -281,7 +293,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     } else {
         __syncthreads();
     }
-    if (warp == 2) {
+    if (warp == kAllocWarp) {
         ptx::tcgen05_fence_after();
         ptx::tmem_dealloc<kCtas>(tmem_base, kTmemCols);
     }
@@ -366,6 +378,26 @@ struct EpiStoreF32 {
                 }
             }
         }
+    }
+};
+
+// Drains the accumulator and discards it (mainloop-only timing in scripts/gemm_tune.py).
+struct EpiNull {
+    struct Params {
+        float* sink;
+    };
+    template <int BN>
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+        float acc = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            __syncwarp();
+            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            acc += __uint_as_float(v[0]) + __uint_as_float(v[31]);
+        }
+        if (acc == 1.2345e30f && p.sink != nullptr) p.sink[0] = acc + row + n_tile + M + N;
     }
 };
 

@@ -151,8 +151,8 @@ static int env_int(const char* name, int dflt) {
 }
 // tile-order group sizes (tunable for experiments; defaults measured on the 7B head)
 static int fwd_group_m() { static int v = env_int("SKYB200_FWD_GROUP_M", 16); return v; }
-static int dh_group_m() { static int v = env_int("SKYB200_DH_GROUP_M", 5); return v; }
-static int dw_group_n() { static int v = env_int("SKYB200_DW_GROUP_N", 7); return v; }
+static int dh_group_m() { static int v = env_int("SKYB200_DH_GROUP_M", 8); return v; }
+static int dw_group_n() { static int v = env_int("SKYB200_DW_GROUP_N", 14); return v; }
 
 
 static int64_t num_slabs(int64_t V) { return (V + kHeadBN - 1) / kHeadBN; }
@@ -794,6 +794,49 @@ extern "C" int skyb200_gemm_selftest(const void* A, const void* B, float* C, int
     if (ctas == 2 && bn == 128)
         return selftest_dispatch<2, 128, 6>(A, B, C, (int)M, (int)N, (int)K, a_mn, b_mn, accumulate, stream);
     return fail(SKYB200_EINVAL, "unsupported selftest configuration ctas=%d bn=%d", ctas, bn);
+}
+
+// Tuning hook: the production GEMM configuration (cta pairs, 256x256, 6 stages) with a chosen epilogue and
+// tile order, K-major operands.  epi: 0 = fp32 store, 1 = bf16 store, 2 = discard, 3 = LSE partials (head forward).
+extern "C" int skyb200_gemm_bench(const void* A, const void* B, void* C, void* scratch, int64_t M, int64_t N,
+                                  int64_t K, int32_t epi, int32_t group, int32_t order, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(A && B, "null pointer");
+    int rc = skyb200_check_device();
+    if (rc) return rc;
+    if (epi == 0) {
+        EpiStoreF32::Params ep{static_cast<float*>(C), N, 0};
+        return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiStoreF32>(A, K, B, K, (int)M, (int)N,
+                                                                                      (int)K, group, ep, stream, order);
+    }
+    if (epi == 1) {
+        EpiStoreBF16::Params ep{static_cast<__nv_bfloat16*>(C), N};
+        return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiStoreBF16>(
+            A, K, B, K, (int)M, (int)N, (int)K, group, ep, stream, order);
+    }
+    if (epi == 2) {
+        EpiNull::Params ep{static_cast<float*>(C)};
+        return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiNull>(A, K, B, K, (int)M, (int)N, (int)K,
+                                                                                  group, ep, stream, order);
+    }
+    if (epi == 3) {
+        SKYB200_REQUIRE(scratch != nullptr, "epi 3 needs scratch: (3*ceil(N/256)+1)*M floats + M int64 labels");
+        const int slabs = (int)num_slabs(N);
+        float* part = static_cast<float*>(scratch);
+        EpiLsePartials::Params ep;
+        ep.scale_log2 = 1.4426950408889634f;
+        ep.part_m = part;
+        ep.part_s = part + (int64_t)slabs * M;
+        ep.part_t = part + 2 * (int64_t)slabs * M;
+        ep.ld = M;
+        ep.label_acc = part + 3 * (int64_t)slabs * M;
+        ep.labels = reinterpret_cast<const int64_t*>(ep.label_acc + M);
+        ep.logits = static_cast<__nv_bfloat16*>(C);  // may be NULL
+        ep.ld_logits = round_up(N, 64);
+        return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
+            A, K, B, K, (int)M, (int)N, (int)K, group, ep, stream, order);
+    }
+    return fail(SKYB200_EINVAL, "epi must be 0..3");
 }
 
 extern "C" const uint32_t* skyb200_gemm_debug_record(void) {
