@@ -38,11 +38,17 @@ extern "C" {
 #define SKYB200_LOSS_REGULAR 0
 #define SKYB200_LOSS_DUAL_CLIP 1
 #define SKYB200_LOSS_GSPO 2
+#define SKYB200_LOSS_SAPO 3                /* sapo_policy_loss, ppo_utils.py:589-658 */
+#define SKYB200_LOSS_CISPO 4               /* compute_policy_loss_cispo, ppo_utils.py:728-761 (eps_clip_* = cispo eps) */
+#define SKYB200_LOSS_CROSS_ENTROPY 5       /* cross_entropy_loss, ppo_utils.py:892-930 (use SKYB200_REDUCE_SUM) */
+#define SKYB200_LOSS_IMPORTANCE_SAMPLING 6 /* importance_sampling_loss, ppo_utils.py:933-981 (SKYB200_REDUCE_SUM) */
+#define SKYB200_LOSS_LAST 6
 
 /* loss_reduction (ppo_utils.py:984-1009) */
 #define SKYB200_REDUCE_TOKEN_MEAN 0
 #define SKYB200_REDUCE_SEQUENCE_MEAN 1
 #define SKYB200_REDUCE_SEQ_MEAN_TOKEN_SUM_NORM 2
+#define SKYB200_REDUCE_SUM 3 /* plain masked sum (Tinker semantics of cross_entropy / importance_sampling) */
 
 /* kl_estimator_type (ppo_utils.py:88-124) */
 #define SKYB200_KL_K1 0
@@ -74,6 +80,8 @@ typedef struct skyb200_loss_params {
     float max_seq_len; /* for SEQ_MEAN_TOKEN_SUM_NORM */
     float kl_loss_coef;
     float entropy_loss_coef;
+    float sapo_tau_pos; /* SAPO gate temperatures (config.sapo.tau_pos / tau_neg) */
+    float sapo_tau_neg;
 } skyb200_loss_params;
 
 /* indices into the fp32 stats vector written by skyb200_policy_loss (SKYB200_LOSS_NSTATS floats) */
@@ -236,14 +244,20 @@ int skyb200_head_backward(const void* hidden, const void* weight, const int64_t*
  * entropy_mask [B*A] fp32 or NULL; log_probs / entropy: [B*A] fp32 out (entropy already * entropy_mask);
  * d_hidden [B*A, H] bf16 and d_weight [V, H] fp32 may be NULL (both NULL = evaluate the loss only);
  * gradients are those of stats[SKYB200_STAT_FINAL_LOSS] with upstream gradient 1.
+ *
+ * Packed (ragged) layout: pass cu_seqlens (device int32 [B + 1], cu[0] = 0, cu[B] = n_tokens).  Every per-token
+ * array is then flat [n_tokens]; sequence b owns tokens [cu[b], cu[b + 1]); A is ignored; positions that a padded
+ * batch would mask out simply do not exist.  Results equal the padded layout with loss_mask = 0 on the padding.
+ * (GSPO is not available in the packed layout.)  Padded layout: cu_seqlens = NULL, n_tokens ignored.
  */
-size_t skyb200_policy_step_workspace(int64_t B, int64_t A, int64_t H, int64_t V, int32_t loss_type,
+size_t skyb200_policy_step_workspace(int64_t B, int64_t A, int64_t n_tokens, int64_t H, int64_t V, int32_t loss_type,
                                      int32_t need_grad);
 int skyb200_policy_step(const void* hidden, const void* weight, const int64_t* labels, const float* old_log_probs,
                         const float* advantages, const float* loss_mask, const float* base_log_probs,
                         const float* entropy_mask, float* log_probs, float* entropy, void* d_hidden, float* d_weight,
                         int32_t accumulate, float* stats, void* workspace, size_t workspace_bytes, int64_t B, int64_t A,
-                        int64_t H, int64_t V, float temperature, const skyb200_loss_params* params, void* stream);
+                        int64_t H, int64_t V, const int32_t* cu_seqlens, int64_t n_tokens, float temperature,
+                        const skyb200_loss_params* params, void* stream);
 
 /*
  * logprobs_from_logits (torch_utils.py:115-177) and chunked_entropy_from_logits (:59-111) on materialised

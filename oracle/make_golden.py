@@ -123,6 +123,24 @@ def gen_losses(pu):
                 out[key + "__loss"] = np.float32(loss.item())
                 out[key + "__clip"] = np.float32(met["clip_ratio"])
                 out[key + "__grad"] = x.grad.numpy()
+    # the rest of the elementwise loss registry (sapo / cispo / cross_entropy / importance_sampling)
+    xcfg = dict(sapo=SimpleNamespace(tau_pos=1.0, tau_neg=2.0),
+                cispo=SimpleNamespace(cispo_eps_clip_low=0.1, cispo_eps_clip_high=0.3))
+    olp_mild = lp + 0.2 * torch.randn(B, A, generator=g)  # importance_sampling has no clamp: keep ratios finite
+    out["olp_mild"] = olp_mild.numpy()
+    for kind, red in (("sapo", "sequence_mean"), ("sapo", "token_mean"), ("cispo", "token_mean"),
+                      ("cispo", "seq_mean_token_sum_norm"), ("cross_entropy", "token_mean"),
+                      ("importance_sampling", "token_mean")):
+        for mname, m in (("mask", fm), ("nomask", None)):
+            c = cfg(policy_loss_type=kind, loss_reduction=red, **xcfg)
+            x = lp.clone().requires_grad_(True)
+            o = olp_mild if kind == "importance_sampling" else olp
+            loss, met = pu.PolicyLossRegistry._functions[kind](x, o, adv, c, loss_mask=m)
+            loss.backward()
+            key = f"{kind}__{red}__{mname}"
+            out[key + "__loss"] = np.float32(loss.item())
+            out[key + "__metric"] = np.float32(list(met.values())[0])
+            out[key + "__grad"] = x.grad.numpy()
     # critic loss (ppo_utils.py:175-193)
     vals = torch.randn(B, A, generator=g)
     old_vals = vals + 0.3 * torch.randn(B, A, generator=g)

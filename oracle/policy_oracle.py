@@ -198,6 +198,32 @@ def policy_loss(lp, olp, adv, cfg, mask=None):
     return reduce_loss(loss, mask, cfg.loss_reduction, getattr(cfg, "max_seq_len", None)), clip_ratio
 
 
+def extra_policy_loss(kind, lp, olp, adv, cfg, mask=None):
+    """sapo (utils/ppo_utils.py:589-658), cispo (:728-761), cross_entropy (:892-930), importance_sampling (:933-981).
+    Returns (loss, metrics)."""
+    if kind == "sapo":
+        ratio = (lp - olp).clamp(-20.0, 20.0).exp()
+        tau = torch.where(adv > 0, torch.as_tensor(cfg.sapo.tau_pos, dtype=adv.dtype),
+                          torch.as_tensor(cfg.sapo.tau_neg, dtype=adv.dtype))
+        gate = torch.sigmoid(tau * (ratio - 1.0)) * (4.0 / tau)
+        return reduce_loss(-gate * adv, mask, cfg.loss_reduction, getattr(cfg, "max_seq_len", None)), {"clip_ratio": 0.0}
+    if kind == "cispo":
+        ratio = (lp - olp).float().clamp(-20.0, 20.0).exp()
+        lo, hi = 1 - cfg.cispo.cispo_eps_clip_low, 1 + cfg.cispo.cispo_eps_clip_high
+        loss = -adv * ratio.clamp(lo, hi).detach() * lp
+        clip = masked_mean(((ratio < lo) | (ratio > hi)).float(), mask).mean().item()
+        return reduce_loss(loss, mask, cfg.loss_reduction, getattr(cfg, "max_seq_len", None)), {"clip_ratio": clip}
+    if kind == "cross_entropy":
+        return ((-lp * mask).sum() if mask is not None else (-lp).sum()), {"clip_ratio": 0.0}
+    if kind == "importance_sampling":
+        ratio = (lp - olp).exp()
+        el = -(ratio * adv)
+        if mask is not None:
+            return (el * mask).sum(), {"importance_ratio": ((ratio * mask).sum() / mask.sum()).item()}
+        return el.sum(), {"importance_ratio": ratio.mean().item()}
+    raise ValueError(kind)
+
+
 def loss_assembly(lp, olp, adv, cfg, mask=None, base=None, entropy=None):
     """workers/worker.py:852-889 — final = policy + kl*coef - entropy*coef; returns (final_loss, status)."""
     pl, clip_ratio = policy_loss(lp, olp, adv, cfg, mask)

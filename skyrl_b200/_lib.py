@@ -13,8 +13,9 @@ _lib = None
 
 # enums (mirror include/skyb200.h)
 MASK_F32, MASK_I64, MASK_NONE = 0, 1, 2
-LOSS_TYPES = {"regular": 0, "dual_clip": 1, "gspo": 2}
-REDUCTIONS = {"token_mean": 0, "sequence_mean": 1, "seq_mean_token_sum_norm": 2}
+LOSS_TYPES = {"regular": 0, "dual_clip": 1, "gspo": 2, "sapo": 3, "cispo": 4, "cross_entropy": 5,
+              "importance_sampling": 6}
+REDUCTIONS = {"token_mean": 0, "sequence_mean": 1, "seq_mean_token_sum_norm": 2, "sum": 3}
 KL_TYPES = {"k1": 0, "abs": 1, "k2": 2, "k3": 3}
 LOSS_NSTATS = 16
 STAT_POLICY_LOSS, STAT_CLIP_RATIO, STAT_KL_LOSS, STAT_ENTROPY, STAT_FINAL_LOSS, STAT_MASK_SUM = 0, 1, 2, 3, 4, 5
@@ -35,6 +36,8 @@ class LossParams(C.Structure):
         ("max_seq_len", C.c_float),
         ("kl_loss_coef", C.c_float),
         ("entropy_loss_coef", C.c_float),
+        ("sapo_tau_pos", C.c_float),
+        ("sapo_tau_neg", C.c_float),
     ]
 
 
@@ -70,9 +73,9 @@ SIGNATURES = {
     "skyb200_head_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I64, _I64, _I64, _F, _I64, _P]),
     "skyb200_head_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _I64, _I64, _I64, _F,
                                         _I64, _P]),
-    "skyb200_policy_step_workspace": (_SZ, [_I64, _I64, _I64, _I64, _I32, _I32]),
+    "skyb200_policy_step_workspace": (_SZ, [_I64, _I64, _I64, _I64, _I64, _I32, _I32]),
     "skyb200_policy_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _SZ, _I64, _I64,
-                                      _I64, _I64, _F, C.POINTER(LossParams), _P]),
+                                      _I64, _I64, _P, _I64, _F, C.POINTER(LossParams), _P]),
     "skyb200_logits_logprob_entropy": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _I64, _I64, _P]),
     "skyb200_logits_backward": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
     "skyb200_gemm_selftest": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P]),

@@ -491,9 +491,8 @@ struct StepPlan {
 int64_t gcd64(int64_t a, int64_t b) { return b == 0 ? a : gcd64(b, a % b); }
 
 // Chunks are flat token ranges; GSPO needs whole sequences per chunk (its ratio is a per-sequence mean).
-StepPlan plan_step(int64_t B, int64_t A, int64_t H, int64_t V, int loss_type, bool need_grad) {
+StepPlan plan_step(int64_t B, int64_t A, int64_t N, int64_t H, int64_t V, int loss_type, bool need_grad) {
     StepPlan p;
-    const int64_t N = B * A;
     int64_t chunk = kDefaultChunk;
     if (loss_type == SKYB200_LOSS_GSPO) {
         const int64_t unit = A / gcd64(A, kTileM) * kTileM;  // lcm(A, 256)
@@ -518,7 +517,8 @@ StepPlan plan_step(int64_t B, int64_t A, int64_t H, int64_t V, int loss_type, bo
         p.off_dent[i] = take((size_t)chunk * 4);
         p.off_S[i] = take(need_grad ? (size_t)chunk * p.ldS * 2 : 0);
     }
-    p.off_loss = take(loss_chunk_ws_bytes(B, A) + (size_t)(N / chunk + 2) * 8 * 4 * 4);
+    p.off_loss = take(loss_chunk_ws_bytes(B, N) + (size_t)(N / chunk + 2) * 8 * 4 * 4);
+    (void)A;
     p.total = off + 512;
     (void)H;
     return p;
@@ -547,9 +547,9 @@ StepStreams* step_streams() {
 
 }  // namespace
 
-extern "C" size_t skyb200_policy_step_workspace(int64_t B, int64_t A, int64_t H, int64_t V, int32_t loss_type,
-                                                int32_t need_grad) {
-    return plan_step(B, A, H, V, loss_type, need_grad != 0).total;
+extern "C" size_t skyb200_policy_step_workspace(int64_t B, int64_t A, int64_t n_tokens, int64_t H, int64_t V,
+                                                int32_t loss_type, int32_t need_grad) {
+    return plan_step(B, A, n_tokens > 0 ? n_tokens : B * A, H, V, loss_type, need_grad != 0).total;
 }
 
 extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const int64_t* labels,
@@ -557,24 +557,27 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
                                    const float* base_log_probs, const float* entropy_mask, float* log_probs,
                                    float* entropy, void* d_hidden, float* d_weight, int32_t accumulate, float* stats,
                                    void* workspace, size_t workspace_bytes, int64_t B, int64_t A, int64_t H, int64_t V,
-                                   float temperature, const skyb200_loss_params* params, void* stream_) {
+                                   const int32_t* cu_seqlens, int64_t n_tokens, float temperature,
+                                   const skyb200_loss_params* params, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SKYB200_REQUIRE(hidden && weight && labels && old_log_probs && advantages && log_probs && entropy && stats &&
                         workspace && params,
                     "null pointer");
+    SKYB200_REQUIRE(cu_seqlens == nullptr || params->loss_type != SKYB200_LOSS_GSPO,
+                    "gspo needs whole sequences per chunk: use the padded [B, A] layout");
+    SKYB200_REQUIRE(cu_seqlens == nullptr || n_tokens > 0, "packed layout needs n_tokens");
     SKYB200_REQUIRE(B > 0 && A > 0 && B < 65536, "need 0 < B < 65536 and A > 0");
     SKYB200_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
     SKYB200_REQUIRE(temperature > 0.f, "temperature must be > 0");
-    SKYB200_REQUIRE(params->loss_type >= 0 && params->loss_type <= SKYB200_LOSS_GSPO, "bad loss_type");
-    SKYB200_REQUIRE(params->reduction >= 0 && params->reduction <= SKYB200_REDUCE_SEQ_MEAN_TOKEN_SUM_NORM,
-                    "bad reduction");
+    SKYB200_REQUIRE(params->loss_type >= 0 && params->loss_type <= SKYB200_LOSS_LAST, "bad loss_type");
+    SKYB200_REQUIRE(params->reduction >= 0 && params->reduction <= SKYB200_REDUCE_SUM, "bad reduction");
     SKYB200_REQUIRE(params->kl_type >= 0 && params->kl_type <= SKYB200_KL_K3, "bad kl_type");
     SKYB200_REQUIRE(params->reduction != SKYB200_REDUCE_SEQ_MEAN_TOKEN_SUM_NORM || params->max_seq_len > 0.f,
                     "max_seq_len must be provided for seq_mean_token_sum_norm");
-    const int64_t N = B * A;
+    const int64_t N = cu_seqlens ? n_tokens : B * A;
     SKYB200_REQUIRE(N < (1ll << 31) && V < (1ll << 31) && H < (1ll << 31), "dimension too large");
     const bool need_grad = (d_hidden != nullptr) || (d_weight != nullptr);
-    const StepPlan plan = plan_step(B, A, H, V, params->loss_type, need_grad);
+    const StepPlan plan = plan_step(B, A, N, H, V, params->loss_type, need_grad);
     if (workspace_bytes < plan.total) return fail(SKYB200_EWORKSPACE, "policy_step workspace too small");
     int rc = skyb200_check_device();
     if (rc) return rc;
@@ -643,7 +646,7 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
         }
         r = loss_flat_range(log_probs, old_log_probs, advantages, loss_mask, base_log_probs, entropy,
                             need_grad ? d_lp - t0 : nullptr, use_ent_grad ? d_ent - t0 : nullptr, lws, B, A, t0,
-                            t0 + rows, slot, *params, aux);
+                            t0 + rows, slot, *params, cu_seqlens, aux);
         if (r) return r;
         if (need_grad) {
             const dim3 grid((unsigned)((V + 4095) / 4096), (unsigned)rows);
@@ -685,7 +688,7 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
     };
 
     // the auxiliary stream starts after everything already queued on the caller's stream (inputs are ready)
-    rc = loss_prepass(loss_mask, lws, B, A, stream);
+    rc = loss_prepass(loss_mask, lws, B, A, cu_seqlens, stream);
     if (rc) return rc;
     SKYB200_CUDA_CHECK(cudaEventRecord(ss->start, stream));
     SKYB200_CUDA_CHECK(cudaStreamWaitEvent(aux, ss->start, 0));

@@ -17,19 +17,22 @@ struct LossChunkWs {
     unsigned int* counters;  // [4]
     float* partials;         // [max_blocks][8]
 };
-size_t loss_chunk_ws_bytes(int64_t B, int64_t A);
+size_t loss_chunk_ws_bytes(int64_t B, int64_t n_tokens);
 void loss_chunk_ws_carve(void* base, int64_t B, int64_t A, LossChunkWs* ws);
 int64_t loss_chunk_blocks(int64_t n_tokens);  // blocks (= partial slots) a flat range of n tokens uses
 
 // row mask sums + global mask sum for the whole batch (needs only the mask)
-int loss_prepass(const float* loss_mask, const LossChunkWs& ws, int64_t B, int64_t A, cudaStream_t stream);
+// cu (device, [B + 1], nullable): packed layout - row b owns tokens [cu[b], cu[b + 1]) instead of [b*A, (b+1)*A)
+int loss_prepass(const float* loss_mask, const LossChunkWs& ws, int64_t B, int64_t A, const int32_t* cu,
+                 cudaStream_t stream);
 // GSPO sequence log-ratios for rows [row0, row0 + rows)
 int loss_row_logratio(const float* lp, const float* olp, const float* loss_mask, const LossChunkWs& ws, int64_t row0,
                       int64_t rows, int64_t A, cudaStream_t stream);
 // per-token pass over flat tokens [t0, t1) of the [B, A] batch; partials go to slots [slot0, slot0 + blocks)
 int loss_flat_range(const float* lp, const float* olp, const float* adv, const float* loss_mask, const float* base,
                     const float* ent, float* d_lp, float* d_ent, const LossChunkWs& ws, int64_t B, int64_t A,
-                    int64_t t0, int64_t t1, int64_t slot0, const skyb200_loss_params& p, cudaStream_t stream);
+                    int64_t t0, int64_t t1, int64_t slot0, const skyb200_loss_params& p, const int32_t* cu,
+                    cudaStream_t stream);
 // fold partial slots [0, nslots) into the packed stats vector
 int loss_finalize(const LossChunkWs& ws, int64_t nslots, bool has_entropy, float* stats, const skyb200_loss_params& p,
                   cudaStream_t stream);

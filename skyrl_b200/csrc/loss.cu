@@ -56,11 +56,13 @@ static size_t loss_ws_layout(int64_t B, int64_t A, LossWs* ws, void* base) {
 __global__ void __launch_bounds__(kLossThreads)
 loss_rowstats_kernel(const float* __restrict__ lp, const float* __restrict__ olp, const float* __restrict__ mask,
                      float* __restrict__ row_msum, float* __restrict__ row_lw, float* __restrict__ total_msum,
-                     unsigned int* __restrict__ counter, int B, int64_t A, int need_lw) {
+                     unsigned int* __restrict__ counter, int B, int64_t A, int need_lw,
+                     const int32_t* __restrict__ cu = nullptr) {
     __shared__ float sh[34];
     __shared__ bool is_last;
     const int row = blockIdx.x;
-    const int64_t base = static_cast<int64_t>(row) * A;
+    const int64_t base = cu ? static_cast<int64_t>(cu[row]) : static_cast<int64_t>(row) * A;
+    if (cu) A = static_cast<int64_t>(cu[row + 1]) - base;  // packed layout: this row's own length
     float ms = 0.f, lw = 0.f;
     for (int64_t t = threadIdx.x; t < A; t += blockDim.x) {
         const float m = mask ? mask[base + t] : 1.f;
@@ -142,36 +144,64 @@ struct LossAcc {
 struct TokenCtx {
     bool gspo, dual, has_mask, has_base;
     float lo, hi, seq_ratio, seq_pass, w_scale, kl_scale, clip_c, kl_grad_scale, d_ent_val;
+    float tau_pos = 1.f, tau_neg = 1.f;
     int kl_type;
+    int loss_type = SKYB200_LOSS_REGULAR;
 };
 
 // One response token: accumulates the reductions, returns d final_loss / d log_prob.
 __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, float lp, float olp, float adv, float m,
                                             float base) {
-    float ratio, dr_dlp;
-    if (cx.gspo) {
-        ratio = cx.seq_ratio;
-        dr_dlp = cx.seq_ratio * cx.seq_pass;
-    } else {
+    float ratio, loss, dl_dlp, clipped = 0.f;
+    if (cx.loss_type <= SKYB200_LOSS_GSPO) {
+        float dr_dlp;
+        if (cx.gspo) {
+            ratio = cx.seq_ratio;
+            dr_dlp = cx.seq_ratio * cx.seq_pass;
+        } else {
+            const float delta = lp - olp;
+            ratio = expf(fminf(fmaxf(delta, -20.f), 20.f));
+            dr_dlp = (delta >= -20.f && delta <= 20.f) ? ratio : 0.f;
+        }
+        const float rc = fminf(fmaxf(ratio, cx.lo), cx.hi);
+        const float in_rng = (ratio >= cx.lo && ratio <= cx.hi) ? 1.f : 0.f;
+        const float s1 = ratio * adv, s2 = rc * adv;
+        loss = -fminf(s1, s2);
+        // d loss / d ratio: torch.min splits ties 50/50 between its two arguments
+        float dl_dr = (s1 < s2) ? -adv : ((s1 > s2) ? -adv * in_rng : -adv * (0.5f + 0.5f * in_rng));
+        clipped = (s2 < s1) ? 1.f : 0.f;  // (-surr2 > -surr1), before dual clip
+        if (cx.dual && adv < 0.f) {
+            const float l3 = -adv * cx.clip_c;
+            if (l3 < loss) {
+                loss = l3;
+                dl_dr = 0.f;
+            } else if (l3 == loss) {
+                dl_dr *= 0.5f;
+            }
+        }
+        dl_dlp = dl_dr * dr_dlp;
+    } else if (cx.loss_type == SKYB200_LOSS_SAPO) {
         const float delta = lp - olp;
         ratio = expf(fminf(fmaxf(delta, -20.f), 20.f));
-        dr_dlp = (delta >= -20.f && delta <= 20.f) ? ratio : 0.f;
-    }
-    const float rc = fminf(fmaxf(ratio, cx.lo), cx.hi);
-    const float in_rng = (ratio >= cx.lo && ratio <= cx.hi) ? 1.f : 0.f;
-    const float s1 = ratio * adv, s2 = rc * adv;
-    float loss = -fminf(s1, s2);
-    // d loss / d ratio: torch.min splits ties 50/50 between its two arguments
-    float dl_dr = (s1 < s2) ? -adv : ((s1 > s2) ? -adv * in_rng : -adv * (0.5f + 0.5f * in_rng));
-    const float clipped = (s2 < s1) ? 1.f : 0.f;  // (-surr2 > -surr1), before dual clip
-    if (cx.dual && adv < 0.f) {
-        const float l3 = -adv * cx.clip_c;
-        if (l3 < loss) {
-            loss = l3;
-            dl_dr = 0.f;
-        } else if (l3 == loss) {
-            dl_dr *= 0.5f;
-        }
+        const float dr_dlp = (delta >= -20.f && delta <= 20.f) ? ratio : 0.f;
+        const float tau = (adv > 0.f) ? cx.tau_pos : cx.tau_neg;
+        const float sg = 1.f / (1.f + expf(-tau * (ratio - 1.f)));
+        loss = -(sg * (4.f / tau)) * adv;
+        dl_dlp = -adv * 4.f * sg * (1.f - sg) * dr_dlp;
+    } else if (cx.loss_type == SKYB200_LOSS_CISPO) {
+        ratio = expf(fminf(fmaxf(lp - olp, -20.f), 20.f));
+        const float rc = fminf(fmaxf(ratio, cx.lo), cx.hi);  // detached: acts as a per-token weight
+        loss = -adv * rc * lp;
+        dl_dlp = -adv * rc;
+        clipped = (ratio < cx.lo || ratio > cx.hi) ? 1.f : 0.f;
+    } else if (cx.loss_type == SKYB200_LOSS_CROSS_ENTROPY) {
+        ratio = 1.f;
+        loss = -lp;
+        dl_dlp = -1.f;
+    } else {  // importance sampling: un-clamped ratio, Tinker semantics
+        ratio = expf(lp - olp);
+        loss = -ratio * adv;
+        dl_dlp = loss;
     }
     const float w = m * cx.w_scale;
     acc.s_loss = fmaf(loss, w, acc.s_loss);
@@ -181,7 +211,7 @@ __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, fl
         acc.r_max = fmaxf(acc.r_max, ratio);
         acc.r_min = fminf(acc.r_min, ratio);
     }
-    float g = w * dl_dr * dr_dlp;
+    float g = w * dl_dlp;
     if (cx.has_base) {
         float dk;
         const float kl = kl_estimate(lp, base, cx.kl_type, &dk);
@@ -208,6 +238,8 @@ __global__ void __launch_bounds__(kLossThreads) loss_main_kernel(LossArgs a) {
         w_scale = inv_total;
     else if (a.p.reduction == SKYB200_REDUCE_SEQUENCE_MEAN)
         w_scale = inv_row / Bf;
+    else if (a.p.reduction == SKYB200_REDUCE_SUM)
+        w_scale = 1.f;
     else
         w_scale = 1.f / (a.p.max_seq_len * Bf);
     const float kl_scale = inv_row / Bf;
@@ -234,6 +266,9 @@ __global__ void __launch_bounds__(kLossThreads) loss_main_kernel(LossArgs a) {
     cx.kl_scale = kl_scale;
     cx.clip_c = a.p.clip_ratio_c;
     cx.kl_type = a.p.kl_type;
+    cx.loss_type = a.p.loss_type;
+    cx.tau_pos = a.p.sapo_tau_pos;
+    cx.tau_neg = a.p.sapo_tau_neg;
     cx.kl_grad_scale = a.p.kl_has_grad ? a.p.kl_loss_coef * kl_scale : 0.f;
     cx.has_mask = (a.mask != nullptr);
     cx.has_base = (a.base != nullptr);
@@ -369,6 +404,7 @@ struct FlatArgs {
     float* d_lp;
     float* d_ent;
     LossChunkWs ws;
+    const int32_t* cu;  // packed layout: row offsets [B + 1], else nullptr
     int B;
     int vec4;
     int64_t A;
@@ -376,6 +412,19 @@ struct FlatArgs {
     int64_t slot0;
     skyb200_loss_params p;
 };
+
+// packed layout: the row that owns flat token i = the largest r with cu[r] <= i
+__device__ __forceinline__ int row_of_token(const int32_t* __restrict__ cu, int B, int64_t i) {
+    int lo = 0, hi = B;  // invariant: cu[lo] <= i < cu[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (static_cast<int64_t>(__ldg(cu + mid)) <= i)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
 
 __global__ void __launch_bounds__(kLossThreads) loss_flat_kernel(FlatArgs a) {
     __shared__ float sh[34];
@@ -395,17 +444,23 @@ __global__ void __launch_bounds__(kLossThreads) loss_flat_kernel(FlatArgs a) {
     cx.seq_pass = 1.f;
     cx.clip_c = a.p.clip_ratio_c;
     cx.kl_type = a.p.kl_type;
+    cx.loss_type = a.p.loss_type;
+    cx.tau_pos = a.p.sapo_tau_pos;
+    cx.tau_neg = a.p.sapo_tau_neg;
     cx.has_mask = (a.mask != nullptr);
     cx.has_base = (a.base != nullptr);
     cx.d_ent_val = use_ent_loss ? -a.p.entropy_loss_coef * inv_total : 0.f;
 
     auto set_row = [&](int64_t row) {
-        const float row_m = a.mask ? __ldcg(&a.ws.row_msum[row]) : static_cast<float>(A);
+        const float row_len = a.cu ? static_cast<float>(a.cu[row + 1] - a.cu[row]) : static_cast<float>(A);
+        const float row_m = a.mask ? __ldcg(&a.ws.row_msum[row]) : row_len;
         const float inv_row = 1.f / fmaxf(row_m, 1.f);
         if (a.p.reduction == SKYB200_REDUCE_TOKEN_MEAN)
             cx.w_scale = inv_total;
         else if (a.p.reduction == SKYB200_REDUCE_SEQUENCE_MEAN)
             cx.w_scale = inv_row / Bf;
+        else if (a.p.reduction == SKYB200_REDUCE_SUM)
+            cx.w_scale = 1.f;
         else
             cx.w_scale = 1.f / (a.p.max_seq_len * Bf);
         cx.kl_scale = inv_row / Bf;
@@ -453,7 +508,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_flat_kernel(FlatArgs a) {
         for (int it = 0; it < 8; ++it) {
             const int64_t i = base_t + static_cast<int64_t>(it) * kLossThreads + threadIdx.x;
             if (i < a.t1) {
-                set_row(i / A);
+                set_row(a.cu ? row_of_token(a.cu, a.B, i) : i / A);
                 const float m = a.mask ? a.mask[i] : 1.f;
                 const float g = loss_token(cx, acc, a.lp[i], a.olp[i], a.adv[i], m, a.base ? a.base[i] : 0.f);
                 if (a.d_lp) a.d_lp[i] = g;
@@ -524,8 +579,8 @@ loss_finalize_kernel(LossChunkWs ws, int64_t nslots, int has_entropy, float* __r
     }
 }
 
-size_t loss_chunk_ws_bytes(int64_t B, int64_t A) {
-    const int64_t slots = loss_chunk_blocks(B * A) + 4 * 64;  // every chunk rounds its block count up
+size_t loss_chunk_ws_bytes(int64_t B, int64_t n_tokens) {
+    const int64_t slots = loss_chunk_blocks(n_tokens) + 4 * 64;  // every chunk rounds its block count up
     return static_cast<size_t>(2 * ((B * 4 + 255) / 256 * 256) + 512 + (slots + B) * kNumPartials * 4 + 512);
 }
 int64_t loss_chunk_blocks(int64_t n_tokens) { return (n_tokens + kFlatTile - 1) / kFlatTile; }
@@ -541,10 +596,11 @@ void loss_chunk_ws_carve(void* base, int64_t B, int64_t A, LossChunkWs* ws) {
     ws->partials = reinterpret_cast<float*>(b + 2 * rb + 256);
 }
 
-int loss_prepass(const float* loss_mask, const LossChunkWs& ws, int64_t B, int64_t A, cudaStream_t stream) {
+int loss_prepass(const float* loss_mask, const LossChunkWs& ws, int64_t B, int64_t A, const int32_t* cu,
+                 cudaStream_t stream) {
     SKYB200_CUDA_CHECK(cudaMemsetAsync(ws.counters, 0, 16, stream));
     loss_rowstats_kernel<<<(unsigned)B, kLossThreads, 0, stream>>>(nullptr, nullptr, loss_mask, ws.row_msum, ws.row_lw,
-                                                                   ws.total_msum, ws.counters, (int)B, A, 0);
+                                                                   ws.total_msum, ws.counters, (int)B, A, 0, cu);
     return check_launch("loss_rowstats_kernel(prepass)");
 }
 
@@ -558,9 +614,11 @@ int loss_row_logratio(const float* lp, const float* olp, const float* loss_mask,
 
 int loss_flat_range(const float* lp, const float* olp, const float* adv, const float* loss_mask, const float* base,
                     const float* ent, float* d_lp, float* d_ent, const LossChunkWs& ws, int64_t B, int64_t A,
-                    int64_t t0, int64_t t1, int64_t slot0, const skyb200_loss_params& p, cudaStream_t stream) {
+                    int64_t t0, int64_t t1, int64_t slot0, const skyb200_loss_params& p, const int32_t* cu,
+                    cudaStream_t stream) {
     if (t1 <= t0) return SKYB200_OK;
     FlatArgs a;
+    a.cu = cu;
     a.lp = lp;
     a.olp = olp;
     a.adv = adv;
@@ -577,7 +635,7 @@ int loss_flat_range(const float* lp, const float* olp, const float* adv, const f
     a.slot0 = slot0;
     a.p = p;
     auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    a.vec4 = (A % 4 == 0) && (t0 % 4 == 0) && al16(lp) && al16(olp) && al16(adv) && al16(loss_mask) && al16(base) &&
+    a.vec4 = (cu == nullptr) && (A % 4 == 0) && (t0 % 4 == 0) && al16(lp) && al16(olp) && al16(adv) && al16(loss_mask) && al16(base) &&
              al16(ent) && al16(d_lp) && al16(d_ent);
     loss_flat_kernel<<<(unsigned)loss_chunk_blocks(t1 - t0), kLossThreads, 0, stream>>>(a);
     return check_launch("loss_flat_kernel");
@@ -746,9 +804,10 @@ extern "C" int skyb200_policy_loss(const float* log_probs, const float* old_log_
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SKYB200_REQUIRE(log_probs && old_log_probs && advantages && stats && workspace && params, "null pointer");
     SKYB200_REQUIRE(B > 0 && A > 0 && B < 65536, "need 0 < B < 65536 and A > 0");
-    SKYB200_REQUIRE(params->loss_type >= 0 && params->loss_type <= SKYB200_LOSS_GSPO, "bad loss_type");
-    SKYB200_REQUIRE(params->reduction >= 0 && params->reduction <= SKYB200_REDUCE_SEQ_MEAN_TOKEN_SUM_NORM,
-                    "bad reduction");
+    SKYB200_REQUIRE(params->loss_type >= 0 && params->loss_type <= SKYB200_LOSS_LAST, "bad loss_type");
+    SKYB200_REQUIRE(params->reduction >= 0 && params->reduction <= SKYB200_REDUCE_SUM, "bad reduction");
+    SKYB200_REQUIRE(params->loss_type != SKYB200_LOSS_SAPO || (params->sapo_tau_pos > 0.f && params->sapo_tau_neg > 0.f),
+                    "sapo needs positive tau_pos / tau_neg");
     SKYB200_REQUIRE(params->kl_type >= 0 && params->kl_type <= SKYB200_KL_K3, "bad kl_type");
     SKYB200_REQUIRE(params->reduction != SKYB200_REDUCE_SEQ_MEAN_TOKEN_SUM_NORM || params->max_seq_len > 0.f,
                     "max_seq_len must be provided for seq_mean_token_sum_norm");

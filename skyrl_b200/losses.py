@@ -21,6 +21,7 @@ import torch
 from . import _lib
 
 _VALID_REDUCTIONS = ("token_mean", "sequence_mean", "seq_mean_token_sum_norm")
+_ALL_REDUCTIONS = _VALID_REDUCTIONS + ("sum",)
 
 
 def _cfg(config, name, default=None):
@@ -42,7 +43,7 @@ def _off_policy_enabled(config, rollout_logprobs) -> bool:
 def _make_params(loss_type: str, reduction: str, config, *, kl_type: str = "k3", kl_coef: float = 0.0,
                  use_entropy_loss: bool = False, entropy_coef: float = 0.0,
                  kl_has_grad: bool = False) -> _lib.LossParams:
-    if reduction not in _VALID_REDUCTIONS:
+    if reduction not in _ALL_REDUCTIONS:
         raise ValueError(f"Invalid loss reduction type: {reduction}")
     max_seq_len = _cfg(config, "max_seq_len", None)
     if reduction == "seq_mean_token_sum_norm":
@@ -55,8 +56,17 @@ def _make_params(loss_type: str, reduction: str, config, *, kl_type: str = "k3",
     p.kl_type = _lib.KL_TYPES[kl_type]
     p.kl_has_grad = int(kl_has_grad)
     p.use_entropy_loss = int(use_entropy_loss)
-    p.eps_clip_low = float(_cfg(config, "eps_clip_low", 0.2))
-    p.eps_clip_high = float(_cfg(config, "eps_clip_high", 0.2))
+    if loss_type == "cispo":  # CISPO clips with its own epsilons (config.cispo.*, ppo_utils.py:746)
+        cis = _cfg(config, "cispo", None)
+        p.eps_clip_low = float(_cfg(cis, "cispo_eps_clip_low"))
+        p.eps_clip_high = float(_cfg(cis, "cispo_eps_clip_high"))
+    else:
+        p.eps_clip_low = float(_cfg(config, "eps_clip_low", 0.2))
+        p.eps_clip_high = float(_cfg(config, "eps_clip_high", 0.2))
+    if loss_type == "sapo":
+        sapo = _cfg(config, "sapo", None)
+        p.sapo_tau_pos = float(_cfg(sapo, "tau_pos"))
+        p.sapo_tau_neg = float(_cfg(sapo, "tau_neg"))
     p.clip_ratio_c = float(_cfg(config, "clip_ratio_c", 3.0))
     p.max_seq_len = float(max_seq_len) if max_seq_len is not None else 0.0
     p.kl_loss_coef = float(kl_coef)
@@ -141,15 +151,18 @@ class _PolicyLossFn(torch.autograd.Function):
         return g_lp, g_ent, None, None, None, None, None, None
 
 
-def _registry_loss(loss_type, log_probs, old_log_probs, advantages, config, loss_mask, rollout_logprobs):
-    if _off_policy_enabled(config, rollout_logprobs):
+def _registry_loss(loss_type, log_probs, old_log_probs, advantages, config, loss_mask, rollout_logprobs,
+                   reduction=None, want_stats=False):
+    if loss_type not in ("cross_entropy", "importance_sampling") and _off_policy_enabled(config, rollout_logprobs):
         raise NotImplementedError(
             "off_policy_correction (tis_ratio_type / sequence_mask_metric) is not fused into the B200 loss kernel "
             "yet; disable it or use the reference loss for this configuration"
         )
-    params = _make_params(loss_type, _cfg(config, "loss_reduction"), config)
+    params = _make_params(loss_type, reduction or _cfg(config, "loss_reduction"), config)
     loss, stats = _PolicyLossFn.apply(log_probs, None, old_log_probs, advantages, loss_mask, None, params,
                                       _lib.STAT_POLICY_LOSS)
+    if want_stats:
+        return loss, stats
     clip_ratio = float(stats[_lib.STAT_CLIP_RATIO].item())  # the single host sync of this call
     return loss, {"clip_ratio": clip_ratio}
 
@@ -187,6 +200,38 @@ def gspo_policy_loss(
             "With GSPO it's recommended to use 'sequence_mean' loss reduction; got %s", _cfg(config, "loss_reduction")
         )
     return _registry_loss("gspo", log_probs, old_log_probs, advantages, config, loss_mask, rollout_logprobs)
+
+
+def sapo_policy_loss(log_probs, old_log_probs, advantages, config, loss_mask=None, rollout_logprobs=None):
+    """SAPO soft-gated objective (reference: ppo_utils.py:589-658); ``clip_ratio`` is reported as 0.0."""
+    if _cfg(config, "loss_reduction") != "sequence_mean":
+        import logging
+
+        logging.getLogger("skyrl_b200").warning(
+            "With SAPO it's recommended to use 'sequence_mean' loss reduction; got %s", _cfg(config, "loss_reduction")
+        )
+    loss, _ = _registry_loss("sapo", log_probs, old_log_probs, advantages, config, loss_mask, rollout_logprobs,
+                             want_stats=True)
+    return loss, {"clip_ratio": 0.0}
+
+
+def compute_policy_loss_cispo(log_probs, old_log_probs, advantages, config, loss_mask=None, rollout_logprobs=None):
+    """CISPO: clipped, detached importance weight times log-prob (reference: ppo_utils.py:728-761)."""
+    return _registry_loss("cispo", log_probs, old_log_probs, advantages, config, loss_mask, rollout_logprobs)
+
+
+def cross_entropy_loss(log_probs, old_log_probs, advantages, config, loss_mask=None, rollout_logprobs=None):
+    """SFT negative log-likelihood, masked SUM (Tinker semantics; reference: ppo_utils.py:892-930)."""
+    loss, _ = _registry_loss("cross_entropy", log_probs, old_log_probs, advantages, config, loss_mask, None,
+                             reduction="sum", want_stats=True)
+    return loss, {"clip_ratio": 0.0}
+
+
+def importance_sampling_loss(log_probs, old_log_probs, advantages, config, loss_mask=None, rollout_logprobs=None):
+    """``-(exp(lp - old_lp) * A)`` masked SUM (Tinker semantics; reference: ppo_utils.py:933-981)."""
+    loss, stats = _registry_loss("importance_sampling", log_probs, old_log_probs, advantages, config, loss_mask, None,
+                                 reduction="sum", want_stats=True)
+    return loss, {"importance_ratio": float(stats[_lib.STAT_RATIO_MEAN].item())}
 
 
 class _CriticLossFn(torch.autograd.Function):

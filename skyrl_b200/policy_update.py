@@ -67,6 +67,7 @@ def policy_update_step(
     chunk: int = 0,
     sync: bool = True,
     fused: bool = True,
+    cu_seqlens: Optional[torch.Tensor] = None,
 ) -> PolicyUpdateOutput:
     """``hidden`` [B, A, H] (or [B*A, H]) bf16, ``weight`` [V, H] bf16, ``labels`` [B, A] int64,
     ``old_log_probs`` / ``advantages`` / ``loss_mask`` / ``base_log_probs`` [B, A] fp32.
@@ -76,6 +77,11 @@ def policy_update_step(
     max_seq_len).  Gradients are those of ``final_loss`` (upstream gradient 1), i.e. what ``loss.backward()``
     delivers in the reference (worker.py:876-877).
 
+    Packed (ragged) layout: pass ``cu_seqlens`` (int32 ``[B + 1]``, ``cu[0] = 0``) and flat per-token tensors —
+    ``hidden`` [N, H], ``labels`` / ``old_log_probs`` / ``advantages`` / ``loss_mask`` / ``base_log_probs`` [N] —
+    with sequence ``b`` owning tokens ``[cu[b], cu[b+1])``.  Nothing is padded; the result equals the padded layout
+    with ``loss_mask = 0`` on the padding (see :func:`pack_by_lengths`).  Outputs are flat [N] then.
+
     ``fused=True`` (default) runs ``skyb200_policy_step``: per token chunk forward GEMM -> loss -> backward GEMMs,
     the forward keeping a bf16 copy of its logits tiles in a bounded [chunk, V] store so the backward does not
     recompute the projection (6*H*V executed flop per token).  ``fused=False`` runs the three C-ABI calls
@@ -84,10 +90,18 @@ def policy_update_step(
     lib = _lib.load()
     if not hidden.is_cuda:
         raise RuntimeError("policy_update_step needs CUDA tensors (no CPU fallback)")
-    B, A = old_log_probs.shape
+    packed = cu_seqlens is not None
+    if packed:
+        if not fused:
+            raise ValueError("the packed layout is only available with fused=True")
+        B = int(cu_seqlens.numel()) - 1
+        N = int(old_log_probs.numel())
+        A = 1
+    else:
+        B, A = old_log_probs.shape
+        N = B * A
     H = hidden.shape[-1]
     V = weight.shape[0]
-    N = B * A
     dev = hidden.device
     h = hidden.reshape(N, H)
     if h.dtype != torch.bfloat16 or not h.is_contiguous():
@@ -133,14 +147,17 @@ def policy_update_step(
                     if d_weight.dtype != torch.float32 or tuple(d_weight.shape) != (V, H) or not d_weight.is_contiguous():
                         raise ValueError("d_weight must be a contiguous fp32 [V, H] tensor")
                     acc = 1 if accumulate_d_weight else 0
-            wsb = lib.skyb200_policy_step_workspace(B, A, H, V, params.loss_type, int(need_grad))
+            cu = None
+            if packed:
+                cu = cu_seqlens.to(device=dev, dtype=torch.int32).contiguous()
+            wsb = lib.skyb200_policy_step_workspace(B, A, N, H, V, params.loss_type, int(need_grad))
             ws = _WS.get("step", wsb, dev)
             _lib.check(
                 lib.skyb200_policy_step(_lib.ptr(h), _lib.ptr(w), _lib.ptr(lab), _lib.ptr(olp), _lib.ptr(adv),
                                         _lib.ptr(mask), _lib.ptr(base) if use_kl else None, _lib.ptr(emask),
                                         _lib.ptr(logprobs), _lib.ptr(ent), _lib.ptr(d_hidden),
                                         _lib.ptr(d_weight) if need_d_weight else None, acc, _lib.ptr(stats),
-                                        _lib.ptr(ws), wsb, B, A, H, V, T, C.byref(params), stream),
+                                        _lib.ptr(ws), wsb, B, A, H, V, _lib.ptr(cu), N, T, C.byref(params), stream),
                 "skyb200_policy_step",
             )
             if sync:
@@ -148,7 +165,9 @@ def policy_update_step(
                 status["response_length"] = A
             else:
                 status = {"packed": stats}
-        return PolicyUpdateOutput(status=status, stats=stats, log_probs=logprobs.view(B, A), entropy=ent.view(B, A),
+        if not packed:
+            logprobs, ent = logprobs.view(B, A), ent.view(B, A)
+        return PolicyUpdateOutput(status=status, stats=stats, log_probs=logprobs, entropy=ent,
                                   d_hidden=d_hidden, d_weight=d_weight if need_d_weight else None)
     with torch.cuda.device(dev):
         logprobs = torch.empty(N, dtype=torch.float32, device=dev)
@@ -207,3 +226,21 @@ def policy_update_step(
             status = {"packed": stats}
     return PolicyUpdateOutput(status=status, stats=stats, log_probs=logprobs.view(B, A), entropy=ent.view(B, A),
                               d_hidden=d_hidden, d_weight=d_weight if need_d_weight else None)
+
+
+def pack_by_lengths(lengths: torch.Tensor, *tensors: torch.Tensor):
+    """Drop the right padding of ``[B, A, ...]`` tensors: returns ``(cu_seqlens int32 [B + 1], packed tensors)``
+    where packed tensor k is ``cat_b tensors[k][b, :lengths[b]]``.  ``None`` entries are passed through."""
+    lengths = lengths.to(torch.int64)
+    B = lengths.numel()
+    cu = torch.zeros(B + 1, dtype=torch.int32, device=lengths.device)
+    cu[1:] = torch.cumsum(lengths, 0).to(torch.int32)
+    out = []
+    for t in tensors:
+        if t is None:
+            out.append(None)
+            continue
+        A = t.shape[1]
+        keep = (torch.arange(A, device=t.device)[None, :] < lengths.to(t.device)[:, None])
+        out.append(t[keep])
+    return cu, out

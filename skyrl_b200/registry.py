@@ -179,6 +179,10 @@ class PolicyLossType(StrEnum):
     REGULAR = "regular"
     DUAL_CLIP = "dual_clip"
     GSPO = "gspo"
+    CISPO = "cispo"
+    SAPO = "sapo"
+    CROSS_ENTROPY = "cross_entropy"
+    IMPORTANCE_SAMPLING = "importance_sampling"
 
 
 class AdvantageEstimatorRegistry(BaseFunctionRegistry):
@@ -203,7 +207,8 @@ class AdvantageEstimatorRegistry(BaseFunctionRegistry):
 
 
 class PolicyLossRegistry(BaseFunctionRegistry):
-    """B200 policy losses: ``regular``, ``dual_clip``, ``gspo`` (ppo_utils.py:463-508)."""
+    """B200 policy losses: ``regular``, ``dual_clip``, ``gspo``, ``sapo``, ``cispo``, ``cross_entropy``,
+    ``importance_sampling`` (ppo_utils.py:463-508; ``clip_cov`` / ``kl_cov`` are not built yet)."""
 
     _actor_name = "policy_loss_registry"
     _function_type = "policy loss"
@@ -217,6 +222,10 @@ class PolicyLossRegistry(BaseFunctionRegistry):
             ("regular", losses.ppo_policy_loss),
             ("dual_clip", losses.ppo_policy_loss),
             ("gspo", losses.gspo_policy_loss),
+            ("sapo", losses.sapo_policy_loss),
+            ("cispo", losses.compute_policy_loss_cispo),
+            ("cross_entropy", losses.cross_entropy_loss),
+            ("importance_sampling", losses.importance_sampling_loss),
         ):
             if name not in have:
                 cls.register(name, fn)
@@ -283,7 +292,10 @@ def install_into_skyrl_train(patch_model_wrapper: bool = True) -> List[str]:
                                          "gae": adv.compute_gae_advantage_return,
                                          "reinforce++": adv.compute_reinforce_plus_plus_outcome_advantage}),
         (pu.PolicyLossRegistry, {"regular": losses.ppo_policy_loss, "dual_clip": losses.ppo_policy_loss,
-                                 "gspo": losses.gspo_policy_loss}),
+                                 "gspo": losses.gspo_policy_loss, "sapo": losses.sapo_policy_loss,
+                                 "cispo": losses.compute_policy_loss_cispo,
+                                 "cross_entropy": losses.cross_entropy_loss,
+                                 "importance_sampling": losses.importance_sampling_loss}),
     ):
         for name, fn in table.items():
             if name in reg.list_available():

@@ -51,7 +51,7 @@ def test_host_only_entry_points(lib):
 
 
 def test_loss_params_layout_matches_header():
-    assert ctypes.sizeof(_lib.LossParams) == 6 * 4 + 6 * 4
+    assert ctypes.sizeof(_lib.LossParams) == 6 * 4 + 8 * 4
 
 
 def test_bad_arguments_report_errors_without_a_gpu(lib):

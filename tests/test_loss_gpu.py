@@ -160,3 +160,25 @@ def test_critic_loss_matches_reference_golden(golden_loss, cname, clip, mname):
     if clip is not None:
         assert_close(clipfrac, g[key + "__clipfrac"], what="clipfrac")
     assert_close(v.grad, g[key + "__grad"], what="grad")
+
+
+_XCFG = dict(sapo=__import__("types").SimpleNamespace(tau_pos=1.0, tau_neg=2.0),
+             cispo=__import__("types").SimpleNamespace(cispo_eps_clip_low=0.1, cispo_eps_clip_high=0.3))
+
+
+@pytest.mark.parametrize("kind,red", [("sapo", "sequence_mean"), ("sapo", "token_mean"), ("cispo", "token_mean"),
+                                      ("cispo", "seq_mean_token_sum_norm"), ("cross_entropy", "token_mean"),
+                                      ("importance_sampling", "token_mean")])
+@pytest.mark.parametrize("mname", ["mask", "nomask"])
+def test_extra_registry_losses_match_reference_golden(golden_loss, kind, red, mname):
+    g = golden_loss
+    cfg = O.make_cfg(policy_loss_type=kind, loss_reduction=red, max_seq_len=64, **_XCFG)
+    lp = _t(g["lp"]).to(DEV).requires_grad_(True)
+    olp = _t(g["olp_mild"] if kind == "importance_sampling" else g["olp"]).to(DEV)
+    mask = _t(g["mask"]).to(DEV) if mname == "mask" else None
+    loss, met = skyrl_b200.PolicyLossRegistry.get(kind)(lp, olp, _t(g["adv"]).to(DEV), cfg, loss_mask=mask)
+    loss.backward()
+    key = f"{kind}__{red}__{mname}"
+    assert_close(loss, g[key + "__loss"], what=key + " loss")
+    assert_close(list(met.values())[0], g[key + "__metric"], what=key + " metric")
+    assert_close(lp.grad, g[key + "__grad"], what=key + " grad")

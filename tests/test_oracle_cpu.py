@@ -230,3 +230,34 @@ def test_golden_critic_loss(golden_loss, cname, clip, mname):
     assert_close(loss, g[key + "__loss"])
     assert_close(-1.0 if clipfrac is None else clipfrac, g[key + "__clipfrac"])
     assert_close(v.grad, g[key + "__grad"])
+
+
+_XCFG = dict(sapo=__import__("types").SimpleNamespace(tau_pos=1.0, tau_neg=2.0),
+             cispo=__import__("types").SimpleNamespace(cispo_eps_clip_low=0.1, cispo_eps_clip_high=0.3))
+_XCASES = [("sapo", "sequence_mean"), ("sapo", "token_mean"), ("cispo", "token_mean"),
+           ("cispo", "seq_mean_token_sum_norm"), ("cross_entropy", "token_mean"), ("importance_sampling", "token_mean")]
+
+
+@pytest.mark.parametrize("kind,red", _XCASES)
+@pytest.mark.parametrize("mname", ["mask", "nomask"])
+def test_golden_extra_losses(golden_loss, kind, red, mname):
+    g = golden_loss
+    lp, adv, fm = _t(g["lp"]), _t(g["adv"]), _t(g["mask"])
+    olp = _t(g["olp_mild"]) if kind == "importance_sampling" else _t(g["olp"])
+    cfg = O.make_cfg(policy_loss_type=kind, loss_reduction=red, max_seq_len=64, **_XCFG)
+    x = lp.clone().requires_grad_(True)
+    loss, met = O.extra_policy_loss(kind, x, olp, adv, cfg, fm if mname == "mask" else None)
+    loss.backward()
+    key = f"{kind}__{red}__{mname}"
+    assert_close(loss, g[key + "__loss"], what="loss")
+    assert_close(list(met.values())[0], g[key + "__metric"], what="metric")
+    assert_close(x.grad, g[key + "__grad"], what="grad")
+
+
+def test_kat_cispo():  # tests/cpu/algorithms/test_losses.py:85-137 -> -0.99768 (cispo eps 0.2 / 0.2 there)
+    from types import SimpleNamespace
+
+    adv, olp, lp = T([[1.0, -1.0, -4.0]]), T([[-1.0, -1.0, -3.0]]), T([[-1.69315, -1.0, -0.69741]])
+    cfg = O.make_cfg(policy_loss_type="cispo", cispo=SimpleNamespace(cispo_eps_clip_low=0.2, cispo_eps_clip_high=0.2))
+    loss, _ = O.extra_policy_loss("cispo", lp, olp, adv, cfg, None)
+    assert abs(loss.item() - (-0.99768)) < 2e-3

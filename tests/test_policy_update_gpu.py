@@ -121,3 +121,51 @@ def test_grpo_config1_slice_end_to_end():
     assert out.status["policy_loss"] == pytest.approx(ref_loss.item(), rel=5e-3, abs=5e-4)
     assert out.d_hidden.shape == (B * A, H) and out.d_weight.shape == (V, H)
     assert torch.isfinite(out.d_weight).all() and torch.isfinite(out.d_hidden.float()).all()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(policy_loss_type="regular", loss_reduction="token_mean", use_kl_loss=True, use_entropy_loss=True),
+    dict(policy_loss_type="dual_clip", loss_reduction="sequence_mean", use_kl_loss=True, use_entropy_loss=False),
+    dict(policy_loss_type="regular", loss_reduction="seq_mean_token_sum_norm", use_kl_loss=False, max_seq_len=700),
+])
+def test_packed_ragged_layout_equals_padded_reference(kw):
+    """Config-5 style ragged batch: the packed layout (no padding rows at all) must give the numbers of the padded
+    reference computation with loss_mask = 0 on the padding, plus an interior hole in the loss mask."""
+    B, A, H, V, T = 7, 600, 64, 1500, 1.0
+    g = torch.Generator().manual_seed(11)
+    hidden = torch.randn(B, A, H, generator=g).bfloat16()
+    weight = (torch.randn(V, H, generator=g) * (1.5 / H ** 0.5)).bfloat16()
+    labels = torch.randint(0, V, (B, A), generator=g)
+    lens = torch.tensor([600, 37, 1, 420, 128, 599, 300])
+    pad_mask = (torch.arange(A)[None] < lens[:, None]).float()
+    loss_mask = pad_mask.clone()
+    loss_mask[3, 100:180] = 0  # tool tokens inside a response
+    cfg = O.make_cfg(**kw)
+    h = hidden.float().reshape(B * A, H).requires_grad_(True)
+    w = weight.float().requires_grad_(True)
+    lp_ref, ent_ref = O.head_logprobs_entropy(h, w, labels.reshape(-1), T)
+    lp_ref, ent_ref = lp_ref.view(B, A), ent_ref.view(B, A)
+    olp = lp_ref.detach() + 0.05 * torch.randn(B, A, generator=g)
+    base = lp_ref.detach() + 0.1 * torch.randn(B, A, generator=g)
+    adv = torch.randn(B, A, generator=g)
+    final_ref, st_ref = O.loss_assembly(lp_ref, olp, adv, cfg, loss_mask, base, ent_ref)
+    final_ref.backward()
+
+    cu, (hp, labp, olpp, advp, maskp, basep) = skyrl_b200.pack_by_lengths(lens, hidden, labels, olp, adv, loss_mask, base)
+    assert cu.tolist()[-1] == int(lens.sum()) and hp.shape == (int(lens.sum()), H)
+    out = skyrl_b200.policy_update_step(hp.to(DEV), weight.to(DEV), labp.to(DEV), olpp.to(DEV), advp.to(DEV), cfg,
+                                        loss_mask=maskp.to(DEV), base_log_probs=basep.to(DEV), temperature=T,
+                                        cu_seqlens=cu.to(DEV))
+    keep = pad_mask.bool()
+    assert (out.log_probs.cpu() - lp_ref.detach()[keep]).abs().max().item() < 1e-3
+    for k in ("final_loss", "policy_loss", "policy_entropy", "loss_metrics/clip_ratio"):
+        assert out.status[k] == pytest.approx(st_ref[k], rel=2e-3, abs=2e-4), k
+    if cfg.use_kl_loss:
+        assert out.status["policy_kl"] == pytest.approx(st_ref["policy_kl"], rel=2e-2, abs=1e-4)
+    rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+    assert rel(out.d_hidden.float(), h.grad.view(B, A, H)[keep]) < 2e-2
+    assert rel(out.d_weight, w.grad) < 2e-2
+    with pytest.raises(RuntimeError, match="gspo"):
+        skyrl_b200.policy_update_step(hp.to(DEV), weight.to(DEV), labp.to(DEV), olpp.to(DEV), advp.to(DEV),
+                                      O.make_cfg(policy_loss_type="gspo", loss_reduction="sequence_mean"),
+                                      loss_mask=maskp.to(DEV), cu_seqlens=cu.to(DEV))
