@@ -65,12 +65,12 @@ def main():
         return f
 
     for name, epi, group, order, cp in [
+        ("skip_tmem_read_g16", 4, 16, 0, None),
         ("null_epilogue_g16", 2, 16, 0, None),
         ("bf16_store_g16", 1, 16, 0, _lib.ptr(Cc)),
         ("lse_g16", 3, 16, 0, None),
         ("lse_store_g16", 3, 16, 0, _lib.ptr(C)),
-        ("lse_g37", 3, 37, 0, None),
-        ("f32_store_g16", 0, 16, 0, "f32"),
+        ("null_epilogue_g16_again", 2, 16, 0, None),
     ]:
         if epi == 1 and N % 16:
             continue

@@ -133,7 +133,13 @@ constexpr int kTileM = kBM * kHeadCtas;
 
 // Token chunk = 37 pair-tiles: 37 * n_tiles is a multiple of the 74 resident CTA pairs, so every GEMM of the
 // chunk runs in whole waves on the 148 SMs.
-constexpr int64_t kDefaultChunk = 37 * kTileM;  // 9472 tokens
+static int env_int(const char* name, int dflt);
+// 37 pair-tiles = 9472 tokens; SKYB200_CHUNK_TILES overrides (multiples of 37 keep whole waves)
+static int64_t default_chunk() {
+    static int64_t v = (int64_t)env_int("SKYB200_CHUNK_TILES", 37) * kTileM;
+    return v;
+}
+#define kDefaultChunk default_chunk()
 
 static int64_t pick_chunk(int64_t N, int64_t chunk) {
     if (chunk <= 0) chunk = kDefaultChunk;
@@ -839,7 +845,12 @@ extern "C" int skyb200_gemm_bench(const void* A, const void* B, void* C, void* s
         return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
             A, K, B, K, (int)M, (int)N, (int)K, group, ep, stream, order);
     }
-    return fail(SKYB200_EINVAL, "epi must be 0..3");
+    if (epi == 4) {
+        EpiSkip::Params ep{static_cast<float*>(C)};
+        return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiSkip>(A, K, B, K, (int)M, (int)N, (int)K,
+                                                                                  group, ep, stream, order);
+    }
+    return fail(SKYB200_EINVAL, "epi must be 0..4");
 }
 
 extern "C" const uint32_t* skyb200_gemm_debug_record(void) {
