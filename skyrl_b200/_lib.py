@@ -8,7 +8,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "libskyb200.so"
+_LIB_PATH = Path(os.environ.get("SKYB200_LIB") or (Path(__file__).resolve().parent / "libskyb200.so"))
 _lib = None
 
 # enums (mirror include/skyb200.h)

@@ -39,6 +39,34 @@ constexpr int kEpiWarp0 = 0, kTmaWarp = 4, kMmaWarp = 5, kAllocWarp = 6;
 constexpr int kEpiWarp0 = 4, kTmaWarp = 0, kMmaWarp = 1, kAllocWarp = 2;
 #endif
 
+// L2 eviction policies (the encodings cuTensorMap / createpolicy produce for fraction 1.0)
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+template <int kCtas>
+__device__ __forceinline__ void tma_load_2d_hint(const void* desc, uint64_t* bar, void* smem_dst, int32_t crd0,
+                                                 int32_t crd1, uint64_t policy) {
+    if constexpr (kCtas == 2) {
+        const uint32_t bar_addr = ptx::smem_u32(bar) & 0xFEFFFFFFu;  // leader CTA's barrier
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+            " [%0], [%1, {%3, %4}], [%2], %5;"
+            :
+            : "r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_addr), "r"(crd0),
+              "r"(crd1), "l"(policy)
+            : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+            " [%0], [%1, {%3, %4}], [%2], %5;"
+            :
+            : "r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(ptx::smem_u32(bar)),
+              "r"(crd0), "r"(crd1), "l"(policy)
+            : "memory");
+    }
+}
+
 // Debug record written to mapped host memory when a barrier wait times out (so a protocol bug shows up
 // as a failed launch with a readable reason instead of a hung GPU).
 struct GemmDebug {
@@ -116,7 +144,8 @@ struct GemmSmem {
 template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
-                  int N, int K, int group_m, int tile_order, typename Epi::Params ep, GemmDebug* dbg) {
+                  int N, int K, int group_m, int tile_order, uint64_t hint_a, uint64_t hint_b, typename Epi::Params ep,
+                  GemmDebug* dbg) {
     using S = GemmSmem<kCtas, BN, kStages>;
     constexpr int TILE_M = kBM * kCtas;
     constexpr uint32_t kTmemCols = 2 * BN;
@@ -196,30 +225,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     if constexpr (kAMn) {
 #pragma unroll
                         for (int j = 0; j < kBM / 64; ++j) {
-                            if constexpr (kCtas == 2)
-                                ptx::tma_load_2d_2sm(&tmap_a, &full_bar[stage], a_dst + j * 8192, m0 + j * 64, k0);
-                            else
-                                ptx::tma_load_2d(&tmap_a, &full_bar[stage], a_dst + j * 8192, m0 + j * 64, k0);
+                            tma_load_2d_hint<kCtas>(&tmap_a, &full_bar[stage], a_dst + j * 8192, m0 + j * 64, k0, hint_a);
                         }
                     } else {
-                        if constexpr (kCtas == 2)
-                            ptx::tma_load_2d_2sm(&tmap_a, &full_bar[stage], a_dst, k0, m0);
-                        else
-                            ptx::tma_load_2d(&tmap_a, &full_bar[stage], a_dst, k0, m0);
+                        tma_load_2d_hint<kCtas>(&tmap_a, &full_bar[stage], a_dst, k0, m0, hint_a);
                     }
                     if constexpr (kBMn) {
 #pragma unroll
                         for (int j = 0; j < static_cast<int>(S::kLoadN) / 64; ++j) {
-                            if constexpr (kCtas == 2)
-                                ptx::tma_load_2d_2sm(&tmap_b, &full_bar[stage], b_dst + j * 8192, n0 + j * 64, k0);
-                            else
-                                ptx::tma_load_2d(&tmap_b, &full_bar[stage], b_dst + j * 8192, n0 + j * 64, k0);
+                            tma_load_2d_hint<kCtas>(&tmap_b, &full_bar[stage], b_dst + j * 8192, n0 + j * 64, k0, hint_b);
                         }
                     } else {
-                        if constexpr (kCtas == 2)
-                            ptx::tma_load_2d_2sm(&tmap_b, &full_bar[stage], b_dst, k0, n0);
-                        else
-                            ptx::tma_load_2d(&tmap_b, &full_bar[stage], b_dst, k0, n0);
+                        tma_load_2d_hint<kCtas>(&tmap_b, &full_bar[stage], b_dst, k0, n0, hint_b);
                     }
                     }  // issuer
                     __syncwarp();
@@ -337,11 +354,26 @@ __device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&r)[8]) {
                  : "l"(p)
                  : "memory");
 }
+// Same, with an L2 evict-first policy: for data that is written (or read) exactly once by this kernel, so it does
+// not push the operand panels the other CTAs are about to reuse out of L2.
+__device__ __forceinline__ void st_global_256_stream(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                     uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7) {
+    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(p), "r"(a0),
+                 "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7), "l"(kEvictFirst)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_256_stream(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.L2::cache_hint.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p), "l"(kEvictFirst)
+                 : "memory");
+}
+
 // 32 fp32 values -> 32 bf16 -> two 32-byte stores (dst must be 32-byte aligned)
 __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float (&d)[32]) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        st_global_256(dst + 16 * h, pack_bf16x2(d[16 * h + 0], d[16 * h + 1]), pack_bf16x2(d[16 * h + 2], d[16 * h + 3]),
+        st_global_256_stream(dst + 16 * h, pack_bf16x2(d[16 * h + 0], d[16 * h + 1]), pack_bf16x2(d[16 * h + 2], d[16 * h + 3]),
                       pack_bf16x2(d[16 * h + 4], d[16 * h + 5]), pack_bf16x2(d[16 * h + 6], d[16 * h + 7]),
                       pack_bf16x2(d[16 * h + 8], d[16 * h + 9]), pack_bf16x2(d[16 * h + 10], d[16 * h + 11]),
                       pack_bf16x2(d[16 * h + 12], d[16 * h + 13]), pack_bf16x2(d[16 * h + 14], d[16 * h + 15]));
@@ -375,12 +407,12 @@ struct EpiStoreF32 {
                         for (int k = 0; k < 8; ++k) o[k] = v[8 * i + k];
                         if (p.accumulate) {
                             uint32_t old[8];
-                            ld_global_256(dst + 8 * i, old);
+                            ld_global_256_stream(dst + 8 * i, old);
 #pragma unroll
                             for (int k = 0; k < 8; ++k)
                                 o[k] = __float_as_uint(__uint_as_float(o[k]) + __uint_as_float(old[k]));
                         }
-                        st_global_256(dst + 8 * i, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+                        st_global_256_stream(dst + 8 * i, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
                     }
                 } else {
                     for (int i = 0; i < 32 && col0 + i < N; ++i) {

@@ -79,7 +79,8 @@ static GemmDebug* debug_record_dev() {
 // A: K-major -> [M, K] with pitch lda; MN-major -> [K, M] with pitch lda.  Same for B with N.
 template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
 static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int group_m,
-                       const typename Epi::Params& ep, cudaStream_t stream, int tile_order = 0) {
+                       const typename Epi::Params& ep, cudaStream_t stream, int tile_order = 0,
+                       uint64_t hint_a = kEvictNormal, uint64_t hint_b = kEvictNormal) {
     using S = GemmSmem<kCtas, BN, kStages>;
     if (M <= 0 || N <= 0 || K <= 0) return SKYB200_OK;
     CUtensorMap ta, tb;
@@ -119,7 +120,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
     cfg.numAttrs = 1;
     GemmDebug* dbg = debug_record_dev();
     if (group_m < 1) group_m = 1;
-    SKYB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group_m, tile_order, ep, dbg));
+    SKYB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group_m, tile_order, hint_a, hint_b, ep, dbg));
     return SKYB200_OK;
 }
 
@@ -158,6 +159,12 @@ static int env_int(const char* name, int dflt) {
 // tile-order group sizes (tunable for experiments; defaults measured on the 7B head)
 static int fwd_group_m() { static int v = env_int("SKYB200_FWD_GROUP_M", 16); return v; }
 static int dh_group_m() { static int v = env_int("SKYB200_DH_GROUP_M", 8); return v; }
+static uint64_t hint_of(const char* name, int dflt) {
+    const int v = env_int(name, dflt);  // 1 = normal, 2 = evict_first, 3 = evict_last
+    return v == 2 ? kEvictFirst : (v == 3 ? kEvictLast : kEvictNormal);
+}
+static uint64_t hint_fwd_a() { static uint64_t v = hint_of("SKYB200_HINT_FWD_A", 3); return v; }
+static uint64_t hint_dw_b() { static uint64_t v = hint_of("SKYB200_HINT_DW_B", 3); return v; }
 static int dw_group_n() { static int v = env_int("SKYB200_DW_GROUP_N", 14); return v; }
 
 
@@ -229,7 +236,7 @@ dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const
 #pragma unroll
             for (int k = 0; k < 8; ++k) r[k] = 0u;
         } else {
-            ld_global_256(ptr, r);
+            ld_global_256_stream(ptr, r);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&r[k]);
@@ -242,7 +249,7 @@ dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const
                 r[k] = pack_bf16x2(d0, d1);
             }
         }
-        st_global_256(ptr, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+        st_global_256(ptr, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);  // re-read by the two GEMMs next
     } else {
         for (int k = 0; k < 16 && col0 + k < V; ++k) {
             float d = 0.f;
@@ -624,7 +631,7 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
         if (ci >= 2) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[p], 0));
         SKYB200_CUDA_CHECK(cudaMemsetAsync(ep.label_acc, 0, (size_t)rows * sizeof(float), stream));
         int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
-            hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream);
+            hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream, 0, hint_fwd_a(), kEvictNormal);
         if (r) return r;
         SKYB200_CUDA_CHECK(cudaEventRecord(ss->fwd[p], stream));
         return SKYB200_OK;
@@ -687,7 +694,8 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
             ew.ldc = H;
             ew.accumulate = (accumulate != 0 || t0 > 0) ? 1 : 0;
             int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
-                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1);
+                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, kEvictNormal,
+                hint_dw_b());
             if (r) return r;
         }
         return SKYB200_OK;
