@@ -105,11 +105,15 @@ size_t skyb200_policy_loss_workspace(int64_t B, int64_t A);
  * d_log_probs: [B, A] fp32 out, = d final_loss / d log_probs (NULL = forward only).
  * d_entropy:   [B, A] fp32 out or NULL; zeros unless params->use_entropy_loss.
  * stats: SKYB200_LOSS_NSTATS floats out.
+ * tis [B, A] fp32 or NULL: detached per-token weight multiplied into the loss (off-policy correction);
+ * clip_mask [B, A] fp32 or NULL: mask for the clip_ratio metric when it differs from loss_mask (the reference
+ * computes clip_ratio with the mask it had BEFORE the off-policy correction shrank it, ppo_utils.py:570-583).
  */
 int skyb200_policy_loss(const float* log_probs, const float* old_log_probs, const float* advantages,
                         const float* loss_mask, const float* base_log_probs, const float* entropy,
                         float* d_log_probs, float* d_entropy, float* stats, void* workspace, size_t workspace_bytes,
-                        int64_t B, int64_t A, const skyb200_loss_params* params, void* stream);
+                        int64_t B, int64_t A, const skyb200_loss_params* params, const float* tis,
+                        const float* clip_mask, void* stream);
 
 /*
  * Critic (value) loss, forward + backward (ppo_critic_loss, ppo_utils.py:175-193):
@@ -121,6 +125,45 @@ int skyb200_policy_loss(const float* log_probs, const float* old_log_probs, cons
 int skyb200_critic_loss(const float* values, const float* old_values, const float* returns, const float* loss_mask,
                         float* d_values, float* stats, void* workspace, size_t workspace_bytes, int64_t B, int64_t A,
                         float value_clip, int32_t use_clip, void* stream);
+
+/*
+ * Off-policy correction (compute_off_policy_correction, off_policy_correction_utils.py:173-262): TIS weights,
+ * outlier-token mask and sequence mask from (old_log_probs, rollout_logprobs, loss_mask).  No gradient.
+ *   tis_out  [B, A]: weight the per-token loss is multiplied with (1 when tis_type == 0)
+ *   mask_out [B, A]: loss_mask * outlier_mask * sequence_mask
+ *   metrics_out: SKYB200_OPC_NMETRICS floats (indices below)
+ */
+typedef struct skyb200_opc_params {
+    int32_t tis_type;      /* 0 none, 1 "token", 2 "sequence" */
+    int32_t seq_mask_type; /* 0 none, 1 "geometric", 2 "product" */
+    int32_t has_outlier_low;
+    int32_t has_outlier_high;
+    float token_tis_cap; /* token_tis_ratio_clip_high */
+    float seq_tis_cap;   /* sequence_tis_ratio_clip_high */
+    float outlier_low;   /* outlier_token_is_threshold_low / _high */
+    float outlier_high;
+    float geo_low; /* geo_mask_low / geo_mask_high */
+    float geo_high;
+    float prod_low; /* product_mask_low / product_mask_high */
+    float prod_high;
+} skyb200_opc_params;
+#define SKYB200_OPC_IS_RATIO_MEAN 0
+#define SKYB200_OPC_IS_RATIO_STD 1
+#define SKYB200_OPC_IS_RATIO_MAX 2
+#define SKYB200_OPC_IS_RATIO_MIN 3
+#define SKYB200_OPC_OUTLIER_MASKED 4
+#define SKYB200_OPC_OUTLIER_OVER_HIGH 5
+#define SKYB200_OPC_OUTLIER_UNDER_LOW 6
+#define SKYB200_OPC_TIS_CLIP_HIGH 7 /* tis_token_clip_high_ratio or tis_seq_clip_high_ratio */
+#define SKYB200_OPC_SEQ_MASKED 8    /* geo_/product_sequence_mask_masked_ratio */
+#define SKYB200_OPC_SEQ_OVER_HIGH 9
+#define SKYB200_OPC_SEQ_UNDER_LOW 10
+#define SKYB200_OPC_NMETRICS 16
+size_t skyb200_off_policy_workspace(int64_t B);
+int skyb200_off_policy_correction(const float* old_log_probs, const float* rollout_logprobs, const float* loss_mask,
+                                  float* tis_out, float* mask_out, float* metrics_out, void* workspace,
+                                  size_t workspace_bytes, int64_t B, int64_t A, const skyb200_opc_params* params,
+                                  void* stream);
 
 /* x[i] *= *scale_dev  (applies an upstream autograd gradient that lives on the device) */
 int skyb200_scale_inplace(float* x, const float* scale_dev, int64_t n, void* stream);

@@ -141,6 +141,35 @@ def gen_losses(pu):
             out[key + "__loss"] = np.float32(loss.item())
             out[key + "__metric"] = np.float32(list(met.values())[0])
             out[key + "__grad"] = x.grad.numpy()
+    # off-policy correction inside ppo_policy_loss (off_policy_correction_utils.py)
+    rlp = olp + 0.15 * torch.randn(B, A, generator=g)
+    rlp[6, 3] = olp[6, 3] - 3.0  # one outlier token (ratio e^3) -> its whole sequence is masked by the outlier rule
+    rlp[7] = olp[7] - 0.05       # a sequence with a uniformly higher ratio
+    out["rlp"] = rlp.numpy()
+    opc_cases = {
+        "token_tis": dict(tis_ratio_type="token", token_tis_ratio_clip_high=1.2),
+        "seq_tis_outlier": dict(tis_ratio_type="sequence", sequence_tis_ratio_clip_high=2.0,
+                                outlier_token_is_threshold_low=0.2, outlier_token_is_threshold_high=5.0),
+        "geo_mask": dict(sequence_mask_metric="geometric", geo_mask_low=0.98, geo_mask_high=1.02),
+        "product_mask_token_tis": dict(tis_ratio_type="token", sequence_mask_metric="product", product_mask_low=0.5,
+                                       product_mask_high=2.0, outlier_token_is_threshold_high=10.0),
+    }
+    defaults = dict(tis_ratio_type=None, token_tis_ratio_clip_high=2.0, sequence_tis_ratio_clip_high=5.0,
+                    sequence_mask_metric=None, geo_mask_high=1.01, geo_mask_low=0.99, product_mask_high=2.0,
+                    product_mask_low=0.5, outlier_token_is_threshold_low=None, outlier_token_is_threshold_high=None)
+    import json as _json
+    for name, kw in opc_cases.items():
+        okw = dict(defaults); okw.update(kw)
+        for kind, red in (("regular", "token_mean"), ("dual_clip", "sequence_mean")):
+            c = cfg(policy_loss_type=kind, loss_reduction=red, off_policy_correction=SimpleNamespace(**okw))
+            x = lp.clone().requires_grad_(True)
+            loss, met = pu.PolicyLossRegistry.get(kind)(x, olp, adv, c, loss_mask=fm, rollout_logprobs=rlp)
+            loss.backward()
+            key = f"opc__{name}__{kind}"
+            out[key + "__loss"] = np.float32(loss.item())
+            out[key + "__grad"] = x.grad.numpy()
+            out[key + "__metrics"] = np.array(_json.dumps(met))
+            out[key + "__cfg"] = np.array(_json.dumps(okw))
     # critic loss (ppo_utils.py:175-193)
     vals = torch.randn(B, A, generator=g)
     old_vals = vals + 0.3 * torch.randn(B, A, generator=g)

@@ -198,6 +198,69 @@ def policy_loss(lp, olp, adv, cfg, mask=None):
     return reduce_loss(loss, mask, cfg.loss_reduction, getattr(cfg, "max_seq_len", None)), clip_ratio
 
 
+def off_policy_correction(olp, rlp, mask, opc):
+    """utils/off_policy_correction_utils.py:173-262 restated: returns (tis or None, metrics, new_mask)."""
+    tis_type, seq_metric = opc.tis_ratio_type, opc.sequence_mask_metric
+    if tis_type is None and seq_metric is None:
+        return None, {}, mask
+    safe = lambda d: d.float().clamp(-20.0, 20.0).exp()
+    d = olp - rlp
+    ratio = safe(d)
+    met = {"is_ratio_mean": masked_mean(ratio, mask).item(), "is_ratio_std": (ratio * mask).std().item(),
+           "is_ratio_max": (ratio * mask).max().item(), "is_ratio_min": (ratio * mask).min().item()}
+    hi, lo = opc.outlier_token_is_threshold_high, opc.outlier_token_is_threshold_low
+    over = (ratio > hi) & (mask > 0) if hi is not None else torch.zeros_like(mask, dtype=torch.bool)
+    under = (ratio < lo) & (mask > 0) if lo is not None else torch.zeros_like(mask, dtype=torch.bool)
+    row_ok = ~(over.any(-1, keepdim=True) | under.any(-1, keepdim=True))
+    B = float(mask.shape[0])
+    met.update(outlier_seq_masked_ratio=((~row_ok).sum() / B).item(), outlier_seq_over_high_ratio=(over.any(-1).sum() / B).item(),
+               outlier_seq_under_low_ratio=(under.any(-1).sum() / B).item())
+    mask = mask * row_ok.float()
+    tis = None
+    if tis_type == "token":
+        cap = opc.token_tis_ratio_clip_high
+        met["tis_token_clip_high_ratio"] = (((ratio > cap) & (mask > 0)).sum() / (mask > 0).sum().clamp(min=1)).item()
+        tis = ratio.clamp(max=cap)
+    elif tis_type == "sequence":
+        sr = safe((d * mask).sum(-1, keepdim=True))
+        cap = opc.sequence_tis_ratio_clip_high
+        met["tis_seq_clip_high_ratio"] = ((sr > cap).sum() / B).item()
+        tis = sr.clamp(max=cap)
+    elif tis_type is not None:
+        raise ValueError(f"Unknown tis_ratio_type: {tis_type}")
+    if seq_metric is not None:
+        s = (d * mask).sum(-1, keepdim=True)
+        if seq_metric == "geometric":
+            val, lo_, hi_, nm = safe(s / mask.sum(-1, keepdim=True).clamp(min=1.0)), opc.geo_mask_low, opc.geo_mask_high, "geo"
+        elif seq_metric == "product":
+            val, lo_, hi_, nm = safe(s), opc.product_mask_low, opc.product_mask_high, "product"
+        else:
+            raise ValueError(f"Unknown sequence_mask_metric: {seq_metric}")
+        so, su = val > hi_, val < lo_
+        keep = ~so & ~su
+        met[f"{nm}_sequence_mask_masked_ratio"] = ((~keep).sum() / B).item()
+        met[f"{nm}_sequence_mask_over_high_ratio"] = (so.sum() / B).item()
+        met[f"{nm}_sequence_mask_under_low_ratio"] = (su.sum() / B).item()
+        mask = mask * keep.float()
+    return tis, met, mask
+
+
+def policy_loss_with_correction(lp, olp, adv, cfg, mask, rlp):
+    """ppo_policy_loss with rollout_logprobs (utils/ppo_utils.py:548-586 incl. :579-583). Returns (loss, metrics)."""
+    ratio = (lp - olp).float().clamp(-20.0, 20.0).exp()
+    s1 = ratio * adv
+    s2 = ratio.clamp(1 - cfg.eps_clip_low, 1 + cfg.eps_clip_high) * adv
+    loss = -torch.min(s1, s2)
+    metrics = {"clip_ratio": masked_mean((-s2 > -s1).float(), mask).mean().item()}
+    if cfg.policy_loss_type == "dual_clip":
+        loss = torch.where(adv < 0, torch.min(-adv * cfg.clip_ratio_c, loss), loss)
+    tis, met, mask = off_policy_correction(olp, rlp, mask, cfg.off_policy_correction)
+    if tis is not None:
+        loss = loss * tis
+    metrics.update(met)
+    return reduce_loss(loss, mask, cfg.loss_reduction, getattr(cfg, "max_seq_len", None)), metrics
+
+
 def extra_policy_loss(kind, lp, olp, adv, cfg, mask=None):
     """sapo (utils/ppo_utils.py:589-658), cispo (:728-761), cross_entropy (:892-930), importance_sampling (:933-981).
     Returns (loss, metrics)."""

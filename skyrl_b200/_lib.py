@@ -41,6 +41,25 @@ class LossParams(C.Structure):
     ]
 
 
+class OpcParams(C.Structure):
+    _fields_ = [
+        ("tis_type", C.c_int32),
+        ("seq_mask_type", C.c_int32),
+        ("has_outlier_low", C.c_int32),
+        ("has_outlier_high", C.c_int32),
+        ("token_tis_cap", C.c_float),
+        ("seq_tis_cap", C.c_float),
+        ("outlier_low", C.c_float),
+        ("outlier_high", C.c_float),
+        ("geo_low", C.c_float),
+        ("geo_high", C.c_float),
+        ("prod_low", C.c_float),
+        ("prod_high", C.c_float),
+    ]
+
+
+OPC_NMETRICS = 16
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _I32 = C.c_int32
@@ -54,7 +73,10 @@ SIGNATURES = {
     "skyb200_check_device": (C.c_int, []),
     "skyb200_policy_loss_workspace": (_SZ, [_I64, _I64]),
     "skyb200_policy_loss": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I64, _I64,
-                                      C.POINTER(LossParams), _P]),
+                                      C.POINTER(LossParams), _P, _P, _P]),
+    "skyb200_off_policy_workspace": (_SZ, [_I64]),
+    "skyb200_off_policy_correction": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _SZ, _I64, _I64, C.POINTER(OpcParams),
+                                                _P]),
     "skyb200_scale_inplace": (C.c_int, [_P, _P, _I64, _P]),
     "skyb200_masked_mean": (C.c_int, [_P, _P, _P, _P, _SZ, _I64, _P]),
     "skyb200_approx_kl": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),

@@ -28,6 +28,7 @@ struct LossWs {
     float* total_msum;        // [1]
     unsigned int* counters;   // [2]
     float* partials;          // [num_blocks][kNumPartials]
+    float* tmp;               // 148*4*2 floats of scratch for small side reductions
 };
 
 static size_t loss_ws_layout(int64_t B, int64_t A, LossWs* ws, void* base) {
@@ -40,7 +41,7 @@ static size_t loss_ws_layout(int64_t B, int64_t A, LossWs* ws, void* base) {
         return o;
     };
     size_t o_rm = take(B * 4), o_lw = take(B * 4), o_tot = take(16), o_cnt = take(16),
-           o_part = take(blocks * kNumPartials * 4);
+           o_part = take(blocks * kNumPartials * 4), o_tmp = take(148 * 4 * 2 * 4 + 64);
     if (ws != nullptr) {
         char* b = static_cast<char*>(base);
         ws->row_msum = reinterpret_cast<float*>(b + o_rm);
@@ -48,6 +49,7 @@ static size_t loss_ws_layout(int64_t B, int64_t A, LossWs* ws, void* base) {
         ws->total_msum = reinterpret_cast<float*>(b + o_tot);
         ws->counters = reinterpret_cast<unsigned int*>(b + o_cnt);
         ws->partials = reinterpret_cast<float*>(b + o_part);
+        ws->tmp = reinterpret_cast<float*>(b + o_tmp);
     }
     return off;
 }
@@ -102,6 +104,8 @@ struct LossArgs {
     const float* mask;
     const float* base;
     const float* ent;
+    const float* tis;        // detached per-token weight (off-policy correction) or nullptr
+    const float* clip_mask;  // mask of the clip_ratio metric when it differs from `mask`, or nullptr
     float* d_lp;
     float* d_ent;
     float* stats;
@@ -151,7 +155,7 @@ struct TokenCtx {
 
 // One response token: accumulates the reductions, returns d final_loss / d log_prob.
 __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, float lp, float olp, float adv, float m,
-                                            float base) {
+                                            float base, float tis = 1.f, float cm = -1.f) {
     float ratio, loss, dl_dlp, clipped = 0.f;
     if (cx.loss_type <= SKYB200_LOSS_GSPO) {
         float dr_dlp;
@@ -203,9 +207,11 @@ __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, fl
         loss = -ratio * adv;
         dl_dlp = loss;
     }
+    loss *= tis;    // off-policy correction weight (detached)
+    dl_dlp *= tis;
     const float w = m * cx.w_scale;
     acc.s_loss = fmaf(loss, w, acc.s_loss);
-    acc.s_clip = fmaf(clipped, m, acc.s_clip);
+    acc.s_clip = fmaf(clipped, cm >= 0.f ? cm : m, acc.s_clip);
     acc.s_ratio = fmaf(ratio, m, acc.s_ratio);
     if (m != 0.f) {
         acc.r_max = fmaxf(acc.r_max, ratio);
@@ -289,11 +295,14 @@ __global__ void __launch_bounds__(kLossThreads) loss_main_kernel(LossArgs a) {
                 if (a.mask) m = ldg_stream(reinterpret_cast<const float4*>(a.mask + i));
                 if (a.base) bs = ldg_stream(reinterpret_cast<const float4*>(a.base + i));
                 if (a.ent) en = ldg_stream(reinterpret_cast<const float4*>(a.ent + i));
+                float4 ti = make_float4(1.f, 1.f, 1.f, 1.f), cm = make_float4(-1.f, -1.f, -1.f, -1.f);
+                if (a.tis) ti = ldg_stream(reinterpret_cast<const float4*>(a.tis + i));
+                if (a.clip_mask) cm = ldg_stream(reinterpret_cast<const float4*>(a.clip_mask + i));
                 float4 g;
-                g.x = loss_token(cx, acc, lp.x, olp.x, adv.x, m.x, bs.x);
-                g.y = loss_token(cx, acc, lp.y, olp.y, adv.y, m.y, bs.y);
-                g.z = loss_token(cx, acc, lp.z, olp.z, adv.z, m.z, bs.z);
-                g.w = loss_token(cx, acc, lp.w, olp.w, adv.w, m.w, bs.w);
+                g.x = loss_token(cx, acc, lp.x, olp.x, adv.x, m.x, bs.x, ti.x, cm.x);
+                g.y = loss_token(cx, acc, lp.y, olp.y, adv.y, m.y, bs.y, ti.y, cm.y);
+                g.z = loss_token(cx, acc, lp.z, olp.z, adv.z, m.z, bs.z, ti.z, cm.z);
+                g.w = loss_token(cx, acc, lp.w, olp.w, adv.w, m.w, bs.w, ti.w, cm.w);
                 if (a.d_lp) *reinterpret_cast<float4*>(a.d_lp + i) = g;
                 if (a.ent) {
                     acc.s_ent = fmaf(en.x, m.x, acc.s_ent);
@@ -313,7 +322,8 @@ __global__ void __launch_bounds__(kLossThreads) loss_main_kernel(LossArgs a) {
             if (t < A) {
                 const int64_t i = rbase + t;
                 const float m = a.mask ? a.mask[i] : 1.f;
-                const float g = loss_token(cx, acc, a.lp[i], a.olp[i], a.adv[i], m, a.base ? a.base[i] : 0.f);
+                const float g = loss_token(cx, acc, a.lp[i], a.olp[i], a.adv[i], m, a.base ? a.base[i] : 0.f,
+                                           a.tis ? a.tis[i] : 1.f, a.clip_mask ? a.clip_mask[i] : -1.f);
                 if (a.d_lp) a.d_lp[i] = g;
                 if (a.ent) {
                     acc.s_ent = fmaf(a.ent[i], m, acc.s_ent);
@@ -370,7 +380,8 @@ __global__ void __launch_bounds__(kLossThreads) loss_main_kernel(LossArgs a) {
     f_max = block_max(f_max, sh);
     f_min = block_min(f_min, sh);
     if (threadIdx.x == 0) {
-        const float clip_ratio = f_clip * inv_total;
+        const float clip_den = a.clip_mask ? fmaxf(__ldcg(a.ws.total_msum + 1), 1.f) : fmaxf(total_m, 1.f);
+        const float clip_ratio = f_clip / clip_den;
         const float ent_mean = f_ent * inv_total;
         float final_loss = f_loss + f_kl * a.p.kl_loss_coef;
         if (use_ent_loss && a.ent != nullptr) final_loss -= ent_mean * a.p.entropy_loss_coef;
@@ -734,6 +745,8 @@ __global__ void __launch_bounds__(kLossThreads) critic_main_kernel(CriticArgs a)
 }
 
 // ---------------------------------------------------------------------------- small helpers
+__global__ void scale_to_sum_kernel(const float* mean, float* out, float n) { *out = *mean * n; }
+
 __global__ void scale_inplace_kernel(float* __restrict__ x, const float* __restrict__ s, int64_t n) {
     const float k = __ldg(s);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -800,7 +813,7 @@ extern "C" int skyb200_policy_loss(const float* log_probs, const float* old_log_
                                    const float* loss_mask, const float* base_log_probs, const float* entropy,
                                    float* d_log_probs, float* d_entropy, float* stats, void* workspace,
                                    size_t workspace_bytes, int64_t B, int64_t A, const skyb200_loss_params* params,
-                                   void* stream_) {
+                                   const float* tis, const float* clip_mask, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SKYB200_REQUIRE(log_probs && old_log_probs && advantages && stats && workspace && params, "null pointer");
     SKYB200_REQUIRE(B > 0 && A > 0 && B < 65536, "need 0 < B < 65536 and A > 0");
@@ -824,7 +837,16 @@ extern "C" int skyb200_policy_loss(const float* log_probs, const float* old_log_
                                                                    need_lw);
     int rc = check_launch("loss_rowstats_kernel");
     if (rc) return rc;
+    if (clip_mask != nullptr) {  // sum(clip_mask) -> total_msum[1]
+        rc = skyb200_masked_mean(clip_mask, nullptr, ws.total_msum + 2, ws.tmp, 148 * 4 * 2 * 4, B * A, stream_);
+        if (rc) return rc;
+        scale_to_sum_kernel<<<1, 1, 0, stream>>>(ws.total_msum + 2, ws.total_msum + 1, static_cast<float>(B * A));
+        rc = check_launch("scale_to_sum_kernel");
+        if (rc) return rc;
+    }
     LossArgs a;
+    a.tis = tis;
+    a.clip_mask = clip_mask;
     a.lp = log_probs;
     a.olp = old_log_probs;
     a.adv = advantages;
@@ -840,7 +862,8 @@ extern "C" int skyb200_policy_loss(const float* log_probs, const float* old_log_
     a.p = *params;
     auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     a.vec4 = (A % 4 == 0) && al16(log_probs) && al16(old_log_probs) && al16(advantages) && al16(loss_mask) &&
-             al16(base_log_probs) && al16(entropy) && al16(d_log_probs) && al16(d_entropy);
+             al16(base_log_probs) && al16(entropy) && al16(d_log_probs) && al16(d_entropy) && al16(tis) &&
+             al16(clip_mask);
     const unsigned chunks = (unsigned)((A + kLossTile - 1) / kLossTile);
     loss_main_kernel<<<dim3(chunks, (unsigned)B), kLossThreads, 0, stream>>>(a);
     return check_launch("loss_main_kernel");

@@ -83,7 +83,7 @@ def _prep(t: Optional[torch.Tensor], ref: torch.Tensor) -> Optional[torch.Tensor
     return t.contiguous()
 
 
-def _run_kernel(lp, olp, adv, mask, base, ent, params, want_d_ent):
+def _run_kernel(lp, olp, adv, mask, base, ent, params, want_d_ent, tis=None, clip_mask=None):
     """Launch skyb200_policy_loss. Returns (stats[16] device tensor, d_lp, d_ent or None)."""
     lib = _lib.load()
     B, A = lp.shape
@@ -96,7 +96,8 @@ def _run_kernel(lp, olp, adv, mask, base, ent, params, want_d_ent):
         _lib.check(
             lib.skyb200_policy_loss(_lib.ptr(lp), _lib.ptr(olp), _lib.ptr(adv), _lib.ptr(mask), _lib.ptr(base),
                                     _lib.ptr(ent), _lib.ptr(d_lp), _lib.ptr(d_ent), _lib.ptr(stats), _lib.ptr(ws),
-                                    ws_bytes, B, A, C.byref(params), _lib.stream_ptr()),
+                                    ws_bytes, B, A, C.byref(params), _lib.ptr(tis), _lib.ptr(clip_mask),
+                                    _lib.stream_ptr()),
             "skyb200_policy_loss",
         )
     return stats, d_lp, d_ent
@@ -116,7 +117,8 @@ class _PolicyLossFn(torch.autograd.Function):
     """loss, stats = f(log_probs [, entropy]); gradients were produced by the forward kernel."""
 
     @staticmethod
-    def forward(ctx, log_probs, entropy, old_log_probs, advantages, loss_mask, base_log_probs, params, stat_index):
+    def forward(ctx, log_probs, entropy, old_log_probs, advantages, loss_mask, base_log_probs, params, stat_index,
+                tis=None, clip_mask=None):
         if not log_probs.is_cuda:
             raise RuntimeError("skyrl_b200 policy losses need CUDA tensors (no CPU fallback)")
         if log_probs.dim() != 2:
@@ -128,7 +130,8 @@ class _PolicyLossFn(torch.autograd.Function):
         base = _prep(base_log_probs, lp)
         ent = _prep(entropy, lp)
         want_d_ent = ent is not None and entropy.requires_grad and bool(params.use_entropy_loss)
-        stats, d_lp, d_ent = _run_kernel(lp, olp, adv, mask, base, ent, params, want_d_ent)
+        stats, d_lp, d_ent = _run_kernel(lp, olp, adv, mask, base, ent, params, want_d_ent, _prep(tis, lp),
+                                         _prep(clip_mask, lp))
         ctx.save_for_backward(d_lp, d_ent if d_ent is not None else torch.empty(0, device=lp.device))
         ctx.has_d_ent = d_ent is not None
         ctx.in_dtype = log_probs.dtype
@@ -148,23 +151,85 @@ class _PolicyLossFn(torch.autograd.Function):
             g_ent = _scale_by_upstream(d_ent.clone(), g_loss)
             if g_ent.dtype != ctx.ent_dtype:
                 g_ent = g_ent.to(ctx.ent_dtype)
-        return g_lp, g_ent, None, None, None, None, None, None
+        return g_lp, g_ent, None, None, None, None, None, None, None, None
+
+
+def compute_off_policy_correction(old_log_probs, rollout_logprobs, loss_mask, off_policy_correction):
+    """TIS weights, outlier-token mask and sequence mask (reference: off_policy_correction_utils.py:173-262).
+
+    Returns ``(tis_ratio [B, A] or None, metrics dict, new_loss_mask [B, A])`` with the reference's metric names.
+    """
+    opc = off_policy_correction
+    tis_type = _cfg(opc, "tis_ratio_type", None)
+    seq_metric = _cfg(opc, "sequence_mask_metric", None)
+    if tis_type is None and seq_metric is None:
+        return None, {}, loss_mask
+    if tis_type not in (None, "token", "sequence"):
+        raise ValueError(f"Unknown tis_ratio_type: {tis_type}")
+    if seq_metric not in (None, "geometric", "product"):
+        raise ValueError(f"Unknown sequence_mask_metric: {seq_metric}")
+    lib = _lib.load()
+    if not old_log_probs.is_cuda:
+        raise RuntimeError("skyrl_b200 off-policy correction needs CUDA tensors (no CPU fallback)")
+    olp = _prep(old_log_probs, old_log_probs)
+    rlp = _prep(rollout_logprobs, olp)
+    mask = _prep(loss_mask, olp) if loss_mask is not None else torch.ones_like(olp)
+    B, A = olp.shape
+    p = _lib.OpcParams()
+    p.tis_type = {None: 0, "token": 1, "sequence": 2}[tis_type]
+    p.seq_mask_type = {None: 0, "geometric": 1, "product": 2}[seq_metric]
+    lo, hi = _cfg(opc, "outlier_token_is_threshold_low", None), _cfg(opc, "outlier_token_is_threshold_high", None)
+    p.has_outlier_low, p.has_outlier_high = int(lo is not None), int(hi is not None)
+    p.outlier_low, p.outlier_high = float(lo or 0.0), float(hi or 0.0)
+    p.token_tis_cap = float(_cfg(opc, "token_tis_ratio_clip_high", 2.0))
+    p.seq_tis_cap = float(_cfg(opc, "sequence_tis_ratio_clip_high", 5.0))
+    p.geo_low, p.geo_high = float(_cfg(opc, "geo_mask_low", 0.99)), float(_cfg(opc, "geo_mask_high", 1.01))
+    p.prod_low, p.prod_high = float(_cfg(opc, "product_mask_low", 0.5)), float(_cfg(opc, "product_mask_high", 2.0))
+    with torch.cuda.device(olp.device):
+        tis = torch.empty_like(olp)
+        mask_out = torch.empty_like(olp)
+        met = torch.empty(_lib.OPC_NMETRICS, dtype=torch.float32, device=olp.device)
+        wsb = lib.skyb200_off_policy_workspace(B)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=olp.device)
+        _lib.check(
+            lib.skyb200_off_policy_correction(_lib.ptr(olp), _lib.ptr(rlp), _lib.ptr(mask), _lib.ptr(tis),
+                                              _lib.ptr(mask_out), _lib.ptr(met), _lib.ptr(ws), wsb, B, A, C.byref(p),
+                                              _lib.stream_ptr()),
+            "skyb200_off_policy_correction",
+        )
+        m = met.tolist()
+    metrics = {"is_ratio_mean": m[0], "is_ratio_std": m[1], "is_ratio_max": m[2], "is_ratio_min": m[3],
+               "outlier_seq_masked_ratio": m[4], "outlier_seq_over_high_ratio": m[5],
+               "outlier_seq_under_low_ratio": m[6]}
+    if tis_type == "token":
+        metrics["tis_token_clip_high_ratio"] = m[7]
+    elif tis_type == "sequence":
+        metrics["tis_seq_clip_high_ratio"] = m[7]
+    if seq_metric is not None:
+        name = "geo" if seq_metric == "geometric" else "product"
+        metrics[f"{name}_sequence_mask_masked_ratio"] = m[8]
+        metrics[f"{name}_sequence_mask_over_high_ratio"] = m[9]
+        metrics[f"{name}_sequence_mask_under_low_ratio"] = m[10]
+    return (tis if tis_type is not None else None), metrics, mask_out
 
 
 def _registry_loss(loss_type, log_probs, old_log_probs, advantages, config, loss_mask, rollout_logprobs,
                    reduction=None, want_stats=False):
+    tis, opc_metrics, clip_mask = None, {}, None
     if loss_type not in ("cross_entropy", "importance_sampling") and _off_policy_enabled(config, rollout_logprobs):
-        raise NotImplementedError(
-            "off_policy_correction (tis_ratio_type / sequence_mask_metric) is not fused into the B200 loss kernel "
-            "yet; disable it or use the reference loss for this configuration"
-        )
+        # the clip_ratio metric keeps the mask it had before the correction (ppo_utils.py:570 vs :579-583)
+        clip_mask = loss_mask if loss_mask is not None else torch.ones_like(old_log_probs, dtype=torch.float32)
+        tis, opc_metrics, loss_mask = compute_off_policy_correction(
+            old_log_probs, rollout_logprobs, loss_mask, _cfg(config, "off_policy_correction"))
     params = _make_params(loss_type, reduction or _cfg(config, "loss_reduction"), config)
     loss, stats = _PolicyLossFn.apply(log_probs, None, old_log_probs, advantages, loss_mask, None, params,
-                                      _lib.STAT_POLICY_LOSS)
+                                      _lib.STAT_POLICY_LOSS, tis, clip_mask)
     if want_stats:
         return loss, stats
     clip_ratio = float(stats[_lib.STAT_CLIP_RATIO].item())  # the single host sync of this call
-    return loss, {"clip_ratio": clip_ratio}
+    metrics = {"clip_ratio": clip_ratio}
+    metrics.update(opc_metrics)
+    return loss, metrics
 
 
 def ppo_policy_loss(
@@ -210,9 +275,9 @@ def sapo_policy_loss(log_probs, old_log_probs, advantages, config, loss_mask=Non
         logging.getLogger("skyrl_b200").warning(
             "With SAPO it's recommended to use 'sequence_mean' loss reduction; got %s", _cfg(config, "loss_reduction")
         )
-    loss, _ = _registry_loss("sapo", log_probs, old_log_probs, advantages, config, loss_mask, rollout_logprobs,
-                             want_stats=True)
-    return loss, {"clip_ratio": 0.0}
+    loss, met = _registry_loss("sapo", log_probs, old_log_probs, advantages, config, loss_mask, rollout_logprobs)
+    met["clip_ratio"] = 0.0
+    return loss, met
 
 
 def compute_policy_loss_cispo(log_probs, old_log_probs, advantages, config, loss_mask=None, rollout_logprobs=None):

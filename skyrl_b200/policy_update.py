@@ -192,7 +192,7 @@ def policy_update_step(
             lib.skyb200_policy_loss(_lib.ptr(logprobs), _lib.ptr(olp), _lib.ptr(adv), _lib.ptr(mask),
                                     _lib.ptr(base) if use_kl else None, _lib.ptr(ent), _lib.ptr(d_lp),
                                     _lib.ptr(d_ent), _lib.ptr(stats), _lib.ptr(ws_l), lb, B, A, C.byref(params),
-                                    stream),
+                                    None, None, stream),
             "skyb200_policy_loss",
         )
         d_hidden = None

@@ -58,7 +58,7 @@ def test_bad_arguments_report_errors_without_a_gpu(lib):
     # argument validation happens before any CUDA call
     p = _lib.LossParams()
     rc = lib.skyb200_policy_loss(None, None, None, None, None, None, None, None, None, None, 0, 4, 4,
-                                 ctypes.byref(p), None)
+                                 ctypes.byref(p), None, None, None)
     assert rc == 1
     assert b"null pointer" in lib.skyb200_last_error()
     rc = lib.skyb200_approx_kl(ctypes.c_void_p(16), ctypes.c_void_p(16), None, ctypes.c_void_p(16), 4, 9, None)

@@ -111,16 +111,11 @@ def test_integer_mask_and_noncontiguous_inputs():
     assert_close(loss, ref)
 
 
-def test_off_policy_correction_is_refused_not_silently_ignored():
-    from types import SimpleNamespace
-
-    cfg = O.make_cfg(off_policy_correction=SimpleNamespace(tis_ratio_type="token", sequence_mask_metric=None))
+def test_disabled_off_policy_correction_is_a_no_op():
     lp = torch.zeros(2, 4, device=DEV, requires_grad=True)
-    with pytest.raises(NotImplementedError):
-        losses.ppo_policy_loss(lp, lp.detach(), lp.detach(), cfg, rollout_logprobs=lp.detach())
-    # disabled correction + rollout logprobs given = the reference's no-op path
-    loss, _ = losses.ppo_policy_loss(lp, lp.detach(), lp.detach(), O.make_cfg(), rollout_logprobs=lp.detach())
-    assert loss.item() == 0.0
+    # correction disabled + rollout logprobs given = the reference's no-op path (off_policy_correction_utils.py:223)
+    loss, met = losses.ppo_policy_loss(lp, lp.detach(), lp.detach(), O.make_cfg(), rollout_logprobs=lp.detach() - 1)
+    assert loss.item() == 0.0 and list(met) == ["clip_ratio"]
 
 
 def test_full_size_properties_c2_shape():
@@ -182,3 +177,28 @@ def test_extra_registry_losses_match_reference_golden(golden_loss, kind, red, mn
     assert_close(loss, g[key + "__loss"], what=key + " loss")
     assert_close(list(met.values())[0], g[key + "__metric"], what=key + " metric")
     assert_close(lp.grad, g[key + "__grad"], what=key + " grad")
+
+
+def test_off_policy_correction_matches_reference_golden(golden_loss):
+    import json
+    from types import SimpleNamespace
+
+    g = golden_loss
+    keys = sorted(k[:-6] for k in g if k.startswith("opc__") and k.endswith("__loss"))
+    assert len(keys) == 8
+    for key in keys:
+        okw, want_met = json.loads(str(g[key + "__cfg"])), json.loads(str(g[key + "__metrics"]))
+        kind = key.split("__")[-1]
+        cfg = O.make_cfg(policy_loss_type=kind, loss_reduction="token_mean" if kind == "regular" else "sequence_mean",
+                         eps_clip_high=0.28 if kind == "dual_clip" else 0.2, max_seq_len=64,
+                         off_policy_correction=SimpleNamespace(**okw))
+        lp = _t(g["lp"]).to(DEV).requires_grad_(True)
+        loss, met = skyrl_b200.PolicyLossRegistry.get(kind)(lp, _t(g["olp"]).to(DEV), _t(g["adv"]).to(DEV), cfg,
+                                                             loss_mask=_t(g["mask"]).to(DEV),
+                                                             rollout_logprobs=_t(g["rlp"]).to(DEV))
+        loss.backward()
+        assert_close(loss, g[key + "__loss"], what=key + " loss")
+        assert_close(lp.grad, g[key + "__grad"], what=key + " grad")
+        assert sorted(met) == sorted(want_met), key  # same metric names as the reference
+        for k in want_met:
+            assert met[k] == pytest.approx(want_met[k], rel=1e-5, abs=1e-6), (key, k)

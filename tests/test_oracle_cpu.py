@@ -261,3 +261,33 @@ def test_kat_cispo():  # tests/cpu/algorithms/test_losses.py:85-137 -> -0.99768 
     cfg = O.make_cfg(policy_loss_type="cispo", cispo=SimpleNamespace(cispo_eps_clip_low=0.2, cispo_eps_clip_high=0.2))
     loss, _ = O.extra_policy_loss("cispo", lp, olp, adv, cfg, None)
     assert abs(loss.item() - (-0.99768)) < 2e-3
+
+
+def _opc_cases(g):
+    import json
+
+    for key in sorted(k[:-6] for k in g if k.startswith("opc__") and k.endswith("__loss")):
+        yield key, json.loads(str(g[key + "__cfg"])), json.loads(str(g[key + "__metrics"]))
+
+
+def test_golden_off_policy_correction(golden_loss):
+    from types import SimpleNamespace
+
+    g = golden_loss
+    lp, olp, adv, fm, rlp = (_t(g[k]) for k in ("lp", "olp", "adv", "mask", "rlp"))
+    n = 0
+    for key, okw, want_met in _opc_cases(g):
+        kind = key.split("__")[-1]
+        cfg = O.make_cfg(policy_loss_type=kind, loss_reduction="token_mean" if kind == "regular" else "sequence_mean",
+                         eps_clip_high=0.28 if kind == "dual_clip" else 0.2, max_seq_len=64,
+                         off_policy_correction=SimpleNamespace(**okw))
+        x = lp.clone().requires_grad_(True)
+        loss, met = O.policy_loss_with_correction(x, olp, adv, cfg, fm, rlp)
+        loss.backward()
+        assert_close(loss, g[key + "__loss"], what=key)
+        assert_close(x.grad, g[key + "__grad"], what=key + " grad")
+        assert sorted(met) == sorted(want_met), key
+        for k in want_met:
+            assert met[k] == pytest.approx(want_met[k], rel=1e-5, abs=1e-6), (key, k)
+        n += 1
+    assert n == 8
