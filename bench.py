@@ -389,7 +389,11 @@ def run_ours(args, w):
                                       "logits tile store, 6*H*V*N executed); peak = " + peaks["source"]},
             "roofline": {"kernel": "gemm_sm100_kernel<2,256,6,K-major,K-major,EpiLsePartials> (head forward)",
                          "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"], "traffic": None,
+                         "frac": achieved / peaks["tflops"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum per full-chunk launch of this kernel with its
+                         # bf16 tile store, from the `ncu --set full` capture in profiles/r01b_gemm_full_metrics.csv
+                         # (5.15 GB read + 2.99 GB written; algorithmic: 1.09 GB weight + 0.07 GB hidden + 2.9 GB store)
+                         "traffic": 8.14e9 if (H, V) == (3584, 152064) else None,
                          "flops_per_launch": flops_fwd_launch, "ms_per_launch": fwd_launch_ms,
                          "note": "per-launch = head_forward call / %d chunks (includes the <1%% merge kernel); peak = %s"
                                  % (n_chunks, peaks["source"])},

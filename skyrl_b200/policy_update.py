@@ -244,3 +244,49 @@ def pack_by_lengths(lengths: torch.Tensor, *tensors: torch.Tensor):
         keep = (torch.arange(A, device=t.device)[None, :] < lengths.to(t.device)[:, None])
         out.append(t[keep])
     return cu, out
+
+
+class _FusedPolicyLossFn(torch.autograd.Function):
+    """final_loss = f(hidden, weight): the whole fused step as ONE autograd node.
+
+    Forward runs ``policy_update_step`` (which already produces d_hidden / d_weight of the final loss); backward
+    hands them to autograd scaled by the upstream gradient, so the trunk's backward continues from ``d_hidden``
+    and the optimizer sees ``weight.grad`` — the 6*H*V path behind a ``loss.backward()`` interface."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight, labels, old_log_probs, advantages, config, loss_mask, base_log_probs,
+                temperature, entropy_mask, cu_seqlens):
+        need_dh, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        out = policy_update_step(hidden.detach(), weight.detach(), labels, old_log_probs, advantages, config,
+                                 loss_mask=loss_mask, base_log_probs=base_log_probs, temperature=temperature,
+                                 entropy_mask=entropy_mask, need_d_hidden=need_dh, need_d_weight=need_dw,
+                                 sync=False, cu_seqlens=cu_seqlens)
+        ctx.save_for_backward(out.d_hidden if out.d_hidden is not None else torch.empty(0, device=hidden.device),
+                              out.d_weight if out.d_weight is not None else torch.empty(0, device=hidden.device))
+        ctx.shapes = (hidden.shape, hidden.dtype, weight.dtype, need_dh, need_dw)
+        stats = out.stats
+        ctx.mark_non_differentiable(stats, out.log_probs, out.entropy)
+        return stats[_lib.STAT_FINAL_LOSS].clone(), stats, out.log_probs, out.entropy
+
+    @staticmethod
+    def backward(ctx, g_loss, _gs, _glp, _gent):
+        d_hidden, d_weight = ctx.saved_tensors
+        h_shape, h_dtype, w_dtype, need_dh, need_dw = ctx.shapes
+        g = g_loss.detach().to(torch.float32)
+        gh = gw = None
+        if need_dh:
+            gh = (d_hidden.float() * g).to(h_dtype).view(h_shape)
+        if need_dw:
+            gw = (d_weight * g).to(w_dtype)
+        return gh, gw, None, None, None, None, None, None, None, None, None
+
+
+def fused_policy_loss(hidden, weight, labels, old_log_probs, advantages, config, loss_mask=None,
+                      base_log_probs=None, temperature: float = 1.0, entropy_mask=None, cu_seqlens=None):
+    """Autograd-facing form of the fused step: returns ``(final_loss, stats, log_probs, entropy)`` where
+    ``final_loss`` is a 0-d tensor whose ``backward()`` delivers ``d_hidden`` to the trunk and ``weight.grad``.
+
+    Equivalent to ``fused_lm_head`` + ``policy_update_loss`` + ``loss.backward()`` (and to the reference's
+    worker.py:787-877) but with the 6*H*V executed-flop schedule of :func:`policy_update_step`."""
+    return _FusedPolicyLossFn.apply(hidden, weight, labels, old_log_probs, advantages, config, loss_mask,
+                                    base_log_probs, temperature, entropy_mask, cu_seqlens)

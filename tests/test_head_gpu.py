@@ -160,3 +160,24 @@ def test_argument_errors():
         skyrl_b200.fused_lm_head(torch.zeros(4, 16, device=DEV, dtype=torch.bfloat16),
                                  torch.zeros(16, 8, device=DEV, dtype=torch.bfloat16),
                                  torch.zeros(4, dtype=torch.long, device=DEV))
+
+
+def test_hidden_size_not_a_multiple_of_the_k_block():
+    """H = 200: the K loop ends in a partial 64-element block (TMA zero fill) and H < one 256-wide N tile."""
+    N, H, V, T = 333, 200, 1000, 1.0
+    g = torch.Generator().manual_seed(4)
+    hidden = torch.randn(N, H, generator=g).bfloat16()
+    weight = (torch.randn(V, H, generator=g) * (1.5 / H ** 0.5)).bfloat16()
+    labels = torch.randint(0, V, (N,), generator=g)
+    g_lp = torch.randn(N, generator=g)
+    h = hidden.float().requires_grad_(True)
+    w = weight.float().requires_grad_(True)
+    lp_ref, _ = O.head_logprobs_entropy(h, w, labels, T)
+    (lp_ref * g_lp).sum().backward()
+    hd = hidden.to(DEV).requires_grad_(True)
+    wd = weight.to(DEV).requires_grad_(True)
+    lp, ent = skyrl_b200.fused_lm_head(hd, wd, labels.to(DEV), temperature=T)
+    (lp * g_lp.to(DEV)).sum().backward()
+    assert (lp.detach().cpu() - lp_ref.detach()).abs().max().item() < LOGPROB_ATOL
+    assert _rel_l2(hd.grad.float(), h.grad) < 1e-2
+    assert _rel_l2(wd.grad.float(), w.grad) < 1e-2

@@ -169,3 +169,53 @@ def test_packed_ragged_layout_equals_padded_reference(kw):
         skyrl_b200.policy_update_step(hp.to(DEV), weight.to(DEV), labp.to(DEV), olpp.to(DEV), advp.to(DEV),
                                       O.make_cfg(policy_loss_type="gspo", loss_reduction="sequence_mean"),
                                       loss_mask=maskp.to(DEV), cu_seqlens=cu.to(DEV))
+
+
+def test_gspo_fused_step_row_aligned_multi_chunk():
+    """GSPO needs whole sequences per chunk: 7 x 4096 tokens -> chunks of 3, 3 and 1 sequences."""
+    B, A, H, V, T = 7, 4096, 64, 512, 1.0
+    g, hidden, weight, labels, mask = _batch(B, A, H, V, 21)
+    cfg = O.make_cfg(policy_loss_type="gspo", loss_reduction="sequence_mean", use_kl_loss=False,
+                     eps_clip_low=0.02, eps_clip_high=0.02)
+    h = hidden.float().reshape(B * A, H).requires_grad_(True)
+    w = weight.float().requires_grad_(True)
+    lp_ref, ent_ref = O.head_logprobs_entropy(h, w, labels.reshape(-1), T)
+    lp_ref = lp_ref.view(B, A)
+    olp = lp_ref.detach() + 0.03 * torch.randn(B, 1, generator=g) + 0.01 * torch.randn(B, A, generator=g)
+    adv = torch.randn(B, A, generator=g)
+    final_ref, st_ref = O.loss_assembly(lp_ref, olp, adv, cfg, mask, None, ent_ref.view(B, A))
+    final_ref.backward()
+    out = skyrl_b200.policy_update_step(hidden.to(DEV), weight.to(DEV), labels.to(DEV), olp.to(DEV), adv.to(DEV), cfg,
+                                        loss_mask=mask.to(DEV), temperature=T)
+    assert 0.0 < st_ref["loss_metrics/clip_ratio"] < 1.0  # the case actually exercises the sequence-level clip
+    for k in ("final_loss", "policy_loss", "loss_metrics/clip_ratio"):
+        assert out.status[k] == pytest.approx(st_ref[k], rel=2e-3, abs=2e-4), k
+    rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+    assert rel(out.d_hidden.float(), h.grad) < 2e-2
+    assert rel(out.d_weight, w.grad) < 2e-2
+
+
+def test_fused_policy_loss_autograd_node():
+    """loss.backward() through the single fused node == the oracle's gradients (incl. a non-unit upstream gradient)."""
+    B, A, H, V, T = 6, 128, 64, 1200, 1.0
+    g, hidden, weight, labels, mask = _batch(B, A, H, V, 31)
+    cfg = O.make_cfg(policy_loss_type="dual_clip", loss_reduction="token_mean", use_kl_loss=True, clip_ratio_c=3.0)
+    h = hidden.float().reshape(B * A, H).requires_grad_(True)
+    w = weight.float().requires_grad_(True)
+    lp_ref, ent_ref = O.head_logprobs_entropy(h, w, labels.reshape(-1), T)
+    olp = lp_ref.detach().view(B, A) + 0.05 * torch.randn(B, A, generator=g)
+    base = lp_ref.detach().view(B, A) + 0.1 * torch.randn(B, A, generator=g)
+    adv = torch.randn(B, A, generator=g)
+    final_ref, st_ref = O.loss_assembly(lp_ref.view(B, A), olp, adv, cfg, mask, base, ent_ref.view(B, A))
+    (3.0 * final_ref).backward()
+    hd = hidden.to(DEV).requires_grad_(True)
+    wd = weight.to(DEV).requires_grad_(True)
+    loss, stats, lp, ent = skyrl_b200.fused_policy_loss(hd, wd, labels.to(DEV), olp.to(DEV), adv.to(DEV), cfg,
+                                                        loss_mask=mask.to(DEV), base_log_probs=base.to(DEV),
+                                                        temperature=T)
+    (3.0 * loss).backward()
+    assert loss.item() == pytest.approx(st_ref["final_loss"], rel=2e-3, abs=2e-4)
+    rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+    assert hd.grad.shape == hd.shape and hd.grad.dtype == torch.bfloat16
+    assert rel(hd.grad.float().reshape(B * A, H), h.grad) < 2e-2
+    assert rel(wd.grad.float(), w.grad) < 2e-2
