@@ -175,8 +175,10 @@ def cpu_port_step(w, sample_tokens, threads, seed=1234):
     hidden = torch.randn(rows * a_len, H, generator=g).to(torch.bfloat16).float()
     weight = (torch.randn(V, H, generator=g) / H ** 0.5).to(torch.bfloat16).float()
     labels = torch.randint(0, V, (rows * a_len,), generator=g)
-    olp = -12.0 + 0.05 * torch.randn(rows, a_len, generator=g)
-    base = -12.0 + 0.1 * torch.randn(rows, a_len, generator=g)
+    with torch.no_grad():  # untimed set-up, as in the GPU arm: old / base log-probs next to the current policy's
+        lp0, _ = O.head_logprobs_entropy(hidden, weight, labels, TEMPERATURE, chunk=256)
+    olp = lp0.view(rows, a_len) + 0.05 * torch.randn(rows, a_len, generator=g)
+    base = lp0.view(rows, a_len) + 0.1 * torch.randn(rows, a_len, generator=g)
     mask = torch.ones(rows, a_len)
     rewards = torch.zeros(B, A)
     rewards[:, -1] = (torch.rand(B, generator=g) < 0.3).float()
@@ -249,6 +251,20 @@ def run_ours(args, w):
     weight = make_weight(w, dev)
     d_weight = torch.zeros((V, H), dtype=torch.float32, device=dev)
     db = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
+    # old / reference log-probs sit next to the current policy's (near on-policy rollouts):
+    # old = lp + N(0, 0.05^2), base = lp + N(0, 0.1^2), 0.1 % outliers of +-25 to hit the +-20 ratio clamps.
+    # (untimed set-up: one no-grad head forward gives lp)
+    with torch.no_grad():
+        lp0 = skyrl_b200.fused_lm_head_logprobs(db["hidden"].view(N, H), weight, db["labels"].view(N)).view(B, A)
+        gd = torch.Generator(device=dev).manual_seed(4321 + rank)
+        olp_d = lp0 + 0.05 * torch.randn(B, A, device=dev, generator=gd)
+        base_d = lp0 + 0.1 * torch.randn(B, A, device=dev, generator=gd)
+        outl = torch.rand(B, A, device=dev, generator=gd) < 1e-3
+        olp_d = torch.where(outl, lp0 + 25.0 * torch.sign(torch.randn(B, A, device=dev, generator=gd)), olp_d)
+        db["olp"], db["base"] = olp_d.contiguous(), base_d.contiguous()
+        hb["olp"].copy_(db["olp"])
+        hb["base"].copy_(db["base"])
+        del lp0, olp_d, base_d, outl
     torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)

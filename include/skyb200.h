@@ -235,6 +235,10 @@ size_t skyb200_normalize_advantages_workspace(void);
 int skyb200_normalize_advantages(const float* advantages, const void* response_mask, int32_t mask_type, float* out,
                                  float* stats_out, void* workspace, size_t workspace_bytes, int64_t n, void* stream);
 
+/* out[b, :] = src[row_index[b], :] (fp32 [*, A]); the step-wise trajectory broadcast of trainer.py:795-804 */
+int skyb200_gather_rows(const float* src, const int32_t* row_index, float* out, int64_t num_src_rows, int64_t B,
+                        int64_t A, void* stream);
+
 /*
  * KL-in-reward (RayPPOTrainer.apply_reward_kl_penalty, trainer.py:981-1035):
  *   kl = compute_approx_kl(lp, base, loss_mask); rewards_out = rewards - kl * max(0, kl_coef)

@@ -89,6 +89,7 @@ SIGNATURES = {
     "skyb200_normalize_advantages_workspace": (_SZ, []),
     "skyb200_normalize_advantages": (C.c_int, [_P, _P, _I32, _P, _P, _P, _SZ, _I64, _P]),
     "skyb200_critic_loss": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _SZ, _I64, _I64, _F, _I32, _P]),
+    "skyb200_gather_rows": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P]),
     "skyb200_reward_kl_penalty": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _F, _P]),
     "skyb200_head_forward_workspace": (_SZ, [_I64, _I64, _I64, _I64]),
     "skyb200_head_backward_workspace": (_SZ, [_I64, _I64, _I64, _I64]),

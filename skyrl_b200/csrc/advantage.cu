@@ -641,6 +641,27 @@ extern "C" int skyb200_reward_kl_penalty(const float* log_probs, const float* ba
     return check_launch("row_means_kernel");
 }
 
+// out[b, :] = src[idx[b], :]   (step-wise trajectories: broadcast the last step's advantages, trainer.py:803-804)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                                          float* __restrict__ out, int64_t A) {
+    const int64_t r = idx[blockIdx.y];
+    const float* s = src + r * A;
+    float* o = out + static_cast<int64_t>(blockIdx.y) * A;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * 4096;
+    const int64_t t1 = min(A, t0 + 4096);
+    for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) o[t] = s[t];
+}
+
+extern "C" int skyb200_gather_rows(const float* src, const int32_t* row_index, float* out, int64_t num_src_rows,
+                                   int64_t B, int64_t A, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (B == 0 || A == 0) return SKYB200_OK;
+    SKYB200_REQUIRE(src && row_index && out, "null pointer");
+    SKYB200_REQUIRE(num_src_rows > 0 && B < 65536, "need source rows and B < 65536");
+    gather_rows_kernel<<<dim3((unsigned)((A + 4095) / 4096), (unsigned)B), 256, 0, stream>>>(src, row_index, out, A);
+    return check_launch("gather_rows_kernel");
+}
+
 static int grid_cap(int64_t n, int per_sm) {
     int64_t b = (n + 255) / 256;
     const int64_t cap = (int64_t)num_sms() * per_sm;

@@ -182,3 +182,45 @@ def test_reinforce_pp_known_answers_and_long_rows():  # reference: tests/cpu/uti
     a, ret = advantages.compute_reinforce_plus_plus_outcome_advantage(rew.to(DEV), mask.to(DEV), 0.999)
     assert_close(ret, r_ref, what="ret")
     assert_close(a, a_ref, what="adv")
+
+
+def test_step_wise_trajectory_broadcast_and_metrics():
+    """trainer.py:777-808: the estimator runs on last-step rows only, every step row of a trajectory gets them."""
+    from types import SimpleNamespace
+
+    from skyrl_b200 import trainer_ops
+
+    g = torch.Generator().manual_seed(12)
+    steps = [3, 1, 2, 4, 2, 1, 3, 2]  # trajectories of a multi-turn rollout, rows = steps
+    Bt, A = sum(steps), 40
+    is_last = torch.zeros(Bt, dtype=torch.bool)
+    is_last[torch.tensor(steps).cumsum(0) - 1] = True
+    traj_uid = [f"prompt-{t // 2}" for t in range(len(steps))]  # two trajectories per prompt
+    uids = [u for u, n in zip(traj_uid, steps) for _ in range(n)]
+    lens = torch.randint(5, A + 1, (Bt,), generator=g)
+    mask = (torch.arange(A)[None] < lens[:, None]).long()
+    rewards = torch.zeros(Bt, A)
+    rewards[is_last, lens[is_last] - 1] = torch.rand(int(is_last.sum()), generator=g)
+    data = {"rewards": rewards.to(DEV), "response_mask": mask.to(DEV), "values": None, "is_last_step": is_last.to(DEV)}
+    cfg = SimpleNamespace(advantage_estimator="grpo", gamma=1.0, lambd=1.0, grpo_norm_by_std=True)
+    data, met = trainer_ops.compute_advantages_and_returns_batch(data, uids, cfg, step_wise_trajectories=True)
+    adv_last, _ = O.grpo_advantage(rewards[is_last], mask[is_last], np.array(uids)[is_last.numpy()])
+    traj_ids = torch.cat([torch.tensor([False]), is_last[:-1]]).int().cumsum(0)
+    want = adv_last[traj_ids]
+    assert_close(data["advantages"], want)
+    assert data["returns"] is data["advantages"]
+    valid = torch.masked_select(want, mask.bool())
+    assert met["avg_advantages"] == pytest.approx(valid.mean().item(), rel=1e-5, abs=1e-6)
+    assert met["avg_advantages_abs"] == pytest.approx(valid.abs().mean().item(), rel=1e-5, abs=1e-6)
+    assert met["avg_final_rewards"] == pytest.approx(rewards.sum(-1)[is_last].mean().item(), rel=1e-5)
+    # plain (non step-wise) path + KL controller plumbing
+    ctrl = trainer_ops.AdaptiveKLController(0.05, target=0.1, horizon=100)
+    d2 = {"rewards": rewards.to(DEV), "loss_mask": mask.float().to(DEV),
+          "action_log_probs": -torch.rand(Bt, A, generator=g).to(DEV),
+          "base_action_log_probs": -torch.rand(Bt, A, generator=g).to(DEV)}
+    want_r, want_m = O.reward_kl_penalty(rewards, d2["action_log_probs"].cpu(), d2["base_action_log_probs"].cpu(),
+                                         mask.float(), "k3", 0.05)
+    d2, m2 = trainer_ops.apply_reward_kl_penalty_batch(d2, SimpleNamespace(kl_estimator_type="k3", kl_loss_coef=1e-3), ctrl)
+    assert_close(d2["rewards"], want_r)
+    assert m2["avg_kl"] == pytest.approx(want_m["avg_kl"], rel=1e-5)
+    assert ctrl.value != 0.05  # the controller moved
