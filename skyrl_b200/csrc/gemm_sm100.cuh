@@ -145,7 +145,7 @@ template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
                   int N, int K, int group_m, int tile_order, uint64_t hint_a, uint64_t hint_b, typename Epi::Params ep,
-                  GemmDebug* dbg) {
+                  GemmDebug* dbg, unsigned int* sync_ctr, int sync_every) {
     using S = GemmSmem<kCtas, BN, kStages>;
     constexpr int TILE_M = kBM * kCtas;
     constexpr uint32_t kTmemCols = 2 * BN;
@@ -209,11 +209,31 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         {
             const bool issuer = ptx::elect_one();
             uint32_t stage = 0, phase = 0;
+            uint32_t sync_step = 0, sync_epoch = 0;
             for (int t = cluster_id; t < total_tiles; t += num_clusters) {
                 const TileCoord tc = decode_tile(t, num_m_tiles, num_n_tiles, group_m, tile_order);
                 const int m0 = tc.m_tile * TILE_M + static_cast<int>(cta_rank) * kBM;
                 const int n0 = tc.n_tile * BN + static_cast<int>(cta_rank * S::kLoadN);
+                // CTAs that are resident at this tile iteration (the last iteration may be partial)
+                const uint32_t active_ctas =
+                    (t - cluster_id + num_clusters <= total_tiles ? num_clusters : total_tiles % num_clusters) * kCtas;
                 for (int kb = 0; kb < num_kb; ++kb) {
+                    // Best-effort lockstep: CTAs that share operand panels through L2 re-align every `sync_every`
+                    // K blocks (bounded wait: a straggler can never dead-lock the others).
+                    if (sync_ctr != nullptr && sync_step++ % static_cast<uint32_t>(sync_every) == 0) {
+                        if (issuer) {
+                            unsigned int* c = sync_ctr + (sync_epoch & 8191u);
+                            atomicAdd(c, 1u);
+                            for (int spin = 0; spin < 400; ++spin) {
+                                unsigned int v;
+                                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c));
+                                if (v >= active_ctas) break;
+                                __nanosleep(50);
+                            }
+                        }
+                        ++sync_epoch;
+                        __syncwarp();
+                    }
                     bounded_wait(&empty_bar[stage], phase ^ 1u, dbg, 0, 0, stage, t);
                     if (issuer) {
                     if (cta_rank == 0) {

@@ -76,11 +76,24 @@ static GemmDebug* debug_record_dev() {
     return g_dbg_dev;
 }
 
+// 8192 epoch counters per device for the best-effort lockstep of the deep-K GEMMs (see gemm_sm100.cuh)
+static unsigned int* lockstep_counters() {
+    static unsigned int* per_dev[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (per_dev[dev] == nullptr) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, 8192 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+        per_dev[dev] = static_cast<unsigned int*>(p);
+    }
+    return per_dev[dev];
+}
+
 // A: K-major -> [M, K] with pitch lda; MN-major -> [K, M] with pitch lda.  Same for B with N.
 template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
 static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int group_m,
                        const typename Epi::Params& ep, cudaStream_t stream, int tile_order = 0,
-                       uint64_t hint_a = kEvictNormal, uint64_t hint_b = kEvictNormal) {
+                       uint64_t hint_a = kEvictNormal, uint64_t hint_b = kEvictNormal, int sync_every = 0) {
     using S = GemmSmem<kCtas, BN, kStages>;
     if (M <= 0 || N <= 0 || K <= 0) return SKYB200_OK;
     CUtensorMap ta, tb;
@@ -120,7 +133,13 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
     cfg.numAttrs = 1;
     GemmDebug* dbg = debug_record_dev();
     if (group_m < 1) group_m = 1;
-    SKYB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group_m, tile_order, hint_a, hint_b, ep, dbg));
+    unsigned int* sync_ctr = nullptr;
+    if (sync_every > 0) {
+        sync_ctr = lockstep_counters();
+        if (sync_ctr != nullptr) SKYB200_CUDA_CHECK(cudaMemsetAsync(sync_ctr, 0, 8192 * sizeof(unsigned int), stream));
+    }
+    SKYB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group_m, tile_order, hint_a, hint_b, ep, dbg,
+                                          sync_ctr, sync_every > 0 ? sync_every : 1));
     return SKYB200_OK;
 }
 
@@ -165,6 +184,13 @@ static uint64_t hint_of(const char* name, int dflt) {
 }
 static uint64_t hint_fwd_a() { static uint64_t v = hint_of("SKYB200_HINT_FWD_A", 3); return v; }
 static uint64_t hint_dw_b() { static uint64_t v = hint_of("SKYB200_HINT_DW_B", 3); return v; }
+static int env_int0(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v == nullptr || *v == 0) ? dflt : atoi(v);
+}
+static int dh_lockstep() { static int v = env_int0("SKYB200_DH_LOCKSTEP", 128); return v; }
+static int fwd_lockstep() { static int v = env_int0("SKYB200_FWD_LOCKSTEP", 0); return v; }
+static int dw_lockstep() { static int v = env_int0("SKYB200_DW_LOCKSTEP", 128); return v; }
 static int dw_group_n() { static int v = env_int("SKYB200_DW_GROUP_N", 14); return v; }
 
 
@@ -471,7 +497,8 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
             eh.C = dhid + r0 * H;
             eh.ldc = H;
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
-                dS, ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream);
+                dS, ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, kEvictNormal, kEvictNormal,
+                dh_lockstep());
             if (rc) return rc;
         }
         // (3) d_weight[V, H] (+)= dS^T[V, rows] * hidden[rows, H]   (both MN-major)
@@ -481,7 +508,8 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
             ew.ldc = H;
             ew.accumulate = (accumulate != 0 || r0 > 0) ? 1 : 0;
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
-                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1);
+                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, kEvictNormal, kEvictLast,
+                dw_lockstep());
             if (rc) return rc;
         }
     }
@@ -631,7 +659,8 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
         if (ci >= 2) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[p], 0));
         SKYB200_CUDA_CHECK(cudaMemsetAsync(ep.label_acc, 0, (size_t)rows * sizeof(float), stream));
         int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
-            hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream, 0, hint_fwd_a(), kEvictNormal);
+            hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream, 0, hint_fwd_a(), kEvictNormal,
+            fwd_lockstep());
         if (r) return r;
         SKYB200_CUDA_CHECK(cudaEventRecord(ss->fwd[p], stream));
         return SKYB200_OK;
@@ -685,7 +714,8 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
             eh.C = dhid + t0 * H;
             eh.ldc = H;
             int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
-                S, plan.ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream);
+                S, plan.ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, kEvictNormal, kEvictNormal,
+                dh_lockstep());
             if (r) return r;
         }
         if (d_weight != nullptr) {
@@ -695,7 +725,7 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
             ew.accumulate = (accumulate != 0 || t0 > 0) ? 1 : 0;
             int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
                 S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, kEvictNormal,
-                hint_dw_b());
+                hint_dw_b(), dw_lockstep());
             if (r) return r;
         }
         return SKYB200_OK;
