@@ -529,6 +529,8 @@ struct EpiLsePartials {
         const bool row_ok = row < M;
         const int lab = row_ok ? static_cast<int>(p.labels[row]) : -1;
         float m2 = -INFINITY, s = 0.f, tt = 0.f;
+        uint32_t held[16];
+        __nv_bfloat16* held_dst = nullptr;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t v[32];
@@ -581,14 +583,36 @@ struct EpiLsePartials {
             if (p.logits != nullptr && row_ok) {
                 __nv_bfloat16* dst = p.logits + static_cast<int64_t>(row) * p.ld_logits + col0;
                 if (nvalid == 32 && (p.ld_logits & 15) == 0 && (reinterpret_cast<uintptr_t>(p.logits) & 31u) == 0) {
-                    float d[32];
+                    // Two 32-column chunks are written together as one full 128-byte line (4 x 32 B issued back
+                    // to back), so the write-once store never leaves a half-written line behind to be re-filled.
+                    uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(v[i]);
-                    store_row32_bf16(dst, d);
+                    for (int i = 0; i < 16; ++i)
+                        pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                    if ((c & 1) == 0) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) held[i] = pk[i];
+                        held_dst = dst;
+                    } else {
+                        if (held_dst != nullptr) {
+                            st_global_256_stream(held_dst, held[0], held[1], held[2], held[3], held[4], held[5], held[6],
+                                                 held[7]);
+                            st_global_256_stream(held_dst + 16, held[8], held[9], held[10], held[11], held[12], held[13],
+                                                 held[14], held[15]);
+                            held_dst = nullptr;
+                        }
+                        st_global_256_stream(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+                        st_global_256_stream(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+                    }
                 } else {
                     for (int i = 0; i < nvalid; ++i) dst[i] = __float2bfloat16_rn(__uint_as_float(v[i]));
                 }
             }
+        }
+        if (held_dst != nullptr) {  // odd number of valid 32-column chunks in this tile
+            st_global_256_stream(held_dst, held[0], held[1], held[2], held[3], held[4], held[5], held[6], held[7]);
+            st_global_256_stream(held_dst + 16, held[8], held[9], held[10], held[11], held[12], held[13], held[14],
+                                 held[15]);
         }
         if (row_ok) {
             const int64_t o = static_cast<int64_t>(n_tile) * p.ld + row;
