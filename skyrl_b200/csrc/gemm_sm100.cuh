@@ -11,8 +11,8 @@
 // contiguous); the backward GEMMs of the fused LM head use the MN-major forms so no transposed copies of
 // the weight / hidden / dlogits matrices are ever made.
 //
-// Warp roles (256 threads):  warps 0..3 = epilogue, warp 4 lane 0 = TMA producer, warp 5 lane 0 = MMA issuer
-// (leader CTA only), warp 6 = TMEM allocator.
+// Warp roles (256 threads):  warps 0..3 = epilogue, warp 4 = TMA producer, warp 5 = MMA issuer (leader CTA
+// only), warp 6 = TMEM allocator; warp 7 idles at the final barrier.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -27,17 +27,11 @@ constexpr int kBM = 128;  // accumulator rows per CTA (= TMEM lanes)
 constexpr int kBK = 64;   // bf16 elements per 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 256;
-// Warp roles.  The control warps get the HIGHER warp ids: the SM's warp arbiter favours higher ids among
-// eligible warps, so the single TMA lane and the single MMA lane are never starved of issue slots by an
-// epilogue warp that shares their scheduler and is in the middle of a long ALU burst.
-#ifndef SKYB200_EPI_FIRST
-#define SKYB200_EPI_FIRST 1
-#endif
-#if SKYB200_EPI_FIRST
+// Warp roles: epilogue warps 0..3 (TMEM lane quarter = warp id), then the three control warps.  The control
+// loops run warp-converged (uniform registers) with one elected lane issuing TMA / tcgen05 instructions: the
+// earlier single-lane form made ptxas emit divergent "waterfall" code around every uniform-datapath operand and
+// cost ~5 % of the tensor pipe (measured, profiles/r01c_*).
 constexpr int kEpiWarp0 = 0, kTmaWarp = 4, kMmaWarp = 5, kAllocWarp = 6;
-#else
-constexpr int kEpiWarp0 = 4, kTmaWarp = 0, kMmaWarp = 1, kAllocWarp = 2;
-#endif
 
 // L2 eviction policies (the encodings cuTensorMap / createpolicy produce for fraction 1.0)
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;

@@ -6,8 +6,11 @@ states: it consumes ``hidden`` instead of logits, never builds ``[tokens x vocab
 dict the reference reports (``final_loss, policy_loss, policy_entropy, policy_kl, loss_metrics/clip_ratio``) plus
 the gradients that continue into the trunk (``d_hidden``) and the lm_head (``d_weight``, fp32).
 
-The three C-ABI calls run back to back on the current stream with no host synchronisation in between; the only
-sync is the single D2H copy of the packed stats vector (skipped with ``sync=False``).
+By default one C-ABI call (``skyb200_policy_step``) runs the whole step chunk by chunk (forward GEMM -> loss ->
+backward GEMMs, 6*H*V executed flop per token, small kernels on an auxiliary stream); ``fused=False`` issues the
+three calls of the autograd path instead.  There is no host synchronisation inside; the only sync is the single
+D2H copy of the packed stats vector (skipped with ``sync=False``).  Use one caller thread per device: the step
+keeps per-device scratch (auxiliary stream, lockstep counters).
 """
 from __future__ import annotations
 
