@@ -687,7 +687,7 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
             if (r) return r;
         }
         r = loss_flat_range(log_probs, old_log_probs, advantages, loss_mask, base_log_probs, entropy,
-                            need_grad ? d_lp - t0 : nullptr, use_ent_grad ? d_ent - t0 : nullptr, lws, B, A, t0,
+                            need_grad ? d_lp : nullptr, use_ent_grad ? d_ent : nullptr, lws, B, A, t0,
                             t0 + rows, slot, *params, cu_seqlens, aux);
         if (r) return r;
         if (need_grad) {

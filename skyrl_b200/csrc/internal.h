@@ -28,7 +28,8 @@ int loss_prepass(const float* loss_mask, const LossChunkWs& ws, int64_t B, int64
 // GSPO sequence log-ratios for rows [row0, row0 + rows)
 int loss_row_logratio(const float* lp, const float* olp, const float* loss_mask, const LossChunkWs& ws, int64_t row0,
                       int64_t rows, int64_t A, cudaStream_t stream);
-// per-token pass over flat tokens [t0, t1) of the [B, A] batch; partials go to slots [slot0, slot0 + blocks)
+// per-token pass over flat tokens [t0, t1) of the [B, A] batch; partials go to slots [slot0, slot0 + blocks).
+// lp / olp / adv / mask / base / ent are whole-batch arrays; d_lp / d_ent are CHUNK-LOCAL (element t0 at index 0).
 int loss_flat_range(const float* lp, const float* olp, const float* adv, const float* loss_mask, const float* base,
                     const float* ent, float* d_lp, float* d_ent, const LossChunkWs& ws, int64_t B, int64_t A,
                     int64_t t0, int64_t t1, int64_t slot0, const skyb200_loss_params& p, const int32_t* cu,

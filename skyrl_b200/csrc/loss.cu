@@ -420,6 +420,7 @@ struct FlatArgs {
     int vec4;
     int64_t A;
     int64_t t0, t1;
+    int64_t out_base;  // d_lp / d_ent are chunk-local: element i of the batch is written at [i - out_base]
     int64_t slot0;
     skyb200_loss_params p;
 };
@@ -502,14 +503,14 @@ __global__ void __launch_bounds__(kLossThreads) loss_flat_kernel(FlatArgs a) {
                 g.y = loss_token(cx, acc, lp.y, olp.y, adv.y, m.y, bs.y);
                 g.z = loss_token(cx, acc, lp.z, olp.z, adv.z, m.z, bs.z);
                 g.w = loss_token(cx, acc, lp.w, olp.w, adv.w, m.w, bs.w);
-                if (a.d_lp) *reinterpret_cast<float4*>(a.d_lp + i) = g;
+                if (a.d_lp) *reinterpret_cast<float4*>(a.d_lp + (i - a.out_base)) = g;
                 if (a.ent) {
                     acc.s_ent = fmaf(en.x, m.x, acc.s_ent);
                     acc.s_ent = fmaf(en.y, m.y, acc.s_ent);
                     acc.s_ent = fmaf(en.z, m.z, acc.s_ent);
                     acc.s_ent = fmaf(en.w, m.w, acc.s_ent);
                     if (a.d_ent)
-                        *reinterpret_cast<float4*>(a.d_ent + i) =
+                        *reinterpret_cast<float4*>(a.d_ent + (i - a.out_base)) =
                             make_float4(cx.d_ent_val * m.x, cx.d_ent_val * m.y, cx.d_ent_val * m.z, cx.d_ent_val * m.w);
                 }
             }
@@ -522,10 +523,10 @@ __global__ void __launch_bounds__(kLossThreads) loss_flat_kernel(FlatArgs a) {
                 set_row(a.cu ? row_of_token(a.cu, a.B, i) : i / A);
                 const float m = a.mask ? a.mask[i] : 1.f;
                 const float g = loss_token(cx, acc, a.lp[i], a.olp[i], a.adv[i], m, a.base ? a.base[i] : 0.f);
-                if (a.d_lp) a.d_lp[i] = g;
+                if (a.d_lp) a.d_lp[i - a.out_base] = g;
                 if (a.ent) {
                     acc.s_ent = fmaf(a.ent[i], m, acc.s_ent);
-                    if (a.d_ent) a.d_ent[i] = cx.d_ent_val * m;
+                    if (a.d_ent) a.d_ent[i - a.out_base] = cx.d_ent_val * m;
                 }
             }
         }
@@ -643,6 +644,7 @@ int loss_flat_range(const float* lp, const float* olp, const float* adv, const f
     a.A = A;
     a.t0 = t0;
     a.t1 = t1;
+    a.out_base = t0;  // the caller passes chunk-local d_lp / d_ent buffers
     a.slot0 = slot0;
     a.p = p;
     auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
