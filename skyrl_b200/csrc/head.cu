@@ -176,7 +176,7 @@ static int env_int(const char* name, int dflt) {
     return x > 0 ? x : dflt;
 }
 // tile-order group sizes (tunable for experiments; defaults measured on the 7B head)
-static int fwd_group_m() { static int v = env_int("SKYB200_FWD_GROUP_M", 16); return v; }
+static int fwd_group_m() { static int v = env_int("SKYB200_FWD_GROUP_M", 19); return v; }
 static int dh_group_m() { static int v = env_int("SKYB200_DH_GROUP_M", 8); return v; }
 static uint64_t hint_of(const char* name, int dflt) {
     const int v = env_int(name, dflt);  // 1 = normal, 2 = evict_first, 3 = evict_last
