@@ -536,8 +536,22 @@ StepPlan plan_step(int64_t B, int64_t A, int64_t N, int64_t H, int64_t V, int lo
     StepPlan p;
     int64_t chunk = kDefaultChunk;
     if (loss_type == SKYB200_LOSS_GSPO) {
-        const int64_t unit = A / gcd64(A, kTileM) * kTileM;  // lcm(A, 256)
-        chunk = unit * std::max<int64_t>(1, (3 * kDefaultChunk / 2) / unit);
+        // whole sequences per chunk: k * lcm(A, 256) tokens, k chosen (up to ~2 default chunks) so that the
+        // d_hidden GEMM of a chunk fills whole waves of the resident CTA pairs as well as possible
+        const int64_t unit = A / gcd64(A, kTileM) * kTileM;
+        const int64_t clusters = std::max(1, num_sms() / kHeadCtas);
+        const int64_t n_tiles_h = (H + kHeadBN - 1) / kHeadBN;
+        int64_t best_k = 1;
+        double best_eff = -1.0;
+        for (int64_t k = 1; k * unit <= std::max<int64_t>(unit, 2 * kDefaultChunk); ++k) {
+            const int64_t tiles = (k * unit / kTileM) * n_tiles_h;
+            const double eff = (double)tiles / (double)(((tiles + clusters - 1) / clusters) * clusters);
+            if (eff > best_eff + 1e-9) {
+                best_eff = eff;
+                best_k = k;
+            }
+        }
+        chunk = best_k * unit;
     }
     chunk = std::min<int64_t>(chunk, round_up(N, kTileM));
     p.chunk = chunk;
@@ -561,7 +575,6 @@ StepPlan plan_step(int64_t B, int64_t A, int64_t N, int64_t H, int64_t V, int lo
     p.off_loss = take(loss_chunk_ws_bytes(B, N) + (size_t)(N / chunk + 2) * 8 * 4 * 4);
     (void)A;
     p.total = off + 512;
-    (void)H;
     return p;
 }
 

@@ -219,3 +219,33 @@ def test_fused_policy_loss_autograd_node():
     assert hd.grad.shape == hd.shape and hd.grad.dtype == torch.bfloat16
     assert rel(hd.grad.float().reshape(B * A, H), h.grad) < 2e-2
     assert rel(wd.grad.float(), w.grad) < 2e-2
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 8, 8), (2, 3, 16, 40), (1, 300, 24, 257), (3, 129, 40, 1000)])
+@pytest.mark.parametrize("fused", [True, False])
+def test_degenerate_shapes(shape, fused):
+    """Tiny / odd shapes: fewer rows than one tile, vocab smaller than one slab, H = one partial K block."""
+    B, A, H, V = shape
+    T = 1.0
+    g = torch.Generator().manual_seed(B * 1000 + A + H + V)
+    hidden = torch.randn(B, A, H, generator=g).bfloat16()
+    weight = (torch.randn(V, H, generator=g) * (1.0 / H ** 0.5)).bfloat16()
+    labels = torch.randint(0, V, (B, A), generator=g)
+    mask = torch.ones(B, A)
+    cfg = O.make_cfg(policy_loss_type="regular", loss_reduction="token_mean", use_kl_loss=True)
+    h = hidden.float().reshape(B * A, H).requires_grad_(True)
+    w = weight.float().requires_grad_(True)
+    lp_ref, ent_ref = O.head_logprobs_entropy(h, w, labels.reshape(-1), T)
+    olp = lp_ref.detach().view(B, A) + 0.05 * torch.randn(B, A, generator=g)
+    base = lp_ref.detach().view(B, A) + 0.1 * torch.randn(B, A, generator=g)
+    adv = torch.randn(B, A, generator=g)
+    final_ref, st_ref = O.loss_assembly(lp_ref.view(B, A), olp, adv, cfg, mask, base, ent_ref.view(B, A))
+    final_ref.backward()
+    out = skyrl_b200.policy_update_step(hidden.to(DEV), weight.to(DEV), labels.to(DEV), olp.to(DEV), adv.to(DEV), cfg,
+                                        loss_mask=mask.to(DEV), base_log_probs=base.to(DEV), temperature=T,
+                                        fused=fused)
+    assert (out.log_probs.cpu() - lp_ref.detach().view(B, A)).abs().max().item() < 1e-3
+    assert out.status["final_loss"] == pytest.approx(st_ref["final_loss"], rel=2e-3, abs=2e-4)
+    rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm().clamp(min=1e-12))
+    assert rel(out.d_hidden.float(), h.grad) < 2e-2
+    assert rel(out.d_weight, w.grad) < 2e-2
