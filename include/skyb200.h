@@ -165,6 +165,18 @@ int skyb200_off_policy_correction(const float* old_log_probs, const float* rollo
                                   size_t workspace_bytes, int64_t B, int64_t A, const skyb200_opc_params* params,
                                   void* stream);
 
+/*
+ * Critic value head (model_wrapper.py:472-489: value_head = nn.Linear(H, 1)): values[r] = <hidden[r, :], w> + bias.
+ * hidden [N, H] bf16, weight [H] fp32, values / g_values [N] fp32, d_hidden [N, H] bf16 (or NULL),
+ * d_weight [H] fp32 (or NULL; += if accumulate).  The gradient of the bias is sum(g_values) (caller's one-liner).
+ */
+int skyb200_value_head_forward(const void* hidden, const float* weight, float bias, float* values, int64_t N,
+                               int64_t H, void* stream);
+size_t skyb200_value_head_backward_workspace(int64_t N, int64_t H);
+int skyb200_value_head_backward(const void* hidden, const float* weight, const float* g_values, void* d_hidden,
+                                float* d_weight, int32_t accumulate, void* workspace, size_t workspace_bytes,
+                                int64_t N, int64_t H, void* stream);
+
 /* x[i] *= *scale_dev  (applies an upstream autograd gradient that lives on the device) */
 int skyb200_scale_inplace(float* x, const float* scale_dev, int64_t n, void* stream);
 

@@ -77,6 +77,9 @@ SIGNATURES = {
     "skyb200_off_policy_workspace": (_SZ, [_I64]),
     "skyb200_off_policy_correction": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _SZ, _I64, _I64, C.POINTER(OpcParams),
                                                 _P]),
+    "skyb200_value_head_forward": (C.c_int, [_P, _P, _F, _P, _I64, _I64, _P]),
+    "skyb200_value_head_backward_workspace": (_SZ, [_I64, _I64]),
+    "skyb200_value_head_backward": (C.c_int, [_P, _P, _P, _P, _P, _I32, _P, _SZ, _I64, _I64, _P]),
     "skyb200_scale_inplace": (C.c_int, [_P, _P, _I64, _P]),
     "skyb200_masked_mean": (C.c_int, [_P, _P, _P, _P, _SZ, _I64, _P]),
     "skyb200_approx_kl": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),

@@ -66,3 +66,27 @@ def test_masked_mean_kernel():
     assert_close(skyrl_b200.masked_mean(x, m), (x * m).sum() / m.sum(), rel=1e-5, floor=1e-3)
     assert skyrl_b200.masked_mean(x, torch.zeros_like(m)).item() == 0.0  # denominator clamped to 1
     assert_close(skyrl_b200.masked_mean(x, m, dim=-1), (x * m).sum(-1) / m.sum(-1).clamp(min=1), rel=1e-5, floor=1e-3)
+
+
+def test_value_head_forward_backward():
+    from skyrl_b200.value_head import action_values, value_head
+
+    g = torch.Generator(device=DEV).manual_seed(5)
+    B, S, H, A = 3, 50, 200, 17
+    hidden = torch.randn(B, S, H, device=DEV, generator=g).bfloat16().requires_grad_(True)
+    lin = torch.nn.Linear(H, 1).to(DEV)
+    v = value_head(hidden, lin.weight, lin.bias)
+    ref = torch.nn.functional.linear(hidden.float(), lin.weight, lin.bias).squeeze(-1)
+    assert_close(v, ref, rel=1e-5, floor=1.0)
+    gv = torch.randn(B, S, device=DEV, generator=g)
+    (v * gv).sum().backward()
+    dh, dw, db = hidden.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone()
+    hidden.grad = None
+    lin.zero_grad()
+    h32 = hidden.detach().float().requires_grad_(True)
+    (torch.nn.functional.linear(h32, lin.weight, lin.bias).squeeze(-1) * gv).sum().backward()
+    assert_close(dh.float(), h32.grad, rel=1e-2, floor=1e-2)  # bf16 output
+    assert_close(dw, lin.weight.grad, rel=1e-4, floor=1e-2)
+    assert_close(db, lin.bias.grad, rel=1e-5, floor=1e-2)
+    av = action_values(hidden.detach(), lin.weight, A, lin.bias)
+    assert torch.equal(av, v.detach()[:, :-1][:, -A:])

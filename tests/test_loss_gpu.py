@@ -202,3 +202,21 @@ def test_off_policy_correction_matches_reference_golden(golden_loss):
         assert sorted(met) == sorted(want_met), key  # same metric names as the reference
         for k in want_met:
             assert met[k] == pytest.approx(want_met[k], rel=1e-5, abs=1e-6), (key, k)
+
+
+def test_off_policy_correction_known_answers():  # reference: tests/cpu/algorithms/test_off_policy_correction.py
+    import opc_kat
+
+    for name, olp, rlp, mask, kw, want_tis, want_keep, want_met in opc_kat.CASES:
+        olp_t, rlp_t, m_t = (torch.tensor(x, device=DEV) for x in (olp, rlp, mask))
+        tis, met, new_mask = losses.compute_off_policy_correction(olp_t, rlp_t, m_t, opc_kat.cfg(**kw))
+        want_mask = torch.tensor(mask) * torch.tensor(want_keep).unsqueeze(-1)
+        assert torch.equal(new_mask.cpu(), want_mask), name
+        if want_tis is not None:
+            assert torch.allclose(tis.cpu(), torch.tensor(want_tis), rtol=1e-3, atol=1e-4), name
+        for k, v in want_met.items():
+            assert abs(met[k] - v) < 0.01, (name, k, met[k], v)
+    with pytest.raises(ValueError, match="Unknown tis_ratio_type"):
+        losses.compute_off_policy_correction(olp_t, rlp_t, m_t, opc_kat.cfg(tis_ratio_type="bogus"))
+    with pytest.raises(ValueError, match="Unknown sequence_mask_metric"):
+        losses.compute_off_policy_correction(olp_t, rlp_t, m_t, opc_kat.cfg(sequence_mask_metric="bogus"))

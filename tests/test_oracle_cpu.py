@@ -291,3 +291,16 @@ def test_golden_off_policy_correction(golden_loss):
             assert met[k] == pytest.approx(want_met[k], rel=1e-5, abs=1e-6), (key, k)
         n += 1
     assert n == 8
+
+
+def test_kat_off_policy_correction():  # tests/cpu/algorithms/test_off_policy_correction.py:20-330
+    import opc_kat
+
+    for name, olp, rlp, mask, kw, want_tis, want_keep, want_met in opc_kat.CASES:
+        olp_t, rlp_t, m_t = T(olp), T(rlp), T(mask)
+        tis, met, new_mask = O.off_policy_correction(olp_t, rlp_t, m_t, opc_kat.cfg(**kw))
+        assert torch.allclose(new_mask, m_t * T(want_keep).unsqueeze(-1), atol=1e-6), name
+        if want_tis is not None:
+            assert torch.allclose(tis.expand_as(olp_t), T(want_tis), rtol=1e-3, atol=1e-4), name
+        for k, v in want_met.items():
+            assert abs(met[k] - v) < 0.01, (name, k, met[k], v)
