@@ -282,6 +282,18 @@ int skyb200_head_forward(const void* hidden, const void* weight, const int64_t* 
                          int64_t N, int64_t H, int64_t V, float temperature, int64_t chunk, void* stream);
 
 /*
+ * Vocab-parallel (tensor-parallel) building block — the B200 counterpart of Megatron's DistributedLogprob /
+ * _VocabParallelEntropy (distributed/megatron/model_utils.py:64-247, 548-590).  `weight` is ONE vocab shard
+ * [V_shard, H]; `labels` are shard-local (global label - shard start; labels outside [0, V_shard) never match).
+ * stats [N, 4] fp32 out = per token {max_j y_j, sum_j 2^(y_j - max), sum_j 2^(y_j - max) * logit_j, logit[label] or 0}
+ * with y = logit * log2(e) / T.  The ranks all-gather these 16 bytes per token and combine them
+ * (skyrl_b200/tp_head.py); the backward is skyb200_head_backward on the shard with the GLOBAL lse2 / entropy.
+ */
+int skyb200_head_forward_stats(const void* hidden, const void* weight, const int64_t* labels, float* stats,
+                               void* workspace, size_t workspace_bytes, int64_t N, int64_t H, int64_t V,
+                               float temperature, int64_t chunk, void* stream);
+
+/*
  * Backward: given g_logprobs [N] and optional g_entropy [N] (upstream grads w.r.t. the forward outputs,
  * g_entropy already multiplied by entropy_mask by the caller if one was used) produce
  *   d_hidden [N, H] bf16   and   d_weight [V, H] fp32 (+= if accumulate != 0, else overwritten).

@@ -10,6 +10,8 @@ Public surface (same names as the reference where one exists):
 * losses: ``ppo_policy_loss``, ``gspo_policy_loss``, ``policy_update_loss``
 * logits helpers: ``logprobs_from_logits``, ``chunked_entropy_from_logits``, ``masked_mean``
 * fused head: ``fused_lm_head``, ``fused_lm_head_logprobs``
+* critic / TP: ``value_head``, ``action_values``, ``vocab_parallel_lm_head``; trainer-side batch helpers in
+  ``skyrl_b200.trainer_ops``
 * the step: ``policy_update_step`` / ``PolicyUpdateConfig`` (skyrl_b200.policy_update)
 
 All arithmetic runs in ``libskyb200.so`` (hand-written sm_100a CUDA, C ABI in include/skyb200.h).  Importing this
@@ -40,6 +42,8 @@ from .registry import (  # noqa: F401
     register_policy_loss,
     repopulate_all_registries,
 )
+from .tp_head import vocab_parallel_lm_head  # noqa: F401
+from .value_head import action_values, value_head  # noqa: F401
 from .torch_utils import (  # noqa: F401
     chunked_entropy_from_logits,
     logprobs_from_logits,

@@ -231,6 +231,27 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float* __restrict
     }
 }
 
+// Vocab-parallel variant: fold the slab partials of ONE vocab shard into per-token (max, sum, weighted sum,
+// label accumulator); the cross-rank combine happens on these 4 numbers per token.
+__global__ void __launch_bounds__(256) head_merge_stats_kernel(const float* __restrict__ part_m,
+                                                               const float* __restrict__ part_s,
+                                                               const float* __restrict__ part_t, int64_t ld, int slabs,
+                                                               const float* __restrict__ label_acc,
+                                                               float* __restrict__ stats, int rows) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float M = -INFINITY;
+    for (int s = 0; s < slabs; ++s) M = fmaxf(M, part_m[(int64_t)s * ld + r]);
+    float S = 0.f, T = 0.f;
+    for (int s = 0; s < slabs; ++s) {
+        const int64_t o = (int64_t)s * ld + r;
+        const float w = exp2f(part_m[o] - M);
+        S = fmaf(part_s[o], w, S);
+        T = fmaf(part_t[o], w, T);
+    }
+    reinterpret_cast<float4*>(stats)[r] = make_float4(M, S, T, label_acc[r]);
+}
+
 // In-place turn of a stored bf16 logits tile store [rows, ld] into d(logits) (fused step, no recompute):
 //   u = z*scale_log2 - lse2 ; p = 2^u ; d = inv_T * ( g_lp*1[j == label] - p*(g_lp + g_ent*(u*ln2 + H)) )
 // One block row per token; each thread owns 16 consecutive vocab entries (one 32-byte access each way).
@@ -442,6 +463,51 @@ extern "C" int skyb200_head_forward(const void* hidden, const void* weight, cons
             part_m, part_s, part_t, c, slabs, label_acc, entropy_mask ? entropy_mask + r0 : nullptr, inv_T,
             logprobs + r0, entropy ? entropy + r0 : nullptr, nullptr, lse2 + r0, rows);
         rc = check_launch("head_merge_kernel");
+        if (rc) return rc;
+    }
+    return SKYB200_OK;
+}
+
+extern "C" int skyb200_head_forward_stats(const void* hidden, const void* weight, const int64_t* labels,
+                                          float* stats, void* workspace, size_t workspace_bytes, int64_t N,
+                                          int64_t H, int64_t V, float temperature, int64_t chunk, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (N == 0) return SKYB200_OK;
+    SKYB200_REQUIRE(hidden && weight && labels && stats && workspace, "null pointer");
+    SKYB200_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
+    SKYB200_REQUIRE(temperature > 0.f, "temperature must be > 0");
+    SKYB200_REQUIRE((reinterpret_cast<uintptr_t>(stats) & 15u) == 0, "stats must be 16-byte aligned");
+    SKYB200_REQUIRE(N < (1ll << 31) && V < (1ll << 31) && H < (1ll << 31), "dimension too large");
+    if (workspace_bytes < skyb200_head_forward_workspace(N, H, V, chunk))
+        return fail(SKYB200_EWORKSPACE, "head_forward workspace too small");
+    int rc = skyb200_check_device();
+    if (rc) return rc;
+    const int64_t c = pick_chunk(N, chunk);
+    const int slabs = (int)num_slabs(V);
+    float* part_m = static_cast<float*>(workspace);
+    float* part_s = part_m + (int64_t)slabs * c;
+    float* part_t = part_s + (int64_t)slabs * c;
+    float* label_acc = part_t + (int64_t)slabs * c;
+    const __nv_bfloat16* hid = static_cast<const __nv_bfloat16*>(hidden);
+    for (int64_t r0 = 0; r0 < N; r0 += c) {
+        const int rows = (int)std::min<int64_t>(c, N - r0);
+        EpiLsePartials::Params ep;
+        ep.scale_log2 = 1.4426950408889634f / temperature;
+        ep.part_m = part_m;
+        ep.part_s = part_s;
+        ep.part_t = part_t;
+        ep.ld = c;
+        ep.labels = labels + r0;
+        ep.label_acc = label_acc;
+        ep.logits = nullptr;
+        ep.ld_logits = 0;
+        SKYB200_CUDA_CHECK(cudaMemsetAsync(label_acc, 0, (size_t)rows * sizeof(float), stream));
+        rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
+            hid + r0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream);
+        if (rc) return rc;
+        head_merge_stats_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(part_m, part_s, part_t, c, slabs, label_acc,
+                                                                        stats + 4 * r0, rows);
+        rc = check_launch("head_merge_stats_kernel");
         if (rc) return rc;
     }
     return SKYB200_OK;

@@ -181,3 +181,58 @@ def test_hidden_size_not_a_multiple_of_the_k_block():
     assert (lp.detach().cpu() - lp_ref.detach()).abs().max().item() < LOGPROB_ATOL
     assert _rel_l2(hd.grad.float(), h.grad) < 1e-2
     assert _rel_l2(wd.grad.float(), w.grad) < 1e-2
+
+
+def test_vocab_parallel_shards_combine_to_the_unsharded_head():
+    """TP head on one GPU: two vocab shards run one after the other, their [N, 4] stats combined like the all-gather
+    would, must reproduce the unsharded fused head; shard backward partials must add up to its gradients."""
+    from skyrl_b200 import tp_head
+
+    N, H, V, T = 500, 128, 3000, 0.8
+    g = torch.Generator().manual_seed(8)
+    hidden = torch.randn(N, H, generator=g).bfloat16().to(DEV)
+    weight = (torch.randn(V, H, generator=g) * (1.5 / H ** 0.5)).bfloat16().to(DEV)
+    labels = torch.randint(0, V, (N,), generator=g).to(DEV)
+    g_lp = torch.randn(N, generator=g).to(DEV)
+    g_ent = (0.05 * torch.randn(N, generator=g)).to(DEV)
+    hd = hidden.clone().requires_grad_(True)
+    wd = weight.clone().requires_grad_(True)
+    lp_full, ent_full = skyrl_b200.fused_lm_head(hd, wd, labels, temperature=T)
+    ((lp_full * g_lp).sum() + (ent_full * g_ent).sum()).backward()
+    cuts = [0, 1408, V]  # uneven shards, neither a multiple of the 256-wide slab
+    stats = [tp_head.shard_forward_stats(hidden, weight[a:b].contiguous(), (labels - a).contiguous(), T)
+             for a, b in zip(cuts[:-1], cuts[1:])]
+    lp, ent, lse2 = tp_head.combine_shard_stats(torch.stack(stats), T)
+    assert (lp - lp_full.detach()).abs().max().item() < 1e-5
+    assert (ent - ent_full.detach()).abs().max().item() < 1e-5
+    dh = torch.zeros(N, H, device=DEV)
+    dws = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        d_h, d_w = tp_head.shard_backward(hidden, weight[a:b].contiguous(), (labels - a).contiguous(), lse2.contiguous(),
+                                          ent.contiguous(), g_lp, g_ent, T)
+        dh += d_h.float()
+        dws.append(d_w)
+    assert _rel_l2(dh, hd.grad.float().cpu()) < 1e-2
+    assert _rel_l2(torch.cat(dws), wd.grad.float().cpu()) < 1e-2
+    # autograd wrapper without a process group = a single shard covering the whole vocabulary
+    h2 = hidden.clone().requires_grad_(True)
+    w2 = weight.clone().requires_grad_(True)
+    lp2, ent2 = tp_head.vocab_parallel_lm_head(h2, w2, labels, 0, temperature=T)
+    ((lp2 * g_lp).sum() + (ent2 * g_ent).sum()).backward()
+    assert (lp2 - lp_full.detach()).abs().max().item() < 1e-5
+    assert _rel_l2(h2.grad.float(), hd.grad.float().cpu()) < 1e-2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (NCCL tensor-parallel group)")
+def test_vocab_parallel_head_over_nccl_two_ranks(tmp_path):
+    import os
+    import subprocess
+    import sys
+
+    script = os.path.join(os.path.dirname(__file__), "tp_worker.py")
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script], env=env, capture_output=True,
+                       text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "TP_OK" in r.stdout
