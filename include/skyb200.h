@@ -331,6 +331,20 @@ int skyb200_policy_step(const void* hidden, const void* weight, const int64_t* l
                         const skyb200_loss_params* params, void* stream);
 
 /*
+ * Same step with the hidden states resident in HOST memory (pinned for an asynchronous copy): hidden_host [N, H]
+ * bf16 is streamed into hidden_staging (device, [N, H] bf16, uninitialised on entry, holds the hidden states on
+ * return) one token chunk at a time on an internal copy stream, ahead of the GEMMs that read it, so only the first
+ * chunk's transfer is exposed.  Everything else as skyb200_policy_step.
+ */
+int skyb200_policy_step_from_host(const void* hidden_host, void* hidden_staging, const void* weight,
+                                  const int64_t* labels, const float* old_log_probs, const float* advantages,
+                                  const float* loss_mask, const float* base_log_probs, const float* entropy_mask,
+                                  float* log_probs, float* entropy, void* d_hidden, float* d_weight,
+                                  int32_t accumulate, float* stats, void* workspace, size_t workspace_bytes, int64_t B,
+                                  int64_t A, int64_t H, int64_t V, const int32_t* cu_seqlens, int64_t n_tokens,
+                                  float temperature, const skyb200_loss_params* params, void* stream);
+
+/*
  * logprobs_from_logits (torch_utils.py:115-177) and chunked_entropy_from_logits (:59-111) on materialised
  * logits [N, V] (bf16 or fp32), for callers that still hold logits.  logits_dtype: 0 = fp32, 1 = bf16.
  * Any output pointer may be NULL.  entropy_mask [N] fp32 or NULL.  lse [N] = natural-log sum-exp (saved for

@@ -647,8 +647,18 @@ StepPlan plan_step(int64_t B, int64_t A, int64_t N, int64_t H, int64_t V, int lo
 // One auxiliary stream + a few events per device, created on first use.
 struct StepStreams {
     cudaStream_t aux = nullptr;
+    cudaStream_t copy = nullptr;  // host -> device staging of hidden chunks (policy_step_from_host)
     cudaEvent_t start = nullptr, fwd[2] = {nullptr, nullptr}, mid[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> copied;  // one per chunk, grown on demand
     bool ok = false;
+    bool grow_copied(size_t n) {
+        while (copied.size() < n) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
+            copied.push_back(e);
+        }
+        return true;
+    }
 };
 StepStreams* step_streams() {
     static StepStreams per_dev[64];
@@ -657,6 +667,7 @@ StepStreams* step_streams() {
     StepStreams& s = per_dev[dev];
     if (!s.ok) {
         if (cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&s.copy, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         cudaEvent_t* evs[5] = {&s.start, &s.fwd[0], &s.fwd[1], &s.mid[0], &s.mid[1]};
         for (auto* e : evs)
             if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -672,13 +683,15 @@ extern "C" size_t skyb200_policy_step_workspace(int64_t B, int64_t A, int64_t n_
     return plan_step(B, A, n_tokens > 0 ? n_tokens : B * A, H, V, loss_type, need_grad != 0).total;
 }
 
-extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const int64_t* labels,
-                                   const float* old_log_probs, const float* advantages, const float* loss_mask,
-                                   const float* base_log_probs, const float* entropy_mask, float* log_probs,
-                                   float* entropy, void* d_hidden, float* d_weight, int32_t accumulate, float* stats,
-                                   void* workspace, size_t workspace_bytes, int64_t B, int64_t A, int64_t H, int64_t V,
-                                   const int32_t* cu_seqlens, int64_t n_tokens, float temperature,
-                                   const skyb200_loss_params* params, void* stream_) {
+// hidden_host != nullptr: `hidden` is an uninitialised device staging buffer [N, H] that this call fills chunk by
+// chunk from (pinned) host memory on a copy stream, ahead of the GEMMs that read it.
+static int policy_step_impl(const void* hidden_host, const void* hidden, const void* weight, const int64_t* labels,
+                            const float* old_log_probs, const float* advantages, const float* loss_mask,
+                            const float* base_log_probs, const float* entropy_mask, float* log_probs, float* entropy,
+                            void* d_hidden, float* d_weight, int32_t accumulate, float* stats, void* workspace,
+                            size_t workspace_bytes, int64_t B, int64_t A, int64_t H, int64_t V,
+                            const int32_t* cu_seqlens, int64_t n_tokens, float temperature,
+                            const skyb200_loss_params* params, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SKYB200_REQUIRE(hidden && weight && labels && old_log_probs && advantages && log_probs && entropy && stats &&
                         workspace && params,
@@ -736,6 +749,7 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
         ep.ld_logits = plan.ldS;
         // the parity buffers were last read by the auxiliary-stream kernels of chunk ci - 2
         if (ci >= 2) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[p], 0));
+        if (hidden_host != nullptr) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->copied[ci], 0));
         SKYB200_CUDA_CHECK(cudaMemsetAsync(ep.label_acc, 0, (size_t)rows * sizeof(float), stream));
         int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
             hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream, 0, hint_fwd_a(), kEvictNormal,
@@ -815,6 +829,20 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
     if (rc) return rc;
     SKYB200_CUDA_CHECK(cudaEventRecord(ss->start, stream));
     SKYB200_CUDA_CHECK(cudaStreamWaitEvent(aux, ss->start, 0));
+    if (hidden_host != nullptr) {
+        // all chunk copies are queued now: PCIe runs ahead of the tensor cores, only chunk 0's copy is exposed
+        if (!ss->grow_copied((size_t)n_chunks)) return fail(SKYB200_ECUDA, "could not create copy events");
+        SKYB200_CUDA_CHECK(cudaStreamWaitEvent(ss->copy, ss->start, 0));
+        const char* src = static_cast<const char*>(hidden_host);
+        char* dst = reinterpret_cast<char*>(const_cast<void*>(hidden));
+        for (int64_t ci = 0; ci < n_chunks; ++ci) {
+            const int64_t t0 = ci * c;
+            const size_t off = (size_t)t0 * (size_t)H * sizeof(__nv_bfloat16);
+            const size_t bytes = (size_t)std::min<int64_t>(c, N - t0) * (size_t)H * sizeof(__nv_bfloat16);
+            SKYB200_CUDA_CHECK(cudaMemcpyAsync(dst + off, src + off, bytes, cudaMemcpyHostToDevice, ss->copy));
+            SKYB200_CUDA_CHECK(cudaEventRecord(ss->copied[ci], ss->copy));
+        }
+    }
 
     std::vector<int64_t> slot_of(n_chunks);
     {
@@ -845,6 +873,33 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
     if (n_chunks > 1) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[(n_chunks - 2) & 1], 0));
     const int64_t total_slots = slot_of[n_chunks - 1] + loss_chunk_blocks(std::min<int64_t>(c, N - (n_chunks - 1) * c));
     return loss_finalize(lws, total_slots, true, stats, *params, stream);
+}
+
+extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const int64_t* labels,
+                                   const float* old_log_probs, const float* advantages, const float* loss_mask,
+                                   const float* base_log_probs, const float* entropy_mask, float* log_probs,
+                                   float* entropy, void* d_hidden, float* d_weight, int32_t accumulate, float* stats,
+                                   void* workspace, size_t workspace_bytes, int64_t B, int64_t A, int64_t H, int64_t V,
+                                   const int32_t* cu_seqlens, int64_t n_tokens, float temperature,
+                                   const skyb200_loss_params* params, void* stream) {
+    return policy_step_impl(nullptr, hidden, weight, labels, old_log_probs, advantages, loss_mask, base_log_probs,
+                            entropy_mask, log_probs, entropy, d_hidden, d_weight, accumulate, stats, workspace,
+                            workspace_bytes, B, A, H, V, cu_seqlens, n_tokens, temperature, params, stream);
+}
+
+extern "C" int skyb200_policy_step_from_host(const void* hidden_host, void* hidden_staging, const void* weight,
+                                             const int64_t* labels, const float* old_log_probs,
+                                             const float* advantages, const float* loss_mask,
+                                             const float* base_log_probs, const float* entropy_mask, float* log_probs,
+                                             float* entropy, void* d_hidden, float* d_weight, int32_t accumulate,
+                                             float* stats, void* workspace, size_t workspace_bytes, int64_t B,
+                                             int64_t A, int64_t H, int64_t V, const int32_t* cu_seqlens,
+                                             int64_t n_tokens, float temperature, const skyb200_loss_params* params,
+                                             void* stream) {
+    SKYB200_REQUIRE(hidden_host && hidden_staging, "null pointer");
+    return policy_step_impl(hidden_host, hidden_staging, weight, labels, old_log_probs, advantages, loss_mask,
+                            base_log_probs, entropy_mask, log_probs, entropy, d_hidden, d_weight, accumulate, stats,
+                            workspace, workspace_bytes, B, A, H, V, cu_seqlens, n_tokens, temperature, params, stream);
 }
 
 extern "C" int skyb200_logits_logprob_entropy(const void* logits, int32_t logits_dtype, const int64_t* labels,

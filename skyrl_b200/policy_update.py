@@ -32,6 +32,7 @@ class PolicyUpdateOutput:
     entropy: torch.Tensor              # [B, A] fp32 (masked by entropy_mask if one was given)
     d_hidden: Optional[torch.Tensor]   # [B*A, H] bf16
     d_weight: Optional[torch.Tensor]   # [V, H] fp32 (the buffer passed in, or a new one)
+    hidden: Optional[torch.Tensor] = None  # device copy of the hidden states when they were streamed in from the host
 
 
 class _Workspace:
@@ -80,6 +81,11 @@ def policy_update_step(
     max_seq_len).  Gradients are those of ``final_loss`` (upstream gradient 1), i.e. what ``loss.backward()``
     delivers in the reference (worker.py:876-877).
 
+    ``hidden`` may also live in (pinned) HOST memory — offloaded activations, or the end-to-end benchmark contract:
+    ``skyb200_policy_step_from_host`` then streams it to the GPU that holds ``weight`` one token chunk at a time on a
+    copy stream, ahead of the GEMMs, so the transfer hides behind the tensor cores (keep the host tensor alive until
+    the step's stream work is done; ``sync=True`` guarantees that).  ``out.hidden`` is the device copy.
+
     Packed (ragged) layout: pass ``cu_seqlens`` (int32 ``[B + 1]``, ``cu[0] = 0``) and flat per-token tensors —
     ``hidden`` [N, H], ``labels`` / ``old_log_probs`` / ``advantages`` / ``loss_mask`` / ``base_log_probs`` [N] —
     with sequence ``b`` owning tokens ``[cu[b], cu[b+1])``.  Nothing is padded; the result equals the padded layout
@@ -91,8 +97,16 @@ def policy_update_step(
     (``head_forward`` / ``policy_loss`` / ``head_backward``) the autograd path uses (8*H*V, fp32 logits in backward).
     """
     lib = _lib.load()
-    if not hidden.is_cuda:
-        raise RuntimeError("policy_update_step needs CUDA tensors (no CPU fallback)")
+    from_host = not hidden.is_cuda
+    if from_host:
+        # host-resident activations (offloaded / e2e contract): the C call streams them in chunk by chunk on a copy
+        # stream ahead of the GEMMs.  Compute still runs on the GPU that holds `weight` -- there is no CPU fallback.
+        if not weight.is_cuda:
+            raise RuntimeError("policy_update_step needs the lm_head weight on a CUDA device (no CPU fallback)")
+        if not fused:
+            raise ValueError("host-resident hidden states are only supported with fused=True")
+        if hidden.dtype != torch.bfloat16 or not hidden.is_contiguous():
+            raise ValueError("host-resident hidden must be a contiguous bf16 tensor (pin it for an async copy)")
     packed = cu_seqlens is not None
     if packed:
         if not fused:
@@ -105,9 +119,9 @@ def policy_update_step(
         N = B * A
     H = hidden.shape[-1]
     V = weight.shape[0]
-    dev = hidden.device
+    dev = weight.device if from_host else hidden.device
     h = hidden.reshape(N, H)
-    if h.dtype != torch.bfloat16 or not h.is_contiguous():
+    if not from_host and (h.dtype != torch.bfloat16 or not h.is_contiguous()):
         h = h.to(torch.bfloat16).contiguous()
     w = weight if (weight.dtype == torch.bfloat16 and weight.is_contiguous()) else weight.to(torch.bfloat16).contiguous()
     lab = labels.reshape(N).to(device=dev, dtype=torch.int64).contiguous()
@@ -155,14 +169,16 @@ def policy_update_step(
                 cu = cu_seqlens.to(device=dev, dtype=torch.int32).contiguous()
             wsb = lib.skyb200_policy_step_workspace(B, A, N, H, V, params.loss_type, int(need_grad))
             ws = _WS.get("step", wsb, dev)
-            _lib.check(
-                lib.skyb200_policy_step(_lib.ptr(h), _lib.ptr(w), _lib.ptr(lab), _lib.ptr(olp), _lib.ptr(adv),
-                                        _lib.ptr(mask), _lib.ptr(base) if use_kl else None, _lib.ptr(emask),
-                                        _lib.ptr(logprobs), _lib.ptr(ent), _lib.ptr(d_hidden),
-                                        _lib.ptr(d_weight) if need_d_weight else None, acc, _lib.ptr(stats),
-                                        _lib.ptr(ws), wsb, B, A, H, V, _lib.ptr(cu), N, T, C.byref(params), stream),
-                "skyb200_policy_step",
-            )
+            tail = (_lib.ptr(w), _lib.ptr(lab), _lib.ptr(olp), _lib.ptr(adv), _lib.ptr(mask),
+                    _lib.ptr(base) if use_kl else None, _lib.ptr(emask), _lib.ptr(logprobs), _lib.ptr(ent),
+                    _lib.ptr(d_hidden), _lib.ptr(d_weight) if need_d_weight else None, acc, _lib.ptr(stats),
+                    _lib.ptr(ws), wsb, B, A, H, V, _lib.ptr(cu), N, T, C.byref(params), stream)
+            if from_host:
+                h_host, h = h, torch.empty((N, H), dtype=torch.bfloat16, device=dev)
+                _lib.check(lib.skyb200_policy_step_from_host(h_host.data_ptr(), _lib.ptr(h), *tail),
+                           "skyb200_policy_step_from_host")
+            else:
+                _lib.check(lib.skyb200_policy_step(_lib.ptr(h), *tail), "skyb200_policy_step")
             if sync:
                 status = status_from_packed(stats.tolist(), use_kl)  # the single host sync of the step
                 status["response_length"] = A
@@ -170,8 +186,11 @@ def policy_update_step(
                 status = {"packed": stats}
         if not packed:
             logprobs, ent = logprobs.view(B, A), ent.view(B, A)
-        return PolicyUpdateOutput(status=status, stats=stats, log_probs=logprobs, entropy=ent,
-                                  d_hidden=d_hidden, d_weight=d_weight if need_d_weight else None)
+        out = PolicyUpdateOutput(status=status, stats=stats, log_probs=logprobs, entropy=ent,
+                                 d_hidden=d_hidden, d_weight=d_weight if need_d_weight else None)
+        if from_host:
+            out.hidden = h  # the device copy of the streamed-in hidden states
+        return out
     with torch.cuda.device(dev):
         logprobs = torch.empty(N, dtype=torch.float32, device=dev)
         ent_raw = torch.empty(N, dtype=torch.float32, device=dev)
