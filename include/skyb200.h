@@ -42,7 +42,10 @@ extern "C" {
 #define SKYB200_LOSS_CISPO 4               /* compute_policy_loss_cispo, ppo_utils.py:728-761 (eps_clip_* = cispo eps) */
 #define SKYB200_LOSS_CROSS_ENTROPY 5       /* cross_entropy_loss, ppo_utils.py:892-930 (use SKYB200_REDUCE_SUM) */
 #define SKYB200_LOSS_IMPORTANCE_SAMPLING 6 /* importance_sampling_loss, ppo_utils.py:933-981 (SKYB200_REDUCE_SUM) */
-#define SKYB200_LOSS_LAST 6
+#define SKYB200_LOSS_KL_COV 7 /* compute_policy_loss_kl_cov, ppo_utils.py:833-888: -A*exp(lp-olp) + w*|lp-olp| where the
+                                 per-token weight w (ppo_kl_coef on the selected tokens, 0 elsewhere; from
+                                 skyb200_cov_select) is passed as `tis`.  skyb200_policy_loss only. */
+#define SKYB200_LOSS_LAST 7
 
 /* loss_reduction (ppo_utils.py:984-1009) */
 #define SKYB200_REDUCE_TOKEN_MEAN 0
@@ -280,6 +283,33 @@ size_t skyb200_head_backward_workspace(int64_t N, int64_t H, int64_t V, int64_t 
 int skyb200_head_forward(const void* hidden, const void* weight, const int64_t* labels, const float* entropy_mask,
                          float* logprobs, float* entropy, float* lse2, void* workspace, size_t workspace_bytes,
                          int64_t N, int64_t H, int64_t V, float temperature, int64_t chunk, void* stream);
+
+/*
+ * Token selection of the covariance losses (detached, no gradient): clip_cov (ppo_utils.py:785-814) and kl_cov
+ * (:857-871).  cov = (adv - mean_adv) * (lp - mean_lp) per valid token.
+ *   SKYB200_COV_KL  : the k = max(1, int(n_valid * frac)) valid tokens with the largest cov are selected
+ *                     (ties: lowest flat index first).  Means are plain means over loss_mask > 0.
+ *   SKYB200_COV_CLIP: candidates = valid tokens the PPO clip does not already clip, with cov_lb < cov < cov_ub;
+ *                     k = min(max(int(frac * sum(mask)), 1), #candidates) of them are drawn uniformly at random
+ *                     (counter-based generator keyed by `seed`: same seed, same draw).  Means are masked means.
+ * out [B, A] fp32 = value_selected on the selected tokens, value_other elsewhere.  counts (device, 2 floats, may be
+ * NULL) = {number selected, number of candidates}.  No host synchronisation: k is computed on the device.
+ */
+#define SKYB200_COV_KL 0
+#define SKYB200_COV_CLIP 1
+typedef struct {
+    int32_t mode; /* SKYB200_COV_* */
+    int32_t reserved0;
+    float eps_clip_low, eps_clip_high; /* PPO clip range (clip_cov only) */
+    float cov_lb, cov_ub;              /* clip_cov only */
+    double frac;                       /* kl_cov_frac or clip_cov.clip_ratio */
+    float value_selected, value_other;
+    uint64_t seed;
+} skyb200_cov_params;
+size_t skyb200_cov_select_workspace(int64_t B, int64_t A);
+int skyb200_cov_select(const float* log_probs, const float* old_log_probs, const float* advantages,
+                       const float* loss_mask, float* out, float* counts, void* workspace, size_t workspace_bytes,
+                       int64_t B, int64_t A, const skyb200_cov_params* params, void* stream);
 
 /*
  * Vocab-parallel (tensor-parallel) building block — the B200 counterpart of Megatron's DistributedLogprob /

@@ -141,6 +141,21 @@ def gen_losses(pu):
             out[key + "__loss"] = np.float32(loss.item())
             out[key + "__metric"] = np.float32(list(met.values())[0])
             out[key + "__grad"] = x.grad.numpy()
+    # covariance-selection losses (ppo_utils.py:765-888).  clip_cov draws torch.randperm from the global CPU generator:
+    # seed it here, the oracle test seeds it the same way and replays the draw.
+    cov_cfg = dict(clip_cov=SimpleNamespace(clip_ratio=0.1, clip_cov_lb=0.05, clip_cov_ub=5.0),
+                   kl_cov=SimpleNamespace(kl_cov_frac=0.2, ppo_kl_coef=1.0))
+    for kind, red in (("clip_cov", "token_mean"), ("clip_cov", "sequence_mean"), ("kl_cov", "token_mean"),
+                      ("kl_cov", "seq_mean_token_sum_norm")):
+        c = cfg(policy_loss_type=kind, loss_reduction=red, **cov_cfg)
+        x = lp.clone().requires_grad_(True)
+        torch.manual_seed(777)
+        loss, met = pu.PolicyLossRegistry._functions[kind](x, olp_mild, adv, c, loss_mask=fm)
+        loss.backward()
+        key = f"{kind}__{red}__mask"
+        out[key + "__loss"] = np.float32(loss.item())
+        out[key + "__metric"] = np.float32(met["clip_ratio"])
+        out[key + "__grad"] = x.grad.numpy()
     # off-policy correction inside ppo_policy_loss (off_policy_correction_utils.py)
     rlp = olp + 0.15 * torch.randn(B, A, generator=g)
     rlp[6, 3] = olp[6, 3] - 3.0  # one outlier token (ratio e^3) -> its whole sequence is masked by the outlier rule

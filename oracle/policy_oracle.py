@@ -8,6 +8,8 @@ from __future__ import annotations
 from types import SimpleNamespace
 from typing import Dict, Optional, Sequence, Tuple
 
+import math
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -285,6 +287,58 @@ def extra_policy_loss(kind, lp, olp, adv, cfg, mask=None):
             return (el * mask).sum(), {"importance_ratio": ((ratio * mask).sum() / mask.sum()).item()}
         return el.sum(), {"importance_ratio": ratio.mean().item()}
     raise ValueError(kind)
+
+
+def cov_selection(kind, lp, olp, adv, cfg, mask, perm_fn=None):
+    """The detached token selection of clip_cov (utils/ppo_utils.py:785-814) / kl_cov (:857-871) as a 0/1 tensor.
+
+    clip_cov draws a random subset of the candidate tokens with ``torch.randperm`` (:806); ``perm_fn(n)`` replaces
+    that draw (default: torch.randperm, so a seeded oracle replays the seeded reference)."""
+    lp_d = lp.detach()
+    sel = torch.zeros_like(adv)
+    if kind == "clip_cov":
+        c = cfg.clip_cov
+        ratio = (lp_d - olp).exp()
+        l1 = -adv * ratio
+        l2 = -adv * ratio.clamp(1 - cfg.eps_clip_low, 1 + cfg.eps_clip_high)
+        by_origin = (l2 > l1) & (mask > 0)
+        cov = (adv - masked_mean(adv, mask)) * (lp_d - masked_mean(lp_d, mask))
+        cov = cov.masked_fill(mask == 0, -math.inf).masked_fill(by_origin, -math.inf)
+        clip_num = max(int(c.clip_ratio * mask.sum().item()), 1)
+        cand = torch.nonzero((cov < c.clip_cov_ub) & (cov > c.clip_cov_lb) & (mask > 0))
+        if len(cand) > 0:
+            perm = (perm_fn or torch.randperm)(len(cand))
+            cand = cand[perm[: min(clip_num, len(cand))]]
+            sel[cand[:, 0], cand[:, 1]] = 1.0
+        return sel
+    if kind == "kl_cov":
+        valid = mask > 0
+        idx = torch.nonzero(valid.reshape(-1), as_tuple=True)[0]
+        a, l = adv[valid].reshape(-1), lp_d[valid].reshape(-1)
+        if len(a) > 0:
+            cov = (a - a.mean()) * (l - l.mean())
+            k = max(1, int(len(cov) * cfg.kl_cov.kl_cov_frac))
+            top = idx[torch.topk(cov, min(k, len(cov)), largest=True).indices]
+            sel.view(-1)[top] = 1.0
+        return sel
+    raise ValueError(kind)
+
+
+def cov_policy_loss(kind, lp, olp, adv, cfg, mask, sel=None, perm_fn=None):
+    """clip_cov (utils/ppo_utils.py:765-829) and kl_cov (:833-888) given (or drawing) the selection.
+    Returns (loss, {"clip_ratio": ...}, sel)."""
+    if sel is None:
+        sel = cov_selection(kind, lp, olp, adv, cfg, mask, perm_fn)
+    d = lp - olp
+    ratio = d.exp()
+    msl = getattr(cfg, "max_seq_len", None)
+    if kind == "clip_cov":
+        l1 = -adv * ratio
+        l2 = -adv * ratio.clamp(1 - cfg.eps_clip_low, 1 + cfg.eps_clip_high)
+        loss = reduce_loss(torch.maximum(l1, l2) * (1.0 - sel), mask, cfg.loss_reduction, msl)
+        return loss, {"clip_ratio": masked_mean(sel, mask).item()}, sel
+    tok = -adv * ratio + sel * cfg.kl_cov.ppo_kl_coef * d.abs()
+    return reduce_loss(tok, mask, cfg.loss_reduction, msl), {"clip_ratio": 0.0}, sel
 
 
 def loss_assembly(lp, olp, adv, cfg, mask=None, base=None, entropy=None):

@@ -59,6 +59,24 @@ class OpcParams(C.Structure):
 
 
 OPC_NMETRICS = 16
+LOSS_KL_COV = 7  # skyb200_policy_loss only (global token selection): not in LOSS_TYPES, the fused step rejects it
+COV_KL, COV_CLIP = 0, 1
+
+
+class CovParams(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("eps_clip_low", C.c_float),
+        ("eps_clip_high", C.c_float),
+        ("cov_lb", C.c_float),
+        ("cov_ub", C.c_float),
+        ("frac", C.c_double),
+        ("value_selected", C.c_float),
+        ("value_other", C.c_float),
+        ("seed", C.c_uint64),
+    ]
+
 
 _P = C.c_void_p
 _I64 = C.c_int64
@@ -97,6 +115,8 @@ SIGNATURES = {
     "skyb200_head_forward_workspace": (_SZ, [_I64, _I64, _I64, _I64]),
     "skyb200_head_backward_workspace": (_SZ, [_I64, _I64, _I64, _I64]),
     "skyb200_head_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _SZ, _I64, _I64, _I64, _F, _I64, _P]),
+    "skyb200_cov_select_workspace": (_SZ, [_I64, _I64]),
+    "skyb200_cov_select": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _SZ, _I64, _I64, C.POINTER(CovParams), _P]),
     "skyb200_head_forward_stats": (C.c_int, [_P, _P, _P, _P, _P, _SZ, _I64, _I64, _I64, _F, _I64, _P]),
     "skyb200_head_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _I64, _I64, _I64, _F,
                                         _I64, _P]),

@@ -18,7 +18,7 @@ INCLUDE = PKG_DIR.parent / "include"
 OBJ_DIR = PKG_DIR / "build"
 LIB_PATH = PKG_DIR / "libskyb200.so"
 
-SOURCES = ["core.cu", "loss.cu", "advantage.cu", "offpolicy.cu", "value_head.cu", "head.cu"]
+SOURCES = ["core.cu", "loss.cu", "advantage.cu", "offpolicy.cu", "covsel.cu", "value_head.cu", "head.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", "gemm_sm100.cuh"]
 
 NVCC_FLAGS = [

@@ -702,7 +702,8 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
     SKYB200_REQUIRE(B > 0 && A > 0 && B < 65536, "need 0 < B < 65536 and A > 0");
     SKYB200_REQUIRE(H % 8 == 0, "H must be a multiple of 8");
     SKYB200_REQUIRE(temperature > 0.f, "temperature must be > 0");
-    SKYB200_REQUIRE(params->loss_type >= 0 && params->loss_type <= SKYB200_LOSS_LAST, "bad loss_type");
+    SKYB200_REQUIRE(params->loss_type >= 0 && params->loss_type <= SKYB200_LOSS_IMPORTANCE_SAMPLING,
+                    "bad loss_type (the covariance losses select over the whole batch: use skyb200_policy_loss)");
     SKYB200_REQUIRE(params->reduction >= 0 && params->reduction <= SKYB200_REDUCE_SUM, "bad reduction");
     SKYB200_REQUIRE(params->kl_type >= 0 && params->kl_type <= SKYB200_KL_K3, "bad kl_type");
     SKYB200_REQUIRE(params->reduction != SKYB200_REDUCE_SEQ_MEAN_TOKEN_SUM_NORM || params->max_seq_len > 0.f,

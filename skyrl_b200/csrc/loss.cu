@@ -202,6 +202,12 @@ __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, fl
         ratio = 1.f;
         loss = -lp;
         dl_dlp = -1.f;
+    } else if (cx.loss_type == SKYB200_LOSS_KL_COV) {  // `tis` carries the per-token KL weight of the selection
+        const float d = lp - olp;
+        ratio = expf(d);
+        loss = fmaf(tis, fabsf(d), -ratio * adv);
+        dl_dlp = fmaf(tis, (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f), -ratio * adv);
+        tis = 1.f;
     } else {  // importance sampling: un-clamped ratio, Tinker semantics
         ratio = expf(lp - olp);
         loss = -ratio * adv;

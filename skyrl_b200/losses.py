@@ -299,6 +299,76 @@ def importance_sampling_loss(log_probs, old_log_probs, advantages, config, loss_
     return loss, {"importance_ratio": float(stats[_lib.STAT_RATIO_MEAN].item())}
 
 
+def cov_token_selection(kind, log_probs, old_log_probs, advantages, config, loss_mask=None, *, value_selected=1.0,
+                        value_other=0.0, seed=None):
+    """The detached token selection of ``clip_cov`` (ppo_utils.py:785-814) / ``kl_cov`` (:857-871) as an fp32
+    ``[B, A]`` tensor (``value_selected`` on the chosen tokens), plus a device tensor ``[n_selected, n_candidates]``.
+
+    ``kl_cov`` is deterministic (top-k of the covariance).  ``clip_cov`` draws its random subset with a counter-based
+    generator on the device; ``seed`` defaults to a draw from torch's global CPU generator, so ``torch.manual_seed``
+    makes it reproducible like the reference's ``torch.randperm`` (the subset itself differs from torch's)."""
+    if kind not in ("clip_cov", "kl_cov"):
+        raise ValueError(kind)
+    if not log_probs.is_cuda:
+        raise RuntimeError("skyrl_b200 covariance losses need CUDA tensors (no CPU fallback)")
+    lib = _lib.load()
+    lp = _prep(log_probs, log_probs)
+    olp, adv, mask = _prep(old_log_probs, lp), _prep(advantages, lp), _prep(loss_mask, lp)
+    B, A = lp.shape
+    p = _lib.CovParams()
+    p.value_selected, p.value_other = float(value_selected), float(value_other)
+    if kind == "clip_cov":
+        c = _cfg(config, "clip_cov")
+        p.mode = _lib.COV_CLIP
+        p.eps_clip_low, p.eps_clip_high = float(_cfg(config, "eps_clip_low", 0.2)), float(_cfg(config, "eps_clip_high", 0.2))
+        p.cov_lb, p.cov_ub = float(_cfg(c, "clip_cov_lb")), float(_cfg(c, "clip_cov_ub"))
+        p.frac = float(_cfg(c, "clip_ratio"))
+        p.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed)
+    else:
+        p.mode = _lib.COV_KL
+        p.frac = float(_cfg(_cfg(config, "kl_cov"), "kl_cov_frac"))
+    with torch.cuda.device(lp.device):
+        out = torch.empty_like(lp)
+        counts = torch.zeros(2, dtype=torch.float32, device=lp.device)
+        wsb = lib.skyb200_cov_select_workspace(B, A)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=lp.device)
+        _lib.check(lib.skyb200_cov_select(_lib.ptr(lp), _lib.ptr(olp), _lib.ptr(adv), _lib.ptr(mask), _lib.ptr(out),
+                                          _lib.ptr(counts), _lib.ptr(ws), wsb, B, A, C.byref(p), _lib.stream_ptr()),
+                   "skyb200_cov_select")
+    return out, counts
+
+
+def compute_policy_loss_clip_cov(log_probs, old_log_probs, advantages, config, loss_mask=None, rollout_logprobs=None):
+    """Clip-Cov (reference: ppo_utils.py:765-829): the PPO clipped loss with a random subset of the
+    covariance-candidate tokens dropped; ``clip_ratio`` = masked fraction of dropped tokens."""
+    if loss_mask is None:  # the reference indexes with the mask unconditionally
+        loss_mask = torch.ones_like(advantages, dtype=torch.float32)
+    corr, _ = cov_token_selection("clip_cov", log_probs.detach(), old_log_probs, advantages, config, loss_mask,
+                                  value_selected=0.0, value_other=1.0)
+    params = _make_params("regular", _cfg(config, "loss_reduction"), config)
+    loss, _stats = _PolicyLossFn.apply(log_probs, None, old_log_probs, advantages, loss_mask, None, params,
+                                       _lib.STAT_POLICY_LOSS, corr, None)  # corr rides in as the detached weight
+    from .torch_utils import masked_mean
+
+    clip_frac = masked_mean(1.0 - corr, _prep(loss_mask, corr))
+    return loss, {"clip_ratio": float(clip_frac.item())}
+
+
+def compute_policy_loss_kl_cov(log_probs, old_log_probs, advantages, config, loss_mask=None, rollout_logprobs=None):
+    """KL-Cov (reference: ppo_utils.py:833-888): ``-A * ratio`` plus ``ppo_kl_coef * |lp - old_lp|`` on the
+    ``kl_cov_frac`` of valid tokens with the largest covariance; ``clip_ratio`` is reported as 0.0."""
+    if loss_mask is None:
+        loss_mask = torch.ones_like(advantages, dtype=torch.float32)
+    coef = float(_cfg(_cfg(config, "kl_cov"), "ppo_kl_coef"))
+    w, _ = cov_token_selection("kl_cov", log_probs.detach(), old_log_probs, advantages, config, loss_mask,
+                               value_selected=coef, value_other=0.0)
+    params = _make_params("regular", _cfg(config, "loss_reduction"), config)
+    params.loss_type = _lib.LOSS_KL_COV
+    loss, _stats = _PolicyLossFn.apply(log_probs, None, old_log_probs, advantages, loss_mask, None, params,
+                                       _lib.STAT_POLICY_LOSS, w, None)
+    return loss, {"clip_ratio": 0.0}
+
+
 class _CriticLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, values, old_values, returns, loss_mask, value_clip):

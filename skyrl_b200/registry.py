@@ -181,6 +181,8 @@ class PolicyLossType(StrEnum):
     GSPO = "gspo"
     CISPO = "cispo"
     SAPO = "sapo"
+    CLIP_COV = "clip_cov"
+    KL_COV = "kl_cov"
     CROSS_ENTROPY = "cross_entropy"
     IMPORTANCE_SAMPLING = "importance_sampling"
 
@@ -207,8 +209,8 @@ class AdvantageEstimatorRegistry(BaseFunctionRegistry):
 
 
 class PolicyLossRegistry(BaseFunctionRegistry):
-    """B200 policy losses: ``regular``, ``dual_clip``, ``gspo``, ``sapo``, ``cispo``, ``cross_entropy``,
-    ``importance_sampling`` (ppo_utils.py:463-508; ``clip_cov`` / ``kl_cov`` are not built yet)."""
+    """B200 policy losses: ``regular``, ``dual_clip``, ``gspo``, ``sapo``, ``cispo``, ``clip_cov``, ``kl_cov``,
+    ``cross_entropy``, ``importance_sampling`` — every name ppo_utils.py:463-508 registers."""
 
     _actor_name = "policy_loss_registry"
     _function_type = "policy loss"
@@ -224,6 +226,8 @@ class PolicyLossRegistry(BaseFunctionRegistry):
             ("gspo", losses.gspo_policy_loss),
             ("sapo", losses.sapo_policy_loss),
             ("cispo", losses.compute_policy_loss_cispo),
+            ("clip_cov", losses.compute_policy_loss_clip_cov),
+            ("kl_cov", losses.compute_policy_loss_kl_cov),
             ("cross_entropy", losses.cross_entropy_loss),
             ("importance_sampling", losses.importance_sampling_loss),
         ):
@@ -294,6 +298,8 @@ def install_into_skyrl_train(patch_model_wrapper: bool = True) -> List[str]:
         (pu.PolicyLossRegistry, {"regular": losses.ppo_policy_loss, "dual_clip": losses.ppo_policy_loss,
                                  "gspo": losses.gspo_policy_loss, "sapo": losses.sapo_policy_loss,
                                  "cispo": losses.compute_policy_loss_cispo,
+                                 "clip_cov": losses.compute_policy_loss_clip_cov,
+                                 "kl_cov": losses.compute_policy_loss_kl_cov,
                                  "cross_entropy": losses.cross_entropy_loss,
                                  "importance_sampling": losses.importance_sampling_loss}),
     ):

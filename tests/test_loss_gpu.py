@@ -220,3 +220,131 @@ def test_off_policy_correction_known_answers():  # reference: tests/cpu/algorith
         losses.compute_off_policy_correction(olp_t, rlp_t, m_t, opc_kat.cfg(tis_ratio_type="bogus"))
     with pytest.raises(ValueError, match="Unknown sequence_mask_metric"):
         losses.compute_off_policy_correction(olp_t, rlp_t, m_t, opc_kat.cfg(sequence_mask_metric="bogus"))
+
+
+# ------------------------------------------------------------------------------------ clip_cov / kl_cov
+_COV_CFG = dict(clip_cov=__import__("types").SimpleNamespace(clip_ratio=0.1, clip_cov_lb=0.05, clip_cov_ub=5.0),
+                kl_cov=__import__("types").SimpleNamespace(kl_cov_frac=0.2, ppo_kl_coef=1.0))
+
+
+@pytest.mark.parametrize("red", ["token_mean", "seq_mean_token_sum_norm"])
+def test_kl_cov_matches_reference_golden(golden_loss, red):
+    g = golden_loss
+    cfg = O.make_cfg(policy_loss_type="kl_cov", loss_reduction=red, max_seq_len=64, **_COV_CFG)
+    lp = _t(g["lp"]).to(DEV).requires_grad_(True)
+    loss, met = skyrl_b200.PolicyLossRegistry.get("kl_cov")(lp, _t(g["olp_mild"]).to(DEV), _t(g["adv"]).to(DEV), cfg,
+                                                            loss_mask=_t(g["mask"]).to(DEV))
+    loss.backward()
+    key = f"kl_cov__{red}__mask"
+    assert met == {"clip_ratio": 0.0}
+    assert_close(loss, g[key + "__loss"], what=key + " loss")
+    assert_close(lp.grad, g[key + "__grad"], what=key + " grad")
+
+
+def _cov_batch(B, A, seed):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(1, A + 1, (B,), generator=g)
+    mask = (torch.arange(A)[None] < lens[:, None]).float()
+    mask[B // 2] = 0.0
+    lp = -torch.rand(B, A, generator=g) * 3
+    olp = lp + 0.2 * torch.randn(B, A, generator=g)
+    adv = torch.randn(B, A, generator=g)
+    return lp, olp, adv, mask
+
+
+@pytest.mark.parametrize("shape", [(7, 33), (64, 1000), (16, 8192)])
+def test_kl_cov_selection_is_the_oracle_topk(shape):
+    """The radix select picks exactly the oracle's torch.topk set (means differ by an ulp at most: allow 2 swaps)."""
+    B, A = shape
+    lp, olp, adv, mask = _cov_batch(B, A, 5 + A)
+    cfg = O.make_cfg(policy_loss_type="kl_cov", loss_reduction="token_mean", **_COV_CFG)
+    want = O.cov_selection("kl_cov", lp, olp, adv, cfg, mask)
+    sel, counts = losses.cov_token_selection("kl_cov", lp.to(DEV), olp.to(DEV), adv.to(DEV), cfg, mask.to(DEV))
+    k = max(1, int(int((mask > 0).sum()) * 0.2))
+    assert counts.tolist() == [float(k), float((mask > 0).sum())]
+    assert int(sel.sum().item()) == k  # exactly k, never k +- ties
+    assert int((sel.cpu() != want).sum()) <= 2
+    x = lp.clone().to(DEV).requires_grad_(True)
+    loss, _ = losses.compute_policy_loss_kl_cov(x, olp.to(DEV), adv.to(DEV), cfg, loss_mask=mask.to(DEV))
+    loss.backward()
+    xr = lp.clone().requires_grad_(True)
+    ref, _, _ = O.cov_policy_loss("kl_cov", xr, olp, adv, cfg, mask, sel=sel.cpu())
+    ref.backward()
+    assert_close(loss, ref, what="kl_cov loss")
+    assert_close(x.grad, xr.grad, what="kl_cov grad")
+
+
+def test_kl_cov_ties_and_empty_mask():
+    B, A = 4, 100
+    lp, olp, adv, mask = _cov_batch(B, A, 3)
+    cfg = O.make_cfg(policy_loss_type="kl_cov", loss_reduction="token_mean", **_COV_CFG)
+    const_adv = torch.ones(B, A)  # adv - mean = 0 -> every cov ties at 0: ties are broken by index, count stays exact
+    sel, counts = losses.cov_token_selection("kl_cov", lp.to(DEV), olp.to(DEV), const_adv.to(DEV), cfg, mask.to(DEV))
+    k = max(1, int(int((mask > 0).sum()) * 0.2))
+    flat_valid = torch.nonzero((mask > 0).reshape(-1)).squeeze(-1)
+    assert int(sel.sum().item()) == k
+    assert torch.equal(torch.nonzero(sel.cpu().reshape(-1)).squeeze(-1), flat_valid[:k])
+    sel0, counts0 = losses.cov_token_selection("kl_cov", lp.to(DEV), olp.to(DEV), adv.to(DEV), cfg,
+                                               torch.zeros(B, A, device=DEV))
+    assert sel0.sum().item() == 0 and counts0.tolist() == [0.0, 0.0]
+    loss, _ = losses.compute_policy_loss_kl_cov(lp.to(DEV), olp.to(DEV), adv.to(DEV), cfg,
+                                                loss_mask=torch.zeros(B, A, device=DEV))
+    assert loss.item() == 0.0
+
+
+@pytest.mark.parametrize("shape,red", [((12, 40), "token_mean"), ((64, 1000), "sequence_mean")])
+def test_clip_cov_selection_properties_and_loss(shape, red):
+    """clip_cov draws a random subset (the reference uses torch.randperm, ppo_utils.py:806), so parity is: the subset
+    lies inside the oracle's candidate set, has exactly min(clip_num, #candidates) tokens, and loss / gradient /
+    clip_ratio equal the oracle's for that same subset."""
+    B, A = shape
+    lp, olp, adv, mask = _cov_batch(B, A, 17 + A)
+    cfg = O.make_cfg(policy_loss_type="clip_cov", loss_reduction=red, **_COV_CFG)
+    cand = O.cov_selection("clip_cov", lp, olp, adv, cfg, mask, perm_fn=lambda n: torch.arange(n))
+    c = cfg.clip_cov  # recompute the full candidate set (the oracle call above returns only the first clip_num)
+    full = O.cov_selection("clip_cov", lp, olp, adv, O.make_cfg(
+        policy_loss_type="clip_cov", clip_cov=__import__("types").SimpleNamespace(
+            clip_ratio=1e9, clip_cov_lb=c.clip_cov_lb, clip_cov_ub=c.clip_cov_ub)), mask,
+        perm_fn=lambda n: torch.arange(n))
+    n_cand = int(full.sum())
+    k = min(max(int(c.clip_ratio * mask.sum().item()), 1), n_cand)
+    assert int(cand.sum()) == k and n_cand > k
+    args = (lp.to(DEV), olp.to(DEV), adv.to(DEV), cfg, mask.to(DEV))
+    sel, counts = losses.cov_token_selection("clip_cov", *args, seed=1234)
+    assert counts.tolist() == [float(k), float(n_cand)]
+    assert int(sel.sum().item()) == k and torch.all(full[sel.cpu() > 0] == 1)
+    again, _ = losses.cov_token_selection("clip_cov", *args, seed=1234)
+    other, _ = losses.cov_token_selection("clip_cov", *args, seed=99)
+    assert torch.equal(sel, again) and not torch.equal(sel, other)
+    # the registry function: seeded through torch's global generator like the reference
+    torch.manual_seed(5)
+    x = lp.clone().to(DEV).requires_grad_(True)
+    loss, met = skyrl_b200.PolicyLossRegistry.get("clip_cov")(x, olp.to(DEV), adv.to(DEV), cfg, loss_mask=mask.to(DEV))
+    loss.backward()
+    torch.manual_seed(5)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    sel5, _ = losses.cov_token_selection("clip_cov", *args, seed=seed)
+    xr = lp.clone().requires_grad_(True)
+    ref, ref_met, _ = O.cov_policy_loss("clip_cov", xr, olp, adv, cfg, mask, sel=sel5.cpu())
+    ref.backward()
+    assert_close(loss, ref, what="clip_cov loss")
+    assert_close(met["clip_ratio"], ref_met["clip_ratio"], what="clip_cov clip_ratio")
+    assert_close(x.grad, xr.grad, what="clip_cov grad")
+
+
+def test_clip_cov_draw_is_uniform_over_candidates():
+    """Every candidate is dropped with probability k / #candidates: frequency over 200 seeds within 5 sigma."""
+    B, A = 8, 64
+    lp, olp, adv, mask = _cov_batch(B, A, 2)
+    cfg = O.make_cfg(policy_loss_type="clip_cov", loss_reduction="token_mean", **_COV_CFG)
+    args = (lp.to(DEV), olp.to(DEV), adv.to(DEV), cfg, mask.to(DEV))
+    total = torch.zeros(B, A, device=DEV)
+    n = 200
+    for s in range(n):
+        sel, counts = losses.cov_token_selection("clip_cov", *args, seed=s)
+        total += sel
+    k, n_cand = counts.tolist()
+    p = k / n_cand
+    freq = total[total > 0] / n
+    assert int((total > 0).sum()) > 0.9 * n_cand  # nearly every candidate shows up at some point
+    assert (freq - p).abs().max().item() < 5 * (p * (1 - p) / n) ** 0.5 + 1e-6

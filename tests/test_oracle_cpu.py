@@ -254,6 +254,29 @@ def test_golden_extra_losses(golden_loss, kind, red, mname):
     assert_close(x.grad, g[key + "__grad"], what="grad")
 
 
+_COV_CFG = dict(clip_cov=__import__("types").SimpleNamespace(clip_ratio=0.1, clip_cov_lb=0.05, clip_cov_ub=5.0),
+                kl_cov=__import__("types").SimpleNamespace(kl_cov_frac=0.2, ppo_kl_coef=1.0))
+_COV_CASES = [("clip_cov", "token_mean"), ("clip_cov", "sequence_mean"), ("kl_cov", "token_mean"),
+              ("kl_cov", "seq_mean_token_sum_norm")]
+
+
+@pytest.mark.parametrize("kind,red", _COV_CASES)
+def test_golden_cov_losses(golden_loss, kind, red):
+    """clip_cov / kl_cov against the reference; clip_cov's torch.randperm draw is replayed from the same seed."""
+    g = golden_loss
+    lp, adv, fm, olp = _t(g["lp"]), _t(g["adv"]), _t(g["mask"]), _t(g["olp_mild"])
+    cfg = O.make_cfg(policy_loss_type=kind, loss_reduction=red, max_seq_len=64, **_COV_CFG)
+    x = lp.clone().requires_grad_(True)
+    torch.manual_seed(777)
+    loss, met, sel = O.cov_policy_loss(kind, x, olp, adv, cfg, fm)
+    loss.backward()
+    key = f"{kind}__{red}__mask"
+    assert_close(loss, g[key + "__loss"], what="loss")
+    assert_close(met["clip_ratio"], g[key + "__metric"], what="metric")
+    assert_close(x.grad, g[key + "__grad"], what="grad")
+    assert sel.sum().item() >= 1 and torch.all(sel[fm == 0] == 0)
+
+
 def test_kat_cispo():  # tests/cpu/algorithms/test_losses.py:85-137 -> -0.99768 (cispo eps 0.2 / 0.2 there)
     from types import SimpleNamespace
 
