@@ -322,6 +322,10 @@ int skyb200_cov_select(const float* log_probs, const float* old_log_probs, const
 int skyb200_head_forward_stats(const void* hidden, const void* weight, const int64_t* labels, float* stats,
                                void* workspace, size_t workspace_bytes, int64_t N, int64_t H, int64_t V,
                                float temperature, int64_t chunk, void* stream);
+/* stats_all [tp, N, 4] (the all-gathered per-shard stats) -> logprobs / entropy / lse2 [N] (lse2 = log2-sum-exp2 of
+ * the scaled logits over the WHOLE vocabulary, what skyb200_head_backward expects). */
+int skyb200_head_combine_stats(const float* stats_all, int32_t tp, int64_t N, float temperature, float* logprobs,
+                               float* entropy, float* lse2, void* stream);
 
 /*
  * Backward: given g_logprobs [N] and optional g_entropy [N] (upstream grads w.r.t. the forward outputs,

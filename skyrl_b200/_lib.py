@@ -118,6 +118,7 @@ SIGNATURES = {
     "skyb200_cov_select_workspace": (_SZ, [_I64, _I64]),
     "skyb200_cov_select": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _SZ, _I64, _I64, C.POINTER(CovParams), _P]),
     "skyb200_head_forward_stats": (C.c_int, [_P, _P, _P, _P, _P, _SZ, _I64, _I64, _I64, _F, _I64, _P]),
+    "skyb200_head_combine_stats": (C.c_int, [_P, _I32, _I64, _F, _P, _P, _P, _P]),
     "skyb200_head_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _I64, _I64, _I64, _F,
                                         _I64, _P]),
     "skyb200_policy_step_workspace": (_SZ, [_I64, _I64, _I64, _I64, _I64, _I32, _I32]),

@@ -252,6 +252,30 @@ __global__ void __launch_bounds__(256) head_merge_stats_kernel(const float* __re
     reinterpret_cast<float4*>(stats)[r] = make_float4(M, S, T, label_acc[r]);
 }
 
+// Cross-shard combine of the vocab-parallel head: stats [tp, N, 4] (all-gathered) -> log-prob, entropy, lse2.
+__global__ void __launch_bounds__(256) head_combine_stats_kernel(const float4* __restrict__ stats, int tp, int64_t N,
+                                                                 float inv_T, float* __restrict__ logprobs,
+                                                                 float* __restrict__ entropy,
+                                                                 float* __restrict__ lse2_out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    float M = -INFINITY;
+    for (int s = 0; s < tp; ++s) M = fmaxf(M, stats[(int64_t)s * N + r].x);
+    float S = 0.f, Tw = 0.f, Z = 0.f;
+    for (int s = 0; s < tp; ++s) {
+        const float4 q = stats[(int64_t)s * N + r];
+        const float w = exp2f(q.x - M);
+        S = fmaf(q.y, w, S);
+        Tw = fmaf(q.z, w, Tw);
+        Z += q.w;  // only the shard that owns the label contributes
+    }
+    const float lse2 = M + log2f(S);
+    const float lse = lse2 * 0.6931471805599453f;
+    logprobs[r] = Z * inv_T - lse;
+    entropy[r] = lse - (Tw / S) * inv_T;
+    lse2_out[r] = lse2;
+}
+
 // In-place turn of a stored bf16 logits tile store [rows, ld] into d(logits) (fused step, no recompute):
 //   u = z*scale_log2 - lse2 ; p = 2^u ; d = inv_T * ( g_lp*1[j == label] - p*(g_lp + g_ent*(u*ln2 + H)) )
 // One block row per token; each thread owns 16 consecutive vocab entries (one 32-byte access each way).
@@ -511,6 +535,20 @@ extern "C" int skyb200_head_forward_stats(const void* hidden, const void* weight
         if (rc) return rc;
     }
     return SKYB200_OK;
+}
+
+extern "C" int skyb200_head_combine_stats(const float* stats_all, int32_t tp, int64_t N, float temperature,
+                                          float* logprobs, float* entropy, float* lse2, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (N == 0) return SKYB200_OK;
+    SKYB200_REQUIRE(stats_all && logprobs && entropy && lse2, "null pointer");
+    SKYB200_REQUIRE(tp >= 1 && temperature > 0.f, "need tp >= 1 and temperature > 0");
+    SKYB200_REQUIRE((reinterpret_cast<uintptr_t>(stats_all) & 15u) == 0, "stats must be 16-byte aligned");
+    int rc = skyb200_check_device();
+    if (rc) return rc;
+    head_combine_stats_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(stats_all), tp, N, 1.0f / temperature, logprobs, entropy, lse2);
+    return check_launch("head_combine_stats_kernel");
 }
 
 extern "C" int skyb200_head_backward(const void* hidden, const void* weight, const int64_t* labels,

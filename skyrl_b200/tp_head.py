@@ -17,21 +17,22 @@ import torch.distributed as dist
 
 from . import _lib
 
-_LN2 = 0.6931471805599453
-
-
 def combine_shard_stats(stats: torch.Tensor, temperature: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """``stats`` [tp, N, 4] = per shard {max, sum, weighted sum, label logit} in log2 units.
+    """``stats`` [tp, N, 4] = per shard {max, sum, weighted sum, label logit} in log2 units (CUDA tensor).
     Returns ``(logprobs, entropy, lse2)`` [N] fp32 — the same numbers the unsharded head produces."""
-    M, S, T, Z = stats.unbind(-1)
-    Mg = M.max(dim=0).values
-    w = torch.exp2(M - Mg)
-    Sg = (S * w).sum(0)
-    Tg = (T * w).sum(0)
-    lse2 = Mg + torch.log2(Sg)
-    lse = lse2 * _LN2
-    inv_t = 1.0 / temperature
-    return Z.sum(0) * inv_t - lse, lse - (Tg / Sg) * inv_t, lse2
+    if not stats.is_cuda:
+        raise RuntimeError("combine_shard_stats needs CUDA tensors (no CPU fallback)")
+    lib = _lib.load()
+    stats = stats.contiguous()
+    tp, N = int(stats.shape[0]), int(stats.shape[1])
+    with torch.cuda.device(stats.device):
+        lp = torch.empty(N, dtype=torch.float32, device=stats.device)
+        ent = torch.empty_like(lp)
+        lse2 = torch.empty_like(lp)
+        _lib.check(lib.skyb200_head_combine_stats(_lib.ptr(stats), tp, N, float(temperature), _lib.ptr(lp),
+                                                  _lib.ptr(ent), _lib.ptr(lse2), _lib.stream_ptr()),
+                   "skyb200_head_combine_stats")
+    return lp, ent, lse2
 
 
 def shard_forward_stats(hidden: torch.Tensor, weight_shard: torch.Tensor, labels_local: torch.Tensor,

@@ -64,30 +64,3 @@ def test_single_process_is_identity():
 
     s = {"a": 1.0, "b_max": 2.0}
     assert sdist.all_reduce_metrics(s) == s
-
-
-def test_combine_shard_stats_is_the_log_sum_exp_merge():
-    """Host logic of the vocab-parallel head on CPU tensors: combining per-shard (max, sum, weighted sum, label logit)
-    equals the direct computation on the full vocabulary."""
-    import math
-
-    from skyrl_b200.tp_head import combine_shard_stats
-
-    g = torch.Generator().manual_seed(0)
-    N, V, T = 50, 300, 0.7
-    logits = torch.randn(N, V, generator=g) * 3
-    labels = torch.randint(0, V, (N,), generator=g)
-    c = math.log2(math.e) / T
-    cuts = [0, 100, 130, V]
-    stats = []
-    for a, b in zip(cuts[:-1], cuts[1:]):
-        y = logits[:, a:b] * c
-        m = y.max(-1).values
-        e = torch.exp2(y - m[:, None])
-        inside = (labels >= a) & (labels < b)
-        z = torch.where(inside, logits.gather(-1, labels[:, None]).squeeze(-1), torch.zeros(N))
-        stats.append(torch.stack([m, e.sum(-1), (e * logits[:, a:b]).sum(-1), z], -1))
-    lp, ent, _ = combine_shard_stats(torch.stack(stats), T)
-    ref = torch.log_softmax(logits / T, -1)
-    assert torch.allclose(lp, ref.gather(-1, labels[:, None]).squeeze(-1), atol=1e-5)
-    assert torch.allclose(ent, -(ref.exp() * ref).sum(-1), atol=1e-5)
