@@ -192,6 +192,8 @@ static int dh_lockstep() { static int v = env_int0("SKYB200_DH_LOCKSTEP", 128); 
 static int fwd_lockstep() { static int v = env_int0("SKYB200_FWD_LOCKSTEP", 0); return v; }
 static int dw_lockstep() { static int v = env_int0("SKYB200_DW_LOCKSTEP", 128); return v; }
 static int dw_group_n() { static int v = env_int("SKYB200_DW_GROUP_N", 14); return v; }
+// cap on the resident blocks of the d(logits) transform pass (0 = one block per item)
+static int transform_blocks() { static int v = env_int0("SKYB200_TRANSFORM_BLOCKS", 0); return v; }
 
 
 static int64_t num_slabs(int64_t V) { return (V + kHeadBN - 1) / kHeadBN; }
@@ -283,10 +285,15 @@ __global__ void __launch_bounds__(256)
 dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const float* __restrict__ lse2,
                          const float* __restrict__ g_lp, const float* __restrict__ g_ent,
                          const float* __restrict__ g_ent_mask, const float* __restrict__ entropy_raw,
-                         const int64_t* __restrict__ labels, float scale_log2, float inv_T) {
-    const int row = blockIdx.y;
-    const int col0 = (blockIdx.x * 256 + threadIdx.x) * 16;
-    if (col0 >= V) return;
+                         const int64_t* __restrict__ labels, float scale_log2, float inv_T, int rows) {
+    // items = (token row, 4096-wide column block), row-major; a block walks them with a grid stride so the launch can
+    // be throttled to a few resident blocks per SM (it runs under the GEMMs of the previous chunk)
+    const int cbs = (V + 4095) / 4096;
+    const int64_t total = (int64_t)rows * cbs;
+    for (int64_t item = blockIdx.x; item < total; item += gridDim.x) {
+    const int row = (int)(item / cbs);
+    const int col0 = ((int)(item % cbs) * 256 + threadIdx.x) * 16;
+    if (col0 >= V) continue;
     const float l2 = lse2[row];
     const float glp = g_lp[row];
     float ge = 0.f, H = 0.f;
@@ -331,6 +338,7 @@ dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const
             }
             ptr[k] = __float2bfloat16_rn(d);
         }
+    }
     }
 }
 
@@ -823,11 +831,12 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
                             t0 + rows, slot, *params, cu_seqlens, aux);
         if (r) return r;
         if (need_grad) {
-            const dim3 grid((unsigned)((V + 4095) / 4096), (unsigned)rows);
-            dlogits_transform_kernel<<<grid, 256, 0, aux>>>(
+            const int64_t items = (int64_t)rows * ((V + 4095) / 4096);
+            const int64_t cap = transform_blocks() > 0 ? transform_blocks() : items;
+            dlogits_transform_kernel<<<(unsigned)std::min<int64_t>(items, cap), 256, 0, aux>>>(
                 reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]), plan.ldS, (int)V, lse2, d_lp,
                 use_ent_grad ? d_ent : nullptr, (use_ent_grad && entropy_mask) ? entropy_mask + t0 : nullptr, ent_raw,
-                labels + t0, scale_log2, inv_T);
+                labels + t0, scale_log2, inv_T, rows);
             r = check_launch("dlogits_transform_kernel");
             if (r) return r;
         }
