@@ -13,7 +13,9 @@ from oracle import policy_oracle as O
 
 def test_builtin_names_registered():
     assert set(AdvantageEstimatorRegistry.list_available()) >= {"grpo", "rloo", "gae"}
-    assert set(PolicyLossRegistry.list_available()) >= {"regular", "dual_clip", "gspo"}
+    assert set(PolicyLossRegistry.list_available()) >= {"regular", "dual_clip", "gspo", "sapo", "cispo", "clip_cov",
+                                                        "kl_cov", "cross_entropy", "importance_sampling"}
+    assert set(AdvantageEstimatorRegistry.list_available()) >= {"reinforce++"}
     assert PolicyLossRegistry.get("regular") is losses.ppo_policy_loss
     assert PolicyLossRegistry.get("dual_clip") is losses.ppo_policy_loss
     assert AdvantageEstimatorRegistry.get(AdvantageEstimator.GRPO) is advantages.compute_grpo_outcome_advantage
@@ -137,3 +139,46 @@ def test_product_code_never_imports_the_oracle():
         if name.endswith(".py"):
             src = open(os.path.join(pkg, name)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{name} imports the oracle"
+
+
+def test_wrapper_glue_selects_the_response_window_rows(monkeypatch):
+    """Host logic of model_wrapper.py (reference model_wrapper.py:278-291, 353-370) with the CUDA head stubbed out:
+    which hidden rows and which labels reach the head, and where the results land in [B, A]."""
+    import torch
+
+    from skyrl_b200 import model_wrapper as mw
+
+    seen = {}
+
+    def fake_head(h, w, labels, temperature=1.0, entropy_mask=None, compute_entropy=True, chunk=0):
+        seen["rows"], seen["labels"], seen["emask"] = h[:, 0].clone(), labels.clone(), entropy_mask
+        return h[:, 0] * 10.0, h[:, 0] * 100.0   # "log-prob" and "entropy" encode the row that produced them
+
+    monkeypatch.setattr(mw, "fused_lm_head", fake_head)
+    B, S, A = 3, 8, 3
+    sequences = torch.arange(B * S).view(B, S) + 1
+    am = torch.tensor([[1, 1, 1, 1, 1, 1, 1, 1], [0, 0, 1, 1, 1, 1, 1, 0], [1, 1, 1, 1, 1, 0, 0, 0]])
+    # ---- padded layout: hidden[b, s, 0] = b * S + s identifies the row
+    hidden = torch.arange(B * S, dtype=torch.float32).view(B, S, 1)
+    lp, ent = mw.action_log_probs_from_hidden(hidden, None, sequences, A, attention_mask=am, compute_entropy=True)
+    want_rows = torch.tensor([[4, 5, 6], [12, 13, 14], [20, 21, 22]], dtype=torch.float32)  # positions S-A-1 .. S-2
+    assert torch.equal(lp, want_rows * 10.0) and torch.equal(ent, want_rows * 100.0)
+    assert torch.equal(seen["labels"].view(B, A), sequences[:, S - A:S])                   # next-token labels
+    assert torch.equal(seen["emask"].view(B, A), am[:, S - A - 1:S - 1])
+    # ---- sample packing: packed row j is the j-th valid token; its label is the NEXT packed token
+    valid_pos = torch.nonzero(am.reshape(-1)).squeeze(-1)
+    packed_hidden = torch.arange(valid_pos.numel(), dtype=torch.float32).view(-1, 1)
+    lp, ent = mw.action_log_probs_from_packed_hidden(packed_hidden, None, sequences, am, A, compute_entropy=True)
+    packed_of = {int(p): j for j, p in enumerate(valid_pos)}
+    packed_tokens = sequences.reshape(-1)[valid_pos]
+    for b in range(B):
+        for k, s in enumerate(range(S - A - 1, S - 1)):
+            if am[b, s]:
+                j = packed_of[b * S + s]
+                assert lp[b, k].item() == j * 10.0 and ent[b, k].item() == j * 100.0
+                assert j in seen["rows"].long().tolist()
+                where = seen["rows"].long().tolist().index(j)
+                assert seen["labels"][where] == packed_tokens[(j + 1) % len(packed_tokens)]
+            else:
+                assert lp[b, k].item() == 0.0 and ent[b, k].item() == 0.0   # pad_input leaves zeros
+    assert seen["rows"].numel() == int(am[:, S - A - 1:S - 1].sum())      # nothing else reached the head
