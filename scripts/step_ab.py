@@ -28,6 +28,9 @@ def main():
     weight = (torch.randn((V, H), generator=gen, device=dev) * (1.5 / H ** 0.5)).bfloat16()
     labels = torch.randint(0, V, (B, A), generator=gen, device=dev)
     mask = torch.ones(B, A, device=dev)
+    if kv.get("ragged"):  # right-padded responses: lengths uniform in [A/8, A] (mean valid fraction ~56 %)
+        lens = torch.randint(A // 8, A + 1, (B,), generator=gen, device=dev)
+        mask = (torch.arange(A, device=dev)[None] < lens[:, None]).float()
     adv = torch.randn((B, 1), generator=gen, device=dev).expand(B, A).contiguous()
     olp = -torch.rand((B, A), generator=gen, device=dev) * 12
     cfg = O.make_cfg(policy_loss_type="regular", loss_reduction="token_mean", use_kl_loss=True)
@@ -51,7 +54,7 @@ def main():
     clocks = cs.stop()
     ms = s.elapsed_time(e) / steps
     print(json.dumps({"tag": kv.get("tag", ""), "ms_per_step": round(ms, 1), "tok_s": round(N / ms * 1e3),
-                      "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")}), flush=True)
+                      "valid_frac": round(float(mask.mean()), 3), "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")}), flush=True)
 
 
 if __name__ == "__main__":

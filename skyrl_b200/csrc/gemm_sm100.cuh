@@ -135,11 +135,23 @@ struct GemmSmem {
     static constexpr uint32_t kTotal = 1024 + kStages * (kABytes + kBBytes) + kBarBytes;
 };
 
+// Optional device-side compaction of the iteration space (all pointers may be null):
+//   m_map / m_count : the kernel visits only the M tiles m_map[0 .. *m_count) (skipped tiles are not written);
+//   k_map / k_count : the reduction visits only the K blocks k_map[0 .. *k_count) (in that order).
+// Used by the fused policy step to skip token rows whose d(logits) is identically zero (masked positions).
+// With *k_count == 0 the launch does nothing (callers use it only with an accumulating epilogue).
+struct GemmMaps {
+    const int* m_map;
+    const int* m_count;
+    const int* k_map;
+    const int* k_count;
+};
+
 template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
                   int N, int K, int group_m, int tile_order, uint64_t hint_a, uint64_t hint_b, typename Epi::Params ep,
-                  GemmDebug* dbg, unsigned int* sync_ctr, int sync_every) {
+                  GemmDebug* dbg, unsigned int* sync_ctr, int sync_every, GemmMaps maps) {
     using S = GemmSmem<kCtas, BN, kStages>;
     constexpr int TILE_M = kBM * kCtas;
     constexpr uint32_t kTmemCols = 2 * BN;
@@ -189,10 +201,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    const int num_m_tiles = (M + TILE_M - 1) / TILE_M;
+    const int num_m_tiles = maps.m_count ? *maps.m_count : (M + TILE_M - 1) / TILE_M;
     const int num_n_tiles = (N + BN - 1) / BN;
-    const int total_tiles = num_m_tiles * num_n_tiles;
-    const int num_kb = (K + kBK - 1) / kBK;
+    const int num_kb = maps.k_count ? *maps.k_count : (K + kBK - 1) / kBK;
+    const int total_tiles = num_kb > 0 ? num_m_tiles * num_n_tiles : 0;
     const int cluster_id = blockIdx.x / kCtas;
     const int num_clusters = gridDim.x / kCtas;
 
@@ -206,12 +218,19 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             uint32_t sync_step = 0, sync_epoch = 0;
             for (int t = cluster_id; t < total_tiles; t += num_clusters) {
                 const TileCoord tc = decode_tile(t, num_m_tiles, num_n_tiles, group_m, tile_order);
-                const int m0 = tc.m_tile * TILE_M + static_cast<int>(cta_rank) * kBM;
+                const int m_tile = maps.m_map ? maps.m_map[tc.m_tile] : tc.m_tile;
+                const int m0 = m_tile * TILE_M + static_cast<int>(cta_rank) * kBM;
                 const int n0 = tc.n_tile * BN + static_cast<int>(cta_rank * S::kLoadN);
+                int k_window = 0;  // lane l holds k_map[32 * (kb / 32) + l]: one coalesced load per 32 K blocks
                 // CTAs that are resident at this tile iteration (the last iteration may be partial)
                 const uint32_t active_ctas =
                     (t - cluster_id + num_clusters <= total_tiles ? num_clusters : total_tiles % num_clusters) * kCtas;
                 for (int kb = 0; kb < num_kb; ++kb) {
+                    int kidx = kb;
+                    if (maps.k_map != nullptr) {
+                        if ((kb & 31) == 0) k_window = (kb + lane < num_kb) ? maps.k_map[kb + lane] : 0;
+                        kidx = __shfl_sync(0xffffffffu, k_window, kb & 31);
+                    }
                     // Best-effort lockstep: CTAs that share operand panels through L2 re-align every `sync_every`
                     // K blocks (bounded wait: a straggler can never dead-lock the others).
                     if (sync_ctr != nullptr && sync_step++ % static_cast<uint32_t>(sync_every) == 0) {
@@ -235,7 +254,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     }
                     uint8_t* a_dst = smem_a + stage * S::kABytes;
                     uint8_t* b_dst = smem_b + stage * S::kBBytes;
-                    const int k0 = kb * kBK;
+                    const int k0 = kidx * kBK;
                     if constexpr (kAMn) {
 #pragma unroll
                         for (int j = 0; j < kBM / 64; ++j) {
@@ -313,7 +332,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             bounded_wait(&tfull_bar[accum], aphase, dbg, 2, 2, accum, t);
             ptx::tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + accum * BN;
-            const int row = tc.m_tile * TILE_M + static_cast<int>(cta_rank) * kBM + q * 32 + lane;
+            const int m_tile = maps.m_map ? maps.m_map[tc.m_tile] : tc.m_tile;
+            const int row = m_tile * TILE_M + static_cast<int>(cta_rank) * kBM + q * 32 + lane;
             Epi::template run<BN>(ep, taddr, row, tc.n_tile, M, N);
             ptx::tcgen05_fence_before();
             __syncwarp();

@@ -93,7 +93,8 @@ static unsigned int* lockstep_counters() {
 template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
 static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int group_m,
                        const typename Epi::Params& ep, cudaStream_t stream, int tile_order = 0,
-                       uint64_t hint_a = kEvictNormal, uint64_t hint_b = kEvictNormal, int sync_every = 0) {
+                       uint64_t hint_a = kEvictNormal, uint64_t hint_b = kEvictNormal, int sync_every = 0,
+                       const GemmMaps* maps_in = nullptr) {
     using S = GemmSmem<kCtas, BN, kStages>;
     if (M <= 0 || N <= 0 || K <= 0) return SKYB200_OK;
     CUtensorMap ta, tb;
@@ -138,8 +139,10 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
         sync_ctr = lockstep_counters();
         if (sync_ctr != nullptr) SKYB200_CUDA_CHECK(cudaMemsetAsync(sync_ctr, 0, 8192 * sizeof(unsigned int), stream));
     }
+    GemmMaps maps = {nullptr, nullptr, nullptr, nullptr};
+    if (maps_in != nullptr) maps = *maps_in;
     SKYB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group_m, tile_order, hint_a, hint_b, ep, dbg,
-                                          sync_ctr, sync_every > 0 ? sync_every : 1));
+                                          sync_ctr, sync_every > 0 ? sync_every : 1, maps));
     return SKYB200_OK;
 }
 
@@ -192,6 +195,8 @@ static int dh_lockstep() { static int v = env_int0("SKYB200_DH_LOCKSTEP", 128); 
 static int fwd_lockstep() { static int v = env_int0("SKYB200_FWD_LOCKSTEP", 0); return v; }
 static int dw_lockstep() { static int v = env_int0("SKYB200_DW_LOCKSTEP", 128); return v; }
 static int dw_group_n() { static int v = env_int("SKYB200_DW_GROUP_N", 14); return v; }
+// skip all-zero d(logits) rows (masked tokens) in the backward GEMMs of the fused step (0 disables)
+static int skip_zero_rows() { static int v = env_int0("SKYB200_SKIP_ZERO_ROWS", 1); return v; }
 // cap on the resident blocks of the d(logits) transform pass (0 = one block per item)
 static int transform_blocks() { static int v = env_int0("SKYB200_TRANSFORM_BLOCKS", 0); return v; }
 
@@ -631,13 +636,77 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
 // ------------------------------------------------------------------------------------------ fused step
 namespace {
 
+// ---- zero-row skipping of the backward GEMMs (fused step)
+// A token whose d(log-prob) and d(entropy) are both zero (masked position) has an all-zero d(logits) row: its
+// 256-row tile contributes nothing to d_hidden and its 64-row K block nothing to d_weight.  live_rows_kernel turns
+// the per-token gradients of a chunk into compacted lists of live tiles / K blocks (layout below); the GEMMs walk the
+// lists (GemmMaps), dead d_hidden tiles are zero-filled.  Results are bit-identical to computing the zeros.
+//   maps[0] = #live M tiles, maps[1] = #live K blocks, maps[2 .. 2+mt) = live flag per M tile,
+//   maps[2+mt .. 2+2mt) = m_map, maps[2+2mt .. 2+2mt+kt) = k_map          (mt = chunk/256, kt = chunk/64)
+static size_t live_maps_ints(int64_t chunk) { return (size_t)(2 + 2 * (chunk / kTileM) + chunk / kBK + 8); }
+
+__global__ void __launch_bounds__(256) live_rows_kernel(const float* __restrict__ d_lp, const float* __restrict__ d_ent,
+                                                        const float* __restrict__ ent_mask, int rows, int* maps, int mt,
+                                                        int kt) {
+    extern __shared__ unsigned char live_k[];  // [kt]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int kb = warp; kb < kt; kb += 8) {
+        bool live = false;
+        for (int j = lane; j < kBK; j += 32) {
+            const int r = kb * kBK + j;
+            if (r < rows) {
+                float ge = 0.f;
+                if (d_ent != nullptr) ge = d_ent[r] * (ent_mask ? ent_mask[r] : 1.f);
+                live |= !(d_lp[r] == 0.f && ge == 0.f);
+            }
+        }
+        live = __any_sync(0xffffffffu, live);
+        if (lane == 0) live_k[kb] = live ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* m_live = maps + 2;
+        int* m_map = maps + 2 + mt;
+        int* k_map = maps + 2 + 2 * mt;
+        int nk = 0, nm = 0;
+        constexpr int per = kTileM / kBK;
+        for (int m = 0; m < mt; ++m) {
+            bool any = false;
+            for (int j = 0; j < per; ++j) {
+                const int kb = m * per + j;
+                if (kb < kt && live_k[kb]) {
+                    k_map[nk++] = kb;
+                    any = true;
+                }
+            }
+            m_live[m] = any ? 1 : 0;
+            if (any) m_map[nm++] = m;
+        }
+        maps[0] = nm;
+        maps[1] = nk;
+    }
+}
+
+// zero the d_hidden rows of the tiles the compacted GEMM does not visit
+__global__ void __launch_bounds__(256) zero_dead_tiles_kernel(__nv_bfloat16* __restrict__ C, int64_t ldc, int H,
+                                                              int rows, const int* __restrict__ m_live) {
+    const int m = blockIdx.x;
+    if (m_live[m]) return;
+    const int r1 = min(rows, (m + 1) * kTileM);
+    const int vec = H / 8;  // H % 8 == 0 (checked by the caller)
+    for (int r = m * kTileM + blockIdx.y; r < r1; r += gridDim.y) {
+        uint4* dst = reinterpret_cast<uint4*>(C + (int64_t)r * ldc);
+        for (int j = threadIdx.x; j < vec; j += blockDim.x) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 struct StepPlan {
     int64_t chunk;  // tokens per chunk (multiple of 256)
     int64_t ldS;    // pitch of the bf16 logits / d_logits store
     int slabs;
     // everything below exists twice (parity of the chunk index): the small kernels of chunk c+1 run on the
     // auxiliary stream while the backward GEMMs of chunk c run on the caller's stream
-    size_t off_part[2], off_label[2], off_lse2[2], off_entraw[2], off_dlp[2], off_dent[2], off_S[2];
+    size_t off_part[2], off_label[2], off_lse2[2], off_entraw[2], off_dlp[2], off_dent[2], off_S[2], off_maps[2];
     size_t off_loss, total;
 };
 
@@ -683,6 +752,7 @@ StepPlan plan_step(int64_t B, int64_t A, int64_t N, int64_t H, int64_t V, int lo
         p.off_dlp[i] = take((size_t)chunk * 4);
         p.off_dent[i] = take((size_t)chunk * 4);
         p.off_S[i] = take(need_grad ? (size_t)chunk * p.ldS * 2 : 0);
+        p.off_maps[i] = take(live_maps_ints(chunk) * sizeof(int));
     }
     p.off_loss = take(loss_chunk_ws_bytes(B, N) + (size_t)(N / chunk + 2) * 8 * 4 * 4);
     (void)A;
@@ -839,6 +909,14 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
                 labels + t0, scale_log2, inv_T, rows);
             r = check_launch("dlogits_transform_kernel");
             if (r) return r;
+            if (skip_zero_rows()) {
+                const int mt = (int)(c / kTileM), kt = (int)(c / kBK);
+                live_rows_kernel<<<1, 256, (size_t)kt, aux>>>(
+                    d_lp, use_ent_grad ? d_ent : nullptr, (use_ent_grad && entropy_mask) ? entropy_mask + t0 : nullptr,
+                    rows, reinterpret_cast<int*>(wb + plan.off_maps[p]), mt, kt);
+                r = check_launch("live_rows_kernel");
+                if (r) return r;
+            }
         }
         SKYB200_CUDA_CHECK(cudaEventRecord(ss->mid[p], aux));
         return SKYB200_OK;
@@ -850,13 +928,24 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
         const int rows = (int)std::min<int64_t>(c, N - t0);
         __nv_bfloat16* S = reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]);
         SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[p], 0));
+        const int mt = (int)(c / kTileM);
+        int* maps = reinterpret_cast<int*>(wb + plan.off_maps[p]);
+        const bool skip = skip_zero_rows() != 0;
+        const GemmMaps m_maps = {maps + 2 + mt, maps, nullptr, nullptr};
+        const GemmMaps k_maps = {nullptr, nullptr, maps + 2 + 2 * mt, maps + 1};
         if (dhid != nullptr) {
             EpiStoreBF16::Params eh;
             eh.C = dhid + t0 * H;
             eh.ldc = H;
+            if (skip) {
+                const dim3 zgrid((unsigned)((rows + kTileM - 1) / kTileM), 32);
+                zero_dead_tiles_kernel<<<zgrid, 256, 0, stream>>>(eh.C, H, (int)H, rows, maps + 2);
+                int rz = check_launch("zero_dead_tiles_kernel");
+                if (rz) return rz;
+            }
             int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
                 S, plan.ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, kEvictNormal, kEvictNormal,
-                dh_lockstep());
+                dh_lockstep(), skip ? &m_maps : nullptr);
             if (r) return r;
         }
         if (d_weight != nullptr) {
@@ -866,7 +955,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             ew.accumulate = (accumulate != 0 || t0 > 0) ? 1 : 0;
             int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
                 S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, kEvictNormal,
-                hint_dw_b(), dw_lockstep());
+                hint_dw_b(), dw_lockstep(), (skip && ew.accumulate) ? &k_maps : nullptr);
             if (r) return r;
         }
         return SKYB200_OK;

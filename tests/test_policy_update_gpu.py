@@ -339,3 +339,28 @@ def test_full_size_config2_sampled_rows_and_checksum_identities():
     assert abs(lhs.item() - rhs.item()) < 1e-5 * rhs_abs.item(), (lhs.item(), rhs.item(), rhs_abs.item())
     print(f"full-size identities: <dW,W>={lhs.item():.6e} <dH,h>={rhs.item():.6e} |.|={rhs_abs.item():.3e} "
           f"colsum={float((col.abs() / scale).max()):.2e} d_hidden rel={rel.item():.2e}")
+
+
+def test_zero_row_skipping_is_bit_identical(tmp_path):
+    """The fused step skips 256-row tiles (d_hidden) and 64-row K blocks (d_weight) whose d(logits) rows are all zero
+    (masked tokens).  Same batch with the skipping on and off, in two processes: every output bit-identical, and the
+    d_hidden rows of masked tokens exactly zero."""
+    import os
+    import subprocess
+    import sys
+
+    worker = os.path.join(os.path.dirname(__file__), "skip_worker.py")
+    res = {}
+    for flag in ("0", "1"):
+        path = str(tmp_path / f"skip{flag}.pt")
+        env = dict(os.environ, SKYB200_SKIP_ZERO_ROWS=flag)
+        r = subprocess.run([sys.executable, worker, path], env=env, capture_output=True, text=True, timeout=280)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        res[flag] = torch.load(path)
+    a, b = res["0"], res["1"]
+    for k in ("d_hidden", "d_weight", "d_weight2", "log_probs"):
+        assert torch.equal(a[k], b[k]), k
+    assert a["status"] == b["status"]
+    dead = a["mask"].reshape(-1) == 0
+    assert dead.sum() > 10000 and torch.all(b["d_hidden"][dead] == 0)
+    assert b["d_hidden"][~dead].abs().sum() > 0
