@@ -436,6 +436,71 @@ __global__ void __launch_bounds__(512) logits_backward_kernel(const T* __restric
     }
 }
 
+// ---- zero-row skipping of the backward GEMMs (fused step and head_backward)
+// A token whose d(log-prob) and d(entropy) are both zero (masked position) has an all-zero d(logits) row: its
+// 256-row tile contributes nothing to d_hidden and its 64-row K block nothing to d_weight.  live_rows_kernel turns
+// the per-token gradients of a chunk into compacted lists of live tiles / K blocks (layout below); the GEMMs walk the
+// lists (GemmMaps), dead d_hidden tiles are zero-filled.  Results are bit-identical to computing the zeros.
+//   maps[0] = #live M tiles, maps[1] = #live K blocks, maps[2 .. 2+mt) = live flag per M tile,
+//   maps[2+mt .. 2+2mt) = m_map, maps[2+2mt .. 2+2mt+kt) = k_map          (mt = chunk/256, kt = chunk/64)
+static size_t live_maps_ints(int64_t chunk) { return (size_t)(2 + 2 * (chunk / kTileM) + chunk / kBK + 8); }
+
+__global__ void __launch_bounds__(256) live_rows_kernel(const float* __restrict__ d_lp, const float* __restrict__ d_ent,
+                                                        const float* __restrict__ ent_mask, int rows, int* maps, int mt,
+                                                        int kt) {
+    extern __shared__ unsigned char live_k[];  // [kt]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int kb = warp; kb < kt; kb += 8) {
+        bool live = false;
+        for (int j = lane; j < kBK; j += 32) {
+            const int r = kb * kBK + j;
+            if (r < rows) {
+                float ge = 0.f;
+                if (d_ent != nullptr) ge = d_ent[r] * (ent_mask ? ent_mask[r] : 1.f);
+                live |= !(d_lp[r] == 0.f && ge == 0.f);
+            }
+        }
+        live = __any_sync(0xffffffffu, live);
+        if (lane == 0) live_k[kb] = live ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* m_live = maps + 2;
+        int* m_map = maps + 2 + mt;
+        int* k_map = maps + 2 + 2 * mt;
+        int nk = 0, nm = 0;
+        constexpr int per = kTileM / kBK;
+        for (int m = 0; m < mt; ++m) {
+            bool any = false;
+            for (int j = 0; j < per; ++j) {
+                const int kb = m * per + j;
+                if (kb < kt && live_k[kb]) {
+                    k_map[nk++] = kb;
+                    any = true;
+                }
+            }
+            m_live[m] = any ? 1 : 0;
+            if (any) m_map[nm++] = m;
+        }
+        maps[0] = nm;
+        maps[1] = nk;
+    }
+}
+
+// zero the d_hidden rows of the tiles the compacted GEMM does not visit
+__global__ void __launch_bounds__(256) zero_dead_tiles_kernel(__nv_bfloat16* __restrict__ C, int64_t ldc, int H,
+                                                              int rows, const int* __restrict__ m_live) {
+    const int m = blockIdx.x;
+    if (m_live[m]) return;
+    const int r1 = min(rows, (m + 1) * kTileM);
+    const int vec = H / 8;  // H % 8 == 0 (checked by the caller)
+    for (int r = m * kTileM + blockIdx.y; r < r1; r += gridDim.y) {
+        uint4* dst = reinterpret_cast<uint4*>(C + (int64_t)r * ldc);
+        for (int j = threadIdx.x; j < vec; j += blockDim.x) dst[j] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+
 }  // namespace skyb200
 
 using namespace skyb200;
@@ -452,7 +517,8 @@ extern "C" size_t skyb200_head_forward_workspace(int64_t N, int64_t H, int64_t V
 extern "C" size_t skyb200_head_backward_workspace(int64_t N, int64_t H, int64_t V, int64_t chunk) {
     (void)H;
     const int64_t c = pick_chunk(N, chunk);
-    return (size_t)(c * round_up(V, 64) * 2 + 1024);  // dS scratch, bf16
+    // dS scratch (bf16) + the live tile / K-block lists of the zero-row skipping
+    return (size_t)round_up(c * round_up(V, 64) * 2, 256) + live_maps_ints(c) * sizeof(int) + 1024;
 }
 
 extern "C" int skyb200_head_forward(const void* hidden, const void* weight, const int64_t* labels,
@@ -588,12 +654,25 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
     const int64_t c = pick_chunk(N, chunk);
     const int64_t ldS = round_up(V, 64);
     __nv_bfloat16* dS = static_cast<__nv_bfloat16*>(workspace);
+    int* maps = reinterpret_cast<int*>(static_cast<char*>(workspace) + round_up(c * ldS * 2, 256));
+    const int mt = (int)(c / kTileM), kt = (int)(c / kBK);
+    const GemmMaps m_maps = {maps + 2 + mt, maps, nullptr, nullptr};
+    const GemmMaps k_maps = {nullptr, nullptr, maps + 2 + 2 * mt, maps + 1};
     const float inv_T = 1.0f / temperature;
     const __nv_bfloat16* hid = static_cast<const __nv_bfloat16*>(hidden);
     __nv_bfloat16* dhid = static_cast<__nv_bfloat16*>(d_hidden);
 
     for (int64_t r0 = 0; r0 < N; r0 += c) {
         const int rows = (int)std::min<int64_t>(c, N - r0);
+        // rows with zero upstream gradients (masked tokens) have all-zero d(logits): skip their tiles / K blocks in
+        // all three GEMMs.  Not on a non-accumulating first chunk, whose d_weight GEMM must see every K block.
+        const bool acc_w = (accumulate != 0 || r0 > 0);
+        const bool skip = skip_zero_rows() != 0 && (d_weight == nullptr || acc_w);
+        if (skip) {
+            live_rows_kernel<<<1, 256, (size_t)kt, stream>>>(g_logprobs + r0, g_entropy ? g_entropy + r0 : nullptr,
+                                                             nullptr, rows, maps, mt, kt);
+            if ((rc = check_launch("live_rows_kernel"))) return rc;
+        }
         // (1) recompute logits tile by tile -> d(logits) bf16
         EpiDLogits::Params ed;
         ed.scale_log2 = 1.4426950408889634f * inv_T;
@@ -606,16 +685,22 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
         ed.dS = dS;
         ed.ld = ldS;
         rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiDLogits>(
-            hid + r0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ed, stream);
+            hid + r0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ed, stream, 0, kEvictNormal, kEvictNormal, 0,
+            skip ? &m_maps : nullptr);
         if (rc) return rc;
         // (2) d_hidden[rows, H] = dS[rows, V] * W[V, H]      (A K-major, B MN-major)
         if (dhid != nullptr) {
             EpiStoreBF16::Params eh;
             eh.C = dhid + r0 * H;
             eh.ldc = H;
+            if (skip) {
+                const dim3 zgrid((unsigned)((rows + kTileM - 1) / kTileM), 32);
+                zero_dead_tiles_kernel<<<zgrid, 256, 0, stream>>>(eh.C, H, (int)H, rows, maps + 2);
+                if ((rc = check_launch("zero_dead_tiles_kernel"))) return rc;
+            }
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
                 dS, ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, kEvictNormal, kEvictNormal,
-                dh_lockstep());
+                dh_lockstep(), skip ? &m_maps : nullptr);
             if (rc) return rc;
         }
         // (3) d_weight[V, H] (+)= dS^T[V, rows] * hidden[rows, H]   (both MN-major)
@@ -623,10 +708,10 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
             EpiStoreF32::Params ew;
             ew.C = d_weight;
             ew.ldc = H;
-            ew.accumulate = (accumulate != 0 || r0 > 0) ? 1 : 0;
+            ew.accumulate = acc_w ? 1 : 0;
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
                 dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, kEvictNormal, kEvictLast,
-                dw_lockstep());
+                dw_lockstep(), skip ? &k_maps : nullptr);
             if (rc) return rc;
         }
     }
@@ -635,70 +720,6 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
 
 // ------------------------------------------------------------------------------------------ fused step
 namespace {
-
-// ---- zero-row skipping of the backward GEMMs (fused step)
-// A token whose d(log-prob) and d(entropy) are both zero (masked position) has an all-zero d(logits) row: its
-// 256-row tile contributes nothing to d_hidden and its 64-row K block nothing to d_weight.  live_rows_kernel turns
-// the per-token gradients of a chunk into compacted lists of live tiles / K blocks (layout below); the GEMMs walk the
-// lists (GemmMaps), dead d_hidden tiles are zero-filled.  Results are bit-identical to computing the zeros.
-//   maps[0] = #live M tiles, maps[1] = #live K blocks, maps[2 .. 2+mt) = live flag per M tile,
-//   maps[2+mt .. 2+2mt) = m_map, maps[2+2mt .. 2+2mt+kt) = k_map          (mt = chunk/256, kt = chunk/64)
-static size_t live_maps_ints(int64_t chunk) { return (size_t)(2 + 2 * (chunk / kTileM) + chunk / kBK + 8); }
-
-__global__ void __launch_bounds__(256) live_rows_kernel(const float* __restrict__ d_lp, const float* __restrict__ d_ent,
-                                                        const float* __restrict__ ent_mask, int rows, int* maps, int mt,
-                                                        int kt) {
-    extern __shared__ unsigned char live_k[];  // [kt]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int kb = warp; kb < kt; kb += 8) {
-        bool live = false;
-        for (int j = lane; j < kBK; j += 32) {
-            const int r = kb * kBK + j;
-            if (r < rows) {
-                float ge = 0.f;
-                if (d_ent != nullptr) ge = d_ent[r] * (ent_mask ? ent_mask[r] : 1.f);
-                live |= !(d_lp[r] == 0.f && ge == 0.f);
-            }
-        }
-        live = __any_sync(0xffffffffu, live);
-        if (lane == 0) live_k[kb] = live ? 1 : 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int* m_live = maps + 2;
-        int* m_map = maps + 2 + mt;
-        int* k_map = maps + 2 + 2 * mt;
-        int nk = 0, nm = 0;
-        constexpr int per = kTileM / kBK;
-        for (int m = 0; m < mt; ++m) {
-            bool any = false;
-            for (int j = 0; j < per; ++j) {
-                const int kb = m * per + j;
-                if (kb < kt && live_k[kb]) {
-                    k_map[nk++] = kb;
-                    any = true;
-                }
-            }
-            m_live[m] = any ? 1 : 0;
-            if (any) m_map[nm++] = m;
-        }
-        maps[0] = nm;
-        maps[1] = nk;
-    }
-}
-
-// zero the d_hidden rows of the tiles the compacted GEMM does not visit
-__global__ void __launch_bounds__(256) zero_dead_tiles_kernel(__nv_bfloat16* __restrict__ C, int64_t ldc, int H,
-                                                              int rows, const int* __restrict__ m_live) {
-    const int m = blockIdx.x;
-    if (m_live[m]) return;
-    const int r1 = min(rows, (m + 1) * kTileM);
-    const int vec = H / 8;  // H % 8 == 0 (checked by the caller)
-    for (int r = m * kTileM + blockIdx.y; r < r1; r += gridDim.y) {
-        uint4* dst = reinterpret_cast<uint4*>(C + (int64_t)r * ldc);
-        for (int j = threadIdx.x; j < vec; j += blockDim.x) dst[j] = make_uint4(0u, 0u, 0u, 0u);
-    }
-}
 
 struct StepPlan {
     int64_t chunk;  // tokens per chunk (multiple of 256)

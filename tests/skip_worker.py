@@ -30,7 +30,13 @@ def main(out_path):
                                         accumulate_d_weight=True)
     out2 = skyrl_b200.policy_update_step(hidden.to(dev), weight.to(dev), labels.to(dev), olp.to(dev), adv.to(dev), cfg,
                                          loss_mask=mask.to(dev), base_log_probs=olp.to(dev))   # fresh d_weight
-    torch.save({"d_hidden": out.d_hidden.cpu(), "d_weight": out.d_weight.cpu(), "d_weight2": out2.d_weight.cpu(),
+    # the autograd path (fused_lm_head + a masked loss): skyb200_head_backward skips the same rows in its 3 GEMMs
+    h = hidden.to(dev).reshape(B * A, H).requires_grad_(True)
+    w = weight.to(dev).requires_grad_(True)
+    lp, ent = skyrl_b200.fused_lm_head(h, w, labels.to(dev).reshape(-1), temperature=0.9)
+    m = mask.to(dev).reshape(-1)
+    ((lp * adv.to(dev).reshape(-1) * m).sum() / m.sum() - 0.01 * (ent * m).sum() / m.sum()).backward()
+    torch.save({"ag_d_hidden": h.grad.cpu(), "ag_d_weight": w.grad.cpu(), "d_hidden": out.d_hidden.cpu(), "d_weight": out.d_weight.cpu(), "d_weight2": out2.d_weight.cpu(),
                 "log_probs": out.log_probs.cpu(), "status": out.status, "mask": mask}, out_path)
 
 

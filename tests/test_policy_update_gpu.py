@@ -358,9 +358,9 @@ def test_zero_row_skipping_is_bit_identical(tmp_path):
         assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
         res[flag] = torch.load(path)
     a, b = res["0"], res["1"]
-    for k in ("d_hidden", "d_weight", "d_weight2", "log_probs"):
+    for k in ("d_hidden", "d_weight", "d_weight2", "log_probs", "ag_d_hidden", "ag_d_weight"):
         assert torch.equal(a[k], b[k]), k
     assert a["status"] == b["status"]
     dead = a["mask"].reshape(-1) == 0
-    assert dead.sum() > 10000 and torch.all(b["d_hidden"][dead] == 0)
+    assert dead.sum() > 10000 and torch.all(b["d_hidden"][dead] == 0) and torch.all(b["ag_d_hidden"][dead] == 0)
     assert b["d_hidden"][~dead].abs().sum() > 0
