@@ -227,6 +227,80 @@ def run_reference(args, w):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+def hbm_kernels(dev, peaks):
+    """The memory-bound kernels of the path (K2 advantages, KL-in-reward, K3 loss) through the C ABI on the
+    config-3 batch shape (512 x 8192 = 4.19 M positions, 50-117 MB per call): algorithmic bytes / CUDA-event time,
+    L2 flushed before every timed call, median of 15.  Reported against the measured HBM copy bandwidth."""
+    import ctypes as C
+
+    from skyrl_b200 import _lib
+
+    lib = _lib.load()
+    B, A, G = 512, 8192, 8
+    n = B * A
+    g = torch.Generator(device=dev).manual_seed(7)
+    f = lambda: torch.randn((B, A), generator=g, device=dev)
+    rewards, values, lp, adv = f(), f(), -f().abs(), f()
+    olp, base = lp + 0.05 * f(), lp + 0.1 * f()
+    lens = torch.randint(A // 2, A + 1, (B,), generator=g, device=dev)
+    mask = (torch.arange(A, device=dev)[None] < lens[:, None]).float().contiguous()
+    out1, out2 = torch.empty_like(lp), torch.empty_like(lp)
+    stats = torch.zeros(64, dtype=torch.float32, device=dev)
+    gid = (torch.arange(B, device=dev) // G).int()
+    gstart = (torch.arange(B // G + 1, device=dev) * G).int()
+    grows = torch.arange(B, device=dev).int()
+    scores = torch.empty(4 * B, dtype=torch.float32, device=dev)
+    gae_ws = torch.empty(lib.skyb200_gae_workspace(B), dtype=torch.uint8, device=dev)
+    loss_ws = torch.empty(lib.skyb200_policy_loss_workspace(B, A), dtype=torch.uint8, device=dev)
+    params = _lib.LossParams()
+    params.loss_type, params.reduction, params.kl_type = 0, 0, 3
+    params.eps_clip_low = params.eps_clip_high = 0.2
+    params.clip_ratio_c, params.kl_loss_coef = 3.0, 1e-3
+    st = _lib.stream_ptr()
+    P = _lib.ptr
+    cases = {
+        # name: (call, algorithmic bytes per position)
+        "grpo_advantage": (lambda: lib.skyb200_group_advantage(P(rewards), P(mask), _lib.MASK_F32, P(gid), P(gstart),
+                                                               P(grows), P(out1), P(scores), B, A, B // G, 0, 1e-6, st),
+                           12),
+        "gae_advantage+whiten": (lambda: lib.skyb200_gae_advantage(P(rewards), P(values), P(mask), _lib.MASK_F32,
+                                                                   P(out1), P(out2), P(stats), P(gae_ws),
+                                                                   gae_ws.numel(), B, A, 1.0, 0.95, st), 28),
+        "reward_kl_penalty": (lambda: lib.skyb200_reward_kl_penalty(P(lp), P(base), P(mask), P(rewards), P(out1),
+                                                                    P(stats), P(scores), B, A, 3, 1e-3, st), 20),
+        "policy_loss_fwd_bwd(+kl)": (lambda: lib.skyb200_policy_loss(P(lp), P(olp), P(adv), P(mask), P(base), None,
+                                                                     P(out1), None, P(stats), P(loss_ws),
+                                                                     loss_ws.numel(), B, A, C.byref(params), None,
+                                                                     None, st), 24),
+    }
+    # L2 flush = streaming READ of 3x the 126 MB L2 (a write flush would leave ~100 MB of dirty lines whose write-back
+    # lands inside the timed region of a 50-100 MB kernel)
+    flush = torch.zeros(96 << 20, dtype=torch.int32, device=dev)
+    res = {}
+    for name, (call, bpt) in cases.items():
+        for _ in range(3):
+            _lib.check(call(), name)
+        times = []
+        for _ in range(15):
+            flush.sum()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = call()
+            e.record()
+            _lib.check(rc, name)
+            torch.cuda.synchronize()
+            times.append(s.elapsed_time(e))
+        times.sort()
+        ms = times[len(times) // 2]
+        gbs = n * bpt / (ms * 1e-3) / 1e9
+        res[name] = {"us": round(ms * 1e3, 1), "bytes_per_position": bpt, "achieved_gbs": round(gbs, 1),
+                     "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)}
+    res["_note"] = ("512 x 8192 positions (config-3 shape), fp32 mask, L2 flushed (384 MB streamed through it) before each "
+                    "timed call, median of 15, "
+                    "CUDA events; hbm peak %.1f GB/s (%s)" % (peaks["hbm"], peaks["source"].split(" (")[0]))
+    return res
+
+
 def run_ours(args, w):
     import torch.distributed as dist
 
@@ -357,7 +431,8 @@ def run_ours(args, w):
     chunk = 37 * 256
     n_chunks = (N + chunk - 1) // chunk
     # GRPO (2) + loss pre-pass + finalize (2) + per chunk: fwd GEMM, merge, loss, d_logits transform, dH GEMM, dW GEMM
-    launches_per_step = 2 + 2 + 6 * n_chunks
+    # (+ live-row lists and dead-tile zero fill of the zero-row skipping per chunk)
+    launches_per_step = 2 + 2 + 8 * n_chunks
 
     # the library GEMM on the same shape and data, sustained (context for the power-capped regime)
     def cublas_same_shape():
@@ -380,6 +455,7 @@ def run_ours(args, w):
         return 2.0 * a.shape[0] * H * V * reps / (s.elapsed_time(e) * 1e-3) / 1e12
 
     cublas_tflops = cublas_same_shape() if rank == 0 else None
+    hbm = hbm_kernels(dev, peaks) if rank == 0 else None
     tok_s = world * N / (ms_step * 1e-3)
     tok_s_e2e = world * N / (ms_e2e * 1e-3)
     flops_fwd_launch = 2.0 * min(chunk, N) * H * V
@@ -400,6 +476,7 @@ def run_ours(args, w):
             "tokens_per_s_per_gpu": tok_s / world,
             "phases_ms": {"advantages": adv_ms, "head_fwd+loss+head_bwd": upd_ms, "head_fwd_alone": ms_fwd},
             "cublas_same_shape_tflops": cublas_tflops,
+            "hbm_kernels": hbm,
             "step_roofline": {"bound": "tensor", "algorithmic_flops_per_token": 6.0 * H * V,
                               "achieved": step_tflops_alg, "peak": peaks["tflops"], "unit": "TFLOP/s",
                               "frac": step_tflops_alg / peaks["tflops"],

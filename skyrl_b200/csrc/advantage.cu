@@ -52,6 +52,31 @@ group_broadcast_kernel(const float* __restrict__ scores, const void* __restrict_
                        float eps) {
     __shared__ float sh[34];
     const int row = blockIdx.y;
+    const int64_t base = static_cast<int64_t>(row) * A;
+    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * kBcastTile;
+    const int64_t t1 = min(A, t0 + kBcastTile);
+    const bool vec = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0) && kMaskType != SKYB200_MASK_NONE;
+    // the mask tile is requested first: its DRAM latency overlaps the chain of dependent loads of the group statistics
+    constexpr int kPer = kBcastTile / (256 * 4);
+    float4 m[kPer];
+    if (vec) {
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int64_t t = t0 + (static_cast<int64_t>(u) * 256 + threadIdx.x) * 4;
+            m[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < t1) {
+                if constexpr (kMaskType == SKYB200_MASK_F32) {
+                    m[u] = __ldcs(reinterpret_cast<const float4*>(static_cast<const float*>(mask) + base + t));
+                } else if constexpr (kMaskType == SKYB200_MASK_I64) {
+                    const longlong2* mp =
+                        reinterpret_cast<const longlong2*>(static_cast<const long long*>(mask) + base + t);
+                    const longlong2 a = __ldcs(mp), b = __ldcs(mp + 1);
+                    m[u] = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+                }
+            }
+        }
+    }
     const int g = group_of_row[row];
     const int beg = group_start[g], end = group_start[g + 1];
     const int n = end - beg;
@@ -79,22 +104,13 @@ group_broadcast_kernel(const float* __restrict__ scores, const void* __restrict_
             value = (sc - mean) / (sd + eps);
         }
     }
-    const int64_t base = static_cast<int64_t>(row) * A;
-    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * kBcastTile;
-    const int64_t t1 = min(A, t0 + kBcastTile);
-    const bool vec = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(mask) & 15u) == 0) && kMaskType != SKYB200_MASK_NONE;
     if (vec) {
-        for (int64_t t = t0 + threadIdx.x * 4; t < t1; t += blockDim.x * 4) {
-            float4 m;
-            if constexpr (kMaskType == SKYB200_MASK_F32) {
-                m = ldg_stream(reinterpret_cast<const float4*>(static_cast<const float*>(mask) + base + t));
-            } else {
-                const longlong2* mp = reinterpret_cast<const longlong2*>(static_cast<const long long*>(mask) + base + t);
-                const longlong2 a = mp[0], b = mp[1];
-                m = make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
-            }
-            *reinterpret_cast<float4*>(out + base + t) = make_float4(value * m.x, value * m.y, value * m.z, value * m.w);
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int64_t t = t0 + (static_cast<int64_t>(u) * 256 + threadIdx.x) * 4;
+            if (t < t1)
+                __stcs(reinterpret_cast<float4*>(out + base + t),
+                       make_float4(value * m[u].x, value * m[u].y, value * m[u].z, value * m[u].w));
         }
     } else {
         for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x)
@@ -122,23 +138,36 @@ __device__ __forceinline__ Affine compose_left_of(const Affine& left, const Affi
     return r;
 }
 
+// Tile pipeline per row (right to left, carry between tiles):
+//   load   coalesced 128-bit loads of rewards / values / mask (12 requests in flight per thread) -> shared memory
+//   pass 1 each thread scans its 16 consecutive positions with zero carry-in -> one affine map per thread
+//   carry  suffix-composition of the 256 maps (warp shuffles + 8 warp totals) -> carry entering every thread
+//   pass 2 the same 16 positions again with the true carry-in (exactly the sequential recurrence, in fp64)
+//   store  coalesced 128-bit stores of advantages and returns (values come from shared memory), row moments
+// The last block to finish folds the per-row moments in a fixed order (no separate fold launch).
 template <int kMaskType>
-__global__ void __launch_bounds__(kGaeThreads)
+__global__ void __launch_bounds__(kGaeThreads, 4)
 gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const void* __restrict__ mask,
                 float* __restrict__ adv_raw, float* __restrict__ returns, double* __restrict__ row_stats, int64_t A,
-                float gamma, float lambd) {
-    __shared__ float s_delta[kGaeThreads * kGaePitch];
+                float gamma, float lambd, double* __restrict__ moments, unsigned int* __restrict__ counter, int B) {
+    __shared__ float s_r[kGaeThreads * kGaePitch + 1];  // rewards -> deltas -> advantages
+    __shared__ float s_v[kGaeThreads * kGaePitch + 1];  // values, plus V of the position right of the tile
     __shared__ double s_wmul[kGaeThreads / 32], s_wadd[kGaeThreads / 32];
     __shared__ double s_carry;
     __shared__ double sh_d[34];
+    __shared__ bool is_last;
     const int row = blockIdx.x;
     const int64_t base = static_cast<int64_t>(row) * A;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double c = static_cast<double>(gamma) * static_cast<double>(lambd);
-    double cpow[kGaePer + 1];
-    cpow[0] = 1.0;
+    double c16 = 1.0;
 #pragma unroll
-    for (int j = 1; j <= kGaePer; ++j) cpow[j] = cpow[j - 1] * c;
+    for (int j = 0; j < kGaePer; ++j) c16 *= c;
+    auto pad = [](int p) { return p + p / kGaePer; };  // 17-float pitch per 16 positions: conflict-free
+    const bool vec = (A % 4 == 0) &&
+                     (((reinterpret_cast<uintptr_t>(rewards) | reinterpret_cast<uintptr_t>(values) |
+                        reinterpret_cast<uintptr_t>(adv_raw) | reinterpret_cast<uintptr_t>(returns) |
+                        reinterpret_cast<uintptr_t>(mask)) & 15u) == 0);
 
     double sum_m = 0.0, sum_mx = 0.0, sum_mxx = 0.0;
     if (tid == 0) s_carry = 0.0;
@@ -146,35 +175,59 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     for (int64_t tile = num_tiles - 1; tile >= 0; --tile) {
         const int64_t t0 = tile * kGaeTile;
         __syncthreads();
-        // coalesced load: delta_t = r_t + gamma * V_{t+1} - V_t   (V_A = 0); positions >= A contribute delta = 0
-#pragma unroll 4
-        for (int k = 0; k < kGaePer; ++k) {
-            const int p = k * kGaeThreads + tid;
-            const int64_t t = t0 + p;
-            float d = 0.f;
-            if (t < A) {
-                const float v = values[base + t];
-                const float vn = (t + 1 < A) ? values[base + t + 1] : 0.f;
-                d = rewards[base + t] + gamma * vn - v;
-            }
-            s_delta[(p / kGaePer) * kGaePitch + (p % kGaePer)] = d;
-        }
-        __syncthreads();
-        // local right-to-left scan of this thread's 16 positions with zero carry-in
-        double x[kGaePer];
-        {
-            double run = 0.0;
+        float4 mk[4];
+        if (vec) {
+            float4 r4[4], v4[4];
 #pragma unroll
-            for (int j = kGaePer - 1; j >= 0; --j) {
-                run = static_cast<double>(s_delta[tid * kGaePitch + j]) + c * run;
-                x[j] = run;
+            for (int k = 0; k < 4; ++k) {
+                const int64_t t = t0 + (k * kGaeThreads + tid) * 4;
+                r4[k] = v4[k] = mk[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t < A) {
+                    r4[k] = __ldcs(reinterpret_cast<const float4*>(rewards + base + t));
+                    v4[k] = __ldcs(reinterpret_cast<const float4*>(values + base + t));
+                    if constexpr (kMaskType == SKYB200_MASK_F32) {
+                        mk[k] = __ldcs(reinterpret_cast<const float4*>(static_cast<const float*>(mask) + base + t));
+                    } else if constexpr (kMaskType == SKYB200_MASK_I64) {
+                        const longlong2* mp =
+                            reinterpret_cast<const longlong2*>(static_cast<const long long*>(mask) + base + t);
+                        const longlong2 ma = __ldcs(mp), mb = __ldcs(mp + 1);
+                        mk[k] = make_float4((float)ma.x, (float)ma.y, (float)mb.x, (float)mb.y);
+                    } else {
+                        mk[k] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int o = pad((k * kGaeThreads + tid) * 4);
+                s_r[o] = r4[k].x, s_r[o + 1] = r4[k].y, s_r[o + 2] = r4[k].z, s_r[o + 3] = r4[k].w;
+                s_v[o] = v4[k].x, s_v[o + 1] = v4[k].y, s_v[o + 2] = v4[k].z, s_v[o + 3] = v4[k].w;
+            }
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < kGaePer; ++k) {
+                const int p = k * kGaeThreads + tid;
+                const int64_t t = t0 + p;
+                s_r[pad(p)] = (t < A) ? rewards[base + t] : 0.f;
+                s_v[pad(p)] = (t < A) ? values[base + t] : 0.f;
             }
         }
-        // suffix-compose the per-thread affine maps: carry_in(tid) = maps of all threads to the right applied to
-        // the tile carry.  Inclusive suffix scan inside the warp, then across the 8 warps.
+        if (tid == 0) s_v[pad(kGaeTile)] = (t0 + kGaeTile < A) ? values[base + t0 + kGaeTile] : 0.f;
+        __syncthreads();
+        // pass 1: delta_t = r_t + gamma * V_{t+1} - V_t (V_A = 0; positions >= A hold zeros), zero carry-in
+        const int o0 = tid * kGaePitch;
+        double run = 0.0;
+#pragma unroll
+        for (int j = kGaePer - 1; j >= 0; --j) {
+            const float vn = s_v[(j == kGaePer - 1) ? o0 + kGaePitch : o0 + j + 1];  // next thread's first / slot 4096
+            const float d = s_r[o0 + j] + gamma * vn - s_v[o0 + j];
+            s_r[o0 + j] = d;
+            run = static_cast<double>(d) + c * run;
+        }
+        // suffix-compose the per-thread affine maps: inclusive suffix scan inside the warp, then across the 8 warps
         Affine incl;
-        incl.mul = cpow[kGaePer];
-        incl.add = x[0];
+        incl.mul = c16;
+        incl.add = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const double om = __shfl_down_sync(0xffffffffu, incl.mul, o);
@@ -191,33 +244,55 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
             s_wadd[warp] = incl.add;
         }
         __syncthreads();
-        // carry entering this warp from the right = warps (warp+1 .. 7) applied to the tile carry
-        double cin = s_carry;
+        double cin = s_carry;  // carry entering this warp = warps to the right applied to the tile carry
         for (int w = kGaeThreads / 32 - 1; w > warp; --w) cin = s_wmul[w] * cin + s_wadd[w];
-        // carry entering this thread: lanes to the right inside the warp = exclusive suffix = incl of lane+1
         const double nm = __shfl_down_sync(0xffffffffu, incl.mul, 1);
         const double na = __shfl_down_sync(0xffffffffu, incl.add, 1);
         const double my_cin = (lane == 31) ? cin : (nm * cin + na);
         __syncthreads();
-        if (tid == 0) s_carry = s_wmul[0] * cin + s_wadd[0];  // warp == 0 here: carry into the next (left) tile
-        // final values, staged through shared memory for coalesced stores
+        if (tid == 0) s_carry = s_wmul[0] * cin + s_wadd[0];  // carry into the next (left) tile
+        // pass 2: the recurrence with the true carry-in
+        run = my_cin;
 #pragma unroll
-        for (int j = 0; j < kGaePer; ++j)
-            s_delta[tid * kGaePitch + j] = static_cast<float>(x[j] + cpow[kGaePer - j] * my_cin);
+        for (int j = kGaePer - 1; j >= 0; --j) {
+            run = static_cast<double>(s_r[o0 + j]) + c * run;
+            s_r[o0 + j] = static_cast<float>(run);
+        }
         __syncthreads();
+        auto moments_of = [&](float a, float m) {
+            const double md = static_cast<double>(m), ad = static_cast<double>(a);
+            sum_m += md;
+            sum_mx += md * ad;
+            sum_mxx += md * ad * ad;
+        };
+        if (vec) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int p = (k * kGaeThreads + tid) * 4;
+                const int64_t t = t0 + p;
+                if (t < A) {
+                    const int o = pad(p);
+                    const float4 a4 = make_float4(s_r[o], s_r[o + 1], s_r[o + 2], s_r[o + 3]);
+                    __stcs(reinterpret_cast<float4*>(adv_raw + base + t), a4);
+                    __stcs(reinterpret_cast<float4*>(returns + base + t),
+                           make_float4(a4.x + s_v[o], a4.y + s_v[o + 1], a4.z + s_v[o + 2], a4.w + s_v[o + 3]));
+                    moments_of(a4.x, mk[k].x);
+                    moments_of(a4.y, mk[k].y);
+                    moments_of(a4.z, mk[k].z);
+                    moments_of(a4.w, mk[k].w);
+                }
+            }
+        } else {
 #pragma unroll 4
-        for (int k = 0; k < kGaePer; ++k) {
-            const int p = k * kGaeThreads + tid;
-            const int64_t t = t0 + p;
-            if (t < A) {
-                const float a = s_delta[(p / kGaePer) * kGaePitch + (p % kGaePer)];
-                adv_raw[base + t] = a;
-                returns[base + t] = a + values[base + t];
-                const double m = static_cast<double>(mask_at<kMaskType>(mask, base + t));
-                const double ad = static_cast<double>(a);
-                sum_m += m;
-                sum_mx += m * ad;
-                sum_mxx += m * ad * ad;
+            for (int k = 0; k < kGaePer; ++k) {
+                const int p = k * kGaeThreads + tid;
+                const int64_t t = t0 + p;
+                if (t < A) {
+                    const float a = s_r[pad(p)];
+                    adv_raw[base + t] = a;
+                    returns[base + t] = a + s_v[pad(p)];
+                    moments_of(a, mask_at<kMaskType>(mask, base + t));
+                }
             }
         }
     }
@@ -228,6 +303,26 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
         row_stats[3 * row + 0] = sum_m;
         row_stats[3 * row + 1] = sum_mx;
         row_stats[3 * row + 2] = sum_mxx;
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == static_cast<unsigned int>(B) - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double n = 0.0, sx = 0.0, sxx = 0.0;  // same fixed order as fold_moments_kernel
+    for (int i = tid; i < B; i += kGaeThreads) {
+        n += __ldcg(&row_stats[3 * i + 0]);
+        sx += __ldcg(&row_stats[3 * i + 1]);
+        sxx += __ldcg(&row_stats[3 * i + 2]);
+    }
+    n = block_sum(n, sh_d);
+    sx = block_sum(sx, sh_d);
+    sxx = block_sum(sxx, sh_d);
+    if (tid == 0) {
+        moments[0] = n;
+        moments[1] = sx;
+        moments[2] = sxx;
+        *counter = 0u;
     }
 }
 
@@ -265,21 +360,56 @@ __global__ void whiten_stats_kernel(const double* __restrict__ moments, float* _
     stats_out[3] = static_cast<float>(1.0 / sqrt(static_cast<double>(static_cast<float>(var)) + 1e-8));
 }
 
-__global__ void __launch_bounds__(256) whiten_apply_kernel(float* __restrict__ x, const float* __restrict__ stats,
-                                                           int64_t n) {
-    const float mean = stats[1], rstd = stats[3];
+// moments -> {n, mean, var, rstd} exactly as whiten_stats_kernel computes them
+__device__ __forceinline__ void whiten_stats_of(const double* __restrict__ moments, float (&st)[4]) {
+    const double n = moments[0], sx = moments[1], sxx = moments[2];
+    const double den = fmax(n, 1.0);
+    const double mean = sx / den;
+    double var = (sxx - 2.0 * mean * sx + mean * mean * n) / den;
+    if (n > 1.0) var *= n / (n - 1.0);
+    st[0] = static_cast<float>(n);
+    st[1] = static_cast<float>(mean);
+    st[2] = static_cast<float>(var);
+    st[3] = static_cast<float>(1.0 / sqrt(static_cast<double>(static_cast<float>(var)) + 1e-8));
+}
+
+// x = (x - mean) * rstd in place; every block derives the statistics from the 3 moments itself (no separate
+// statistics launch), block 0 publishes them.  Four 128-bit loads in flight per thread.
+__global__ void __launch_bounds__(256) whiten_apply_kernel(float* __restrict__ x, const double* __restrict__ moments,
+                                                           float* __restrict__ stats_out, int64_t n) {
+    float st[4];
+    whiten_stats_of(moments, st);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        stats_out[0] = st[0];
+        stats_out[1] = st[1];
+        stats_out[2] = st[2];
+        stats_out[3] = st[3];
+    }
+    const float mean = st[1], rstd = st[3];
     const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (vec) {
         float4* x4 = reinterpret_cast<float4*>(x);
-        for (int64_t i = tid; i < n / 4; i += stride) {
-            float4 v = x4[i];
-            v.x = (v.x - mean) * rstd;
-            v.y = (v.y - mean) * rstd;
-            v.z = (v.z - mean) * rstd;
-            v.w = (v.w - mean) * rstd;
-            x4[i] = v;
+        const int64_t n4 = n / 4;
+        for (int64_t i0 = tid; i0 < n4; i0 += 4 * stride) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i < n4) v[u] = __ldcs(x4 + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i < n4) {
+                    v[u].x = (v[u].x - mean) * rstd;
+                    v[u].y = (v[u].y - mean) * rstd;
+                    v[u].z = (v[u].z - mean) * rstd;
+                    v[u].w = (v[u].w - mean) * rstd;
+                    __stcs(x4 + i, v[u]);
+                }
+            }
         }
     } else {
         for (int64_t i = tid; i < n; i += stride) x[i] = (x[i] - mean) * rstd;
@@ -487,15 +617,53 @@ reward_kl_kernel(const float* __restrict__ lp, const float* __restrict__ base_lp
     const int row = blockIdx.x;
     const int64_t base = static_cast<int64_t>(row) * A;
     float s_km = 0.f, s_m = 0.f, mx = 0.f;
-    for (int64_t t = threadIdx.x; t < A; t += blockDim.x) {
-        const int64_t i = base + t;
-        const float m = mask ? mask[i] : 1.f;
-        float kl = kl_value(lp[i], base_lp[i], kl_type);
+    auto one = [&](float l, float b, float m, float r) {
+        float kl = kl_value(l, b, kl_type);
         if (mask) kl *= m;
-        rewards_out[i] = rewards[i] - kl * coef;
         mx = fmaxf(mx, fabsf(kl));
         s_km = fmaf(kl, m, s_km);
         s_m += m;
+        return r - kl * coef;
+    };
+    const bool vec = (A % 4 == 0) &&
+                     (((reinterpret_cast<uintptr_t>(lp) | reinterpret_cast<uintptr_t>(base_lp) |
+                        reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(rewards) |
+                        reinterpret_cast<uintptr_t>(rewards_out)) & 15u) == 0);
+    if (vec) {
+        // two rounds of 128-bit loads (up to 8 requests) in flight per thread
+        const int64_t n4 = A / 4;
+        const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        for (int64_t i0 = threadIdx.x; i0 < n4; i0 += 2 * blockDim.x) {
+            float4 l[2], b[2], m[2], r[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int64_t i = i0 + u * blockDim.x;
+                if (i < n4) {
+                    const int64_t e = base + 4 * i;
+                    l[u] = __ldcs(reinterpret_cast<const float4*>(lp + e));
+                    b[u] = __ldcs(reinterpret_cast<const float4*>(base_lp + e));
+                    r[u] = __ldcs(reinterpret_cast<const float4*>(rewards + e));
+                    m[u] = mask ? __ldcs(reinterpret_cast<const float4*>(mask + e)) : one4;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int64_t i = i0 + u * blockDim.x;
+                if (i < n4) {
+                    float4 o;
+                    o.x = one(l[u].x, b[u].x, m[u].x, r[u].x);
+                    o.y = one(l[u].y, b[u].y, m[u].y, r[u].y);
+                    o.z = one(l[u].z, b[u].z, m[u].z, r[u].z);
+                    o.w = one(l[u].w, b[u].w, m[u].w, r[u].w);
+                    __stcs(reinterpret_cast<float4*>(rewards_out + base + 4 * i), o);
+                }
+            }
+        }
+    } else {
+        for (int64_t t = threadIdx.x; t < A; t += blockDim.x) {
+            const int64_t i = base + t;
+            rewards_out[i] = one(lp[i], base_lp[i], mask ? mask[i] : 1.f, rewards[i]);
+        }
     }
     s_km = block_sum(s_km, sh);
     s_m = block_sum(s_m, sh);
@@ -559,7 +727,7 @@ extern "C" int skyb200_group_advantage(const float* rewards, const void* respons
     return check_launch("group_broadcast_kernel");
 }
 
-extern "C" size_t skyb200_gae_workspace(int64_t B) { return (size_t)((B * 3 + 3) * sizeof(double) + 512); }
+extern "C" size_t skyb200_gae_workspace(int64_t B) { return (size_t)((B * 3 + 6) * sizeof(double) + 512); }
 
 extern "C" int skyb200_gae_scan(const float* rewards, const float* values, const void* response_mask,
                                 int32_t mask_type, float* adv_raw, float* returns, double* moments, void* workspace,
@@ -572,41 +740,41 @@ extern "C" int skyb200_gae_scan(const float* rewards, const float* values, const
     SKYB200_REQUIRE((reinterpret_cast<uintptr_t>(moments) & 7u) == 0, "moments must be 8-byte aligned");
     if (workspace_bytes < skyb200_gae_workspace(B)) return fail(SKYB200_EWORKSPACE, "gae workspace too small");
     double* row_stats = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    // completion counter of the last-block fold, behind the row stats and the 3 moments of skyb200_gae_advantage
+    unsigned int* counter = reinterpret_cast<unsigned int*>(row_stats + 3 * B + 4);
+    SKYB200_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
     switch (mask_type) {
         case SKYB200_MASK_F32:
             gae_scan_kernel<SKYB200_MASK_F32><<<(unsigned)B, kGaeThreads, 0, stream>>>(
-                rewards, values, response_mask, adv_raw, returns, row_stats, A, gamma, lambd);
+                rewards, values, response_mask, adv_raw, returns, row_stats, A, gamma, lambd, moments, counter, (int)B);
             break;
         case SKYB200_MASK_I64:
             gae_scan_kernel<SKYB200_MASK_I64><<<(unsigned)B, kGaeThreads, 0, stream>>>(
-                rewards, values, response_mask, adv_raw, returns, row_stats, A, gamma, lambd);
+                rewards, values, response_mask, adv_raw, returns, row_stats, A, gamma, lambd, moments, counter, (int)B);
             break;
         case SKYB200_MASK_NONE:
             gae_scan_kernel<SKYB200_MASK_NONE><<<(unsigned)B, kGaeThreads, 0, stream>>>(
-                rewards, values, response_mask, adv_raw, returns, row_stats, A, gamma, lambd);
+                rewards, values, response_mask, adv_raw, returns, row_stats, A, gamma, lambd, moments, counter, (int)B);
             break;
         default:
             return fail(SKYB200_EINVAL, "bad mask_type %d", mask_type);
     }
-    int rc = check_launch("gae_scan_kernel");
-    if (rc) return rc;
-    fold_moments_kernel<<<1, 256, 0, stream>>>(row_stats, (int)B, moments);
-    return check_launch("fold_moments_kernel");
+    return check_launch("gae_scan_kernel");
 }
 
 extern "C" int skyb200_whiten_from_moments(float* x, const double* moments, float* stats_out, int64_t n,
                                            void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SKYB200_REQUIRE(x && moments && stats_out, "null pointer");
-    whiten_stats_kernel<<<1, 32, 0, stream>>>(moments, stats_out);
-    int rc = check_launch("whiten_stats_kernel");
-    if (rc) return rc;
-    if (n == 0) return SKYB200_OK;
-    int64_t blocks = (n / 4 + 255) / 256;
+    if (n == 0) {
+        whiten_stats_kernel<<<1, 32, 0, stream>>>(moments, stats_out);
+        return check_launch("whiten_stats_kernel");
+    }
+    int64_t blocks = (n / 16 + 255) / 256;  // 4 x 128-bit accesses per thread
     const int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    whiten_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, stats_out, n);
+    whiten_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, moments, stats_out, n);
     return check_launch("whiten_apply_kernel");
 }
 

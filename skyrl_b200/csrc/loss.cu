@@ -11,6 +11,9 @@
 // Two launches: (1) per-row mask sums (+ the GSPO sequence log-ratio) and the global mask sum;
 // (2) the per-token pass that writes d_log_probs / d_entropy and reduces every scalar the worker reports.
 // All reductions are order-deterministic (per-block partials, last block folds them in index order).
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -20,6 +23,7 @@ constexpr int kLossThreads = 256;
 constexpr int kLossVec = 4;
 constexpr int kLossIters = 4;  // elements per block = 256 * 4 * 4 = 4096
 constexpr int kLossTile = kLossThreads * kLossVec * kLossIters;
+constexpr int kMaxMainGrid = 1024;
 constexpr int kNumPartials = 8;
 
 struct LossWs {
@@ -33,7 +37,7 @@ struct LossWs {
 
 static size_t loss_ws_layout(int64_t B, int64_t A, LossWs* ws, void* base) {
     const int64_t chunks = (A + kLossTile - 1) / kLossTile;
-    const int64_t blocks = B * chunks;
+    const int64_t blocks = B * chunks + kMaxMainGrid;  // the token pass runs on at most kMaxMainGrid blocks
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t o = off;
@@ -66,10 +70,50 @@ loss_rowstats_kernel(const float* __restrict__ lp, const float* __restrict__ olp
     const int64_t base = cu ? static_cast<int64_t>(cu[row]) : static_cast<int64_t>(row) * A;
     if (cu) A = static_cast<int64_t>(cu[row + 1]) - base;  // packed layout: this row's own length
     float ms = 0.f, lw = 0.f;
-    for (int64_t t = threadIdx.x; t < A; t += blockDim.x) {
-        const float m = mask ? mask[base + t] : 1.f;
-        ms += m;
-        if (need_lw) lw += (lp[base + t] - olp[base + t]) * m;
+    const bool al = ((base & 3) == 0) && (A % 4 == 0) && (mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 15u) == 0) &&
+                    (!need_lw || (((reinterpret_cast<uintptr_t>(lp) | reinterpret_cast<uintptr_t>(olp)) & 15u) == 0));
+    if (al && mask != nullptr) {
+        // 128-bit loads, four of them in flight per thread (plain loads: the mask stays in L2 for the token pass)
+        const float4* m4 = reinterpret_cast<const float4*>(mask + base);
+        const float4* l4 = reinterpret_cast<const float4*>(lp + base);
+        const float4* o4 = reinterpret_cast<const float4*>(olp + base);
+        const int64_t n4 = A / 4;
+        if (!need_lw) {
+            for (int64_t i0 = threadIdx.x; i0 < n4; i0 += 8 * blockDim.x) {
+                float4 m[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t i = i0 + u * blockDim.x;
+                    m[u] = (i < n4) ? __ldg(m4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ms += (m[u].x + m[u].y) + (m[u].z + m[u].w);
+            }
+        } else {
+            for (int64_t i0 = threadIdx.x; i0 < n4; i0 += 2 * blockDim.x) {
+                float4 m[2], a[2], b[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int64_t i = i0 + u * blockDim.x;
+                    const bool ok = i < n4;
+                    m[u] = ok ? __ldg(m4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    a[u] = ok ? __ldg(l4 + i) : m[u];
+                    b[u] = ok ? __ldg(o4 + i) : m[u];
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    lw += (a[u].x - b[u].x) * m[u].x + (a[u].y - b[u].y) * m[u].y + (a[u].z - b[u].z) * m[u].z +
+                          (a[u].w - b[u].w) * m[u].w;
+                    ms += (m[u].x + m[u].y) + (m[u].z + m[u].w);
+                }
+            }
+        }
+    } else {
+        for (int64_t t = threadIdx.x; t < A; t += blockDim.x) {
+            const float m = mask ? mask[base + t] : 1.f;
+            ms += m;
+            if (need_lw) lw += (lp[base + t] - olp[base + t]) * m;
+        }
     }
     ms = block_sum(ms, sh);
     if (need_lw) lw = block_sum(lw, sh);
@@ -154,12 +198,19 @@ struct TokenCtx {
 };
 
 // One response token: accumulates the reductions, returns d final_loss / d log_prob.
+// kType / kBase >= 0 fix the loss type / the presence of base log-probs at compile time (the [B, A] token pass is
+// instantiated per loss type: it is instruction-bound, not only memory-bound); -1 = decide at run time.
+template <int kType = -1, int kBase = -1>
 __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, float lp, float olp, float adv, float m,
                                             float base, float tis = 1.f, float cm = -1.f) {
+    const int loss_type = (kType >= 0) ? kType : loss_type;
+    const bool is_gspo = (kType >= 0) ? (kType == SKYB200_LOSS_GSPO) : cx.gspo;
+    const bool is_dual = (kType >= 0) ? (kType == SKYB200_LOSS_DUAL_CLIP) : cx.dual;
+    const bool has_base = (kBase >= 0) ? (kBase != 0) : cx.has_base;
     float ratio, loss, dl_dlp, clipped = 0.f;
-    if (cx.loss_type <= SKYB200_LOSS_GSPO) {
+    if (loss_type <= SKYB200_LOSS_GSPO) {
         float dr_dlp;
-        if (cx.gspo) {
+        if (is_gspo) {
             ratio = cx.seq_ratio;
             dr_dlp = cx.seq_ratio * cx.seq_pass;
         } else {
@@ -174,7 +225,7 @@ __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, fl
         // d loss / d ratio: torch.min splits ties 50/50 between its two arguments
         float dl_dr = (s1 < s2) ? -adv : ((s1 > s2) ? -adv * in_rng : -adv * (0.5f + 0.5f * in_rng));
         clipped = (s2 < s1) ? 1.f : 0.f;  // (-surr2 > -surr1), before dual clip
-        if (cx.dual && adv < 0.f) {
+        if (is_dual && adv < 0.f) {
             const float l3 = -adv * cx.clip_c;
             if (l3 < loss) {
                 loss = l3;
@@ -184,7 +235,7 @@ __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, fl
             }
         }
         dl_dlp = dl_dr * dr_dlp;
-    } else if (cx.loss_type == SKYB200_LOSS_SAPO) {
+    } else if (loss_type == SKYB200_LOSS_SAPO) {
         const float delta = lp - olp;
         ratio = expf(fminf(fmaxf(delta, -20.f), 20.f));
         const float dr_dlp = (delta >= -20.f && delta <= 20.f) ? ratio : 0.f;
@@ -192,17 +243,17 @@ __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, fl
         const float sg = 1.f / (1.f + expf(-tau * (ratio - 1.f)));
         loss = -(sg * (4.f / tau)) * adv;
         dl_dlp = -adv * 4.f * sg * (1.f - sg) * dr_dlp;
-    } else if (cx.loss_type == SKYB200_LOSS_CISPO) {
+    } else if (loss_type == SKYB200_LOSS_CISPO) {
         ratio = expf(fminf(fmaxf(lp - olp, -20.f), 20.f));
         const float rc = fminf(fmaxf(ratio, cx.lo), cx.hi);  // detached: acts as a per-token weight
         loss = -adv * rc * lp;
         dl_dlp = -adv * rc;
         clipped = (ratio < cx.lo || ratio > cx.hi) ? 1.f : 0.f;
-    } else if (cx.loss_type == SKYB200_LOSS_CROSS_ENTROPY) {
+    } else if (loss_type == SKYB200_LOSS_CROSS_ENTROPY) {
         ratio = 1.f;
         loss = -lp;
         dl_dlp = -1.f;
-    } else if (cx.loss_type == SKYB200_LOSS_KL_COV) {  // `tis` carries the per-token KL weight of the selection
+    } else if (loss_type == SKYB200_LOSS_KL_COV) {  // `tis` carries the per-token KL weight of the selection
         const float d = lp - olp;
         ratio = expf(d);
         loss = fmaf(tis, fabsf(d), -ratio * adv);
@@ -224,7 +275,7 @@ __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, fl
         acc.r_min = fminf(acc.r_min, ratio);
     }
     float g = w * dl_dlp;
-    if (cx.has_base) {
+    if (has_base) {
         float dk;
         const float kl = kl_estimate(lp, base, cx.kl_type, &dk);
         const float km = cx.has_mask ? kl * m : kl;  // compute_approx_kl multiplies by the mask ...
@@ -234,109 +285,165 @@ __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, fl
     return g;
 }
 
-__global__ void __launch_bounds__(kLossThreads) loss_main_kernel(LossArgs a) {
+// One 1024-position tile of one row as a thread sees it: 4 positions (consecutive in the 128-bit path, strided by the
+// block size otherwise) of every input, plus the row's normalisers.
+constexpr int kMainTile = kLossThreads * 4;
+struct TileIn {
+    float lp[4], olp[4], adv[4], m[4], bs[4], en[4], ti[4], cm[4];
+    int64_t i0;        // flat index of component 0; component u sits at i0 + u * stride
+    unsigned ok;       // bit u set = component u is a real position
+    float row_m, row_lw;
+};
+
+__device__ __forceinline__ void ld4(const float* p, int64_t i, float (&dst)[4]) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(p + i));
+    dst[0] = v.x;
+    dst[1] = v.y;
+    dst[2] = v.z;
+    dst[3] = v.w;
+}
+
+__device__ __forceinline__ void tile_load(const LossArgs& a, int64_t tile, int64_t total_tiles, int64_t tiles_per_row,
+                                          bool gspo, TileIn& d) {
+    d.ok = 0u;
+    d.i0 = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        d.lp[u] = d.olp[u] = d.adv[u] = d.m[u] = d.bs[u] = d.en[u] = 0.f;
+        d.ti[u] = 1.f;
+        d.cm[u] = -1.f;
+    }
+    if (tile >= total_tiles) return;
+    const int row = static_cast<int>(tile / tiles_per_row);
+    const int64_t t0 = (tile - static_cast<int64_t>(row) * tiles_per_row) * kMainTile;
+    const int64_t rbase = static_cast<int64_t>(row) * a.A;
+    if (a.vec4) {
+        const int64_t t = t0 + static_cast<int64_t>(threadIdx.x) * 4;
+        if (t >= a.A) return;
+        const int64_t i = rbase + t;
+        ld4(a.lp, i, d.lp);
+        ld4(a.olp, i, d.olp);
+        ld4(a.adv, i, d.adv);
+        if (a.mask) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(a.mask + i));  // L2 hit after the row-stats pass
+            d.m[0] = v.x, d.m[1] = v.y, d.m[2] = v.z, d.m[3] = v.w;
+        } else {
+            d.m[0] = d.m[1] = d.m[2] = d.m[3] = 1.f;
+        }
+        if (a.base) ld4(a.base, i, d.bs);
+        if (a.ent) ld4(a.ent, i, d.en);
+        if (a.tis) ld4(a.tis, i, d.ti);
+        if (a.clip_mask) ld4(a.clip_mask, i, d.cm);
+        d.ok = 0xFu;
+        d.i0 = i;
+    } else {
+        d.i0 = rbase + t0 + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t t = t0 + static_cast<int64_t>(u) * kLossThreads + threadIdx.x;
+            if (t < a.A) {
+                const int64_t i = rbase + t;
+                d.ok |= 1u << u;
+                d.lp[u] = a.lp[i];
+                d.olp[u] = a.olp[i];
+                d.adv[u] = a.adv[i];
+                d.m[u] = a.mask ? a.mask[i] : 1.f;
+                if (a.base) d.bs[u] = a.base[i];
+                if (a.ent) d.en[u] = a.ent[i];
+                if (a.tis) d.ti[u] = a.tis[i];
+                if (a.clip_mask) d.cm[u] = a.clip_mask[i];
+            }
+        }
+    }
+    if (d.ok) {
+        d.row_m = __ldcg(&a.ws.row_msum[row]);
+        d.row_lw = gspo ? __ldcg(&a.ws.row_lw[row]) : 0.f;
+    }
+}
+
+// Persistent grid (a few blocks per SM): every block walks 1024-position tiles with a grid stride, two tiles in
+// flight per thread (all loads of both tiles are issued before the first is consumed), one block reduction at the end.
+template <int kInFlight, int kMinBlocks, int kType, int kBase>
+__global__ void __launch_bounds__(kLossThreads, kMinBlocks) loss_main_kernel(LossArgs a) {
     __shared__ float sh[34];
     __shared__ bool is_last;
-    const int row = blockIdx.y;
     const int64_t A = a.A;
-    const int64_t rbase = static_cast<int64_t>(row) * A;
     const float total_m = __ldcg(a.ws.total_msum);
-    const float row_m = __ldcg(&a.ws.row_msum[row]);
     const float Bf = static_cast<float>(a.B);
     const float inv_total = 1.f / fmaxf(total_m, 1.f);
-    const float inv_row = 1.f / fmaxf(row_m, 1.f);
-    float w_scale;
-    if (a.p.reduction == SKYB200_REDUCE_TOKEN_MEAN)
-        w_scale = inv_total;
-    else if (a.p.reduction == SKYB200_REDUCE_SEQUENCE_MEAN)
-        w_scale = inv_row / Bf;
-    else if (a.p.reduction == SKYB200_REDUCE_SUM)
-        w_scale = 1.f;
-    else
-        w_scale = 1.f / (a.p.max_seq_len * Bf);
-    const float kl_scale = inv_row / Bf;
     const bool gspo = (a.p.loss_type == SKYB200_LOSS_GSPO);
-    const bool dual = (a.p.loss_type == SKYB200_LOSS_DUAL_CLIP);
-    const float lo = 1.f - a.p.eps_clip_low, hi = 1.f + a.p.eps_clip_high;
-    float seq_ratio = 1.f, seq_pass = 1.f;
-    if (gspo) {
-        const float lw = __ldcg(&a.ws.row_lw[row]);
-        seq_ratio = expf(fminf(lw, 10.f));
-        seq_pass = (lw <= 10.f) ? 1.f : 0.f;
-    }
     const bool use_ent_loss = (a.p.use_entropy_loss != 0);
 
     LossAcc acc;
     TokenCtx cx;
     cx.gspo = gspo;
-    cx.dual = dual;
-    cx.lo = lo;
-    cx.hi = hi;
-    cx.seq_ratio = seq_ratio;
-    cx.seq_pass = seq_pass;
-    cx.w_scale = w_scale;
-    cx.kl_scale = kl_scale;
+    cx.dual = (a.p.loss_type == SKYB200_LOSS_DUAL_CLIP);
+    cx.lo = 1.f - a.p.eps_clip_low;
+    cx.hi = 1.f + a.p.eps_clip_high;
+    cx.seq_ratio = 1.f;
+    cx.seq_pass = 1.f;
     cx.clip_c = a.p.clip_ratio_c;
     cx.kl_type = a.p.kl_type;
     cx.loss_type = a.p.loss_type;
     cx.tau_pos = a.p.sapo_tau_pos;
     cx.tau_neg = a.p.sapo_tau_neg;
-    cx.kl_grad_scale = a.p.kl_has_grad ? a.p.kl_loss_coef * kl_scale : 0.f;
     cx.has_mask = (a.mask != nullptr);
     cx.has_base = (a.base != nullptr);
     cx.d_ent_val = use_ent_loss ? -a.p.entropy_loss_coef * inv_total : 0.f;
 
-    const int64_t t0 = static_cast<int64_t>(blockIdx.x) * kLossTile;
-    if (a.vec4) {
-        // 128-bit path: every array is 16-byte aligned and A % 4 == 0, so rows start on 16-byte boundaries
+    auto consume = [&](const TileIn& d) {
+        if (!d.ok) return;
+        const float inv_row = 1.f / fmaxf(d.row_m, 1.f);
+        if (a.p.reduction == SKYB200_REDUCE_TOKEN_MEAN)
+            cx.w_scale = inv_total;
+        else if (a.p.reduction == SKYB200_REDUCE_SEQUENCE_MEAN)
+            cx.w_scale = inv_row / Bf;
+        else if (a.p.reduction == SKYB200_REDUCE_SUM)
+            cx.w_scale = 1.f;
+        else
+            cx.w_scale = 1.f / (a.p.max_seq_len * Bf);
+        cx.kl_scale = inv_row / Bf;
+        cx.kl_grad_scale = a.p.kl_has_grad ? a.p.kl_loss_coef * cx.kl_scale : 0.f;
+        if (gspo) {
+            cx.seq_ratio = expf(fminf(d.row_lw, 10.f));
+            cx.seq_pass = (d.row_lw <= 10.f) ? 1.f : 0.f;
+        }
+        float g[4];
 #pragma unroll
-        for (int it = 0; it < kLossIters; ++it) {
-            const int64_t t = t0 + (static_cast<int64_t>(it) * kLossThreads + threadIdx.x) * 4;
-            if (t < A) {
-                const int64_t i = rbase + t;
-                const float4 lp = ldg_stream(reinterpret_cast<const float4*>(a.lp + i));
-                const float4 olp = ldg_stream(reinterpret_cast<const float4*>(a.olp + i));
-                const float4 adv = ldg_stream(reinterpret_cast<const float4*>(a.adv + i));
-                float4 m = make_float4(1.f, 1.f, 1.f, 1.f), bs = make_float4(0.f, 0.f, 0.f, 0.f), en = bs;
-                if (a.mask) m = ldg_stream(reinterpret_cast<const float4*>(a.mask + i));
-                if (a.base) bs = ldg_stream(reinterpret_cast<const float4*>(a.base + i));
-                if (a.ent) en = ldg_stream(reinterpret_cast<const float4*>(a.ent + i));
-                float4 ti = make_float4(1.f, 1.f, 1.f, 1.f), cm = make_float4(-1.f, -1.f, -1.f, -1.f);
-                if (a.tis) ti = ldg_stream(reinterpret_cast<const float4*>(a.tis + i));
-                if (a.clip_mask) cm = ldg_stream(reinterpret_cast<const float4*>(a.clip_mask + i));
-                float4 g;
-                g.x = loss_token(cx, acc, lp.x, olp.x, adv.x, m.x, bs.x, ti.x, cm.x);
-                g.y = loss_token(cx, acc, lp.y, olp.y, adv.y, m.y, bs.y, ti.y, cm.y);
-                g.z = loss_token(cx, acc, lp.z, olp.z, adv.z, m.z, bs.z, ti.z, cm.z);
-                g.w = loss_token(cx, acc, lp.w, olp.w, adv.w, m.w, bs.w, ti.w, cm.w);
-                if (a.d_lp) *reinterpret_cast<float4*>(a.d_lp + i) = g;
-                if (a.ent) {
-                    acc.s_ent = fmaf(en.x, m.x, acc.s_ent);
-                    acc.s_ent = fmaf(en.y, m.y, acc.s_ent);
-                    acc.s_ent = fmaf(en.z, m.z, acc.s_ent);
-                    acc.s_ent = fmaf(en.w, m.w, acc.s_ent);
-                    if (a.d_ent)
-                        *reinterpret_cast<float4*>(a.d_ent + i) =
-                            make_float4(cx.d_ent_val * m.x, cx.d_ent_val * m.y, cx.d_ent_val * m.z, cx.d_ent_val * m.w);
+        for (int u = 0; u < 4; ++u) {
+            g[u] = 0.f;
+            if (d.ok >> u & 1u) {
+                g[u] = loss_token<kType, kBase>(cx, acc, d.lp[u], d.olp[u], d.adv[u], d.m[u], d.bs[u], d.ti[u], d.cm[u]);
+                if (a.ent) acc.s_ent = fmaf(d.en[u], d.m[u], acc.s_ent);
+            }
+        }
+        if (a.vec4) {
+            if (a.d_lp) __stcs(reinterpret_cast<float4*>(a.d_lp + d.i0), make_float4(g[0], g[1], g[2], g[3]));
+            if (a.ent && a.d_ent)
+                __stcs(reinterpret_cast<float4*>(a.d_ent + d.i0),
+                       make_float4(cx.d_ent_val * d.m[0], cx.d_ent_val * d.m[1], cx.d_ent_val * d.m[2],
+                                   cx.d_ent_val * d.m[3]));
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (d.ok >> u & 1u) {
+                    const int64_t i = d.i0 + static_cast<int64_t>(u) * kLossThreads;
+                    if (a.d_lp) a.d_lp[i] = g[u];
+                    if (a.ent && a.d_ent) a.d_ent[i] = cx.d_ent_val * d.m[u];
                 }
             }
         }
-    } else {
-#pragma unroll 4
-        for (int it = 0; it < kLossIters * kLossVec; ++it) {
-            const int64_t t = t0 + static_cast<int64_t>(it) * kLossThreads + threadIdx.x;
-            if (t < A) {
-                const int64_t i = rbase + t;
-                const float m = a.mask ? a.mask[i] : 1.f;
-                const float g = loss_token(cx, acc, a.lp[i], a.olp[i], a.adv[i], m, a.base ? a.base[i] : 0.f,
-                                           a.tis ? a.tis[i] : 1.f, a.clip_mask ? a.clip_mask[i] : -1.f);
-                if (a.d_lp) a.d_lp[i] = g;
-                if (a.ent) {
-                    acc.s_ent = fmaf(a.ent[i], m, acc.s_ent);
-                    if (a.d_ent) a.d_ent[i] = cx.d_ent_val * m;
-                }
-            }
-        }
+    };
+
+    const int64_t tiles_per_row = (A + kMainTile - 1) / kMainTile;
+    const int64_t total_tiles = tiles_per_row * a.B;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += kInFlight * static_cast<int64_t>(gridDim.x)) {
+        TileIn d[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u)
+            tile_load(a, tile + static_cast<int64_t>(u) * gridDim.x, total_tiles, tiles_per_row, gspo, d[u]);
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) consume(d[u]);
     }
     float s_loss = acc.s_loss, s_clip = acc.s_clip, s_kl = acc.s_kl, s_ent = acc.s_ent, s_ratio = acc.s_ratio;
     float r_max = acc.r_max, r_min = acc.r_min;
@@ -872,8 +979,29 @@ extern "C" int skyb200_policy_loss(const float* log_probs, const float* old_log_
     a.vec4 = (A % 4 == 0) && al16(log_probs) && al16(old_log_probs) && al16(advantages) && al16(loss_mask) &&
              al16(base_log_probs) && al16(entropy) && al16(d_log_probs) && al16(d_entropy) && al16(tis) &&
              al16(clip_mask);
-    const unsigned chunks = (unsigned)((A + kLossTile - 1) / kLossTile);
-    loss_main_kernel<<<dim3(chunks, (unsigned)B), kLossThreads, 0, stream>>>(a);
+    const int64_t tiles = ((A + kLossThreads * 4 - 1) / (kLossThreads * 4)) * B;
+    const unsigned grid = (unsigned)std::max<int64_t>(
+        1, std::min<int64_t>(tiles, std::min<int64_t>((int64_t)num_sms() * 4, (int64_t)kMaxMainGrid)));
+#define SKYB200_LOSS_CASE(T)                                                                  \
+    case T:                                                                                   \
+        if (base_log_probs)                                                                   \
+            loss_main_kernel<1, 4, T, 1><<<grid, kLossThreads, 0, stream>>>(a);               \
+        else                                                                                  \
+            loss_main_kernel<1, 4, T, 0><<<grid, kLossThreads, 0, stream>>>(a);               \
+        break;
+    switch (params->loss_type) {
+        SKYB200_LOSS_CASE(SKYB200_LOSS_REGULAR)
+        SKYB200_LOSS_CASE(SKYB200_LOSS_DUAL_CLIP)
+        SKYB200_LOSS_CASE(SKYB200_LOSS_GSPO)
+        SKYB200_LOSS_CASE(SKYB200_LOSS_SAPO)
+        SKYB200_LOSS_CASE(SKYB200_LOSS_CISPO)
+        SKYB200_LOSS_CASE(SKYB200_LOSS_CROSS_ENTROPY)
+        SKYB200_LOSS_CASE(SKYB200_LOSS_IMPORTANCE_SAMPLING)
+        SKYB200_LOSS_CASE(SKYB200_LOSS_KL_COV)
+        default:
+            return fail(SKYB200_EINVAL, "bad loss_type %d", params->loss_type);
+    }
+#undef SKYB200_LOSS_CASE
     return check_launch("loss_main_kernel");
 }
 
