@@ -451,21 +451,17 @@ rpp_scan_kernel(const float* __restrict__ rewards, const void* __restrict__ mask
             s_mul[o] = c;
         }
         __syncthreads();
-        double x[kGaePer], pr[kGaePer];  // local scan and the product of multipliers from j to the segment end
-        {
-            double run = 0.0, prod = 1.0;
+        // pass 1: this thread's 16 positions with zero carry-in -> its affine map (product of multipliers, local sum)
+        double run = 0.0, prod = 1.0;
 #pragma unroll
-            for (int j = kGaePer - 1; j >= 0; --j) {
-                const double c = static_cast<double>(s_mul[tid * kGaePitch + j]);
-                run = static_cast<double>(s_val[tid * kGaePitch + j]) + c * run;
-                prod *= c;
-                x[j] = run;
-                pr[j] = prod;
-            }
+        for (int j = kGaePer - 1; j >= 0; --j) {
+            const double c = static_cast<double>(s_mul[tid * kGaePitch + j]);
+            run = static_cast<double>(s_val[tid * kGaePitch + j]) + c * run;
+            prod *= c;
         }
         Affine incl;
-        incl.mul = pr[0];
-        incl.add = x[0];
+        incl.mul = prod;
+        incl.add = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const double om = __shfl_down_sync(0xffffffffu, incl.mul, o);
@@ -489,8 +485,13 @@ rpp_scan_kernel(const float* __restrict__ rewards, const void* __restrict__ mask
         const double my_cin = (lane == 31) ? cin : (nm * cin + na);
         __syncthreads();
         if (tid == 0) s_carry = s_wmul[0] * cin + s_wadd[0];
+        // pass 2: the recurrence again with the true carry-in (no 2 x 16 fp64 register arrays)
+        run = my_cin;
 #pragma unroll
-        for (int j = 0; j < kGaePer; ++j) s_val[tid * kGaePitch + j] = static_cast<float>(x[j] + pr[j] * my_cin);
+        for (int j = kGaePer - 1; j >= 0; --j) {
+            run = static_cast<double>(s_val[tid * kGaePitch + j]) + static_cast<double>(s_mul[tid * kGaePitch + j]) * run;
+            s_val[tid * kGaePitch + j] = static_cast<float>(run);
+        }
         __syncthreads();
 #pragma unroll 4
         for (int k = 0; k < kGaePer; ++k) {
