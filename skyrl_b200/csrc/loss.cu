@@ -303,8 +303,8 @@ __device__ __forceinline__ void ld4(const float* p, int64_t i, float (&dst)[4]) 
     dst[3] = v.w;
 }
 
-__device__ __forceinline__ void tile_load(const LossArgs& a, int64_t tile, int64_t total_tiles, int64_t tiles_per_row,
-                                          bool gspo, TileIn& d) {
+__device__ __forceinline__ void tile_load(const LossArgs& a, int row, int tile_in_row, bool valid, bool gspo,
+                                          TileIn& d) {
     d.ok = 0u;
     d.i0 = 0;
 #pragma unroll
@@ -313,9 +313,8 @@ __device__ __forceinline__ void tile_load(const LossArgs& a, int64_t tile, int64
         d.ti[u] = 1.f;
         d.cm[u] = -1.f;
     }
-    if (tile >= total_tiles) return;
-    const int row = static_cast<int>(tile / tiles_per_row);
-    const int64_t t0 = (tile - static_cast<int64_t>(row) * tiles_per_row) * kMainTile;
+    if (!valid) return;
+    const int64_t t0 = static_cast<int64_t>(tile_in_row) * kMainTile;
     const int64_t rbase = static_cast<int64_t>(row) * a.A;
     if (a.vec4) {
         const int64_t t = t0 + static_cast<int64_t>(threadIdx.x) * 4;
@@ -435,13 +434,22 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) loss_main_kernel(Los
         }
     };
 
-    const int64_t tiles_per_row = (A + kMainTile - 1) / kMainTile;
-    const int64_t total_tiles = tiles_per_row * a.B;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += kInFlight * static_cast<int64_t>(gridDim.x)) {
+    // (row, tile-in-row) advance incrementally by the grid stride: no 64-bit divisions inside the loop
+    const unsigned tiles_per_row = static_cast<unsigned>((A + kMainTile - 1) / kMainTile);
+    const unsigned step_rows = gridDim.x / tiles_per_row, step_tiles = gridDim.x % tiles_per_row;
+    unsigned row = blockIdx.x / tiles_per_row, tir = blockIdx.x % tiles_per_row;
+    while (row < static_cast<unsigned>(a.B)) {
         TileIn d[kInFlight];
 #pragma unroll
-        for (int u = 0; u < kInFlight; ++u)
-            tile_load(a, tile + static_cast<int64_t>(u) * gridDim.x, total_tiles, tiles_per_row, gspo, d[u]);
+        for (int u = 0; u < kInFlight; ++u) {
+            tile_load(a, static_cast<int>(row), static_cast<int>(tir), row < static_cast<unsigned>(a.B), gspo, d[u]);
+            row += step_rows;
+            tir += step_tiles;
+            if (tir >= tiles_per_row) {
+                tir -= tiles_per_row;
+                ++row;
+            }
+        }
 #pragma unroll
         for (int u = 0; u < kInFlight; ++u) consume(d[u]);
     }
