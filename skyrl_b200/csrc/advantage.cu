@@ -24,6 +24,7 @@ __device__ __forceinline__ float mask_at(const void* mask, int64_t i) {
 __global__ void __launch_bounds__(256) row_sum_kernel(const float* __restrict__ x, float* __restrict__ scores,
                                                       int64_t A) {
     __shared__ float sh[34];
+    pdl_launch_dependents();  // the broadcast pass may start prefetching its mask tiles while this one still runs
     const int64_t base = static_cast<int64_t>(blockIdx.x) * A;
     float s = 0.f;
     const bool vec = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
@@ -80,6 +81,7 @@ group_broadcast_kernel(const float* __restrict__ scores, const void* __restrict_
     const int g = group_of_row[row];
     const int beg = group_start[g], end = group_start[g + 1];
     const int n = end - beg;
+    pdl_wait();  // the row sums of the preceding kernel are complete and visible from here on
     float value;
     {
         float s = 0.f;
@@ -156,6 +158,7 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     __shared__ double s_carry;
     __shared__ double sh_d[34];
     __shared__ bool is_last;
+    pdl_launch_dependents();  // lets the whitening pass get scheduled behind the last blocks of the scan
     const int row = blockIdx.x;
     const int64_t base = static_cast<int64_t>(row) * A;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -377,6 +380,7 @@ __device__ __forceinline__ void whiten_stats_of(const double* __restrict__ momen
 // statistics launch), block 0 publishes them.  Four 128-bit loads in flight per thread.
 __global__ void __launch_bounds__(256) whiten_apply_kernel(float* __restrict__ x, const double* __restrict__ moments,
                                                            float* __restrict__ stats_out, int64_t n) {
+    pdl_wait();  // moments (and x itself) come from the preceding scan
     float st[4];
     whiten_stats_of(moments, st);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -615,6 +619,7 @@ reward_kl_kernel(const float* __restrict__ lp, const float* __restrict__ base_lp
                  const float* __restrict__ rewards, float* __restrict__ rewards_out, float* __restrict__ row_mean,
                  float* __restrict__ row_max, int64_t A, int kl_type, float coef) {
     __shared__ float sh[34];
+    pdl_launch_dependents();
     const int row = blockIdx.x;
     const int64_t base = static_cast<int64_t>(row) * A;
     float s_km = 0.f, s_m = 0.f, mx = 0.f;
@@ -678,6 +683,7 @@ reward_kl_kernel(const float* __restrict__ lp, const float* __restrict__ base_lp
 __global__ void __launch_bounds__(256) row_means_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                         int B, float* __restrict__ out) {
     __shared__ float sh[34];
+    pdl_wait();  // per-row results of the preceding kernel
     float sa = 0.f, sb = 0.f;
     for (int i = threadIdx.x; i < B; i += blockDim.x) {
         sa += a[i];
@@ -711,16 +717,19 @@ extern "C" int skyb200_group_advantage(const float* rewards, const void* respons
     const dim3 grid((unsigned)((A + kBcastTile - 1) / kBcastTile), (unsigned)B);
     switch (mask_type) {
         case SKYB200_MASK_F32:
-            group_broadcast_kernel<SKYB200_MASK_F32><<<grid, 256, 0, stream>>>(
-                scores_ws, response_mask, group_of_row, group_start, group_rows, out, A, mode, epsilon);
+            SKYB200_CUDA_CHECK(launch_pdl(group_broadcast_kernel<SKYB200_MASK_F32>, grid, dim3(256), 0, stream,
+                                          scores_ws, response_mask, group_of_row, group_start, group_rows, out, A,
+                                          mode, epsilon));
             break;
         case SKYB200_MASK_I64:
-            group_broadcast_kernel<SKYB200_MASK_I64><<<grid, 256, 0, stream>>>(
-                scores_ws, response_mask, group_of_row, group_start, group_rows, out, A, mode, epsilon);
+            SKYB200_CUDA_CHECK(launch_pdl(group_broadcast_kernel<SKYB200_MASK_I64>, grid, dim3(256), 0, stream,
+                                          scores_ws, response_mask, group_of_row, group_start, group_rows, out, A,
+                                          mode, epsilon));
             break;
         case SKYB200_MASK_NONE:
-            group_broadcast_kernel<SKYB200_MASK_NONE><<<grid, 256, 0, stream>>>(
-                scores_ws, response_mask, group_of_row, group_start, group_rows, out, A, mode, epsilon);
+            SKYB200_CUDA_CHECK(launch_pdl(group_broadcast_kernel<SKYB200_MASK_NONE>, grid, dim3(256), 0, stream,
+                                          scores_ws, response_mask, group_of_row, group_start, group_rows, out, A,
+                                          mode, epsilon));
             break;
         default:
             return fail(SKYB200_EINVAL, "bad mask_type %d", mask_type);
@@ -775,7 +784,8 @@ extern "C" int skyb200_whiten_from_moments(float* x, const double* moments, floa
     const int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    whiten_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, moments, stats_out, n);
+    SKYB200_CUDA_CHECK(launch_pdl(whiten_apply_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, moments,
+                                  stats_out, n));
     return check_launch("whiten_apply_kernel");
 }
 
@@ -806,7 +816,8 @@ extern "C" int skyb200_reward_kl_penalty(const float* log_probs, const float* ba
                                                       row_ws, row_ws + B, A, kl_type, coef);
     int rc = check_launch("reward_kl_kernel");
     if (rc) return rc;
-    row_means_kernel<<<1, 256, 0, stream>>>(row_ws, row_ws + B, (int)B, metrics_out);
+    SKYB200_CUDA_CHECK(launch_pdl(row_means_kernel, dim3(1), dim3(256), 0, stream, (const float*)row_ws,
+                                  (const float*)(row_ws + B), (int)B, metrics_out));
     return check_launch("row_means_kernel");
 }
 

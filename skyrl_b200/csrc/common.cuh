@@ -40,6 +40,28 @@ inline int check_launch(const char* what) {
 
 int num_sms();  // cached SM count of the current device
 
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still running; it must call pdl_wait() before touching anything the predecessor writes.  The predecessor
+// calls pdl_launch_dependents() as early as it likes (it only releases the launch, not the data).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers shared by the memory-bound kernels
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

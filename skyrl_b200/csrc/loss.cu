@@ -66,6 +66,7 @@ loss_rowstats_kernel(const float* __restrict__ lp, const float* __restrict__ olp
                      const int32_t* __restrict__ cu = nullptr) {
     __shared__ float sh[34];
     __shared__ bool is_last;
+    pdl_launch_dependents();  // the token pass may be scheduled while this pre-pass drains (it waits before reading)
     const int row = blockIdx.x;
     const int64_t base = cu ? static_cast<int64_t>(cu[row]) : static_cast<int64_t>(row) * A;
     if (cu) A = static_cast<int64_t>(cu[row + 1]) - base;  // packed layout: this row's own length
@@ -366,6 +367,7 @@ template <int kInFlight, int kMinBlocks, int kType, int kBase>
 __global__ void __launch_bounds__(kLossThreads, kMinBlocks) loss_main_kernel(LossArgs a) {
     __shared__ float sh[34];
     __shared__ bool is_last;
+    pdl_wait();  // row / total mask sums of the pre-pass are complete and visible
     const int64_t A = a.A;
     const float total_m = __ldcg(a.ws.total_msum);
     const float Bf = static_cast<float>(a.B);
@@ -993,9 +995,9 @@ extern "C" int skyb200_policy_loss(const float* log_probs, const float* old_log_
 #define SKYB200_LOSS_CASE(T)                                                                  \
     case T:                                                                                   \
         if (base_log_probs)                                                                   \
-            loss_main_kernel<1, 4, T, 1><<<grid, kLossThreads, 0, stream>>>(a);               \
+            SKYB200_CUDA_CHECK(launch_pdl(loss_main_kernel<1, 4, T, 1>, dim3(grid), dim3(kLossThreads), 0, stream, a)); \
         else                                                                                  \
-            loss_main_kernel<1, 4, T, 0><<<grid, kLossThreads, 0, stream>>>(a);               \
+            SKYB200_CUDA_CHECK(launch_pdl(loss_main_kernel<1, 4, T, 0>, dim3(grid), dim3(kLossThreads), 0, stream, a)); \
         break;
     switch (params->loss_type) {
         SKYB200_LOSS_CASE(SKYB200_LOSS_REGULAR)
