@@ -201,7 +201,8 @@ struct TokenCtx {
 // One response token: accumulates the reductions, returns d final_loss / d log_prob.
 // kType / kBase >= 0 fix the loss type / the presence of base log-probs at compile time (the [B, A] token pass is
 // instantiated per loss type: it is instruction-bound, not only memory-bound); -1 = decide at run time.
-template <int kType = -1, int kBase = -1>
+// kKl == SKYB200_KL_K3 additionally fixes "k3 estimator, KL term without gradient" (the reference's KL loss).
+template <int kType = -1, int kBase = -1, int kKl = -1>
 __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, float lp, float olp, float adv, float m,
                                             float base, float tis = 1.f, float cm = -1.f) {
     const int loss_type = (kType >= 0) ? kType : loss_type;
@@ -277,11 +278,18 @@ __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, fl
     }
     float g = w * dl_dlp;
     if (has_base) {
-        float dk;
-        const float kl = kl_estimate(lp, base, cx.kl_type, &dk);
-        const float km = cx.has_mask ? kl * m : kl;  // compute_approx_kl multiplies by the mask ...
-        acc.s_kl = fmaf(km * m, cx.kl_scale, acc.s_kl);  // ... and masked_mean multiplies again
-        g = fmaf(cx.kl_grad_scale * m * (cx.has_mask ? m : 1.f), dk, g);
+        if constexpr (kKl == SKYB200_KL_K3) {  // value only: same arithmetic as kl_estimate's k3 branch
+            const float x = fminf(fmaxf(base - lp, -20.f), 20.f);
+            const float kl = fminf(fmaxf(expf(x) - x - 1.f, -10.f), 10.f);
+            const float km = cx.has_mask ? kl * m : kl;
+            acc.s_kl = fmaf(km * m, cx.kl_scale, acc.s_kl);
+        } else {
+            float dk;
+            const float kl = kl_estimate(lp, base, cx.kl_type, &dk);
+            const float km = cx.has_mask ? kl * m : kl;  // compute_approx_kl multiplies by the mask ...
+            acc.s_kl = fmaf(km * m, cx.kl_scale, acc.s_kl);  // ... and masked_mean multiplies again
+            g = fmaf(cx.kl_grad_scale * m * (cx.has_mask ? m : 1.f), dk, g);
+        }
     }
     return g;
 }
@@ -304,22 +312,16 @@ __device__ __forceinline__ void ld4(const float* p, int64_t i, float (&dst)[4]) 
     dst[3] = v.w;
 }
 
+template <bool kVec>
 __device__ __forceinline__ void tile_load(const LossArgs& a, int row, int tile_in_row, bool valid, bool gspo,
                                           TileIn& d) {
     d.ok = 0u;
-    d.i0 = 0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        d.lp[u] = d.olp[u] = d.adv[u] = d.m[u] = d.bs[u] = d.en[u] = 0.f;
-        d.ti[u] = 1.f;
-        d.cm[u] = -1.f;
-    }
     if (!valid) return;
     const int64_t t0 = static_cast<int64_t>(tile_in_row) * kMainTile;
     const int64_t rbase = static_cast<int64_t>(row) * a.A;
-    if (a.vec4) {
+    if constexpr (kVec) {
         const int64_t t = t0 + static_cast<int64_t>(threadIdx.x) * 4;
-        if (t >= a.A) return;
+        if (t >= a.A) return;  // consume() skips tiles with ok == 0: nothing else needs a value
         const int64_t i = rbase + t;
         ld4(a.lp, i, d.lp);
         ld4(a.olp, i, d.olp);
@@ -332,8 +334,16 @@ __device__ __forceinline__ void tile_load(const LossArgs& a, int row, int tile_i
         }
         if (a.base) ld4(a.base, i, d.bs);
         if (a.ent) ld4(a.ent, i, d.en);
-        if (a.tis) ld4(a.tis, i, d.ti);
-        if (a.clip_mask) ld4(a.clip_mask, i, d.cm);
+        if (a.tis) {
+            ld4(a.tis, i, d.ti);
+        } else {
+            d.ti[0] = d.ti[1] = d.ti[2] = d.ti[3] = 1.f;
+        }
+        if (a.clip_mask) {
+            ld4(a.clip_mask, i, d.cm);
+        } else {
+            d.cm[0] = d.cm[1] = d.cm[2] = d.cm[3] = -1.f;
+        }
         d.ok = 0xFu;
         d.i0 = i;
     } else {
@@ -341,6 +351,9 @@ __device__ __forceinline__ void tile_load(const LossArgs& a, int row, int tile_i
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t t = t0 + static_cast<int64_t>(u) * kLossThreads + threadIdx.x;
+            d.lp[u] = d.olp[u] = d.adv[u] = d.m[u] = d.bs[u] = d.en[u] = 0.f;
+            d.ti[u] = 1.f;
+            d.cm[u] = -1.f;
             if (t < a.A) {
                 const int64_t i = rbase + t;
                 d.ok |= 1u << u;
@@ -363,7 +376,7 @@ __device__ __forceinline__ void tile_load(const LossArgs& a, int row, int tile_i
 
 // Persistent grid (a few blocks per SM): every block walks 1024-position tiles with a grid stride, two tiles in
 // flight per thread (all loads of both tiles are issued before the first is consumed), one block reduction at the end.
-template <int kInFlight, int kMinBlocks, int kType, int kBase>
+template <int kInFlight, int kMinBlocks, int kType, int kBase, int kKl, bool kVec>
 __global__ void __launch_bounds__(kLossThreads, kMinBlocks) loss_main_kernel(LossArgs a) {
     __shared__ float sh[34];
     __shared__ bool is_last;
@@ -414,11 +427,11 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) loss_main_kernel(Los
         for (int u = 0; u < 4; ++u) {
             g[u] = 0.f;
             if (d.ok >> u & 1u) {
-                g[u] = loss_token<kType, kBase>(cx, acc, d.lp[u], d.olp[u], d.adv[u], d.m[u], d.bs[u], d.ti[u], d.cm[u]);
+                g[u] = loss_token<kType, kBase, kKl>(cx, acc, d.lp[u], d.olp[u], d.adv[u], d.m[u], d.bs[u], d.ti[u], d.cm[u]);
                 if (a.ent) acc.s_ent = fmaf(d.en[u], d.m[u], acc.s_ent);
             }
         }
-        if (a.vec4) {
+        if constexpr (kVec) {
             if (a.d_lp) __stcs(reinterpret_cast<float4*>(a.d_lp + d.i0), make_float4(g[0], g[1], g[2], g[3]));
             if (a.ent && a.d_ent)
                 __stcs(reinterpret_cast<float4*>(a.d_ent + d.i0),
@@ -444,7 +457,7 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) loss_main_kernel(Los
         TileIn d[kInFlight];
 #pragma unroll
         for (int u = 0; u < kInFlight; ++u) {
-            tile_load(a, static_cast<int>(row), static_cast<int>(tir), row < static_cast<unsigned>(a.B), gspo, d[u]);
+            tile_load<kVec>(a, static_cast<int>(row), static_cast<int>(tir), row < static_cast<unsigned>(a.B), gspo, d[u]);
             row += step_rows;
             tir += step_tiles;
             if (tir >= tiles_per_row) {
@@ -992,12 +1005,20 @@ extern "C" int skyb200_policy_loss(const float* log_probs, const float* old_log_
     const int64_t tiles = ((A + kLossThreads * 4 - 1) / (kLossThreads * 4)) * B;
     const unsigned grid = (unsigned)std::max<int64_t>(
         1, std::min<int64_t>(tiles, std::min<int64_t>((int64_t)num_sms() * 4, (int64_t)kMaxMainGrid)));
-#define SKYB200_LOSS_CASE(T)                                                                  \
-    case T:                                                                                   \
-        if (base_log_probs)                                                                   \
-            SKYB200_CUDA_CHECK(launch_pdl(loss_main_kernel<1, 4, T, 1>, dim3(grid), dim3(kLossThreads), 0, stream, a)); \
-        else                                                                                  \
-            SKYB200_CUDA_CHECK(launch_pdl(loss_main_kernel<1, 4, T, 0>, dim3(grid), dim3(kLossThreads), 0, stream, a)); \
+    // instantiated per loss type x {no base, base with the reference's value-only k3 KL term, base (general)} x
+    // {128-bit path, scalar path}: the pass is instruction-bound, dead branches cost throughput
+    const bool k3_value_only = (params->kl_type == SKYB200_KL_K3) && (params->kl_has_grad == 0);
+#define SKYB200_LOSS_LAUNCH(T, BASE, KL)                                                                           \
+    (a.vec4 ? launch_pdl(loss_main_kernel<1, 4, T, BASE, KL, true>, dim3(grid), dim3(kLossThreads), 0, stream, a)  \
+            : launch_pdl(loss_main_kernel<1, 4, T, BASE, KL, false>, dim3(grid), dim3(kLossThreads), 0, stream, a))
+#define SKYB200_LOSS_CASE(T)                                                            \
+    case T:                                                                             \
+        if (!base_log_probs)                                                            \
+            SKYB200_CUDA_CHECK(SKYB200_LOSS_LAUNCH(T, 0, -1));                          \
+        else if (k3_value_only)                                                         \
+            SKYB200_CUDA_CHECK(SKYB200_LOSS_LAUNCH(T, 1, SKYB200_KL_K3));               \
+        else                                                                            \
+            SKYB200_CUDA_CHECK(SKYB200_LOSS_LAUNCH(T, 1, -1));                          \
         break;
     switch (params->loss_type) {
         SKYB200_LOSS_CASE(SKYB200_LOSS_REGULAR)
@@ -1012,6 +1033,7 @@ extern "C" int skyb200_policy_loss(const float* log_probs, const float* old_log_
             return fail(SKYB200_EINVAL, "bad loss_type %d", params->loss_type);
     }
 #undef SKYB200_LOSS_CASE
+#undef SKYB200_LOSS_LAUNCH
     return check_launch("loss_main_kernel");
 }
 
