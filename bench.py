@@ -12,6 +12,11 @@ bf16) per GPU.  N > 1 (launched by torchrun, one rank per GPU) is weak scaling: 
 prompt-group shard of that size; per step the packed stats vector and the fp32 lm_head weight gradient are
 all-reduced over NCCL.  Rank 0 prints ONE JSON line.
 
+Besides the contract keys the line carries `roofline` (forward GEMM kernel vs the measured sustained bf16 peak),
+`step_roofline` (6*H*V*N algorithmic flops over the step time), `hbm_kernels` (the memory-bound kernels of the path
+alone, L2 flushed, vs the measured HBM copy peak), `cpu_baseline`, `e2e` (pinned host buffers in, python floats out),
+`gpu_launches` and `clocks`.
+
 `--impl reference` times the CPU restatement of the reference's torch path (oracle/, "port": the Python reference
 cannot travel to the GPU box) on a bounded token sample with all host threads.
 """
