@@ -182,3 +182,46 @@ def test_wrapper_glue_selects_the_response_window_rows(monkeypatch):
             else:
                 assert lp[b, k].item() == 0.0 and ent[b, k].item() == 0.0   # pad_input leaves zeros
     assert seen["rows"].numel() == int(am[:, S - A - 1:S - 1].sum())      # nothing else reached the head
+
+
+def test_kl_controllers_match_reference_update_rule():  # reference: utils/ppo_utils.py:45-70
+    from skyrl_b200 import trainer_ops
+
+    ctrl = trainer_ops.AdaptiveKLController(0.05, target=0.1, horizon=100)
+    ctrl.update(current=0.2, n_steps=10)          # error clipped to +0.2 -> x (1 + 0.2 * 10 / 100)
+    assert ctrl.value == pytest.approx(0.05 * 1.02)
+    ctrl.update(current=0.095, n_steps=20)        # error -0.05 -> x (1 - 0.05 * 20 / 100)
+    assert ctrl.value == pytest.approx(0.05 * 1.02 * 0.99)
+    ctrl.update(current=0.0, n_steps=100)         # clipped to -0.2 -> x 0.8
+    assert ctrl.value == pytest.approx(0.05 * 1.02 * 0.99 * 0.8)
+    fixed = trainer_ops.FixedKLController(0.3)
+    fixed.update(current=123.0, n_steps=7)
+    assert fixed.value == 0.3
+
+
+def test_pack_by_lengths_drops_right_padding_and_builds_cu_seqlens():
+    import torch
+
+    from skyrl_b200 import pack_by_lengths
+
+    B, A, H = 4, 6, 3
+    lens = torch.tensor([6, 0, 2, 5])
+    x = torch.arange(B * A * H, dtype=torch.float32).view(B, A, H)
+    y = torch.arange(B * A).view(B, A)
+    cu, (xp, none, yp) = pack_by_lengths(lens, x, None, y)
+    assert cu.dtype == torch.int32 and cu.tolist() == [0, 6, 6, 8, 13]
+    assert none is None and xp.shape == (13, H) and yp.shape == (13,)
+    for b in range(B):
+        assert torch.equal(xp[cu[b]:cu[b + 1]], x[b, :lens[b]])
+        assert torch.equal(yp[cu[b]:cu[b + 1]], y[b, :lens[b]])
+
+
+def test_reduce_metrics_mean_max_min():  # reference: workers/worker_utils.py:8-22
+    from skyrl_b200.dist import reduce_metrics
+
+    out = reduce_metrics({"loss": [1.0, 2.0, 6.0], "ratio_max": [1.0, 5.0, 2.0], "ratio_min": [0.5, 0.1, 0.9]})
+    assert out == {"loss": 3.0, "ratio_max": 5.0, "ratio_min": 0.1}
+    with pytest.raises(AssertionError):
+        reduce_metrics({"loss": []})
+    with pytest.raises(AssertionError):
+        reduce_metrics({"loss": [1.0, "x"]})
