@@ -196,6 +196,49 @@ def test_oracle_vs_live_reference_random():
     assert_close(O.entropy_from_logits(z), tu.chunked_entropy_from_logits(z))
 
 
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_oracle_losses_vs_live_reference_random(seed):
+    """Every loss of the registry, oracle vs the unmodified reference on fresh random inputs (value, metric and
+    gradient); clip_cov replays the reference's torch.randperm draw from the same global seed."""
+    from types import SimpleNamespace as NS
+
+    pu, _ = ref_loader.load()
+    g = torch.Generator().manual_seed(100 + seed)
+    B, A = 9, 37
+    lens = torch.randint(1, A + 1, (B,), generator=g)
+    mask = (torch.arange(A)[None] < lens[:, None]).float()
+    mask[seed % B] = 0.0
+    lp = -torch.rand(B, A, generator=g) * 3
+    olp = lp + 0.2 * torch.randn(B, A, generator=g)
+    adv = torch.randn(B, A, generator=g)
+    extra = dict(sapo=NS(tau_pos=1.0, tau_neg=1.05), cispo=NS(cispo_eps_clip_low=0.2, cispo_eps_clip_high=0.25),
+                 clip_cov=NS(clip_ratio=0.2, clip_cov_lb=0.01, clip_cov_ub=4.0),
+                 kl_cov=NS(kl_cov_frac=0.3, ppo_kl_coef=0.7), max_seq_len=A,
+                 off_policy_correction=NS(tis_ratio_type=None, sequence_mask_metric=None))
+    for kind, red in (("regular", "token_mean"), ("dual_clip", "sequence_mean"), ("gspo", "sequence_mean"),
+                      ("sapo", "sequence_mean"), ("cispo", "seq_mean_token_sum_norm"), ("clip_cov", "token_mean"),
+                      ("kl_cov", "sequence_mean")):
+        cfg = O.make_cfg(policy_loss_type=kind, loss_reduction=red, **extra)
+        x_ref = lp.clone().requires_grad_(True)
+        torch.manual_seed(5 + seed)
+        loss_ref, met_ref = pu.PolicyLossRegistry._functions[kind](x_ref, olp, adv, cfg, loss_mask=mask)
+        loss_ref.backward()
+        x = lp.clone().requires_grad_(True)
+        torch.manual_seed(5 + seed)
+        if kind in ("regular", "dual_clip", "gspo"):
+            loss, clip = O.policy_loss(x, olp, adv, cfg, mask)
+            met = {"clip_ratio": clip}
+        elif kind in ("clip_cov", "kl_cov"):
+            loss, met, _ = O.cov_policy_loss(kind, x, olp, adv, cfg, mask)
+        else:
+            loss, met = O.extra_policy_loss(kind, x, olp, adv, cfg, mask)
+        loss.backward()
+        assert_close(loss, loss_ref, what=f"{kind} loss")
+        assert_close(met["clip_ratio"], met_ref["clip_ratio"], what=f"{kind} clip_ratio")
+        assert_close(x.grad, x_ref.grad, what=f"{kind} grad")
+
+
 # ---------------------------------------------------------------- "next" rows (SURVEY 8f-1)
 def test_golden_reinforce_pp_and_normalize(golden_adv):
     g = golden_adv
