@@ -6,8 +6,8 @@ library calls it uses: bf16 F.linear (cuBLASLt) -> logits.div_(T) -> flash-attn 
 (torch elementwise) -> backward.  It materialises [tokens, vocab] logits, so it only fits micro-batches; tokens/s
 is reported for the micro-batch size given (default 8192 tokens, the largest that is comfortable in fp32 temps).
 
-This is NOT the oracle and not part of the product; it uses the oracle's torch restatement of the loss only to
-avoid importing /root/reference (absent on the GPU box).  Output: one JSON line.
+This is NOT the oracle and not part of the product, and it imports neither: the few torch elementwise ops of the
+loss are written out below (/root/reference is absent on the GPU box).  Output: one JSON line.
 """
 import json
 import os
@@ -19,8 +19,6 @@ sys.path.insert(0, ROOT)
 
 import torch
 import torch.nn.functional as F
-
-from oracle import policy_oracle as O
 
 
 def main():
@@ -39,7 +37,7 @@ def main():
     base = -12.0 + 0.1 * torch.randn(rows, a_len, device=dev, generator=g)
     adv = torch.randn(rows, a_len, device=dev, generator=g)
     mask = torch.ones(rows, a_len, device=dev)
-    cfg = O.make_cfg()
+    eps, kl_coef = 0.2, 1e-3
 
     def step():
         hidden.grad = None
@@ -52,7 +50,16 @@ def main():
             for s in range(0, tokens, 1024):                  # torch_utils.py:59-111
                 lsm = F.log_softmax(logits[s:s + 1024], dim=-1)
                 ent[s:s + 1024] = -(lsm.exp() * lsm).sum(-1)
-        final, _ = O.loss_assembly(lp.view(rows, a_len), olp, adv, cfg, mask, base, ent.view(rows, a_len).float())
+        lp2 = lp.view(rows, a_len)
+        ratio = torch.exp(torch.clamp(lp2 - olp, -20.0, 20.0))            # ppo_utils.py:548-586, "regular"
+        surr = -torch.min(ratio * adv, ratio.clamp(1 - eps, 1 + eps) * adv)
+        denom = mask.sum().clamp(min=1.0)
+        policy = (surr * mask).sum() / denom                               # token_mean
+        with torch.no_grad():                                              # k3 KL term: value only (worker.py:865)
+            x = torch.clamp(base - lp2, -20.0, 20.0)
+            kl = (torch.clamp(torch.exp(x) - x - 1, -10.0, 10.0) * mask).sum(-1) / mask.sum(-1).clamp(min=1.0)
+            ent_mean = (ent.view(rows, a_len).float() * mask).sum() / denom
+        final = policy + kl.mean() * kl_coef - ent_mean * 0.0
         final.backward()
         return final
 

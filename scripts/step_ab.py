@@ -11,8 +11,7 @@ import torch
 
 sys.path.insert(0, ".")
 import skyrl_b200  # noqa: E402
-from bench import ClockSampler  # noqa: E402
-from oracle import policy_oracle as O  # noqa: E402  (config namespace only)
+from bench import ClockSampler, make_cfg  # noqa: E402
 
 
 def main():
@@ -33,7 +32,7 @@ def main():
         mask = (torch.arange(A, device=dev)[None] < lens[:, None]).float()
     adv = torch.randn((B, 1), generator=gen, device=dev).expand(B, A).contiguous()
     olp = -torch.rand((B, A), generator=gen, device=dev) * 12
-    cfg = O.make_cfg(policy_loss_type="regular", loss_reduction="token_mean", use_kl_loss=True)
+    cfg = make_cfg()  # regular / token_mean / k3 KL loss: the bench configuration
     dw = torch.empty((V, H), dtype=torch.float32, device=dev)
 
     def step():
