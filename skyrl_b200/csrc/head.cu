@@ -111,10 +111,12 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
     if (rc) return rc;
 
     auto kern = gemm_sm100_kernel<kCtas, BN, kStages, kAMn, kBMn, Epi>;
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // per template instantiation and per device (the attribute is per context)
+    int dev = 0;
+    SKYB200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         SKYB200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kTotal));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int tile_m = kBM * kCtas;
     const int64_t tiles = (int64_t)((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
