@@ -1,0 +1,148 @@
+"""BASELINE configs 3, 4 and 5 at their real head / sequence shapes (a per-GPU slice of the batch dimension), through
+the public API and checked with tests/step_checker.py: the status dict and the loss gradients against the oracle on
+the step's own forward outputs, sampled token rows against the fp32 oracle head (forward and d_hidden), and the
+size-independent identities over the whole d_weight / d_hidden.  Config 2 at full size lives in
+test_policy_update_gpu.py::test_full_size_config2_sampled_rows_and_checksum_identities.
+"""
+import numpy as np
+import pytest
+import torch
+
+import skyrl_b200
+from oracle import policy_oracle as O
+from conftest import assert_close
+from step_checker import check_step
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _need_free(gb):
+    torch.cuda.empty_cache()  # blocks cached from earlier tests of this process do not count as used
+    free, _ = torch.cuda.mem_get_info()
+    if free < gb * 1e9:
+        pytest.skip(f"needs ~{gb} GB of free HBM")
+
+
+def _head(N, H, V, gen):
+    hidden = torch.empty((N, H), dtype=torch.bfloat16, device=DEV)
+    for r0 in range(0, N, 65536):
+        hidden[r0:r0 + 65536] = torch.randn((min(65536, N - r0), H), generator=gen, device=DEV)
+    weight = torch.empty((V, H), dtype=torch.bfloat16, device=DEV)
+    for v0 in range(0, V, 16384):
+        n = min(16384, V - v0)
+        weight[v0:v0 + n] = torch.randn((n, H), generator=gen, device=DEV) * (1.5 / H ** 0.5)
+    labels = torch.randint(0, V, (N,), generator=gen, device=DEV)
+    return hidden, weight, labels
+
+
+def _current_log_probs(hidden, weight, labels, shape, cfg, T, **kw):
+    """A loss-only pass: the forward does not depend on the loss inputs, so this yields the current log-probs."""
+    z = torch.zeros(shape, device=DEV)
+    return skyrl_b200.policy_update_step(hidden, weight, labels, z, z, cfg, need_d_hidden=False, need_d_weight=False,
+                                         temperature=T, **kw).log_probs
+
+
+def test_config3_ppo_gae_kl_in_reward_shape():
+    """Config 3 (PPO: GAE gamma=1 lambda=0.95 + KL-in-reward, Qwen2.5-7B head, 8192-token responses), 32 sequences
+    (half of one GPU's 64-sequence shard): KL-in-reward and GAE against the oracle on the whole slice, then the step."""
+    _need_free(40)
+    B, A, H, V, T = 32, 8192, 3584, 152064, 1.0
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    hidden, weight, labels = _head(B * A, H, V, gen)
+    lens = torch.randint(A // 4, A + 1, (B,), generator=gen, device=DEV)
+    mask = (torch.arange(A, device=DEV)[None] < lens[:, None]).float()
+    cfg = O.make_cfg(policy_loss_type="regular", loss_reduction="token_mean", use_kl_loss=True)
+    lp0 = _current_log_probs(hidden, weight, labels, (B, A), cfg, T, loss_mask=mask)
+    olp = lp0 + 0.05 * torch.randn((B, A), generator=gen, device=DEV)
+    base = lp0 + 0.1 * torch.randn((B, A), generator=gen, device=DEV)
+    rewards = torch.zeros(B, A, device=DEV)
+    rewards[torch.arange(B, device=DEV), lens - 1] = (torch.rand(B, generator=gen, device=DEV) < 0.3).float()
+    values = torch.randn((B, A), generator=gen, device=DEV)  # including the padding positions (SURVEY trap 1)
+
+    r_kl, met = skyrl_b200.apply_reward_kl_penalty(rewards, lp0, base, mask, "k3", 1e-3)
+    want_r, want_met = O.reward_kl_penalty(rewards.cpu(), lp0.cpu(), base.cpu(), mask.cpu(), "k3", 1e-3)
+    assert_close(r_kl, want_r, what="KL-in-reward")
+    assert met["avg_kl"] == pytest.approx(want_met["avg_kl"], rel=1e-4)
+    assert met["avg_kl_max"] == pytest.approx(want_met["avg_kl_max"], rel=1e-4)
+    adv, ret = skyrl_b200.compute_gae_advantage_return(r_kl, values, mask, 1.0, 0.95)
+    want_adv, want_ret = O.gae_advantage_return(r_kl.cpu(), values.cpu(), mask.cpu(), 1.0, 0.95)
+    assert_close(ret, want_ret, what="GAE returns")
+    assert_close(adv, want_adv, what="GAE advantages")
+
+    out = skyrl_b200.policy_update_step(hidden, weight, labels, olp, adv, cfg, loss_mask=mask, base_log_probs=base,
+                                        temperature=T)
+    assert torch.equal(out.log_probs, lp0)
+    print("config 3:", check_step(out, hidden, weight, labels, olp, adv, cfg, mask, base, T))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(policy_loss_type="gspo", loss_reduction="sequence_mean", eps_clip_low=3e-4, eps_clip_high=4e-4),
+    dict(policy_loss_type="gspo", loss_reduction="sequence_mean", eps_clip_low=0.2, eps_clip_high=0.2),
+    dict(policy_loss_type="dual_clip", loss_reduction="token_mean", eps_clip_low=0.2, eps_clip_high=0.28,
+         clip_ratio_c=3.0),
+], ids=["gspo-3e-4", "gspo-0.2", "dual_clip"])
+def test_config4_long_horizon_32b_head_shape(kw):
+    """Config 4 (dual-clip / GSPO, Qwen3-32B-shaped head H=5120 V=151936, 32K-token trajectories), 2 sequences.
+    GSPO chunks are whole sequences (one 32768-token chunk each, a 10 GB logits tile store per parity)."""
+    _need_free(60)
+    B, A, H, V, T = 2, 32768, 5120, 151936, 1.0
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    hidden, weight, labels = _head(B * A, H, V, gen)
+    lens = torch.randint(24 * 1024, A + 1, (B,), generator=gen, device=DEV)
+    mask = (torch.arange(A, device=DEV)[None] < lens[:, None]).float()
+    mask[0, 5000:7000] = 0  # tool-call tokens inside the trajectory
+    cfg = O.make_cfg(use_kl_loss=False, **kw)
+    lp0 = _current_log_probs(hidden, weight, labels, (B, A), cfg, T, loss_mask=mask)
+    if kw["policy_loss_type"] == "gspo":
+        # sequence log-ratio = masked mean_t(lp - olp) = off_b + O(1e-5): sequence 0 stays inside the clip range (it
+        # carries the gradient), sequence 1 leaves it on the side its positive advantage clips
+        eps = kw["eps_clip_high"]
+        off = torch.tensor([[eps / 4], [3 * eps]], device=DEV)
+        olp = lp0 - off + 0.002 * torch.randn((B, A), generator=gen, device=DEV)
+        adv = torch.tensor([[-0.7], [1.3]], device=DEV).expand(B, A).contiguous()
+    else:
+        olp = lp0 + 0.5 * torch.randn((B, A), generator=gen, device=DEV)  # both clips and the dual clip are hit
+        adv = torch.randn((B, A), generator=gen, device=DEV)
+    out = skyrl_b200.policy_update_step(hidden, weight, labels, olp, adv, cfg, loss_mask=mask, temperature=T)
+    assert torch.equal(out.log_probs, lp0)
+    assert 0.0 < out.status["loss_metrics/clip_ratio"] < 1.0  # the clip is exercised, and not everywhere
+    print("config 4:", kw["policy_loss_type"], check_step(out, hidden, weight, labels, olp, adv, cfg, mask, None, T))
+
+
+def test_config5_rloo_entropy_bonus_ragged_packed_shape():
+    """Config 5 (RLOO, group 16, entropy bonus, ragged response lengths 128-16K, Qwen2.5-7B head): 32 sequences = 2
+    groups.  Advantages on the padded [B, A] batch as the trainer calls them, then the step on the PACKED layout
+    (no padding row reaches the GEMMs) with the entropy gradient switched on."""
+    _need_free(40)
+    B, A, H, V, G, T = 32, 16384, 3584, 152064, 16, 1.0
+    g = torch.Generator().manual_seed(5)
+    lens = torch.randint(128, A + 1, (B,), generator=g)
+    lens[0], lens[1] = 128, A  # both ends of the range
+    keep = torch.arange(A)[None] < lens[:, None]
+    mask = keep.float()
+    mask[3, 10:60] = 0
+    uids = np.array([f"prompt-{i // G}" for i in range(B)])[torch.randperm(B, generator=g).numpy()]
+    rewards = torch.zeros(B, A)
+    rewards[torch.arange(B), lens - 1] = torch.randn(B, generator=g)
+    adv, ret = skyrl_b200.compute_rloo_outcome_advantage(rewards.to(DEV), keep.long().to(DEV), uids)
+    want_adv, _ = O.rloo_advantage(rewards, keep.long(), uids)
+    assert_close(adv, want_adv, what="RLOO advantages")
+    assert torch.equal(adv.cpu() == 0, want_adv == 0) and adv.data_ptr() == ret.data_ptr()
+
+    N = int(lens.sum())
+    gen = torch.Generator(device=DEV).manual_seed(55)
+    hidden, weight, labels = _head(N, H, V, gen)
+    # a large entropy coefficient so that the entropy-gradient term is a visible share of d_hidden
+    cfg = O.make_cfg(policy_loss_type="regular", loss_reduction="token_mean", use_kl_loss=False,
+                     use_entropy_loss=True, entropy_loss_coef=0.5)
+    cu, (advp, maskp) = skyrl_b200.pack_by_lengths(lens, adv.cpu(), mask)
+    cu, advp, maskp = cu.to(DEV), advp.to(DEV), maskp.to(DEV)
+    lp0 = _current_log_probs(hidden, weight, labels, (N,), cfg, T, loss_mask=maskp, cu_seqlens=cu)
+    olpp = lp0 + 0.05 * torch.randn((N,), generator=gen, device=DEV)
+    out = skyrl_b200.policy_update_step(hidden, weight, labels, olpp, advp, cfg, loss_mask=maskp, temperature=T,
+                                        cu_seqlens=cu)
+    assert torch.equal(out.log_probs, lp0) and out.log_probs.shape == (N,)
+    olp = torch.zeros(B, A)
+    olp[keep] = olpp.cpu()
+    print("config 5:", check_step(out, hidden, weight, labels, olp, adv, cfg, mask, None, T, keep=keep))
