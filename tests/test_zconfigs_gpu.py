@@ -3,6 +3,9 @@ the public API and checked with tests/step_checker.py: the status dict and the l
 the step's own forward outputs, sampled token rows against the fp32 oracle head (forward and d_hidden), and the
 size-independent identities over the whole d_weight / d_hidden.  Config 2 at full size lives in
 test_policy_update_gpu.py::test_full_size_config2_sampled_rows_and_checksum_identities.
+
+(The file name sorts last on purpose: these are the largest allocations of the suite - up to 27 GB - and run after
+everything else.)
 """
 import numpy as np
 import pytest
