@@ -343,7 +343,14 @@ def cov_policy_loss(kind, lp, olp, adv, cfg, mask, sel=None, perm_fn=None):
 
 def loss_assembly(lp, olp, adv, cfg, mask=None, base=None, entropy=None):
     """workers/worker.py:852-889 — final = policy + kl*coef - entropy*coef; returns (final_loss, status)."""
-    pl, clip_ratio = policy_loss(lp, olp, adv, cfg, mask)
+    kind = cfg.policy_loss_type
+    if kind in ("sapo", "cispo", "cross_entropy", "importance_sampling"):
+        pl, met = extra_policy_loss(kind, lp, olp, adv, cfg, mask)
+        clip_ratio = met.get("clip_ratio", 0.0)
+        if kind == "cross_entropy":  # SFT path (worker.py:810-813): no KL / entropy term
+            return pl, {"policy_loss": pl.item(), "final_loss": pl.item(), "loss_metrics/clip_ratio": 0.0}
+    else:
+        pl, clip_ratio = policy_loss(lp, olp, adv, cfg, mask)
     status = {"policy_loss": pl.item(), "loss_metrics/clip_ratio": clip_ratio}
     ent_term = torch.tensor(0.0)
     if entropy is not None:

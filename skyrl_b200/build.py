@@ -26,6 +26,9 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
+    # "variable used before its value is set" is an error: it once let the compiler drop whole loss-type branches
+    # of a kernel without a word at run time
+    "--diag-error", "549",
 ]
 
 

@@ -200,12 +200,13 @@ struct TokenCtx {
 
 // One response token: accumulates the reductions, returns d final_loss / d log_prob.
 // kType / kBase >= 0 fix the loss type / the presence of base log-probs at compile time (the [B, A] token pass is
-// instantiated per loss type: it is instruction-bound, not only memory-bound); -1 = decide at run time.
+// instantiated per loss type: it is instruction-bound, not only memory-bound); -1 = decide at run time;
+// kType == -2 = decide at run time among the clipped-surrogate family only (regular / dual_clip / gspo).
 // kKl == SKYB200_KL_K3 additionally fixes "k3 estimator, KL term without gradient" (the reference's KL loss).
 template <int kType = -1, int kBase = -1, int kKl = -1>
 __device__ __forceinline__ float loss_token(const TokenCtx& cx, LossAcc& acc, float lp, float olp, float adv, float m,
                                             float base, float tis = 1.f, float cm = -1.f) {
-    const int loss_type = (kType >= 0) ? kType : loss_type;
+    const int loss_type = (kType >= 0) ? kType : (kType == -2 ? static_cast<int>(SKYB200_LOSS_REGULAR) : cx.loss_type);
     const bool is_gspo = (kType >= 0) ? (kType == SKYB200_LOSS_GSPO) : cx.gspo;
     const bool is_dual = (kType >= 0) ? (kType == SKYB200_LOSS_DUAL_CLIP) : cx.dual;
     const bool has_base = (kBase >= 0) ? (kBase != 0) : cx.has_base;
@@ -574,6 +575,8 @@ __device__ __forceinline__ int row_of_token(const int32_t* __restrict__ cu, int 
     return lo;
 }
 
+// kType: -2 = clipped-surrogate family (the three north-star losses, no dead branches of the others), -1 = any type
+template <int kType>
 __global__ void __launch_bounds__(kLossThreads) loss_flat_kernel(FlatArgs a) {
     __shared__ float sh[34];
     const int64_t A = a.A;
@@ -635,10 +638,10 @@ __global__ void __launch_bounds__(kLossThreads) loss_flat_kernel(FlatArgs a) {
                 if (a.base) bs = ldg_stream(reinterpret_cast<const float4*>(a.base + i));
                 if (a.ent) en = ldg_stream(reinterpret_cast<const float4*>(a.ent + i));
                 float4 g;
-                g.x = loss_token(cx, acc, lp.x, olp.x, adv.x, m.x, bs.x);
-                g.y = loss_token(cx, acc, lp.y, olp.y, adv.y, m.y, bs.y);
-                g.z = loss_token(cx, acc, lp.z, olp.z, adv.z, m.z, bs.z);
-                g.w = loss_token(cx, acc, lp.w, olp.w, adv.w, m.w, bs.w);
+                g.x = loss_token<kType>(cx, acc, lp.x, olp.x, adv.x, m.x, bs.x);
+                g.y = loss_token<kType>(cx, acc, lp.y, olp.y, adv.y, m.y, bs.y);
+                g.z = loss_token<kType>(cx, acc, lp.z, olp.z, adv.z, m.z, bs.z);
+                g.w = loss_token<kType>(cx, acc, lp.w, olp.w, adv.w, m.w, bs.w);
                 if (a.d_lp) *reinterpret_cast<float4*>(a.d_lp + (i - a.out_base)) = g;
                 if (a.ent) {
                     acc.s_ent = fmaf(en.x, m.x, acc.s_ent);
@@ -658,7 +661,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_flat_kernel(FlatArgs a) {
             if (i < a.t1) {
                 set_row(a.cu ? row_of_token(a.cu, a.B, i) : i / A);
                 const float m = a.mask ? a.mask[i] : 1.f;
-                const float g = loss_token(cx, acc, a.lp[i], a.olp[i], a.adv[i], m, a.base ? a.base[i] : 0.f);
+                const float g = loss_token<kType>(cx, acc, a.lp[i], a.olp[i], a.adv[i], m, a.base ? a.base[i] : 0.f);
                 if (a.d_lp) a.d_lp[i - a.out_base] = g;
                 if (a.ent) {
                     acc.s_ent = fmaf(a.ent[i], m, acc.s_ent);
@@ -786,7 +789,11 @@ int loss_flat_range(const float* lp, const float* olp, const float* adv, const f
     auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     a.vec4 = (cu == nullptr) && (A % 4 == 0) && (t0 % 4 == 0) && al16(lp) && al16(olp) && al16(adv) && al16(loss_mask) && al16(base) &&
              al16(ent) && al16(d_lp) && al16(d_ent);
-    loss_flat_kernel<<<(unsigned)loss_chunk_blocks(t1 - t0), kLossThreads, 0, stream>>>(a);
+    const unsigned grid = (unsigned)loss_chunk_blocks(t1 - t0);
+    if (p.loss_type <= SKYB200_LOSS_GSPO)
+        loss_flat_kernel<-2><<<grid, kLossThreads, 0, stream>>>(a);
+    else
+        loss_flat_kernel<-1><<<grid, kLossThreads, 0, stream>>>(a);
     return check_launch("loss_flat_kernel");
 }
 

@@ -24,7 +24,6 @@ struct RowOut {      // per-row results, folded by opc_metrics_kernel
     float sm_over, sm_under, sm_keep;  // sequence mask decision
     float s_rm, s_m, s_x, s_xx, x_max, x_min;  // is_ratio statistics on the original mask, x = ratio * mask
 };
-constexpr int kRowOutFloats = sizeof(RowOut) / 4;
 
 __device__ __forceinline__ float safe_exp20(float d) { return expf(fminf(fmaxf(d, -20.f), 20.f)); }
 

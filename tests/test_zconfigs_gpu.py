@@ -149,3 +149,44 @@ def test_config5_rloo_entropy_bonus_ragged_packed_shape():
     olp = torch.zeros(B, A)
     olp[keep] = olpp.cpu()
     print("config 5:", check_step(out, hidden, weight, labels, olp, adv, cfg, mask, None, T, keep=keep))
+
+
+@pytest.mark.parametrize("kind,red", [("sapo", "sequence_mean"), ("cispo", "token_mean"),
+                                      ("importance_sampling", "token_mean"), ("cross_entropy", "token_mean")])
+def test_fused_step_runs_the_rest_of_the_registry(kind, red):
+    """sapo / cispo / importance_sampling / cross_entropy through the ONE-call fused step (the run-time-typed
+    loss_flat_kernel, not the per-type instantiations the registry functions launch) against the oracle composed as
+    the worker composes it: RL losses add the KL and entropy terms, cross_entropy is the bare masked sum
+    (worker.py:810-877); the last two reduce with a masked SUM whatever `loss_reduction` says."""
+    from types import SimpleNamespace as NS
+
+    B, A, H, V, T = 6, 200, 64, 1200, 0.9
+    g = torch.Generator().manual_seed(31)
+    hidden = torch.randn(B, A, H, generator=g).bfloat16()
+    weight = (torch.randn(V, H, generator=g) * (1.5 / H ** 0.5)).bfloat16()
+    labels = torch.randint(0, V, (B, A), generator=g)
+    lens = torch.randint(A // 2, A + 1, (B,), generator=g)
+    mask = (torch.arange(A)[None] < lens[:, None]).float()
+    cfg = O.make_cfg(policy_loss_type=kind, loss_reduction=red, use_kl_loss=True, use_entropy_loss=True,
+                     sapo=NS(tau_pos=1.0, tau_neg=1.05), cispo=NS(cispo_eps_clip_low=0.1, cispo_eps_clip_high=0.15))
+    h = hidden.float().reshape(B * A, H).requires_grad_(True)
+    w = weight.float().requires_grad_(True)
+    lp_ref, ent_ref = O.head_logprobs_entropy(h, w, labels.reshape(-1), T)
+    lp_ref, ent_ref = lp_ref.view(B, A), ent_ref.view(B, A)
+    olp = lp_ref.detach() + 0.1 * torch.randn(B, A, generator=g)
+    base = lp_ref.detach() + 0.1 * torch.randn(B, A, generator=g)
+    adv = torch.randn(B, A, generator=g)
+    final_ref, st_ref = O.loss_assembly(lp_ref, olp, adv, cfg, mask, base, ent_ref)
+    final_ref.backward()
+    out = skyrl_b200.policy_update_step(hidden.to(DEV), weight.to(DEV), labels.to(DEV), olp.to(DEV), adv.to(DEV), cfg,
+                                        loss_mask=mask.to(DEV), base_log_probs=base.to(DEV), temperature=T)
+    for k in ("final_loss", "policy_loss"):
+        assert out.status[k] == pytest.approx(st_ref[k], rel=2e-3, abs=2e-4), (kind, k)
+    # the oracle clips on ITS log-probs (1e-5 away from the kernel's): allow two tokens to sit on a clip boundary
+    assert abs(out.status["loss_metrics/clip_ratio"] - st_ref["loss_metrics/clip_ratio"]) <= 2.5 / mask.sum().item()
+    if kind != "cross_entropy":
+        assert out.status["policy_kl"] == pytest.approx(st_ref["policy_kl"], rel=2e-2, abs=1e-4)
+        assert out.status["policy_entropy"] == pytest.approx(st_ref["policy_entropy"], rel=2e-3)
+    rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+    assert rel(out.d_hidden.float(), h.grad) < 2e-2
+    assert rel(out.d_weight, w.grad) < 2e-2
