@@ -446,9 +446,14 @@ def policy_update_loss(
         raise ValueError(f"policy loss '{loss_type}' has no fused B200 kernel; available: {list(_lib.LOSS_TYPES)}")
     use_kl = bool(_cfg(config, "use_kl_loss", False)) and base_log_probs is not None
     use_ent = bool(_cfg(config, "use_entropy_loss", False))
+    reduction = _cfg(config, "loss_reduction", "token_mean")
+    if loss_type in ("cross_entropy", "importance_sampling"):
+        reduction = "sum"  # Tinker semantics: masked SUM whatever loss_reduction says (ppo_utils.py:892-981)
+    if loss_type == "cross_entropy":
+        use_kl = use_ent = False  # the SFT path of the worker adds no KL / entropy term (worker.py:810-813)
     params = _make_params(
         loss_type,
-        _cfg(config, "loss_reduction", "token_mean"),
+        reduction,
         config,
         kl_type=_cfg(config, "kl_estimator_type", "k3"),
         kl_coef=float(_cfg(config, "kl_loss_coef", 0.0)) if use_kl else 0.0,

@@ -190,3 +190,91 @@ def test_fused_step_runs_the_rest_of_the_registry(kind, red):
     rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
     assert rel(out.d_hidden.float(), h.grad) < 2e-2
     assert rel(out.d_weight, w.grad) < 2e-2
+
+
+@pytest.mark.parametrize("kind", ["k1", "abs", "k2", "k3"])
+def test_kl_loss_term_with_the_gradient_flag(kind):
+    """The reference's KL-loss term carries no gradient (compute_approx_kl runs under no_grad, SURVEY trap 6) and that
+    is the default here; `kl_has_grad=True` is the opt-in "fixed" behaviour: d(kl_coef * mean_b masked_mean_t kl)/d lp,
+    including the clamp pass-through rules of k3, against autograd."""
+    B, A, coef = 5, 300, 0.3
+    g = torch.Generator().manual_seed(17)
+    lp = -3.0 * torch.rand(B, A, generator=g)
+    olp = lp + 0.1 * torch.randn(B, A, generator=g)
+    base = lp + 0.3 * torch.randn(B, A, generator=g)
+    base[0, :4] += torch.tensor([25.0, -25.0, 2.5, -2.5])  # beyond the +-20 clamp of x, and exp(x) - x - 1 > 10
+    adv = torch.randn(B, A, generator=g)
+    lens = torch.randint(1, A + 1, (B,), generator=g)
+    lens[0] = A
+    mask = (torch.arange(A)[None] < lens[:, None]).float()
+    cfg = O.make_cfg(policy_loss_type="regular", loss_reduction="token_mean", use_kl_loss=True,
+                     kl_estimator_type=kind, kl_loss_coef=coef)
+    x = lp.clone().requires_grad_(True)
+    pl, _ = O.policy_loss(x, olp, adv, cfg, mask)
+    d = x - base
+    if kind == "k3":
+        z = (-d).clamp(-20.0, 20.0)
+        kl = (z.exp() - z - 1.0).clamp(-10.0, 10.0)
+    else:
+        kl = {"k1": d, "abs": d.abs(), "k2": 0.5 * d * d}[kind]
+    klm = O.masked_mean(kl * mask, mask, dim=-1).mean()
+    (pl + coef * klm).backward()
+
+    y = lp.to(DEV).requires_grad_(True)
+    loss, st = skyrl_b200.policy_update_loss(y, olp.to(DEV), adv.to(DEV), cfg, loss_mask=mask.to(DEV),
+                                             base_log_probs=base.to(DEV), kl_has_grad=True)
+    loss.backward()
+    assert_close(loss, pl + coef * klm, what="final loss")
+    assert st["policy_kl"] == pytest.approx(klm.item(), rel=1e-5, abs=1e-5)
+    assert_close(y.grad, x.grad, floor=1e-4, what=f"d_log_probs with the {kind} KL gradient")  # KL part ~ 6e-5
+    # and the default: the KL term moves the value only
+    y0 = lp.to(DEV).requires_grad_(True)
+    loss0, _ = skyrl_b200.policy_update_loss(y0, olp.to(DEV), adv.to(DEV), cfg, loss_mask=mask.to(DEV),
+                                             base_log_probs=base.to(DEV))
+    loss0.backward()
+    x0 = lp.clone().requires_grad_(True)
+    O.policy_loss(x0, olp, adv, cfg, mask)[0].backward()
+    assert_close(loss0, loss)
+    assert_close(y0.grad, x0.grad, floor=1e-4, what="d_log_probs without the KL gradient")
+
+
+def test_sharded_gae_equals_the_batch_gae():
+    """GAE whitening statistics are global (the trainer computes advantages before sharding, SURVEY trap 12).
+    dist.gae_advantage_sharded = scan -> all-reduce of the fp64 moments {sum m, sum m*x, sum m*x^2} -> whitening:
+    with world size 1 it must be compute_gae_advantage_return bit for bit, and two half-batches whose moments are
+    added (what the all-reduce does) must reproduce the whole-batch result."""
+    from skyrl_b200 import _lib
+    from skyrl_b200 import dist as sdist
+
+    B, A = 6, 3000
+    g = torch.Generator().manual_seed(23)
+    lens = torch.randint(A // 2, A + 1, (B,), generator=g)
+    mask = (torch.arange(A)[None] < lens[:, None]).float().to(DEV)
+    r = torch.zeros(B, A)
+    r[torch.arange(B), lens - 1] = torch.randn(B, generator=g)
+    r, v = r.to(DEV), torch.randn(B, A, generator=g).to(DEV)
+    a0, r0 = skyrl_b200.compute_gae_advantage_return(r, v, mask, 1.0, 0.95)
+    a1, r1 = sdist.gae_advantage_sharded(r, v, mask, 1.0, 0.95)
+    assert torch.equal(a0, a1) and torch.equal(r0, r1)
+
+    lib = _lib.load()
+    halves, moments = [], []
+    for rows in (slice(0, 2), slice(2, B)):  # uneven shards
+        rr, vv, mm = r[rows].contiguous(), v[rows].contiguous(), mask[rows].contiguous()
+        b = rr.shape[0]
+        adv, ret = torch.empty_like(rr), torch.empty_like(rr)
+        mom = torch.zeros(3, dtype=torch.float64, device=DEV)
+        ws = torch.empty(lib.skyb200_gae_workspace(b), dtype=torch.uint8, device=DEV)
+        _lib.check(lib.skyb200_gae_scan(_lib.ptr(rr), _lib.ptr(vv), _lib.ptr(mm), _lib.MASK_F32, _lib.ptr(adv),
+                                        _lib.ptr(ret), _lib.ptr(mom), _lib.ptr(ws), ws.numel(), b, A, 1.0, 0.95,
+                                        _lib.stream_ptr()), "skyb200_gae_scan")
+        halves.append((adv, ret))
+        moments.append(mom)
+    total = moments[0] + moments[1]
+    stats = torch.empty(4, dtype=torch.float32, device=DEV)
+    for adv, _ in halves:
+        _lib.check(lib.skyb200_whiten_from_moments(_lib.ptr(adv), _lib.ptr(total), _lib.ptr(stats), adv.numel(),
+                                                   _lib.stream_ptr()), "skyb200_whiten_from_moments")
+    assert stats[0].item() == mask.sum().item()
+    assert torch.equal(torch.cat([h[1] for h in halves]), r0)            # returns do not depend on the statistics
+    assert_close(torch.cat([h[0] for h in halves]), a0, rel=1e-6, what="advantages from summed shard moments")
