@@ -343,7 +343,8 @@ int skyb200_head_backward(const void* hidden, const void* weight, const int64_t*
  * (replaces worker.py:787-877 after the trunk).  Because the loss gradient of a chunk is available as soon as its
  * log-probs are (normalisers come from a mask-only pre-pass), the forward GEMM keeps a bf16 copy of its logits
  * tiles in a bounded [chunk, V] store and the backward reads it instead of recomputing the projection:
- * 6*H*V executed flop per token instead of 8*H*V.  GSPO uses row-aligned chunks (needs A*k tokens per chunk).
+ * 6*H*V executed flop per token instead of 8*H*V.  GSPO chunks are whole sequences (k * A tokens; A need not be
+ * a multiple of the 256-row tile).
  *
  * old_log_probs / advantages / loss_mask / base_log_probs: [B, A] fp32 (mask / base may be NULL);
  * entropy_mask [B*A] fp32 or NULL; log_probs / entropy: [B*A] fp32 out (entropy already * entropy_mask);
@@ -357,6 +358,13 @@ int skyb200_head_backward(const void* hidden, const void* weight, const int64_t*
  */
 size_t skyb200_policy_step_workspace(int64_t B, int64_t A, int64_t n_tokens, int64_t H, int64_t V, int32_t loss_type,
                                      int32_t need_grad);
+/*
+ * How skyb200_policy_step will cut that batch into token chunks (host-only, no CUDA call): plan_out[0] = row capacity
+ * of the per-chunk buffers (a multiple of 256), [1] = tokens one chunk covers (== capacity, except GSPO, whose chunks
+ * are whole sequences: k * A tokens for any padded length A, tile-aligned or not), [2] = number of chunks.
+ */
+int skyb200_policy_step_plan(int64_t B, int64_t A, int64_t n_tokens, int64_t H, int64_t V, int32_t loss_type,
+                             int32_t need_grad, int64_t* plan_out);
 int skyb200_policy_step(const void* hidden, const void* weight, const int64_t* labels, const float* old_log_probs,
                         const float* advantages, const float* loss_mask, const float* base_log_probs,
                         const float* entropy_mask, float* log_probs, float* entropy, void* d_hidden, float* d_weight,

@@ -122,6 +122,7 @@ SIGNATURES = {
     "skyb200_head_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _I64, _I64, _I64, _F,
                                         _I64, _P]),
     "skyb200_policy_step_workspace": (_SZ, [_I64, _I64, _I64, _I64, _I64, _I32, _I32]),
+    "skyb200_policy_step_plan": (C.c_int, [_I64, _I64, _I64, _I64, _I64, _I32, _I32, C.POINTER(C.c_int64)]),
     "skyb200_policy_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _SZ, _I64, _I64,
                                       _I64, _I64, _P, _I64, _F, C.POINTER(LossParams), _P]),
     "skyb200_policy_step_from_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _SZ,

@@ -747,8 +747,9 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
 namespace {
 
 struct StepPlan {
-    int64_t chunk;  // tokens per chunk (multiple of 256)
-    int64_t ldS;    // pitch of the bf16 logits / d_logits store
+    int64_t chunk;   // token CAPACITY of the per-chunk buffers (multiple of 256)
+    int64_t stride;  // tokens a chunk actually covers: == chunk, except GSPO (whole sequences: k * A <= chunk)
+    int64_t ldS;     // pitch of the bf16 logits / d_logits store
     int slabs;
     // everything below exists twice (parity of the chunk index): the small kernels of chunk c+1 run on the
     // auxiliary stream while the backward GEMMs of chunk c run on the caller's stream
@@ -756,32 +757,37 @@ struct StepPlan {
     size_t off_loss, total;
 };
 
-int64_t gcd64(int64_t a, int64_t b) { return b == 0 ? a : gcd64(b, a % b); }
-
 // Chunks are flat token ranges; GSPO needs whole sequences per chunk (its ratio is a per-sequence mean).
 StepPlan plan_step(int64_t B, int64_t A, int64_t N, int64_t H, int64_t V, int loss_type, bool need_grad) {
     StepPlan p;
     int64_t chunk = kDefaultChunk;
+    int64_t stride = 0;
     if (loss_type == SKYB200_LOSS_GSPO) {
-        // whole sequences per chunk: k * lcm(A, 256) tokens, k chosen (up to ~2 default chunks) so that the
-        // d_hidden GEMM of a chunk fills whole waves of the resident CTA pairs as well as possible
-        const int64_t unit = A / gcd64(A, kTileM) * kTileM;
+        // whole sequences per chunk: k * A tokens in buffers of round_up(k * A, 256) rows.  The padded response
+        // length A is whatever the longest response of the batch was, so it need not be a multiple of the tile
+        // height: the chunk START is then not tile-aligned (every consumer takes a plain row offset) and the last
+        // tile of a chunk is partial.  k (up to ~2 default chunks) is chosen so that the d_hidden GEMM of a chunk
+        // fills whole waves of the resident CTA pairs as well as possible.
         const int64_t clusters = std::max(1, num_sms() / kHeadCtas);
         const int64_t n_tiles_h = (H + kHeadBN - 1) / kHeadBN;
         int64_t best_k = 1;
         double best_eff = -1.0;
-        for (int64_t k = 1; k * unit <= std::max<int64_t>(unit, 2 * kDefaultChunk); ++k) {
-            const int64_t tiles = (k * unit / kTileM) * n_tiles_h;
-            const double eff = (double)tiles / (double)(((tiles + clusters - 1) / clusters) * clusters);
+        for (int64_t k = 1; k * A <= std::max<int64_t>(A, 2 * kDefaultChunk); ++k) {
+            const int64_t tiles = ((k * A + kTileM - 1) / kTileM) * n_tiles_h;
+            const double eff = (double)(k * A) * (double)n_tiles_h /
+                               ((double)kTileM * (double)(((tiles + clusters - 1) / clusters) * clusters));
             if (eff > best_eff + 1e-9) {
                 best_eff = eff;
                 best_k = k;
             }
         }
-        chunk = best_k * unit;
+        stride = std::min<int64_t>(best_k * A, N);
+        chunk = round_up(stride, kTileM);
     }
     chunk = std::min<int64_t>(chunk, round_up(N, kTileM));
+    if (stride == 0) stride = chunk;
     p.chunk = chunk;
+    p.stride = stride;
     p.ldS = round_up(V, 64);
     p.slabs = (int)num_slabs(V);
     size_t off = 0;
@@ -800,8 +806,8 @@ StepPlan plan_step(int64_t B, int64_t A, int64_t N, int64_t H, int64_t V, int lo
         p.off_S[i] = take(need_grad ? (size_t)chunk * p.ldS * 2 : 0);
         p.off_maps[i] = take(live_maps_ints(chunk) * sizeof(int));
     }
-    p.off_loss = take(loss_chunk_ws_bytes(B, N) + (size_t)(N / chunk + 2) * 8 * 4 * 4);
-    (void)A;
+    // every chunk rounds its loss-partial slots up: 4 spare slots (128 bytes) per chunk
+    p.off_loss = take(loss_chunk_ws_bytes(B, N) + (size_t)(N / stride + 2) * 8 * 4 * 4);
     p.total = off + 512;
     return p;
 }
@@ -845,6 +851,18 @@ extern "C" size_t skyb200_policy_step_workspace(int64_t B, int64_t A, int64_t n_
     return plan_step(B, A, n_tokens > 0 ? n_tokens : B * A, H, V, loss_type, need_grad != 0).total;
 }
 
+extern "C" int skyb200_policy_step_plan(int64_t B, int64_t A, int64_t n_tokens, int64_t H, int64_t V,
+                                        int32_t loss_type, int32_t need_grad, int64_t* plan_out) {
+    SKYB200_REQUIRE(plan_out != nullptr, "null pointer");
+    SKYB200_REQUIRE(B > 0 && A > 0 && H > 0 && V > 0, "bad shape");
+    const int64_t N = n_tokens > 0 ? n_tokens : B * A;
+    const StepPlan p = plan_step(B, A, N, H, V, loss_type, need_grad != 0);
+    plan_out[0] = p.chunk;
+    plan_out[1] = p.stride;
+    plan_out[2] = (N + p.stride - 1) / p.stride;
+    return SKYB200_OK;
+}
+
 // hidden_host != nullptr: `hidden` is an uninitialised device staging buffer [N, H] that this call fills chunk by
 // chunk from (pinned) host memory on a copy stream, ahead of the GEMMs that read it.
 static int policy_step_impl(const void* hidden_host, const void* hidden, const void* weight, const int64_t* labels,
@@ -882,7 +900,8 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
     cudaStream_t aux = ss->aux;
 
     char* wb = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
-    const int64_t c = plan.chunk;
+    const int64_t c = plan.chunk;        // buffer capacity (rows) of a chunk
+    const int64_t stride = plan.stride;  // tokens per chunk (== c unless GSPO keeps whole sequences together)
     LossChunkWs lws;
     loss_chunk_ws_carve(wb + plan.off_loss, B, A, &lws);
     const float inv_T = 1.0f / temperature;
@@ -890,15 +909,15 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
     const __nv_bfloat16* hid = static_cast<const __nv_bfloat16*>(hidden);
     __nv_bfloat16* dhid = static_cast<__nv_bfloat16*>(d_hidden);
     const bool use_ent_grad = need_grad && params->use_entropy_loss != 0;
-    const int64_t n_chunks = (N + c - 1) / c;
+    const int64_t n_chunks = (N + stride - 1) / stride;
 
     auto fptr = [&](size_t off) { return reinterpret_cast<float*>(wb + off); };
 
     // ---- stage A (caller's stream): logits tiles -> online-softmax partials (+ bf16 copy of the tile)
     auto issue_fwd = [&](int64_t ci) -> int {
         const int p = (int)(ci & 1);
-        const int64_t t0 = ci * c;
-        const int rows = (int)std::min<int64_t>(c, N - t0);
+        const int64_t t0 = ci * stride;
+        const int rows = (int)std::min<int64_t>(stride, N - t0);
         float* part_m = fptr(plan.off_part[p]);
         EpiLsePartials::Params ep;
         ep.scale_log2 = scale_log2;
@@ -924,8 +943,8 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
     // ---- stage B (auxiliary stream, overlaps the GEMMs): merge -> loss of the token range -> d(logits) in place
     auto issue_mid = [&](int64_t ci, int64_t slot) -> int {
         const int p = (int)(ci & 1);
-        const int64_t t0 = ci * c;
-        const int rows = (int)std::min<int64_t>(c, N - t0);
+        const int64_t t0 = ci * stride;
+        const int rows = (int)std::min<int64_t>(stride, N - t0);
         float* part_m = fptr(plan.off_part[p]);
         float* lse2 = fptr(plan.off_lse2[p]);
         float* ent_raw = fptr(plan.off_entraw[p]);
@@ -970,8 +989,8 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
     // ---- stage C (caller's stream): d_hidden = dS * W ; d_weight (+)= dS^T * hidden
     auto issue_bwd = [&](int64_t ci) -> int {
         const int p = (int)(ci & 1);
-        const int64_t t0 = ci * c;
-        const int rows = (int)std::min<int64_t>(c, N - t0);
+        const int64_t t0 = ci * stride;
+        const int rows = (int)std::min<int64_t>(stride, N - t0);
         __nv_bfloat16* S = reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]);
         SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[p], 0));
         const int mt = (int)(c / kTileM);
@@ -1019,9 +1038,9 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
         const char* src = static_cast<const char*>(hidden_host);
         char* dst = reinterpret_cast<char*>(const_cast<void*>(hidden));
         for (int64_t ci = 0; ci < n_chunks; ++ci) {
-            const int64_t t0 = ci * c;
+            const int64_t t0 = ci * stride;
             const size_t off = (size_t)t0 * (size_t)H * sizeof(__nv_bfloat16);
-            const size_t bytes = (size_t)std::min<int64_t>(c, N - t0) * (size_t)H * sizeof(__nv_bfloat16);
+            const size_t bytes = (size_t)std::min<int64_t>(stride, N - t0) * (size_t)H * sizeof(__nv_bfloat16);
             SKYB200_CUDA_CHECK(cudaMemcpyAsync(dst + off, src + off, bytes, cudaMemcpyHostToDevice, ss->copy));
             SKYB200_CUDA_CHECK(cudaEventRecord(ss->copied[ci], ss->copy));
         }
@@ -1032,7 +1051,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
         int64_t slot = 0;
         for (int64_t ci = 0; ci < n_chunks; ++ci) {
             slot_of[ci] = slot;
-            slot += loss_chunk_blocks(std::min<int64_t>(c, N - ci * c));
+            slot += loss_chunk_blocks(std::min<int64_t>(stride, N - ci * stride));
         }
     }
     rc = issue_fwd(0);
@@ -1054,7 +1073,8 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
     // join: the caller's stream continues only after the last auxiliary-stream work
     SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[(n_chunks - 1) & 1], 0));
     if (n_chunks > 1) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[(n_chunks - 2) & 1], 0));
-    const int64_t total_slots = slot_of[n_chunks - 1] + loss_chunk_blocks(std::min<int64_t>(c, N - (n_chunks - 1) * c));
+    const int64_t total_slots =
+        slot_of[n_chunks - 1] + loss_chunk_blocks(std::min<int64_t>(stride, N - (n_chunks - 1) * stride));
     return loss_finalize(lws, total_slots, true, stats, *params, stream);
 }
 

@@ -50,6 +50,33 @@ def test_host_only_entry_points(lib):
     assert bwd < 4 * 2**30 and fwd < 2**30
 
 
+def _plan(lib, B, A, H, V, loss, n_tokens=0, need_grad=1):
+    out = (ctypes.c_int64 * 3)()
+    assert lib.skyb200_policy_step_plan(B, A, n_tokens, H, V, _lib.LOSS_TYPES[loss], need_grad, out) == 0
+    ws = lib.skyb200_policy_step_workspace(B, A, n_tokens, H, V, _lib.LOSS_TYPES[loss], need_grad)
+    return out[0], out[1], out[2], ws
+
+
+def test_fused_step_chunk_plan(lib):
+    """Host-only planning of the fused step: bounded scratch for every loss and any padded response length."""
+    H, V = 3584, 152064
+    cap, stride, n, ws = _plan(lib, 256, 4096, H, V, "regular")
+    assert (cap, stride, n) == (9472, 9472, 111) and ws < 7 * 2**30            # 37 pair-tiles, 2 x 2.9 GB store
+    assert _plan(lib, 1024, 4096, H, V, "regular")[3] - ws < 2**20             # independent of the batch size
+    assert _plan(lib, 4, 100, H, V, "dual_clip")[:3] == (512, 512, 1)          # a batch smaller than one chunk
+    # GSPO: whole sequences per chunk; the chunk count covers the batch exactly
+    for B, A in ((256, 4096), (8, 32768), (40, 1000), (256, 3917), (7, 4099), (3, 70000), (5, 1)):
+        cap, stride, n, ws = _plan(lib, B, A, H, V, "gspo")
+        assert stride % A == 0 and cap % 256 == 0 and stride <= cap < stride + 256, (B, A, cap, stride)
+        assert n == -(-B * A // stride)
+        assert cap <= max(2 * 9472, -(-A // 256) * 256), (B, A, cap)             # ~2 default chunks, or one sequence
+        assert ws < 2 * cap * (V + 64) * 2 + 2 * cap * (3 * 595 + 6) * 4 + (B + n) * 64 + 2**22, (B, A, ws)
+    # a response length that shares no factor with the 256-row tile used to need lcm(A, 256) = 1 M tokens (611 GB)
+    assert _plan(lib, 256, 3917, H, V, "gspo")[3] < 12 * 2**30
+    # the packed layout plans over n_tokens
+    assert _plan(lib, 64, 1, H, V, "regular", n_tokens=500000)[2] == -(-500000 // 9472)
+
+
 def test_loss_params_layout_matches_header():
     assert ctypes.sizeof(_lib.LossParams) == 6 * 4 + 8 * 4
 

@@ -278,3 +278,46 @@ def test_sharded_gae_equals_the_batch_gae():
     assert stats[0].item() == mask.sum().item()
     assert torch.equal(torch.cat([h[1] for h in halves]), r0)            # returns do not depend on the statistics
     assert_close(torch.cat([h[0] for h in halves]), a0, rel=1e-6, what="advantages from summed shard moments")
+
+
+@pytest.mark.parametrize("A", [1000, 1001])
+def test_gspo_fused_step_with_a_response_length_off_the_tile_grid(A):
+    """The padded response length is whatever the longest response of the batch was.  GSPO chunks are whole
+    sequences, so with A % 256 != 0 the chunks start off the 256-row tile grid (here 18 sequences per chunk: token
+    offsets 18000 / 18018, 36000 / 36036) and end in a partial tile; A = 1001 also takes the scalar paths."""
+    from skyrl_b200 import _lib
+    import ctypes
+
+    B, H, V, T = 40, 64, 512, 1.0
+    plan = (ctypes.c_int64 * 3)()
+    _lib.load().skyb200_policy_step_plan(B, A, 0, H, V, _lib.LOSS_TYPES["gspo"], 1, plan)
+    assert plan[1] % A == 0 and plan[1] % 256 != 0 and plan[2] >= 3, list(plan)
+    g = torch.Generator().manual_seed(77)
+    hidden = torch.randn(B, A, H, generator=g).bfloat16()
+    weight = (torch.randn(V, H, generator=g) * (1.5 / H ** 0.5)).bfloat16()
+    labels = torch.randint(0, V, (B, A), generator=g)
+    lens = torch.randint(A // 2, A + 1, (B,), generator=g)
+    mask = (torch.arange(A)[None] < lens[:, None]).float()
+    cfg = O.make_cfg(policy_loss_type="gspo", loss_reduction="sequence_mean", use_kl_loss=True, use_entropy_loss=True,
+                     eps_clip_low=0.02, eps_clip_high=0.02)
+    h = hidden.float().reshape(B * A, H).requires_grad_(True)
+    w = weight.float().requires_grad_(True)
+    lp_ref, ent_ref = O.head_logprobs_entropy(h, w, labels.reshape(-1), T)
+    lp_ref, ent_ref = lp_ref.view(B, A), ent_ref.view(B, A)
+    olp = lp_ref.detach() + 0.03 * torch.randn(B, 1, generator=g) + 0.01 * torch.randn(B, A, generator=g)
+    base = lp_ref.detach() + 0.1 * torch.randn(B, A, generator=g)
+    adv = torch.randn(B, A, generator=g)
+    final_ref, st_ref = O.loss_assembly(lp_ref, olp, adv, cfg, mask, base, ent_ref)
+    final_ref.backward()
+    out = skyrl_b200.policy_update_step(hidden.to(DEV), weight.to(DEV), labels.to(DEV), olp.to(DEV), adv.to(DEV), cfg,
+                                        loss_mask=mask.to(DEV), base_log_probs=base.to(DEV), temperature=T)
+    assert (out.log_probs.cpu() - lp_ref.detach()).abs().max().item() < 1e-3
+    assert (out.entropy.cpu() - ent_ref.detach()).abs().max().item() < 1e-3
+    assert 0.0 < st_ref["loss_metrics/clip_ratio"] < 1.0
+    for k in ("final_loss", "policy_loss", "policy_entropy"):
+        assert out.status[k] == pytest.approx(st_ref[k], rel=2e-3, abs=2e-4), k
+    # a whole sequence flips its clip state if its ratio sits within 1e-5 of a boundary: allow one
+    assert abs(out.status["loss_metrics/clip_ratio"] - st_ref["loss_metrics/clip_ratio"]) <= 1.2 * A / mask.sum().item()
+    rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+    assert rel(out.d_hidden.float(), h.grad) < 2e-2
+    assert rel(out.d_weight, w.grad) < 2e-2
