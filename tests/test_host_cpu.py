@@ -226,3 +226,42 @@ def test_reduce_metrics_mean_max_min():  # reference: workers/worker_utils.py:8-
         reduce_metrics({"loss": []})
     with pytest.raises(AssertionError):
         reduce_metrics({"loss": [1.0, "x"]})
+
+
+def test_install_into_the_live_reference_registries(monkeypatch):
+    """install_into_skyrl_train() against the UNMODIFIED reference registries (build container only): every name
+    the reference registers ends up bound to the skyrl_b200 callable through the reference's own
+    unregister/register API, the model_wrapper helpers are rebound, and the reference's dispatcher
+    (compute_advantages_and_returns, ppo_utils.py:1190-1214) then reaches our code - which refuses CPU tensors
+    instead of falling back."""
+    import sys
+    import types
+
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    pu, _ = ref_loader.load()
+    saved = {reg: dict(reg._functions) for reg in (pu.AdvantageEstimatorRegistry, pu.PolicyLossRegistry)}
+    fake_mw = types.ModuleType("skyrl_train.model_wrapper")
+    fake_mw.logprobs_from_logits = fake_mw.chunked_entropy_from_logits = None
+    monkeypatch.setitem(sys.modules, "skyrl_train.model_wrapper", fake_mw)
+    try:
+        done = skyrl_b200.install_into_skyrl_train()
+        assert set(done) >= {"grpo", "rloo", "gae", "reinforce++", "regular", "dual_clip", "gspo", "sapo", "cispo",
+                             "clip_cov", "kl_cov", "cross_entropy", "importance_sampling", "logprobs_from_logits"}
+        for name in ("grpo", "rloo", "gae", "reinforce++"):
+            assert pu.AdvantageEstimatorRegistry.get(name).__module__ == "skyrl_b200.advantages", name
+        for name in pu.PolicyLossRegistry.list_available():
+            assert pu.PolicyLossRegistry.get(name).__module__ == "skyrl_b200.losses", name
+        assert fake_mw.logprobs_from_logits is skyrl_b200.logprobs_from_logits
+        assert fake_mw.chunked_entropy_from_logits is skyrl_b200.chunked_entropy_from_logits
+        if not torch.cuda.is_available():
+            with pytest.raises(RuntimeError, match="CUDA"):
+                pu.compute_advantages_and_returns(
+                    token_level_rewards=torch.zeros(2, 3), response_mask=torch.ones(2, 3), index=["a", "a"],
+                    adv_estimator="grpo", config=None)
+    finally:
+        for reg, fns in saved.items():
+            reg._functions.clear()
+            reg._functions.update(fns)
