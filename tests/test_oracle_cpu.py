@@ -239,6 +239,103 @@ def test_oracle_losses_vs_live_reference_random(seed):
         assert_close(x.grad, x_ref.grad, what=f"{kind} grad")
 
 
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_advantages_vs_live_reference_property():
+    """Property test (hypothesis): all four estimators, KL estimators and KL-in-reward arithmetic of the oracle against
+    the unmodified reference over drawn shapes, group structures (singletons, shuffled uids, one big group), interior
+    mask holes, fully masked rows and gamma / lambda - the inputs the fixed-seed tests do not vary."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    pu, _ = ref_loader.load()
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(B=st.integers(1, 9), A=st.integers(1, 40), G=st.integers(1, 5), seed=st.integers(0, 10_000),
+           gamma=st.sampled_from([1.0, 0.99, 0.5]), lambd=st.sampled_from([1.0, 0.95, 0.3]),
+           shuffle=st.booleans(), hole=st.booleans(), int_mask=st.booleans())
+    def run(B, A, G, seed, gamma, lambd, shuffle, hole, int_mask):
+        g = torch.Generator().manual_seed(seed)
+        lens = torch.randint(1, A + 1, (B,), generator=g)
+        mask = (torch.arange(A)[None] < lens[:, None]).float()
+        if hole and A > 3:
+            mask[:, 1:3] = 0.0
+        if B > 2 and seed % 3 == 0:
+            mask[0] = 0.0
+        m = mask.long() if int_mask else mask
+        idx = np.array([f"uid{i // G}" for i in range(B)])
+        if shuffle:
+            idx = idx[torch.randperm(B, generator=g).numpy()]
+        r = torch.randn(B, A, generator=g) * mask
+        v = torch.randn(B, A, generator=g)
+        assert_close(O.grpo_advantage(r, m, idx)[0], pu.compute_grpo_outcome_advantage(r.clone(), m, idx)[0])
+        assert_close(O.grpo_advantage(r, m, idx, norm_by_std=False)[0],
+                     pu.compute_grpo_outcome_advantage(r.clone(), m, idx, grpo_norm_by_std=False)[0])
+        assert_close(O.rloo_advantage(r, m, idx)[0], pu.compute_rloo_outcome_advantage(r.clone(), m, idx)[0])
+        if mask.sum() >= 2:
+            a1, r1 = pu.compute_gae_advantage_return(r, v, mask, gamma=gamma, lambd=lambd)
+            a2, r2 = O.gae_advantage_return(r, v, mask, gamma, lambd)
+            assert_close(r2, r1, what="gae returns")
+            assert_close(a2, a1, rel=1e-4, what="gae advantages")  # whitening amplifies fp32 summation-order noise
+            a1, r1 = pu.compute_reinforce_plus_plus_outcome_advantage(r, mask, gamma=gamma)
+            a2, r2 = O.reinforce_pp_advantage(r, mask, gamma)
+            assert_close(r2, r1, what="reinforce++ returns")
+            assert_close(a2, a1, rel=1e-4, what="reinforce++ advantages")
+        lp, base = -torch.rand(B, A, generator=g) * 3, -torch.rand(B, A, generator=g) * 3
+        for kind in ("k1", "abs", "k2", "k3"):
+            assert_close(O.approx_kl(lp, base, mask, kind), pu.compute_approx_kl(lp, base, mask, kind))
+            assert_close(O.approx_kl(lp, base, None, kind), pu.compute_approx_kl(lp, base, None, kind))
+
+    run()
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_losses_vs_live_reference_property():
+    """Property test (hypothesis): regular / dual_clip / gspo x the three reductions x {mask, no mask} against the
+    unmodified reference - loss, clip ratio and the autograd gradient - with the inputs that hit the special cases:
+    log-ratios beyond the +-20 clamp, exact ties of the two surrogates (lp == old_lp), zero and negative advantages,
+    fully masked rows."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    pu, _ = ref_loader.load()
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(B=st.integers(1, 7), A=st.integers(1, 24), seed=st.integers(0, 10_000),
+           kind=st.sampled_from(["regular", "dual_clip", "gspo"]),
+           red=st.sampled_from(["token_mean", "sequence_mean", "seq_mean_token_sum_norm"]),
+           use_mask=st.booleans(), eps=st.sampled_from([(0.2, 0.2), (0.2, 0.28), (3e-4, 4e-4)]),
+           c=st.sampled_from([3.0, 10.0]))
+    def run(B, A, seed, kind, red, use_mask, eps, c):
+        g = torch.Generator().manual_seed(seed)
+        lens = torch.randint(1, A + 1, (B,), generator=g)
+        mask = (torch.arange(A)[None] < lens[:, None]).float()
+        if B > 1:
+            mask[seed % B] = 0.0
+        lp = -torch.rand(B, A, generator=g) * 3
+        olp = lp + 0.3 * torch.randn(B, A, generator=g)
+        tie = torch.rand(B, A, generator=g) < 0.3
+        olp = torch.where(tie, lp, olp)                                   # exact ties of the two surrogates
+        if kind != "gspo":
+            far = torch.rand(B, A, generator=g) < 0.1
+            olp = torch.where(far, lp + 25.0 * torch.sign(torch.randn(B, A, generator=g)), olp)  # beyond the clamp
+        adv = torch.randn(B, A, generator=g)
+        adv = torch.where(torch.rand(B, A, generator=g) < 0.1, torch.zeros(()), adv)
+        cfg = O.make_cfg(policy_loss_type=kind, loss_reduction=red, eps_clip_low=eps[0], eps_clip_high=eps[1],
+                         clip_ratio_c=c, max_seq_len=A + 3)
+        m = mask if use_mask else None
+        x_ref = lp.clone().requires_grad_(True)
+        loss_ref, met_ref = pu.PolicyLossRegistry._functions[kind](x_ref, olp, adv, cfg, loss_mask=m)
+        loss_ref.backward()
+        x = lp.clone().requires_grad_(True)
+        loss, clip = O.policy_loss(x, olp, adv, cfg, m)
+        loss.backward()
+        assert_close(loss, loss_ref, what=f"{kind}/{red} loss")
+        assert clip == pytest.approx(met_ref["clip_ratio"], abs=1e-7)
+        assert_close(x.grad, x_ref.grad, what=f"{kind}/{red} grad")
+
+    run()
+
+
 # ---------------------------------------------------------------- "next" rows (SURVEY 8f-1)
 def test_golden_reinforce_pp_and_normalize(golden_adv):
     g = golden_adv
