@@ -172,7 +172,7 @@ def test_packed_ragged_layout_equals_padded_reference(kw):
 
 
 def test_gspo_fused_step_row_aligned_multi_chunk():
-    """GSPO needs whole sequences per chunk: 7 x 4096 tokens -> chunks of 3, 3 and 1 sequences."""
+    """GSPO needs whole sequences per chunk: 7 x 4096 tokens -> chunks of 4 and 3 sequences (skyb200_policy_step_plan)."""
     B, A, H, V, T = 7, 4096, 64, 512, 1.0
     g, hidden, weight, labels, mask = _batch(B, A, H, V, 21)
     cfg = O.make_cfg(policy_loss_type="gspo", loss_reduction="sequence_mean", use_kl_loss=False,
