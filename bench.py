@@ -49,12 +49,25 @@ TEMPERATURE = 1.0
 
 
 def measured_peaks():
+    """Roofline denominators: the driver-written measurement of this pool's B200s, else (per key) the fallback
+    B200_PROFILING.md states - the `source` string says which."""
+    fallback = dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0)
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
+    try:
         d = json.load(open(p))
-        return dict(tflops=float(d["bf16_tflops_sustained"]), tflops_burst=float(d["bf16_tflops"]),
-                    hbm=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json, sustained bf16)")
-    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+    except (OSError, ValueError):
+        return dict(fallback, source="fallback (B200_PROFILING.md)")
+    keys = dict(tflops="bf16_tflops_sustained", tflops_burst="bf16_tflops", hbm="hbm_gbs")
+    out, missing = {}, []
+    for k, name in keys.items():
+        try:
+            out[k] = float(d[name])
+        except (KeyError, TypeError, ValueError):
+            out[k] = fallback[k]
+            missing.append(name)
+    out["source"] = "measured (MEASURED_PEAKS.json, sustained bf16)" + (
+        "; fallback (B200_PROFILING.md) for " + ", ".join(missing) if missing else "")
+    return out
 
 
 def config_dict(w, world):
