@@ -30,7 +30,11 @@ from .advantages import (  # noqa: F401
 )
 from .fused_head import fused_lm_head, fused_lm_head_logprobs  # noqa: F401
 from .losses import gspo_policy_loss, policy_update_loss, ppo_critic_loss, ppo_policy_loss  # noqa: F401
-from .model_wrapper import action_log_probs_from_hidden, action_log_probs_from_packed_hidden  # noqa: F401
+from .model_wrapper import (  # noqa: F401
+    action_log_probs_from_hidden,
+    action_log_probs_from_packed_hidden,
+    action_log_probs_from_sp_hidden,
+)
 from .policy_update import PolicyUpdateOutput, fused_policy_loss, pack_by_lengths, policy_update_step  # noqa: F401
 from .registry import (  # noqa: F401
     AdvantageEstimator,

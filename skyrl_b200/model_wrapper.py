@@ -104,3 +104,105 @@ def action_log_probs_from_packed_hidden(
         return full.view(B, S)[:, S - A - 1:S - 1]
 
     return unpack(lp), (unpack(ent) if compute_entropy else None)
+
+
+class _SeqParallelGather(torch.autograd.Function):
+    """All-gather of ``[B, L]`` shards along the sequence dimension.  Mirrors the reference's ``Gather``
+    (skyrl_train/distributed/ulysses/utils.py:199-239): backward hands every rank its own slice of the upstream
+    gradient, multiplied by the group size when ``grad_scaler`` (the reference's default)."""
+
+    @staticmethod
+    def forward(ctx, local, group, grad_scaler):
+        import torch.distributed as dist
+
+        ctx.ws, ctx.rank = dist.get_world_size(group), dist.get_rank(group)
+        ctx.scale, ctx.part = bool(grad_scaler), local.shape[1]
+        parts = [torch.empty_like(local) for _ in range(ctx.ws)]
+        dist.all_gather(parts, local.contiguous(), group=group)
+        return torch.cat(parts, dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.scale:
+            g = g * ctx.ws
+        return g.split(ctx.part, dim=1)[ctx.rank].contiguous(), None, None
+
+
+class _ZeroAnchor(torch.autograd.Function):
+    """``zeros([B, L])`` that still depends on ``hidden_local``: a rank whose slice holds no response position must
+    run the trunk's backward too (its attention backward is a collective), with a zero gradient - which is what the
+    reference's sliced-away log-probs deliver."""
+
+    @staticmethod
+    def forward(ctx, hidden_local):
+        ctx.meta = (hidden_local.shape, hidden_local.dtype)
+        return hidden_local.new_zeros(hidden_local.shape[:2], dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, dtype = ctx.meta
+        return g.new_zeros(shape, dtype=dtype)
+
+
+def action_log_probs_from_sp_hidden(
+    hidden_local: torch.Tensor,
+    lm_head_weight: torch.Tensor,
+    sequences: torch.Tensor,
+    num_actions: int,
+    attention_mask: Optional[torch.Tensor] = None,
+    temperature: float = 1.0,
+    compute_entropy: bool = False,
+    group=None,
+    grad_scaler: bool = True,
+    chunk: int = 0,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """The Ulysses sequence-parallel branch of the wrapper (model_wrapper.py:292-305, 319-355; padded layout).
+
+    The trunk ran on this rank's slice of the sequence dimension (``ulysses_pad_and_slice_inputs``: ``S`` padded to a
+    multiple of the group size, rank r owns columns ``[r*L, (r+1)*L)``); ``hidden_local`` [B, L, H] is its last hidden
+    state, ``sequences`` / ``attention_mask`` are the full [B, S] tensors every rank holds.  The head is per token,
+    so each rank runs the fused head on the response-window rows **of its own slice only** and the ranks all-gather
+    the fp32 log-probs (4 bytes per position; the reference gathers the same tensor after projecting all ``S/sp``
+    positions to the vocabulary).  Returns ``(action_log_probs [B, A], entropy [B, A] or None)`` on every rank.
+    """
+    import torch.distributed as dist
+
+    if hidden_local.dim() != 3 or sequences.dim() != 2 or hidden_local.shape[0] != sequences.shape[0]:
+        raise ValueError(f"expected hidden_local [B, S/sp, H] and sequences [B, S], got {tuple(hidden_local.shape)} "
+                         f"{tuple(sequences.shape)}")
+    sp, rank = dist.get_world_size(group), dist.get_rank(group)
+    B, L, H = hidden_local.shape
+    S = sequences.shape[1]
+    A = int(num_actions)
+    if not 0 < A < S:
+        raise ValueError(f"num_actions must be in (0, {S}), got {A}")
+    pad = (sp - S % sp) % sp
+    if L * sp != S + pad:
+        raise ValueError(f"hidden_local has {L} positions per rank, expected {(S + pad) // sp} (= ceil({S} / {sp}))")
+    if compute_entropy and attention_mask is not None and attention_mask.shape != (B, S):
+        raise ValueError(
+            f"attention_mask shape {attention_mask.shape} does not match logits shape "
+            f"(batch_size={B}, seqlen={S}). Expected attention_mask shape: ({B}, {S})"
+        )
+    lo, hi = S - A - 1, S - 1                                  # the response window in global columns
+    g0 = rank * L
+    c0, c1 = min(max(lo - g0, 0), L), min(max(hi - g0, 0), L)  # ... and in this rank's columns
+    n = c1 - c0
+    lp_local = ent_local = _ZeroAnchor.apply(hidden_local)
+    if n > 0:
+        rolled = torch.roll(sequences, shifts=-1, dims=1)[:, g0 + c0:g0 + c1]
+        emask = None
+        if compute_entropy and attention_mask is not None:
+            emask = attention_mask[:, g0 + c0:g0 + c1].reshape(B * n)
+        lp, ent = fused_lm_head(hidden_local[:, c0:c1, :].reshape(B * n, H), lm_head_weight, rolled.reshape(B * n),
+                                temperature=temperature, entropy_mask=emask, compute_entropy=compute_entropy,
+                                chunk=chunk)
+        place = lambda x: torch.nn.functional.pad(x.view(B, n), (c0, L - c1))
+        lp_local = lp_local + place(lp)
+        if compute_entropy:
+            ent_local = ent_local + place(ent)
+    full = _SeqParallelGather.apply(lp_local, group, grad_scaler)
+    out_ent = None
+    if compute_entropy:
+        out_ent = _SeqParallelGather.apply(ent_local, group, grad_scaler)[:, lo:hi]
+    return full[:, lo:hi], out_ent

@@ -64,3 +64,28 @@ def test_single_process_is_identity():
 
     s = {"a": 1.0, "b_max": 2.0}
     assert sdist.all_reduce_metrics(s) == s
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 3])
+def test_sequence_parallel_wrapper_glue(world, tmp_path):
+    """action_log_probs_from_sp_hidden (Ulysses branch, model_wrapper.py:292-355) over gloo with a stand-in head:
+    every rank ends up with the single-process [B, A] log-probs and entropies, the gradient of its own hidden slice
+    (times the group size with the reference's grad_scaler, :229-231), and the weight gradients add up - including
+    sequence lengths that need padding and ranks whose slice holds no response position at all."""
+    import subprocess
+    import sys
+
+    port = str(_free_port())
+    out = str(tmp_path / "sp")
+    worker = os.path.join(os.path.dirname(__file__), "sp_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), str(world), port, out]) for r in range(world)]
+    for p in procs:
+        assert p.wait(timeout=150) == 0
+    empty_slices = 0
+    for r in range(world):
+        res = torch.load(f"{out}.{r}")
+        for case, v in res.items():
+            assert v["fwd"] and v["dh"] and v["dw"], (world, r, case, v)
+            empty_slices += v["rows_here"] == 0
+    assert empty_slices > 0  # the zero-anchor path (a rank without response rows still back-propagates) was taken
