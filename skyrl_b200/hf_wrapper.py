@@ -1,0 +1,64 @@
+"""Drop-in for ``HFModelWrapper.forward`` (skyrl-train/skyrl_train/model_wrapper.py:261-375) on a Hugging Face causal
+LM: the transformer trunk runs as before, but the ``lm_head`` GEMM, ``logits.div_(T)``, the flash-attn cross-entropy
+and the chunked entropy are replaced by the fused head on the ``num_actions`` response rows of every sequence -
+``[B, S, V]`` logits are never built.
+
+    policy = FusedHeadPolicy(AutoModelForCausalLM.from_pretrained(...))       # what HFModelWrapper holds as .model
+    action_log_probs, output = policy(sequences, num_actions, attention_mask, temperature=T,
+                                      return_output=True, compute_entropy=True, entropy_requires_grad=use_entropy_loss)
+
+Same call signature and return convention as the reference wrapper: ``action_log_probs`` is ``[B, A]`` and
+``output["entropy"]`` is ``[B, S]`` so that the worker's own slice ``[:, -A-1:-1]`` (worker.py:855) keeps working
+(positions outside the response window hold zeros - the worker never reads them).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import model_wrapper as _glue
+
+
+class FusedHeadPolicy(nn.Module):
+    def __init__(self, model: nn.Module, sequence_parallel_group=None):
+        super().__init__()
+        self.model = model
+        self.sequence_parallel_group = sequence_parallel_group
+        trunk = model.get_decoder() if hasattr(model, "get_decoder") else getattr(model, "model", None)
+        head = model.get_output_embeddings() if hasattr(model, "get_output_embeddings") else getattr(model, "lm_head", None)
+        if trunk is None or head is None or getattr(head, "bias", None) is not None:
+            raise ValueError("FusedHeadPolicy needs a causal LM with a decoder trunk and a bias-free lm_head")
+        self._trunk, self._head = [trunk], [head]  # lists: not registered twice as sub-modules
+
+    def forward(self, sequences: torch.LongTensor, num_actions, attention_mask: Optional[torch.Tensor] = None,
+                temperature: float = 1.0, return_output: bool = False, compute_entropy: bool = False,
+                entropy_requires_grad: bool = True):
+        if isinstance(num_actions, (list, tuple)):  # model_wrapper.py:363-367
+            if len(num_actions) != 1:
+                raise ValueError("per-sample num_actions is not supported by the fused head (use the padded batch)")
+            num_actions = num_actions[0]
+        A = int(num_actions)
+        if attention_mask is None:
+            attention_mask = torch.ones_like(sequences)
+        position_ids = attention_mask.long().cumsum(-1) - 1   # model_wrapper.py:272-273
+        position_ids.masked_fill_(attention_mask == 0, 1)
+        hidden = self._trunk[0](sequences, attention_mask=attention_mask, position_ids=position_ids).last_hidden_state
+        weight = self._head[0].weight
+        if self.sequence_parallel_group is not None:
+            lp, ent = _glue.action_log_probs_from_sp_hidden(hidden, weight, sequences, A, attention_mask, temperature,
+                                                            compute_entropy, group=self.sequence_parallel_group)
+        else:
+            lp, ent = _glue.action_log_probs_from_hidden(hidden, weight, sequences, A, attention_mask, temperature,
+                                                         compute_entropy)
+        if not return_output:
+            return lp
+        output = {}
+        if compute_entropy:
+            if not entropy_requires_grad:
+                ent = ent.detach()
+            S = sequences.shape[1]
+            output["entropy"] = F.pad(ent, (S - A - 1, 1))    # [B, S]; the worker slices [:, -A-1:-1]
+        return lp, output

@@ -265,3 +265,49 @@ def test_install_into_the_live_reference_registries(monkeypatch):
         for reg, fns in saved.items():
             reg._functions.clear()
             reg._functions.update(fns)
+
+
+def test_fused_head_policy_is_the_hf_logits_path(monkeypatch):
+    """FusedHeadPolicy (drop-in for HFModelWrapper.forward, model_wrapper.py:261-375) on a tiny random Qwen2 with the
+    CUDA head replaced by the fp32 oracle head: action log-probs and the worker's entropy slice must equal the
+    reference recipe on the model's own logits - logits / T, log_softmax + gather against roll(sequences, -1),
+    entropy * attention_mask, slice [:, -A-1:-1] - and gradients must reach the trunk and the lm_head."""
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+
+    from oracle import policy_oracle as O
+    from skyrl_b200 import model_wrapper as mw
+
+    def oracle_head(h, w, labels, temperature=1.0, entropy_mask=None, compute_entropy=True, chunk=0):
+        lp, ent = O.head_logprobs_entropy(h.float(), w.float(), labels, temperature)
+        return lp, (ent * entropy_mask.float() if entropy_mask is not None else ent)
+
+    monkeypatch.setattr(mw, "fused_lm_head", oracle_head)
+    torch.manual_seed(0)
+    cfg = Qwen2Config(vocab_size=300, hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64,
+                      tie_word_embeddings=False)
+    model = Qwen2ForCausalLM(cfg).float()
+    policy = skyrl_b200.FusedHeadPolicy(model)
+    B, S, A, T = 3, 12, 5, 0.7
+    sequences = torch.randint(0, 300, (B, S))
+    am = torch.ones(B, S, dtype=torch.long)
+    am[0, :3] = 0   # left padding of the prompt
+    am[2, -2:] = 0  # right padding of the response
+    lp, out = policy(sequences, A, am, temperature=T, return_output=True, compute_entropy=True)
+    pos = am.cumsum(-1) - 1
+    pos.masked_fill_(am == 0, 1)
+    logits = model(sequences, attention_mask=am, position_ids=pos).logits / T
+    want_lp = O.logprobs_from_logits(logits, torch.roll(sequences, -1, 1))[:, -A - 1:-1]
+    want_ent = O.entropy_from_logits(logits, am)[:, -A - 1:-1]
+    assert lp.shape == (B, A) and out["entropy"].shape == (B, S)
+    assert torch.allclose(lp, want_lp, atol=1e-5)
+    assert torch.allclose(out["entropy"][:, -A - 1:-1], want_ent, atol=1e-5)
+    (lp.sum() + out["entropy"][:, -A - 1:-1].sum()).backward()
+    g_fused = [model.lm_head.weight.grad.clone(), model.model.layers[0].mlp.up_proj.weight.grad.clone()]
+    model.zero_grad()
+    (want_lp.sum() + want_ent.sum()).backward()
+    assert torch.allclose(g_fused[0], model.lm_head.weight.grad, atol=1e-4)
+    assert torch.allclose(g_fused[1], model.model.layers[0].mlp.up_proj.weight.grad, atol=1e-4)
+    assert isinstance(policy(sequences, [A], am), torch.Tensor)        # return_output=False, list form of num_actions
+    _, out2 = policy(sequences, A, am, return_output=True, compute_entropy=True, entropy_requires_grad=False)
+    assert not out2["entropy"].requires_grad

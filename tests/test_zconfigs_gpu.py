@@ -321,3 +321,40 @@ def test_gspo_fused_step_with_a_response_length_off_the_tile_grid(A):
     rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
     assert rel(out.d_hidden.float(), h.grad) < 2e-2
     assert rel(out.d_weight, w.grad) < 2e-2
+
+
+def test_fused_head_policy_on_a_tiny_qwen2():
+    """FusedHeadPolicy (the drop-in for HFModelWrapper.forward) end to end on the GPU: bf16 trunk of a tiny random
+    Qwen2 -> CUDA fused head.  Log-probs / entropy against the oracle head on the trunk's own hidden states (the
+    parity definition: fp32 logits from the bf16 operands, 1e-3 abs); gradients reach the lm_head and the trunk."""
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+
+    torch.manual_seed(0)
+    cfg = Qwen2Config(vocab_size=1000, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=128,
+                      tie_word_embeddings=False)
+    model = Qwen2ForCausalLM(cfg).to(device=DEV, dtype=torch.bfloat16)
+    policy = skyrl_b200.FusedHeadPolicy(model)
+    B, S, A, T = 4, 40, 17, 0.8
+    sequences = torch.randint(0, 1000, (B, S), device=DEV)
+    am = torch.ones(B, S, dtype=torch.long, device=DEV)
+    am[0, :5] = 0
+    am[3, -3:] = 0
+    lp, out = policy(sequences, A, am, temperature=T, return_output=True, compute_entropy=True)
+    assert lp.shape == (B, A) and out["entropy"].shape == (B, S) and lp.dtype == torch.float32
+    with torch.no_grad():
+        pos = am.cumsum(-1) - 1
+        pos.masked_fill_(am == 0, 1)
+        hidden = model.model(sequences, attention_mask=am, position_ids=pos).last_hidden_state
+    sl = slice(S - A - 1, S - 1)
+    lp_ref, ent_ref = O.head_logprobs_entropy(hidden[:, sl].reshape(B * A, -1).float().cpu(),
+                                              model.lm_head.weight.detach().float().cpu(),
+                                              torch.roll(sequences, -1, 1)[:, sl].reshape(-1).cpu(), T)
+    assert (lp.detach().cpu() - lp_ref.view(B, A)).abs().max().item() < 1e-3
+    want_ent = ent_ref.view(B, A) * am[:, sl].cpu().float()
+    assert (out["entropy"][:, sl].detach().cpu() - want_ent).abs().max().item() < 1e-3
+    assert torch.count_nonzero(out["entropy"][:, :S - A - 1]) == 0
+    (lp.mean() - 0.01 * out["entropy"][:, sl].mean()).backward()
+    gw, gt = model.lm_head.weight.grad, model.model.layers[0].mlp.up_proj.weight.grad
+    assert gw is not None and gt is not None and torch.isfinite(gw).all() and torch.isfinite(gt).all()
+    assert gw.abs().max().item() > 0 and gt.abs().max().item() > 0
