@@ -525,115 +525,149 @@ struct EpiStoreBF16 {
 //   y = acc * scale_log2  (scale_log2 = log2(e) / temperature)
 //   part_m = max_j y_j ; part_s = sum_j 2^(y_j - part_m) ; part_t = sum_j 2^(y_j - part_m) * acc_j
 // and the raw accumulator at the label column (written by the one slab that contains it).
-struct EpiLsePartials {
-    struct Params {
-        float scale_log2;
-        float* part_m;  // [num_n_tiles][ld]
-        float* part_s;
-        float* part_t;
-        int64_t ld;
-        const int64_t* labels;  // [M]
-        float* label_acc;       // [M]
-        __nv_bfloat16* logits;  // [M, ld_logits] bf16 copy of the raw accumulators, or nullptr
-        int64_t ld_logits;
-    };
-    template <int BN>
-    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
-        const int n0 = n_tile * BN;
-        const bool row_ok = row < M;
-        const int lab = row_ok ? static_cast<int>(p.labels[row]) : -1;
-        float m2 = -INFINITY, s = 0.f, tt = 0.f;
-        uint32_t held[16];
-        __nv_bfloat16* held_dst = nullptr;
+//
+// kStored (EpiLsePartialsStored): additionally part_sb = sum_j 2^(bf16(acc_j) * scale_log2 - part_m), the same sum
+// over the bf16-ROUNDED logits that go to the tile store.  The backward of the fused step reads that store; with the
+// log-sum-exp of the rounded logits its p = 2^(bf16(z) * scale - lse_b) is exactly softmax(bf16 logits) - a
+// distribution, and the arithmetic the reference differentiates (its lm_head emits bf16 logits) - instead of rounded
+// logits against the exact normaliser, whose probabilities miss 1 by up to 0.25 ulp(bf16) * |z| per element.
+struct LsePartialsParams {
+    float scale_log2;
+    float* part_m;  // [num_n_tiles][ld]
+    float* part_s;
+    float* part_t;
+    int64_t ld;
+    const int64_t* labels;  // [M]
+    float* label_acc;       // [M]
+    __nv_bfloat16* logits;  // [M, ld_logits] bf16 copy of the raw accumulators, or nullptr
+    int64_t ld_logits;
+};
+struct LsePartialsStoredParams : LsePartialsParams {
+    float* part_sb;  // [num_n_tiles][ld]
+};
+
+template <int BN, bool kStored, class P>
+__device__ __forceinline__ void lse_partials_tile(const P& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+    const int n0 = n_tile * BN;
+    const bool row_ok = row < M;
+    const int lab = row_ok ? static_cast<int>(p.labels[row]) : -1;
+    float m2 = -INFINITY, s = 0.f, tt = 0.f;
+    [[maybe_unused]] float sb = 0.f;
+    uint32_t held[16];
+    __nv_bfloat16* held_dst = nullptr;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            __syncwarp();
-            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
-            ptx::tmem_ld_wait();
-            const int col0 = n0 + c * 32;
-            if (col0 >= N) continue;  // uniform across the whole warp
-            const int nvalid = min(32, N - col0);
-            float cm = -INFINITY;
-            if (nvalid == 32) {
+    for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+        ptx::tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (col0 >= N) continue;  // uniform across the whole warp
+        const int nvalid = min(32, N - col0);
+        float cm = -INFINITY;
+        if (nvalid == 32) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]));
-            } else {
+            for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]));
+        } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (i < nvalid) cm = fmaxf(cm, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; ++i)
+                if (i < nvalid) cm = fmaxf(cm, __uint_as_float(v[i]));
+        }
+        const float m_new = fmaxf(m2, cm * p.scale_log2);
+        const float corr = ex2_approx(m2 - m_new);  // 0 on the first chunk (m2 = -inf)
+        s *= corr;
+        tt *= corr;
+        if constexpr (kStored) sb *= corr;
+        m2 = m_new;
+        if (nvalid == 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float a = __uint_as_float(v[i]);
+                const float e = ex2_approx(fmaf(a, p.scale_log2, -m2));
+                s += e;
+                tt = fmaf(e, a, tt);
+                if constexpr (kStored) {
+                    const float r = __bfloat162float(__float2bfloat16_rn(a));
+                    sb += ex2_approx(fmaf(r, p.scale_log2, -m2));
+                }
             }
-            const float m_new = fmaxf(m2, cm * p.scale_log2);
-            const float corr = ex2_approx(m2 - m_new);  // 0 on the first chunk (m2 = -inf)
-            s *= corr;
-            tt *= corr;
-            m2 = m_new;
-            if (nvalid == 32) {
+        } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 32; ++i) {
+                if (i < nvalid) {
                     const float a = __uint_as_float(v[i]);
                     const float e = ex2_approx(fmaf(a, p.scale_log2, -m2));
                     s += e;
                     tt = fmaf(e, a, tt);
+                    if constexpr (kStored) {
+                        const float r = __bfloat162float(__float2bfloat16_rn(a));
+                        sb += ex2_approx(fmaf(r, p.scale_log2, -m2));
+                    }
+                }
+            }
+        }
+        if (lab >= col0 && lab < col0 + nvalid) {
+            float z = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (col0 + i == lab) z = __uint_as_float(v[i]);
+            p.label_acc[row] = z;
+        }
+        if (p.logits != nullptr && row_ok) {
+            __nv_bfloat16* dst = p.logits + static_cast<int64_t>(row) * p.ld_logits + col0;
+            if (nvalid == 32 && (p.ld_logits & 15) == 0 && (reinterpret_cast<uintptr_t>(p.logits) & 31u) == 0) {
+                // Two 32-column chunks are written together as one full 128-byte line (4 x 32 B issued back
+                // to back), so the write-once store never leaves a half-written line behind to be re-filled.
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                if ((c & 1) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) held[i] = pk[i];
+                    held_dst = dst;
+                } else {
+                    if (held_dst != nullptr) {
+                        st_global_256_stream(held_dst, held[0], held[1], held[2], held[3], held[4], held[5], held[6],
+                                             held[7]);
+                        st_global_256_stream(held_dst + 16, held[8], held[9], held[10], held[11], held[12], held[13],
+                                             held[14], held[15]);
+                        held_dst = nullptr;
+                    }
+                    st_global_256_stream(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+                    st_global_256_stream(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
                 }
             } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (i < nvalid) {
-                        const float a = __uint_as_float(v[i]);
-                        const float e = ex2_approx(fmaf(a, p.scale_log2, -m2));
-                        s += e;
-                        tt = fmaf(e, a, tt);
-                    }
-                }
-            }
-            if (lab >= col0 && lab < col0 + nvalid) {
-                float z = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (col0 + i == lab) z = __uint_as_float(v[i]);
-                p.label_acc[row] = z;
-            }
-            if (p.logits != nullptr && row_ok) {
-                __nv_bfloat16* dst = p.logits + static_cast<int64_t>(row) * p.ld_logits + col0;
-                if (nvalid == 32 && (p.ld_logits & 15) == 0 && (reinterpret_cast<uintptr_t>(p.logits) & 31u) == 0) {
-                    // Two 32-column chunks are written together as one full 128-byte line (4 x 32 B issued back
-                    // to back), so the write-once store never leaves a half-written line behind to be re-filled.
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                    if ((c & 1) == 0) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) held[i] = pk[i];
-                        held_dst = dst;
-                    } else {
-                        if (held_dst != nullptr) {
-                            st_global_256_stream(held_dst, held[0], held[1], held[2], held[3], held[4], held[5], held[6],
-                                                 held[7]);
-                            st_global_256_stream(held_dst + 16, held[8], held[9], held[10], held[11], held[12], held[13],
-                                                 held[14], held[15]);
-                            held_dst = nullptr;
-                        }
-                        st_global_256_stream(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
-                        st_global_256_stream(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
-                    }
-                } else {
-                    for (int i = 0; i < nvalid; ++i) dst[i] = __float2bfloat16_rn(__uint_as_float(v[i]));
-                }
+                for (int i = 0; i < nvalid; ++i) dst[i] = __float2bfloat16_rn(__uint_as_float(v[i]));
             }
         }
-        if (held_dst != nullptr) {  // odd number of valid 32-column chunks in this tile
-            st_global_256_stream(held_dst, held[0], held[1], held[2], held[3], held[4], held[5], held[6], held[7]);
-            st_global_256_stream(held_dst + 16, held[8], held[9], held[10], held[11], held[12], held[13], held[14],
-                                 held[15]);
-        }
-        if (row_ok) {
-            const int64_t o = static_cast<int64_t>(n_tile) * p.ld + row;
-            p.part_m[o] = m2;
-            p.part_s[o] = s;
-            p.part_t[o] = tt;
-        }
+    }
+    if (held_dst != nullptr) {  // odd number of valid 32-column chunks in this tile
+        st_global_256_stream(held_dst, held[0], held[1], held[2], held[3], held[4], held[5], held[6], held[7]);
+        st_global_256_stream(held_dst + 16, held[8], held[9], held[10], held[11], held[12], held[13], held[14],
+                             held[15]);
+    }
+    if (row_ok) {
+        const int64_t o = static_cast<int64_t>(n_tile) * p.ld + row;
+        p.part_m[o] = m2;
+        p.part_s[o] = s;
+        p.part_t[o] = tt;
+        if constexpr (kStored) p.part_sb[o] = sb;
+    }
+}
+
+struct EpiLsePartials {
+    using Params = LsePartialsParams;
+    template <int BN>
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+        lse_partials_tile<BN, false>(p, taddr, row, n_tile, M, N);
+    }
+};
+struct EpiLsePartialsStored {
+    using Params = LsePartialsStoredParams;
+    template <int BN>
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+        lse_partials_tile<BN, true>(p, taddr, row, n_tile, M, N);
     }
 };
 

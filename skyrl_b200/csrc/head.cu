@@ -199,6 +199,9 @@ static int dw_lockstep() { static int v = env_int0("SKYB200_DW_LOCKSTEP", 128); 
 static int dw_group_n() { static int v = env_int("SKYB200_DW_GROUP_N", 14); return v; }
 // skip all-zero d(logits) rows (masked tokens) in the backward GEMMs of the fused step (0 disables)
 static int skip_zero_rows() { static int v = env_int0("SKYB200_SKIP_ZERO_ROWS", 1); return v; }
+// fused step: normalise the backward's probabilities with the log-sum-exp of the bf16-ROUNDED logits it reads from
+// the tile store (softmax(bf16 logits), what the reference differentiates) instead of the exact forward lse
+static int stored_lse() { static int v = env_int0("SKYB200_STORED_LSE", 0); return v; }
 // cap on the resident blocks of the d(logits) transform pass (0 = one block per item)
 static int transform_blocks() { static int v = env_int0("SKYB200_TRANSFORM_BLOCKS", 0); return v; }
 
@@ -269,6 +272,42 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float* __restrict
         if (entropy_mask != nullptr) h *= entropy_mask[r];
         if (entropy != nullptr) entropy[r] = h;
     }
+}
+
+// log2-sum-exp of the bf16-rounded logits of the tile store (EpiLsePartialsStored): the slab sums part_sb are taken
+// against the slab maxima part_m of the exact logits, so they merge with the same rescaling as part_s.  Same block
+// layout as head_merge_kernel: 32 rows x 8 slab-splitting warps, fixed-order fold.
+__global__ void __launch_bounds__(256) head_merge_stored_kernel(const float* __restrict__ part_m,
+                                                                const float* __restrict__ part_sb, int64_t ld,
+                                                                int slabs, float* __restrict__ lse2_stored, int rows) {
+    __shared__ float sm[8][kMergeRows], ss[8][kMergeRows];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r = blockIdx.x * kMergeRows + lane;
+    float m = -INFINITY, sv = 0.f;
+    if (r < rows) {
+#pragma unroll 4
+        for (int sl = w; sl < slabs; sl += 8) {
+            const int64_t o = (int64_t)sl * ld + r;
+            const float pm = __ldcs(part_m + o), ps = __ldcs(part_sb + o);
+            const float nm = fmaxf(m, pm);
+            sv = fmaf(sv, exp2f(m - nm), ps * exp2f(pm - nm));  // m = -inf on the first step: factor 0
+            m = nm;
+        }
+    }
+    sm[w][lane] = m;
+    ss[w][lane] = sv;
+    __syncthreads();
+    if (w != 0 || r >= rows) return;
+    float M = sm[0][lane], S = ss[0][lane];
+#pragma unroll
+    for (int x = 1; x < 8; ++x) {
+        if (x < slabs) {
+            const float nm = fmaxf(M, sm[x][lane]);
+            S = fmaf(S, exp2f(M - nm), ss[x][lane] * exp2f(sm[x][lane] - nm));
+            M = nm;
+        }
+    }
+    lse2_stored[r] = M + log2f(S);
 }
 
 // Vocab-parallel variant: fold the slab partials of ONE vocab shard into per-token (max, sum, weighted sum,
@@ -754,6 +793,7 @@ struct StepPlan {
     // everything below exists twice (parity of the chunk index): the small kernels of chunk c+1 run on the
     // auxiliary stream while the backward GEMMs of chunk c run on the caller's stream
     size_t off_part[2], off_label[2], off_lse2[2], off_entraw[2], off_dlp[2], off_dent[2], off_S[2], off_maps[2];
+    size_t off_partsb[2], off_lse2s[2];  // SKYB200_STORED_LSE: slab sums / log-sum-exp of the stored (bf16) logits
     size_t off_loss, total;
 };
 
@@ -805,6 +845,9 @@ StepPlan plan_step(int64_t B, int64_t A, int64_t N, int64_t H, int64_t V, int lo
         p.off_dent[i] = take((size_t)chunk * 4);
         p.off_S[i] = take(need_grad ? (size_t)chunk * p.ldS * 2 : 0);
         p.off_maps[i] = take(live_maps_ints(chunk) * sizeof(int));
+        const bool stored = need_grad && stored_lse() != 0;
+        p.off_partsb[i] = take(stored ? (size_t)p.slabs * chunk * 4 : 0);
+        p.off_lse2s[i] = take(stored ? (size_t)chunk * 4 : 0);
     }
     // every chunk rounds its loss-partial slots up: 4 spare slots (128 bytes) per chunk
     p.off_loss = take(loss_chunk_ws_bytes(B, N) + (size_t)(N / stride + 2) * 8 * 4 * 4);
@@ -909,6 +952,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
     const __nv_bfloat16* hid = static_cast<const __nv_bfloat16*>(hidden);
     __nv_bfloat16* dhid = static_cast<__nv_bfloat16*>(d_hidden);
     const bool use_ent_grad = need_grad && params->use_entropy_loss != 0;
+    const bool use_stored_lse = need_grad && stored_lse() != 0;
     const int64_t n_chunks = (N + stride - 1) / stride;
 
     auto fptr = [&](size_t off) { return reinterpret_cast<float*>(wb + off); };
@@ -919,7 +963,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
         const int64_t t0 = ci * stride;
         const int rows = (int)std::min<int64_t>(stride, N - t0);
         float* part_m = fptr(plan.off_part[p]);
-        EpiLsePartials::Params ep;
+        EpiLsePartialsStored::Params ep;  // the plain epilogue takes its base-class slice
         ep.scale_log2 = scale_log2;
         ep.part_m = part_m;
         ep.part_s = part_m + (int64_t)plan.slabs * c;
@@ -929,13 +973,20 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
         ep.label_acc = fptr(plan.off_label[p]);
         ep.logits = need_grad ? reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]) : nullptr;
         ep.ld_logits = plan.ldS;
+        ep.part_sb = use_stored_lse ? fptr(plan.off_partsb[p]) : nullptr;
         // the parity buffers were last read by the auxiliary-stream kernels of chunk ci - 2
         if (ci >= 2) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[p], 0));
         if (hidden_host != nullptr) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->copied[ci], 0));
         SKYB200_CUDA_CHECK(cudaMemsetAsync(ep.label_acc, 0, (size_t)rows * sizeof(float), stream));
-        int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
-            hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream, 0, hint_fwd_a(), kEvictNormal,
-            fwd_lockstep());
+        int r;
+        if (use_stored_lse)
+            r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartialsStored>(
+                hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream, 0, hint_fwd_a(),
+                kEvictNormal, fwd_lockstep());
+        else
+            r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
+                hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(),
+                static_cast<const EpiLsePartials::Params&>(ep), stream, 0, hint_fwd_a(), kEvictNormal, fwd_lockstep());
         if (r) return r;
         SKYB200_CUDA_CHECK(cudaEventRecord(ss->fwd[p], stream));
         return SKYB200_OK;
@@ -966,10 +1017,19 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
                             t0 + rows, slot, *params, cu_seqlens, aux);
         if (r) return r;
         if (need_grad) {
+            const float* lse2_bwd = lse2;  // normaliser of the backward's probabilities
+            if (use_stored_lse) {
+                float* lse2s = fptr(plan.off_lse2s[p]);
+                head_merge_stored_kernel<<<(rows + kMergeRows - 1) / kMergeRows, 256, 0, aux>>>(
+                    part_m, fptr(plan.off_partsb[p]), c, plan.slabs, lse2s, rows);
+                r = check_launch("head_merge_stored_kernel");
+                if (r) return r;
+                lse2_bwd = lse2s;
+            }
             const int64_t items = (int64_t)rows * ((V + 4095) / 4096);
             const int64_t cap = transform_blocks() > 0 ? transform_blocks() : items;
             dlogits_transform_kernel<<<(unsigned)std::min<int64_t>(items, cap), 256, 0, aux>>>(
-                reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]), plan.ldS, (int)V, lse2, d_lp,
+                reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]), plan.ldS, (int)V, lse2_bwd, d_lp,
                 use_ent_grad ? d_ent : nullptr, (use_ent_grad && entropy_mask) ? entropy_mask + t0 : nullptr, ent_raw,
                 labels + t0, scale_log2, inv_T, rows);
             r = check_launch("dlogits_transform_kernel");

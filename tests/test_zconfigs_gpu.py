@@ -358,3 +358,83 @@ def test_fused_head_policy_on_a_tiny_qwen2():
     gw, gt = model.lm_head.weight.grad, model.model.layers[0].mlp.up_proj.weight.grad
     assert gw is not None and gt is not None and torch.isfinite(gw).all() and torch.isfinite(gt).all()
     assert gw.abs().max().item() > 0 and gt.abs().max().item() > 0
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_sharply_peaked_logits(fused):
+    """A trained policy is nearly deterministic on most tokens: logits with std ~13 (std 8 / T = 0.6), a third of the
+    labels at the arg-max (log-prob ~ 0, entropy ~ 1e-3) and the rest far in the tail (log-prob ~ -40).  The online
+    softmax, the entropy as a difference of two large numbers and both backward paths (fp32 recompute, and the fused
+    step's bf16 logits store) against the fp32 oracle."""
+    N, H, V, T = 768, 256, 5000, 0.6
+    g = torch.Generator().manual_seed(9)
+    hidden = torch.randn(N, H, generator=g).bfloat16()
+    weight = (torch.randn(V, H, generator=g) * (8.0 / H ** 0.5)).bfloat16()
+    labels = torch.randint(0, V, (N,), generator=g)
+    labels[: N // 3] = (hidden[: N // 3].float() @ weight.float().t()).argmax(-1)
+    h = hidden.float().requires_grad_(True)
+    w = weight.float().requires_grad_(True)
+    lp_ref, ent_ref = O.head_logprobs_entropy(h, w, labels, T)
+    assert lp_ref[: N // 3].max().item() > -0.05 and lp_ref.min().item() < -25.0 and ent_ref.median().item() < 1.0
+    rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+    if not fused:
+        g_lp, g_ent = torch.randn(N, generator=g), 0.3 * torch.randn(N, generator=g)
+        ((lp_ref * g_lp).sum() + (ent_ref * g_ent).sum()).backward()
+        hd, wd = hidden.to(DEV).requires_grad_(True), weight.to(DEV).requires_grad_(True)
+        lp, ent = skyrl_b200.fused_lm_head(hd, wd, labels.to(DEV), temperature=T)
+        ((lp * g_lp.to(DEV)).sum() + (ent * g_ent.to(DEV)).sum()).backward()
+        d_hidden, d_weight = hd.grad.float(), wd.grad.float()
+    else:
+        B, A = 3, N // 3
+        cfg = O.make_cfg(policy_loss_type="regular", loss_reduction="token_mean", use_kl_loss=False,
+                         use_entropy_loss=True, entropy_loss_coef=0.3)
+        olp = lp_ref.detach().view(B, A) + 0.05 * torch.randn(B, A, generator=g)
+        adv = torch.randn(B, A, generator=g)
+        final, _ = O.loss_assembly(lp_ref.view(B, A), olp, adv, cfg, torch.ones(B, A), None, ent_ref.view(B, A))
+        final.backward()
+        out = skyrl_b200.policy_update_step(hidden.to(DEV), weight.to(DEV), labels.to(DEV).view(B, A), olp.to(DEV),
+                                            adv.to(DEV), cfg, loss_mask=torch.ones(B, A, device=DEV), temperature=T)
+        lp, ent, d_hidden, d_weight = out.log_probs.reshape(-1), out.entropy.reshape(-1), out.d_hidden.float(), out.d_weight
+        assert out.status["final_loss"] == pytest.approx(final.item(), rel=2e-3, abs=2e-4)
+    assert (lp.detach().cpu() - lp_ref.detach()).abs().max().item() < 1e-3
+    assert (ent.detach().cpu() - ent_ref.detach()).abs().max().item() < 1e-3
+    # The fp32 recompute of the autograd path holds the usual bound.  The fused step reads bf16-ROUNDED logits
+    # (|z| up to ~70 here: ulp 0.5) back against the exact normaliser, so its probabilities carry up to 28 % error per
+    # element: ~6 % on d_hidden at this logit scale (CPU emulation in DESIGN 7; the reference's own bf16-logits path:
+    # 2.7 %; SKYB200_STORED_LSE=1: 1.6 %, see test_stored_lse_flag).  Pinned here so a regression shows.
+    bound = 0.12 if fused else 2e-2
+    assert rel(d_hidden, h.grad) < bound and rel(d_weight, w.grad) < bound
+
+
+@pytest.mark.skipif(__import__("os").environ.get("SKYB200_TEST_EXPERIMENTAL") != "1",
+                    reason="SKYB200_STORED_LSE is an experimental, default-off kernel variant that has not run on a B200 "
+                           "yet (written after the round-1 GPU budget was spent); opt in with SKYB200_TEST_EXPERIMENTAL=1")
+def test_stored_lse_flag(tmp_path):
+    """SKYB200_STORED_LSE=1: the fused step normalises its backward probabilities with the log-sum-exp of the bf16
+    logits it stored (softmax of the rounded logits - the reference's arithmetic) instead of the exact forward lse.
+    Forward outputs must not move; on sharply peaked logits the gradient error against fp32 math must drop to the level
+    of the reference's own bf16-logits path (CPU emulation: 1.6 % vs 6.3 % for d_hidden) and every d_logits row must sum
+    to zero again."""
+    import os
+    import subprocess
+    import sys
+
+    worker = os.path.join(os.path.dirname(__file__), "lse_worker.py")
+    res = {}
+    for flag in ("0", "1"):
+        path = str(tmp_path / f"lse{flag}.pt")
+        r = subprocess.run([sys.executable, worker, path], env=dict(os.environ, SKYB200_STORED_LSE=flag),
+                           capture_output=True, text=True, timeout=280)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        res[flag] = torch.load(path)
+    for name in ("peaked", "mild"):
+        off, on = res["0"][name], res["1"][name]
+        print(name, {k: (off[k], on[k]) for k in ("rel_dh", "rel_dw", "colsum", "lp_err")})
+        assert torch.allclose(off["log_probs"], on["log_probs"], atol=1e-6, rtol=0)
+        assert torch.allclose(off["entropy"], on["entropy"], atol=1e-6, rtol=0)
+        assert on["lp_err"] < 1e-3 and on["final"] == pytest.approx(on["final_ref"], rel=2e-3, abs=2e-4)
+        assert on["rel_dh"] <= off["rel_dh"] * 1.05 and on["colsum"] < 1e-3
+    assert res["1"]["mild"]["rel_dh"] < 1e-2 and res["1"]["mild"]["rel_dw"] < 1e-2
+    assert res["1"]["peaked"]["rel_dh"] < 2.5e-2 and res["1"]["peaked"]["rel_dw"] < 2.5e-2
+    assert res["1"]["peaked"]["rel_dh"] < 0.5 * res["0"]["peaked"]["rel_dh"]
+    assert res["1"]["peaked"]["colsum"] < 0.2 * res["0"]["peaked"]["colsum"]   # rows of d_logits sum to zero again
