@@ -29,7 +29,7 @@ from .advantages import (  # noqa: F401
     compute_rloo_outcome_advantage,
 )
 from .fused_head import fused_lm_head, fused_lm_head_logprobs  # noqa: F401
-from .hf_wrapper import FusedHeadPolicy  # noqa: F401
+from .hf_wrapper import FusedHeadPolicy, ValueHeadCritic  # noqa: F401
 from .losses import gspo_policy_loss, policy_update_loss, ppo_critic_loss, ppo_policy_loss  # noqa: F401
 from .model_wrapper import (  # noqa: F401
     action_log_probs_from_hidden,

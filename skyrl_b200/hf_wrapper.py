@@ -62,3 +62,36 @@ class FusedHeadPolicy(nn.Module):
             S = sequences.shape[1]
             output["entropy"] = F.pad(ent, (S - A - 1, 1))    # [B, S]; the worker slices [:, -A-1:-1]
         return lp, output
+
+
+class ValueHeadCritic(nn.Module):
+    """Drop-in for the reference's ``CriticModel.forward`` (model_wrapper.py:425-500, padded layout): the trunk's last
+    hidden state goes through the CUDA value head on the ``num_actions`` response rows only, returning what the
+    reference returns as ``values[:, :-1][:, -num_actions:]``.
+
+    ``trunk`` is the base model (``AutoModel``), ``value_head`` the reference's ``nn.Linear(hidden_size, 1, bias=False)``
+    (a bias is honoured if present)."""
+
+    def __init__(self, trunk: nn.Module, value_head: nn.Linear):
+        super().__init__()
+        self.trunk, self.value_head = trunk, value_head
+
+    def forward(self, input_ids: torch.LongTensor, num_actions=None, attention_mask: Optional[torch.Tensor] = None,
+                return_output: bool = False):
+        from .value_head import action_values
+
+        if attention_mask is None:
+            attention_mask = torch.ones_like(input_ids)
+        position_ids = attention_mask.long().cumsum(-1) - 1
+        position_ids.masked_fill_(attention_mask == 0, 1)
+        outputs = self.trunk(input_ids, attention_mask=attention_mask, position_ids=position_ids)
+        if num_actions is None:
+            assert return_output
+            return outputs
+        if isinstance(num_actions, (list, tuple)):
+            if len(num_actions) != 1:
+                raise ValueError("per-sample num_actions is not supported (use the padded batch)")
+            num_actions = num_actions[0]
+        values = action_values(outputs.last_hidden_state, self.value_head.weight, int(num_actions),
+                               getattr(self.value_head, "bias", None))
+        return (values, outputs) if return_output else values

@@ -311,3 +311,33 @@ def test_fused_head_policy_is_the_hf_logits_path(monkeypatch):
     assert isinstance(policy(sequences, [A], am), torch.Tensor)        # return_output=False, list form of num_actions
     _, out2 = policy(sequences, A, am, return_output=True, compute_entropy=True, entropy_requires_grad=False)
     assert not out2["entropy"].requires_grad
+
+
+def test_value_head_critic_is_the_reference_slice(monkeypatch):
+    """ValueHeadCritic (drop-in for CriticModel.forward, model_wrapper.py:425-500) on a tiny random Qwen2 trunk with the
+    CUDA value head replaced by a matmul: values[:, :-1][:, -num_actions:] of Linear(hidden, 1) over all positions."""
+    from transformers import Qwen2Config, Qwen2Model
+
+    import importlib
+
+    vh = importlib.import_module("skyrl_b200.value_head")  # the package re-exports the function under this name
+
+    def matmul_head(hidden, weight, bias=None):
+        v = hidden.float() @ weight.float().reshape(-1)
+        return v + (bias.float().reshape(-1)[0] if bias is not None else 0.0)
+
+    monkeypatch.setattr(vh, "value_head", matmul_head)
+    torch.manual_seed(0)
+    cfg = Qwen2Config(vocab_size=300, hidden_size=32, intermediate_size=64, num_hidden_layers=1,
+                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64)
+    trunk = Qwen2Model(cfg).float()
+    head = torch.nn.Linear(32, 1, bias=False)
+    critic = skyrl_b200.ValueHeadCritic(trunk, head)
+    B, S, A = 2, 11, 4
+    ids = torch.randint(0, 300, (B, S))
+    am = torch.ones(B, S, dtype=torch.long)
+    am[0, :2] = 0
+    values, outputs = critic(ids, A, am, return_output=True)
+    want = head(outputs.last_hidden_state).squeeze(-1)[:, :-1][:, -A:]
+    assert values.shape == (B, A) and torch.allclose(values, want, atol=1e-6)
+    assert critic(ids, None, am, return_output=True).last_hidden_state.shape == (B, S, 32)
