@@ -35,6 +35,7 @@ from .model_wrapper import (  # noqa: F401
     action_log_probs_from_hidden,
     action_log_probs_from_packed_hidden,
     action_log_probs_from_sp_hidden,
+    action_log_probs_from_sp_packed_hidden,
 )
 from .policy_update import PolicyUpdateOutput, fused_policy_loss, pack_by_lengths, policy_update_step  # noqa: F401
 from .registry import (  # noqa: F401

@@ -206,3 +206,70 @@ def action_log_probs_from_sp_hidden(
     if compute_entropy:
         out_ent = _SeqParallelGather.apply(ent_local, group, grad_scaler)[:, lo:hi]
     return full[:, lo:hi], out_ent
+
+
+def action_log_probs_from_sp_packed_hidden(
+    hidden_local: torch.Tensor,
+    lm_head_weight: torch.Tensor,
+    sequences: torch.Tensor,
+    attention_mask: torch.Tensor,
+    num_actions: int,
+    temperature: float = 1.0,
+    compute_entropy: bool = False,
+    group=None,
+    grad_scaler: bool = True,
+    chunk: int = 0,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Sample packing **and** Ulysses sequence parallelism (model_wrapper.py:278-305, 319-358): the un-padded token
+    stream ``[1, nnz]`` was padded to a multiple of the group size and rank r ran the trunk on packed positions
+    ``[r*L, (r+1)*L)``; ``hidden_local`` is ``[L, H]`` (or ``[1, L, H]``).
+
+    Each rank projects only the packed rows of its slice that land in a response window ``[-A-1:-1]`` of their
+    sequence (labels: the packed stream rolled by one *before* slicing, as the reference does), the ranks all-gather
+    the fp32 results along the packed dimension, and every rank pads them back to ``[B, S]`` (zeros at masked
+    positions, like ``pad_input``) and slices.  Returns ``(action_log_probs [B, A], entropy [B, A] or None)``.
+    """
+    import torch.distributed as dist
+
+    if hidden_local.dim() == 3:
+        if hidden_local.shape[0] != 1:
+            raise ValueError(f"packed hidden must be [L, H] or [1, L, H], got {tuple(hidden_local.shape)}")
+        hidden_local = hidden_local[0]
+    if sequences.dim() != 2 or attention_mask.shape != sequences.shape:
+        raise ValueError("sequences and attention_mask must both be [B, S]")
+    sp, rank = dist.get_world_size(group), dist.get_rank(group)
+    B, S = sequences.shape
+    A = int(num_actions)
+    if not 0 < A < S:
+        raise ValueError(f"num_actions must be in (0, {S}), got {A}")
+    dev = hidden_local.device
+    L = hidden_local.shape[0]
+    valid = attention_mask.to(dev).reshape(-1) != 0
+    nnz_positions = torch.nonzero(valid).squeeze(-1)          # padded flat position of every packed token
+    nnz = int(nnz_positions.numel())
+    pad = (sp - nnz % sp) % sp
+    if L * sp != nnz + pad:
+        raise ValueError(f"hidden_local has {L} rows per rank, expected {(nnz + pad) // sp} (= ceil({nnz} / {sp}))")
+    packed_tokens = sequences.to(dev).reshape(-1)[nnz_positions]
+    rolled = torch.roll(packed_tokens, shifts=-1, dims=0)     # rolled over the whole stream, then sliced
+    window = torch.zeros((B, S), dtype=torch.bool, device=dev)
+    window[:, S - A - 1:S - 1] = True
+    in_window = window.reshape(-1)[nnz_positions]             # per packed token
+    g0 = rank * L
+    mine = torch.nonzero(in_window[g0:min(g0 + L, nnz)]).squeeze(-1)   # local rows that reach the head
+    anchor = _ZeroAnchor.apply(hidden_local.unsqueeze(0))              # [1, L], keeps the trunk's backward alive
+    lp_local = ent_local = anchor
+    if mine.numel() > 0:
+        lp, ent = fused_lm_head(hidden_local[mine], lm_head_weight, rolled[g0 + mine], temperature=temperature,
+                                compute_entropy=compute_entropy, chunk=chunk)
+        place = lambda x: x.new_zeros(L).index_copy(0, mine, x).unsqueeze(0)
+        lp_local = anchor + place(lp)
+        if compute_entropy:
+            ent_local = anchor + place(ent)
+
+    def finish(local):
+        stream = _SeqParallelGather.apply(local, group, grad_scaler)[0, :nnz]      # [nnz]
+        full = stream.new_zeros(B * S).index_copy(0, nnz_positions, stream)       # pad_input
+        return full.view(B, S)[:, S - A - 1:S - 1]
+
+    return finish(lp_local), (finish(ent_local) if compute_entropy else None)

@@ -60,6 +60,36 @@ def main():
                 dh=bool(h1.grad is not None and torch.allclose(h1.grad, want_h, atol=1e-5)),
                 dw=bool(torch.allclose(dw, w0.grad * scale, atol=1e-4)),
                 rows_here=int(min(max(S - 1 - rank * L, 0), L) - min(max(S - A - 1 - rank * L, 0), L)))
+        # ---- sample packing + sequence parallelism against the single-process packed glue
+        for case, (B, S, A, Hd, V) in enumerate([(3, 13, 4, 8, 11), (2, 16, 9, 8, 11), (4, 9, 2, 4, 5)]):
+            g = torch.Generator().manual_seed(200 + case)
+            weight = torch.randn(V, Hd, generator=g)
+            sequences = torch.randint(0, V, (B, S), generator=g)
+            am = (torch.rand(B, S, generator=g) > 0.25).long()
+            am[0] = 1
+            nnz = int(am.sum())
+            packed = torch.randn(nnz, Hd, generator=g)
+            coef = torch.randn(B, A, generator=g)
+            h0 = packed.clone().requires_grad_(True)
+            w0 = weight.clone().requires_grad_(True)
+            lp0, ent0 = mw.action_log_probs_from_packed_hidden(h0, w0, sequences, am, A, temperature=0.7,
+                                                               compute_entropy=True)
+            ((lp0 * coef).sum() + 0.3 * (ent0 * coef).sum()).backward()
+            pad = (world - nnz % world) % world
+            L = (nnz + pad) // world
+            hp = torch.nn.functional.pad(packed, (0, 0, 0, pad))
+            h1 = hp[rank * L:(rank + 1) * L].clone().requires_grad_(True)
+            w1 = weight.clone().requires_grad_(True)
+            lp1, ent1 = mw.action_log_probs_from_sp_packed_hidden(h1, w1, sequences, am, A, temperature=0.7,
+                                                                  compute_entropy=True)
+            ((lp1 * coef).sum() + 0.3 * (ent1 * coef).sum()).backward()
+            want_h = torch.nn.functional.pad(h0.grad, (0, 0, 0, pad))[rank * L:(rank + 1) * L] * world
+            dw = w1.grad.clone() if w1.grad is not None else torch.zeros_like(weight)
+            dist.all_reduce(dw)
+            res[10 + case] = dict(
+                fwd=bool(torch.allclose(lp1, lp0, atol=1e-6) and torch.allclose(ent1, ent0, atol=1e-6)),
+                dh=bool(h1.grad is not None and torch.allclose(h1.grad, want_h, atol=1e-5)),
+                dw=bool(torch.allclose(dw, w0.grad * world, atol=1e-4)), rows_here=1)
         torch.save(res, f"{out}.{rank}")
     finally:
         dist.destroy_process_group()
