@@ -19,7 +19,7 @@ def kernels(path):
         m = re.search(r"Function : (\S+)", line)
         if m:
             name = m.group(1)
-        elif name:
+        elif name and re.match(r"\s+(/\*[0-9a-f]{4}\*/|/\* 0x[0-9a-f]+ \*/|\.L_)", line):  # instruction and label lines only
             body[name].append(re.sub(r"/\*[0-9a-f]{4}\*/", "", line))
     return {k: (hashlib.md5("\n".join(v).encode()).hexdigest(), len(v)) for k, v in body.items()}
 
