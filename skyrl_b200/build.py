@@ -19,7 +19,7 @@ OBJ_DIR = PKG_DIR / "build"
 LIB_PATH = PKG_DIR / "libskyb200.so"
 
 SOURCES = ["core.cu", "loss.cu", "advantage.cu", "offpolicy.cu", "covsel.cu", "value_head.cu", "head.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", "gemm_sm100.cuh", "internal.h", "loss_token.cuh"]
+HEADERS = ["common.cuh", "ptx.cuh", "gemm_sm100.cuh", "internal.h", "loss_token.cuh", "tile_order.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
