@@ -1,6 +1,7 @@
 """The oracle (oracle/policy_oracle.py) against (1) the golden fixtures generated from the unmodified reference,
 (2) the known-answer vectors of the reference's own unit tests, (3) the live reference when /root/reference exists."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -467,3 +468,20 @@ def test_kat_off_policy_correction():  # tests/cpu/algorithms/test_off_policy_co
             assert torch.allclose(tis.expand_as(olp_t), T(want_tis), rtol=1e-3, atol=1e-4), name
         for k, v in want_met.items():
             assert abs(met[k] - v) < 0.01, (name, k, met[k], v)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_committed_goldens_are_what_the_reference_produces_today(tmp_path, monkeypatch):
+    """tests/golden/*.npz regenerated with the committed script from the unmodified reference: bit-identical, so the
+    fixtures that travel to the GPU box are neither stale nor hand-edited."""
+    from oracle import make_golden as mg
+
+    real = mg.OUT
+    monkeypatch.setattr(mg, "OUT", str(tmp_path))
+    mg.main()
+    for name in ("advantages.npz", "losses.npz", "head.npz"):
+        old, new = dict(np.load(os.path.join(real, name))), dict(np.load(os.path.join(str(tmp_path), name)))
+        assert sorted(old) == sorted(new), name
+        for k in old:
+            same = np.array_equal(old[k], new[k], equal_nan=old[k].dtype.kind == "f")
+            assert old[k].dtype == new[k].dtype and same, (name, k)
