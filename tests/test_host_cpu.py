@@ -104,6 +104,30 @@ def test_shard_prompt_groups_keeps_groups_whole_and_balanced():
         assert max(loads) <= 1.15 * (sum(loads) / ws)
 
 
+def test_sharded_group_advantages_equal_the_whole_batch():
+    """N-GPU == 1-GPU for the advantage stage: with whole prompt groups per rank (shard_prompt_groups) the GRPO / RLOO
+    advantages each rank computes from ITS rows are the rows of the whole-batch result - no collective needed.
+    (Arithmetic by the oracle; what is under test is the partition.)  A row-contiguous split, the reference's
+    dispatch (dispatch.py:186-205), does not have that property for shuffled uids."""
+    from oracle import policy_oracle as O
+
+    g = torch.Generator().manual_seed(0)
+    B, A, G = 48, 20, 6
+    uids = np.array([f"p{i // G}" for i in range(B)])[torch.randperm(B, generator=g).numpy()]
+    lens = torch.randint(1, A + 1, (B,), generator=g)
+    mask = (torch.arange(A)[None] < lens[:, None]).float()
+    r = torch.zeros(B, A)
+    r[torch.arange(B), lens - 1] = torch.randn(B, generator=g)
+    for fn in (O.grpo_advantage, O.rloo_advantage):
+        whole, _ = fn(r, mask, uids)
+        for ws in (2, 3, 8):
+            for rows in sdist.shard_prompt_groups(uids, lens.tolist(), ws):
+                part, _ = fn(r[rows], mask[rows], uids[rows])
+                assert torch.equal(part, whole[rows])
+        split = [list(range(0, B // 2)), list(range(B // 2, B))]
+        assert any(not torch.equal(fn(r[rows], mask[rows], uids[rows])[0], whole[rows]) for rows in split)
+
+
 def test_config_validation_matches_reference_messages():
     lp = torch.zeros(2, 3)
     with pytest.raises(AssertionError, match="loss_type must be either"):

@@ -438,3 +438,21 @@ def test_stored_lse_flag(tmp_path):
     assert res["1"]["peaked"]["rel_dh"] < 2.5e-2 and res["1"]["peaked"]["rel_dw"] < 2.5e-2
     assert res["1"]["peaked"]["rel_dh"] < 0.5 * res["0"]["peaked"]["rel_dh"]
     assert res["1"]["peaked"]["colsum"] < 0.2 * res["0"]["peaked"]["colsum"]   # rows of d_logits sum to zero again
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (NCCL data-parallel group)")
+def test_data_parallel_step_over_nccl_two_ranks():
+    """N-GPU == 1-GPU on the same batch: whole prompt groups per rank -> local GRPO advantages, per-rank fused step,
+    packed-stats and fp32 d_weight all-reduce (mean of per-rank means, the reference's semantics) against the
+    single-GPU step on the whole batch; GAE with the three whitening moments all-reduced against the whole-batch GAE."""
+    import os
+    import subprocess
+    import sys
+
+    script = os.path.join(os.path.dirname(__file__), "dp_worker.py")
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", script], env=env, capture_output=True,
+                       text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "DP_OK" in r.stdout
