@@ -313,6 +313,27 @@ def hbm_kernels(dev, peaks):
         gbs = n * bpt / (ms * 1e-3) / 1e9
         res[name] = {"us": round(ms * 1e3, 1), "bytes_per_position": bpt, "achieved_gbs": round(gbs, 1),
                      "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)}
+    # calibration: what a one-launch library elementwise kernel reaches at this problem size with the same timing
+    # method (the kernels above move 50-117 MB: launch ramp and tail are a visible share of 20-40 us)
+    try:
+        a, b, c = rewards, values, out1
+        times = []
+        for it in range(18):
+            flush.sum()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            torch.add(a, b, out=c)
+            e.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                times.append(s.elapsed_time(e))
+        times.sort()
+        ms = times[len(times) // 2]
+        gbs = n * 12 / (ms * 1e-3) / 1e9
+        res["_calibration_torch_add"] = {"us": round(ms * 1e3, 1), "bytes_per_position": 12,
+                                         "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)}
+    except Exception as exc:  # noqa: BLE001  (context only: never fail the bench over it)
+        res["_calibration_torch_add"] = {"error": str(exc)[:200]}
     res["_note"] = ("512 x 8192 positions (config-3 shape), fp32 mask, L2 flushed (384 MB streamed through it) before each "
                     "timed call, median of 15, "
                     "CUDA events; hbm peak %.1f GB/s (%s)" % (peaks["hbm"], peaks["source"].split(" (")[0]))
