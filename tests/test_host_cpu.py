@@ -365,3 +365,106 @@ def test_value_head_critic_is_the_reference_slice(monkeypatch):
     want = head(outputs.last_hidden_state).squeeze(-1)[:, :-1][:, -A:]
     assert values.shape == (B, A) and torch.allclose(values, want, atol=1e-6)
     assert critic(ids, None, am, return_output=True).last_hidden_state.shape == (B, S, 32)
+
+
+# ------------------------------------------------------------------------------------------ Ray mirror of the registries
+class _FakeRay:
+    """The slice of the Ray API the registries use (reference: ppo_utils.py:245-262, 335-361), in process: named
+    actors created with ``ray.remote(cls).options(name=..., get_if_exists=True).remote()``, method calls through
+    ``.remote()`` returning handles that ``ray.get`` resolves, ``get_actor`` raising ValueError for unknown names."""
+
+    def __init__(self):
+        self.actors = {}
+
+    def is_initialized(self):
+        return True
+
+    def remote(self, cls):
+        fake = self
+
+        class _Remote:
+            def options(self, name=None, get_if_exists=False, **_):
+                self.name, self.get_if_exists = name, get_if_exists
+                return self
+
+            def remote(self, *a, **k):
+                if self.name in fake.actors:
+                    if not self.get_if_exists:
+                        raise ValueError(f"actor {self.name} exists")
+                    return fake.actors[self.name]
+                handle = _Handle(cls(*a, **k))
+                fake.actors[self.name] = handle
+                return handle
+
+        return _Remote()
+
+    def get(self, ref):
+        return ref
+
+    def get_actor(self, name):
+        if name not in self.actors:
+            raise ValueError(f"Failed to look up actor with name '{name}'")
+        return self.actors[name]
+
+    def kill(self, handle):
+        for k, v in list(self.actors.items()):
+            if v is handle:
+                del self.actors[k]
+
+
+class _Handle:
+    def __init__(self, obj):
+        self._obj = obj
+
+    def __getattr__(self, name):
+        method = getattr(self._obj, name)
+
+        class _M:
+            @staticmethod
+            def remote(*a, **k):
+                return method(*a, **k)
+
+        return _M()
+
+
+def _module_level_estimator(token_level_rewards, response_mask, index, **kwargs):
+    return token_level_rewards, token_level_rewards
+
+
+def test_registries_mirror_through_a_named_actor_when_ray_is_live(monkeypatch):
+    """With a Ray session the registries keep a named actor in sync (cloudpickled callables), so a function registered
+    in the driver process is found by the registry of another process (reference: test_ppo_utils.py:405-557).  Ray is
+    not installed here: the test drives the same code with an in-process fake of the Ray calls it makes."""
+    from skyrl_b200 import registry as reg
+
+    fake = _FakeRay()
+    monkeypatch.setattr(reg, "_ray", lambda: fake)
+
+    class Driver(reg.BaseFunctionRegistry):
+        _actor_name = "test_registry_actor"
+        _function_type = "Advantage estimator"
+
+    class Worker(reg.BaseFunctionRegistry):       # the registry object of a different process: same actor name
+        _actor_name = "test_registry_actor"
+        _function_type = "Advantage estimator"
+
+    Driver.register("mine", _module_level_estimator)
+    assert "test_registry_actor" in fake.actors
+    assert Worker.get("mine") is _module_level_estimator           # pickled by reference, found through the actor
+    assert sorted(Worker.list_available()) == ["mine"]
+    with pytest.raises(ValueError, match="already registered"):
+        Driver.register("mine", _module_level_estimator)
+    Worker.register("theirs", skyrl_b200.compute_grpo_outcome_advantage)   # library functions pickle by reference too
+    assert Driver.get("theirs") is skyrl_b200.compute_grpo_outcome_advantage
+    Driver.unregister("mine")
+    assert "mine" not in fake.actors["test_registry_actor"]._obj.table
+    with pytest.raises(ValueError, match="Unknown advantage estimator 'nope'"):
+        Driver.get("nope")
+    with pytest.raises(ValueError, match="not registered"):
+        Driver.unregister("nope")
+    # a new Ray session (the actor is gone): the next call re-creates it and re-publishes the local table
+    fake.actors.clear()
+    assert Driver.get("theirs") is skyrl_b200.compute_grpo_outcome_advantage
+    assert "theirs" in fake.actors["test_registry_actor"]._obj.table
+    Driver.reset()
+    assert Driver._functions == {} and "test_registry_actor" not in fake.actors
