@@ -1,6 +1,8 @@
 """bench.py contract on CPU: the reference arm (the oracle port timed on host cores) prints ONE JSON line with the
 keys the driver reads; the two arms describe the same workload with the same `config` object."""
 import json
+
+import pytest
 import os
 import subprocess
 import sys
@@ -35,3 +37,34 @@ def test_both_arms_share_metric_and_config():
     assert bench.METRIC.startswith("policy-update tokens/sec/GPU")
     peaks = bench.measured_peaks()
     assert peaks["tflops"] > 0 and peaks["hbm"] > 0
+
+
+def test_clock_sampler_parses_nvidia_smi_lines():
+    """The `clocks` object of the bench line (median SM clock under load, max clock, throttle reasons) from the
+    nvidia-smi CSV the sampler reads (B200_PROFILING.md recipe); malformed lines are skipped, not fatal."""
+    import bench
+
+    class _Done:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+        def kill(self):
+            pass
+
+    s = bench.ClockSampler(0)
+    s.proc = _Done()
+    s.lines = [
+        "0, 1965, 1965, 180.2, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active",
+        "0, 1320, 1965, 995.1, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+        "0, 1305, 1965, 998.7, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+        "0, [N/A], 1965, [N/A], 0x0, Not Active, Not Active, Not Active, Not Active",
+        "garbage",
+    ]
+    c = s.stop()
+    assert c["sm_mhz"] == 1320.0 and c["sm_max_mhz"] == 1965.0 and c["reasons"] == ["sw_power_cap"]
+    assert c["samples"] == 3 and c["power_w_max"] == pytest.approx(998.7)
+    s2 = bench.ClockSampler(0)
+    assert s2.stop()["reasons"] == ["nvidia-smi unavailable"]      # never started: no nvidia-smi, still a dict
