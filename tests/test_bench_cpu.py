@@ -1,11 +1,11 @@
 """bench.py contract on CPU: the reference arm (the oracle port timed on host cores) prints ONE JSON line with the
 keys the driver reads; the two arms describe the same workload with the same `config` object."""
 import json
-
-import pytest
 import os
 import subprocess
 import sys
+
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
