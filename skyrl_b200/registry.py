@@ -278,8 +278,10 @@ def sync_registries() -> None:
 def install_into_skyrl_train(patch_model_wrapper: bool = True) -> List[str]:
     """Swap the B200 kernels into a live ``skyrl_train`` install (the drop-in step of INTEGRATION.md).
 
-    Replaces the ``grpo``/``rloo``/``gae`` estimators and ``regular``/``dual_clip``/``gspo`` losses in
-    skyrl_train's own registries and points ``skyrl_train.model_wrapper.logprobs_from_logits`` /
+    Replaces every name skyrl_train registers - the ``grpo`` / ``rloo`` / ``gae`` / ``reinforce++`` estimators and the
+    ``regular`` / ``dual_clip`` / ``gspo`` / ``sapo`` / ``cispo`` / ``clip_cov`` / ``kl_cov`` / ``cross_entropy`` /
+    ``importance_sampling`` losses - in skyrl_train's own registries (through their ``unregister`` / ``register``, so a
+    live Ray mirror follows) and points ``skyrl_train.model_wrapper.logprobs_from_logits`` /
     ``chunked_entropy_from_logits`` at the CUDA versions.  Returns the list of names it replaced.
     """
     import importlib
