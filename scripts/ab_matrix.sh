@@ -24,6 +24,7 @@ for round in 1 2; do
     run lock256 - SKYB200_DH_LOCKSTEP=256 SKYB200_DW_LOCKSTEP=256
     run fwdlock128 - SKYB200_FWD_LOCKSTEP=128
     run chunk74_fwdgrp37 - SKYB200_CHUNK_TILES=74 SKYB200_FWD_GROUP_M=37
+    run chunk148 - SKYB200_CHUNK_TILES=148
     run stored_lse - SKYB200_STORED_LSE=1
     run ragged_base ragged=1
 done
