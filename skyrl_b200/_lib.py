@@ -190,3 +190,22 @@ def gemm_debug_record():
         return None
     names = ["flag", "role", "which", "stage", "parity", "tile", "block", "pad"]
     return {n: int(rec[i]) for i, n in enumerate(names)}
+
+
+class _NullRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def nvtx_range(name: str):
+    """``with nvtx_range("skyb200/policy_step"):`` - an NVTX range when ``SKYB200_NVTX=1`` (for
+    ``ncu --nvtx --nvtx-include "skyb200/policy_step/"``), otherwise free."""
+    if os.environ.get("SKYB200_NVTX", "0") != "1":
+        return _NullRange()
+    import torch
+
+    return torch.cuda.nvtx.range(name)
+

@@ -178,12 +178,13 @@ def policy_update_step(
                     _lib.ptr(base) if use_kl else None, _lib.ptr(emask), _lib.ptr(logprobs), _lib.ptr(ent),
                     _lib.ptr(d_hidden), _lib.ptr(d_weight) if need_d_weight else None, acc, _lib.ptr(stats),
                     _lib.ptr(ws), wsb, B, A, H, V, _lib.ptr(cu), N, T, C.byref(params), stream)
-            if from_host:
-                h_host, h = h, torch.empty((N, H), dtype=torch.bfloat16, device=dev)
-                _lib.check(lib.skyb200_policy_step_from_host(h_host.data_ptr(), _lib.ptr(h), *tail),
-                           "skyb200_policy_step_from_host")
-            else:
-                _lib.check(lib.skyb200_policy_step(_lib.ptr(h), *tail), "skyb200_policy_step")
+            with _lib.nvtx_range("skyb200/policy_step"):
+                if from_host:
+                    h_host, h = h, torch.empty((N, H), dtype=torch.bfloat16, device=dev)
+                    _lib.check(lib.skyb200_policy_step_from_host(h_host.data_ptr(), _lib.ptr(h), *tail),
+                               "skyb200_policy_step_from_host")
+                else:
+                    _lib.check(lib.skyb200_policy_step(_lib.ptr(h), *tail), "skyb200_policy_step")
             if sync:
                 status = status_from_packed(stats.tolist(), use_kl)  # the single host sync of the step
                 status["response_length"] = A
