@@ -10,6 +10,10 @@ and the chunked entropy are replaced by the fused head on the ``num_actions`` re
 Same call signature and return convention as the reference wrapper: ``action_log_probs`` is ``[B, A]`` and
 ``output["entropy"]`` is ``[B, S]`` so that the worker's own slice ``[:, -A-1:-1]`` (worker.py:855) keeps working
 (positions outside the response window hold zeros - the worker never reads them).
+
+Padded layout, one trunk per GPU.  A trunk that runs on sample-packed or Ulysses-sliced inputs (both need the
+reference's attention patches around the HF model) calls the matching glue function of :mod:`skyrl_b200.model_wrapper`
+on its own hidden states instead: ``action_log_probs_from_packed_hidden`` / ``_from_sp_hidden`` / ``_from_sp_packed_hidden``.
 """
 from __future__ import annotations
 
@@ -23,10 +27,9 @@ from . import model_wrapper as _glue
 
 
 class FusedHeadPolicy(nn.Module):
-    def __init__(self, model: nn.Module, sequence_parallel_group=None):
+    def __init__(self, model: nn.Module):
         super().__init__()
         self.model = model
-        self.sequence_parallel_group = sequence_parallel_group
         trunk = model.get_decoder() if hasattr(model, "get_decoder") else getattr(model, "model", None)
         head = model.get_output_embeddings() if hasattr(model, "get_output_embeddings") else getattr(model, "lm_head", None)
         if trunk is None or head is None or getattr(head, "bias", None) is not None:
@@ -47,12 +50,8 @@ class FusedHeadPolicy(nn.Module):
         position_ids.masked_fill_(attention_mask == 0, 1)
         hidden = self._trunk[0](sequences, attention_mask=attention_mask, position_ids=position_ids).last_hidden_state
         weight = self._head[0].weight
-        if self.sequence_parallel_group is not None:
-            lp, ent = _glue.action_log_probs_from_sp_hidden(hidden, weight, sequences, A, attention_mask, temperature,
-                                                            compute_entropy, group=self.sequence_parallel_group)
-        else:
-            lp, ent = _glue.action_log_probs_from_hidden(hidden, weight, sequences, A, attention_mask, temperature,
-                                                         compute_entropy)
+        lp, ent = _glue.action_log_probs_from_hidden(hidden, weight, sequences, A, attention_mask, temperature,
+                                                     compute_entropy)
         if not return_output:
             return lp
         output = {}
