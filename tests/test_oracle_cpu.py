@@ -337,6 +337,50 @@ def test_oracle_losses_vs_live_reference_property():
     run()
 
 
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_off_policy_correction_vs_live_reference_property():
+    """Property test (hypothesis): TIS (token / sequence), outlier-token thresholds and the geometric / product
+    sequence masks of the oracle against the unmodified reference (off_policy_correction_utils.py:186-260) over drawn
+    configurations - TIS weights, the updated loss mask and every metric the reference reports."""
+    import importlib
+
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+    from types import SimpleNamespace as NS
+
+    ref_loader.load()
+    opc_ref = importlib.import_module("skyrl_train.utils.off_policy_correction_utils")
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(B=st.integers(1, 6), A=st.integers(1, 20), seed=st.integers(0, 10_000),
+           tis=st.sampled_from([None, "token", "sequence"]), seqm=st.sampled_from([None, "geometric", "product"]),
+           out_lo=st.sampled_from([None, 0.3, 0.8]), out_hi=st.sampled_from([None, 1.5, 4.0]),
+           spread=st.sampled_from([0.05, 0.3, 1.0]))
+    def run(B, A, seed, tis, seqm, out_lo, out_hi, spread):
+        g = torch.Generator().manual_seed(seed)
+        lens = torch.randint(1, A + 1, (B,), generator=g)
+        mask = (torch.arange(A)[None] < lens[:, None]).float()
+        olp = -torch.rand(B, A, generator=g) * 3
+        rlp = olp + spread * torch.randn(B, A, generator=g)
+        cfg = NS(tis_ratio_type=tis, sequence_mask_metric=seqm, token_tis_ratio_clip_high=2.0,
+                 sequence_tis_ratio_clip_high=5.0, outlier_token_is_threshold_low=out_lo,
+                 outlier_token_is_threshold_high=out_hi, geo_mask_low=0.9, geo_mask_high=1.1,
+                 product_mask_low=0.5, product_mask_high=2.0)
+        t_ref, m_ref, k_ref = opc_ref.compute_off_policy_correction(olp, rlp, mask.clone(), cfg)
+        t, m, k = O.off_policy_correction(olp, rlp, mask.clone(), cfg)
+        assert (t is None) == (t_ref is None)
+        if t is not None:
+            assert_close(t.expand_as(olp) if t.shape != olp.shape else t,
+                         t_ref.expand_as(olp) if t_ref.shape != olp.shape else t_ref, what="tis weights")
+        assert torch.equal(k, k_ref), "updated loss mask"
+        assert sorted(m) == sorted(m_ref), (sorted(m), sorted(m_ref))
+        for key, v in m_ref.items():
+            if not (math.isnan(v) and math.isnan(m[key])):     # std of a single element is NaN on both sides
+                assert m[key] == pytest.approx(v, rel=1e-5, abs=1e-6), key
+
+    run()
+
+
 # ---------------------------------------------------------------- "next" rows (SURVEY 8f-1)
 def test_golden_reinforce_pp_and_normalize(golden_adv):
     g = golden_adv
