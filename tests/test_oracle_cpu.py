@@ -381,6 +381,44 @@ def test_oracle_off_policy_correction_vs_live_reference_property():
     run()
 
 
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_critic_loss_and_normalisation_vs_live_reference_property():
+    """Property test (hypothesis): the clipped value loss (value, clip fraction, gradient; exact ties of the two
+    surrogates included) and normalize_advantages_dict of the oracle against the unmodified reference."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+    from types import SimpleNamespace as NS
+
+    pu, _ = ref_loader.load()
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(B=st.integers(1, 7), A=st.integers(1, 24), seed=st.integers(0, 10_000),
+           clip=st.sampled_from([None, 0.2, 0.05]), use_mask=st.booleans())
+    def run(B, A, seed, clip, use_mask):
+        g = torch.Generator().manual_seed(seed)
+        lens = torch.randint(1, A + 1, (B,), generator=g)
+        mask = (torch.arange(A)[None] < lens[:, None]).float()
+        values = torch.randn(B, A, generator=g)
+        old = values + 0.15 * torch.randn(B, A, generator=g)
+        old = torch.where(torch.rand(B, A, generator=g) < 0.3, values, old)      # ties: surr1 == surr2
+        returns = torch.randn(B, A, generator=g)
+        m = mask if use_mask else None
+        x_ref = values.clone().requires_grad_(True)
+        loss_ref, cf_ref = pu.ppo_critic_loss(x_ref, old, returns, NS(value_clip=clip), loss_mask=m)
+        loss_ref.backward()
+        x = values.clone().requires_grad_(True)
+        loss, cf = O.critic_loss(x, old, returns, clip, m)
+        loss.backward()
+        assert_close(loss, loss_ref, what="critic loss")
+        assert (cf is None) == (cf_ref is None) and (cf is None or cf == pytest.approx(cf_ref, abs=1e-7))
+        assert_close(x.grad, x_ref.grad, what="critic gradient")
+        adv = torch.randn(B, A, generator=g) * 3 + 1
+        want = pu.normalize_advantages_dict({"advantages": adv.clone(), "response_mask": mask})["advantages"]
+        assert_close(O.normalize_advantages(adv, mask), want, what="normalize_advantages_dict")
+
+    run()
+
+
 # ---------------------------------------------------------------- "next" rows (SURVEY 8f-1)
 def test_golden_reinforce_pp_and_normalize(golden_adv):
     g = golden_adv
