@@ -90,3 +90,31 @@ def test_bad_arguments_report_errors_without_a_gpu(lib):
     assert b"null pointer" in lib.skyb200_last_error()
     rc = lib.skyb200_approx_kl(ctypes.c_void_p(16), ctypes.c_void_p(16), None, ctypes.c_void_p(16), 4, 9, None)
     assert rc == 1 and b"Invalid KL estimator type" in lib.skyb200_last_error()
+
+
+def test_header_is_plain_c_and_a_c_program_links_the_library(lib, tmp_path):
+    """The boundary is a C ABI: the header must compile as C11 (no C++-isms), and a C program with no Python or
+    torch in sight links libskyb200.so and calls it (host-only entry points: runs without a GPU)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include")
+    r = subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(inc, "skyb200.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    libdir = str(_lib.lib_path().parent)
+    exe = str(tmp_path / "c_abi_client")
+    r = subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", inc,
+                        os.path.join(root, "tests", "host", "c_abi_client.c"), "-L", libdir,
+                        "-l:" + _lib.lib_path().name, "-Wl,-rpath," + libdir, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = r.stdout.split(maxsplit=5)
+    assert out[:3] == ["9472", "9472", "111"] and int(out[3]) > 5 * 2**30 and out[4] == "1"
+    assert "null pointer" in out[5]
+
