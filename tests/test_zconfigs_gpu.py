@@ -400,7 +400,7 @@ def test_sharply_peaked_logits(fused):
     assert (ent.detach().cpu() - ent_ref.detach()).abs().max().item() < 1e-3
     # The fp32 recompute of the autograd path holds the usual bound.  The fused step reads bf16-ROUNDED logits
     # (|z| up to ~70 here: ulp 0.5) back against the exact normaliser, so its probabilities carry up to 28 % error per
-    # element: ~6 % on d_hidden at this logit scale (CPU emulation in DESIGN 7; the reference's own bf16-logits path:
+    # element: ~6 % on d_hidden at this logit scale (CPU emulation in DESIGN section 6; the reference's own bf16-logits path:
     # 2.7 %; SKYB200_STORED_LSE=1: 1.6 %, see test_stored_lse_flag).  Pinned here so a regression shows.
     bound = 0.12 if fused else 2e-2
     assert rel(d_hidden, h.grad) < bound and rel(d_weight, w.grad) < bound
