@@ -38,6 +38,8 @@ checks = [("fused sapo", lambda: z.test_fused_step_runs_the_rest_of_the_registry
           ("fused cross_entropy", lambda: z.test_fused_step_runs_the_rest_of_the_registry("cross_entropy", "token_mean")),
           ("gspo off-grid A=1000", lambda: z.test_gspo_fused_step_with_a_response_length_off_the_tile_grid(1000)),
           ("gspo off-grid A=1001", lambda: z.test_gspo_fused_step_with_a_response_length_off_the_tile_grid(1001)),
+          ("gspo all-dead chunk 0", lambda: z.test_gspo_chunk_whose_every_row_is_dead(0)),
+          ("gspo all-dead chunk 1", lambda: z.test_gspo_chunk_whose_every_row_is_dead(1)),
           ("sharded gae", z.test_sharded_gae_equals_the_batch_gae),
           ("kl gradient k3", lambda: z.test_kl_loss_term_with_the_gradient_flag("k3")),
           ("peaked logits, autograd path", lambda: z.test_sharply_peaked_logits(False)),

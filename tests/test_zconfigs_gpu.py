@@ -456,3 +456,44 @@ def test_data_parallel_step_over_nccl_two_ranks():
                        text=True, timeout=280)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DP_OK" in r.stdout
+
+
+@pytest.mark.parametrize("dead", [0, 1, 2])
+def test_gspo_chunk_whose_every_row_is_dead(dead):
+    """GSPO clips whole sequences: a sequence whose ratio left the clip range on the side its advantage clips carries
+    no gradient at all, and with long sequences that is a whole chunk of all-zero d(logits) rows - the compacted
+    backward GEMMs then run over ZERO live tiles / K blocks (first chunk: plain GEMM over zeros, it must still
+    initialise d_weight).  Three sequences of 20000 tokens = three chunks; each of them dead in turn."""
+    from skyrl_b200 import _lib
+    import ctypes
+
+    B, A, H, V, T = 3, 20000, 64, 512, 1.0
+    plan = (ctypes.c_int64 * 3)()
+    _lib.load().skyb200_policy_step_plan(B, A, 0, H, V, _lib.LOSS_TYPES["gspo"], 1, plan)
+    assert plan[1] == A and plan[2] == 3, list(plan)                       # one sequence per chunk
+    g = torch.Generator().manual_seed(13)
+    hidden = torch.randn(B, A, H, generator=g).bfloat16()
+    weight = (torch.randn(V, H, generator=g) * (1.5 / H ** 0.5)).bfloat16()
+    labels = torch.randint(0, V, (B, A), generator=g)
+    lens = torch.tensor([A, A - 777, A - 5000])
+    mask = (torch.arange(A)[None] < lens[:, None]).float()
+    cfg = O.make_cfg(policy_loss_type="gspo", loss_reduction="sequence_mean", use_kl_loss=False,
+                     eps_clip_low=0.05, eps_clip_high=0.05)
+    h = hidden.float().reshape(B * A, H).requires_grad_(True)
+    w = weight.float().requires_grad_(True)
+    lp_ref, ent_ref = O.head_logprobs_entropy(h, w, labels.reshape(-1), T)
+    lp_ref, ent_ref = lp_ref.view(B, A), ent_ref.view(B, A)
+    off = torch.full((B, 1), 0.01)
+    off[dead] = 0.2                                                        # ratio e^0.2 = 1.22 > 1.05 with A > 0: clipped
+    olp = lp_ref.detach() - off + 0.002 * torch.randn(B, A, generator=g)
+    adv = torch.tensor([[0.8], [1.1], [0.6]]).expand(B, A).contiguous()
+    final_ref, st_ref = O.loss_assembly(lp_ref, olp, adv, cfg, mask, None, ent_ref)
+    final_ref.backward()
+    assert h.grad.view(B, A, H)[dead].abs().max().item() == 0.0            # the oracle agrees: no gradient there
+    out = skyrl_b200.policy_update_step(hidden.to(DEV), weight.to(DEV), labels.to(DEV), olp.to(DEV), adv.to(DEV), cfg,
+                                        loss_mask=mask.to(DEV), temperature=T)
+    assert out.status["final_loss"] == pytest.approx(st_ref["final_loss"], rel=2e-3, abs=2e-4)
+    assert torch.count_nonzero(out.d_hidden.view(B, A, H)[dead]) == 0
+    rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+    assert rel(out.d_hidden.float(), h.grad) < 2e-2
+    assert rel(out.d_weight, w.grad) < 2e-2
