@@ -6,7 +6,7 @@
 set -u
 mkdir -p gpurun_out
 # 1. the whole GPU parity suite, including the opt-in test of the default-off SKYB200_STORED_LSE kernels
-SKYB200_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests -m gpu -q -x -s -p no:cacheprovider \
+SKYB200_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests -m gpu -q -s -p no:cacheprovider \
     > gpurun_out/gpu_tests.log 2>&1
 echo "pytest rc=$?" | tee -a gpurun_out/gpu_tests.log
 tail -5 gpurun_out/gpu_tests.log
