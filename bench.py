@@ -12,13 +12,23 @@ bf16) per GPU.  N > 1 (launched by torchrun, one rank per GPU) is weak scaling: 
 prompt-group shard of that size; per step the packed stats vector and the fp32 lm_head weight gradient are
 all-reduced over NCCL.  Rank 0 prints ONE JSON line.
 
-Besides the contract keys the line carries `roofline` (forward GEMM kernel vs the measured sustained bf16 peak),
-`step_roofline` (6*H*V*N algorithmic flops over the step time), `hbm_kernels` (the memory-bound kernels of the path
-alone, L2 flushed, vs the measured HBM copy peak), `cpu_baseline`, `e2e` (pinned host buffers in, python floats out),
-`gpu_launches` and `clocks`.
+Besides the contract keys the line carries
+  `roofline`          the SLOWEST of the step's three GEMM kernels as the step runs them - its algorithmic flops per
+                      launch over its average launch duration, measured LIVE with CUDA events around every launch
+                      inside the timed steps (skyb200_policy_step_timing) - and `roofline_kernels` = all three;
+                      `traffic` = dram bytes per launch from the committed ncu capture (profiles/r02_traffic.json),
+                      null when the kernel sources changed after the capture;
+  `step_roofline`     6*H*V*N algorithmic flops over the step time (the headline fraction);
+  `hbm_kernels`       the memory-bound kernels of the path alone, L2 flushed, vs the measured HBM copy peak;
+  `cpu_baseline`      the UNMODIFIED reference (baseline/_ref, kind "reference") on this box's host cores;
+  `ref_gpu_path`      the UNMODIFIED reference's own GPU path (cuBLAS lm_head + flash-attn Triton CE + chunked entropy +
+                      registry loss) on this GPU, and `vs_ref_gpu_path` = value / that;
+  `other_configs`     BASELINE configs 1, 3, 4 (dual-clip, GSPO), 5 and the fixed-size config-3 split (strong scaling);
+  `e2e`, `gpu_launches`, `clocks`; for N > 1 also `dp_check`, `allreduce_exposed_ms`, `per_rank_step_ms`.
 
-`--impl reference` times the CPU restatement of the reference's torch path (oracle/, "port": the Python reference
-cannot travel to the GPU box) on a bounded token sample with all host threads.
+`--impl reference` times the reference's own CPU implementation of the path (baseline/ref_path.py drives the
+unmodified skyrl_train functions; oracle/ restatement only if no copy of the reference is present) on a bounded
+token sample with all host threads.
 """
 from __future__ import annotations
 
@@ -180,42 +190,12 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_port_step(w, sample_tokens, threads, seed=1234):
-    """The reference's torch CPU path (restated in oracle/): GRPO advantages on the full [B, A] batch + head and
-    loss fwd/bwd (fp32) on `sample_tokens` tokens.  Returns seconds for the sample."""
-    from oracle import policy_oracle as O
+def cpu_reference_step(w, sample_tokens, threads, seed=1234):
+    """The reference's torch CPU path on a bounded sample: (seconds, tokens, kind).  kind "reference" = the unmodified
+    skyrl_train functions (baseline/ref_path.py), "port" = the oracle restatement when no copy is present."""
+    from baseline import ref_path
 
-    torch.set_num_threads(threads)
-    B, A, H, V, G = w["B"], w["A"], w["H"], w["V"], w["G"]
-    g = torch.Generator().manual_seed(seed)
-    rows = max(1, sample_tokens // A) if sample_tokens >= A else 1
-    a_len = A if sample_tokens >= A else sample_tokens
-    hidden = torch.randn(rows * a_len, H, generator=g).to(torch.bfloat16).float()
-    weight = (torch.randn(V, H, generator=g) / H ** 0.5).to(torch.bfloat16).float()
-    labels = torch.randint(0, V, (rows * a_len,), generator=g)
-    with torch.no_grad():  # untimed set-up, as in the GPU arm: old / base log-probs next to the current policy's
-        lp0, _ = O.head_logprobs_entropy(hidden, weight, labels, TEMPERATURE, chunk=256)
-    olp = lp0.view(rows, a_len) + 0.05 * torch.randn(rows, a_len, generator=g)
-    base = lp0.view(rows, a_len) + 0.1 * torch.randn(rows, a_len, generator=g)
-    mask = torch.ones(rows, a_len)
-    rewards = torch.zeros(B, A)
-    rewards[:, -1] = (torch.rand(B, generator=g) < 0.3).float()
-    uids = np.array([f"p{i // G}" for i in range(B)])
-    cfg = make_cfg()
-    t0 = time.perf_counter()
-    adv_full, _ = O.grpo_advantage(rewards, torch.ones(B, A), uids)
-    t_adv = time.perf_counter() - t0
-    adv = adv_full[:rows, :a_len]
-    h = hidden.requires_grad_(True)
-    wt = weight.requires_grad_(True)
-    t0 = time.perf_counter()
-    lp, ent = O.head_logprobs_entropy(h, wt, labels, TEMPERATURE, chunk=256)
-    final, _ = O.loss_assembly(lp.view(rows, a_len), olp, adv, cfg, mask, base, ent.view(rows, a_len))
-    final.backward()
-    t_head = time.perf_counter() - t0
-    n_tok = rows * a_len
-    # advantages are O(B*A) for the whole batch; scale them to the sample so the figure is per-token consistent
-    return t_head + t_adv * (n_tok / (B * A)), n_tok
+    return ref_path.cpu_step(w, make_cfg(), sample_tokens, threads, TEMPERATURE, seed)
 
 
 def run_reference(args, w):
@@ -226,19 +206,21 @@ def run_reference(args, w):
     sample = 1024 if w["V"] > 100000 else 4096
     times = []
     for i in range(args.warmup + args.steps):
-        dt, n_tok = cpu_port_step(w, sample, threads, seed=1234 + i)
+        dt, n_tok, kind = cpu_reference_step(w, sample, threads, seed=1234 + i)
         if i >= args.warmup:
             times.append(dt)
     t = float(np.mean(times))
     value = n_tok / t
+    what = ("unmodified skyrl_train functions (baseline/_ref) driven as worker.py:787-877" if kind == "reference"
+            else "oracle/policy_oracle.py restatement (no copy of the reference present)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(w, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": kind,
                          "sample": f"{n_tok} tokens/step of the same workload (head+loss fwd/bwd fp32, GRPO advantages "
-                                   f"pro-rated); oracle/policy_oracle.py = restatement of the reference torch path"},
+                                   f"pro-rated); {what}"},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -340,6 +322,38 @@ def hbm_kernels(dev, peaks):
     return res
 
 
+KERNEL_SOURCES = ["gemm_sm100.cuh", "head.cu", "ptx.cuh", "tile_order.cuh"]
+
+
+def kernel_source_hash():
+    """sha256 over the sources of the GEMM kernels: ties an ncu capture under profiles/ to the code it measured."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "skyrl_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(H, V):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the three GEMMs, from the committed `ncu --set full`
+    capture of THIS build (profiles/r02_traffic.json, written by scripts/ncu_traffic.py from the capture's CSV).
+    Returns ({kind: bytes}, note).  A capture of other sources or another head shape is refused loudly (traffic null)."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    try:
+        d = json.load(open(path))
+    except (OSError, ValueError):
+        return {}, "no ncu capture committed for this build (profiles/r02_traffic.json missing)"
+    if d.get("source_hash") != kernel_source_hash():
+        print(f"bench.py: profiles/r02_traffic.json was captured from other kernel sources "
+              f"({d.get('source_hash')} != {kernel_source_hash()}): roofline.traffic = null", file=sys.stderr)
+        return {}, "STALE: the kernel sources changed after the ncu capture in profiles/r02_traffic.json"
+    if (d.get("H"), d.get("V")) != (H, V):
+        return {}, f"capture is for H={d.get('H')}, V={d.get('V')}"
+    return {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in d["kernels"].items()}, d.get("capture", "")
+
+
 def run_ours(args, w):
     import torch.distributed as dist
 
@@ -381,29 +395,31 @@ def run_ours(args, w):
     torch.cuda.synchronize()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    phase_ms = {"adv": [], "step": []}
+    phase_ms = {"_ev": []}
 
     def device_step(record):
         """Inputs already resident in HBM."""
-        e0, e1, e2 = ev(), ev(), ev()
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
         e0.record()
         adv, _ = skyrl_b200.compute_grpo_outcome_advantage(db["rewards"], db["mask"], db["uids"])
         e1.record()
         out = skyrl_b200.policy_update_step(db["hidden"], weight, db["labels"], db["olp"], adv, cfg,
                                             loss_mask=db["mask"], base_log_probs=db["base"], temperature=TEMPERATURE,
-                                            d_weight=d_weight, accumulate_d_weight=False, sync=False)
+                                            d_weight=d_weight, accumulate_d_weight=False, sync=False, timing=record)
         e2.record()
         if world > 1:
             sdist.all_reduce_packed_stats(out.stats)
             sdist.all_reduce_d_weight(out.d_weight)
+        e3.record()
         if record:
-            phase_ms["_ev"].append((e0, e1, e2))
+            phase_ms["_ev"].append((e0, e1, e2, e3))
         return out
 
     def e2e_step():
         """Host buffers in, python-float status out: what a user of the plugin API pays per step."""
-        # the small per-token arrays go up front; the 7.5 GB of hidden states stay in pinned host memory and are
-        # streamed in chunk by chunk inside the step (skyb200_policy_step_from_host), overlapping the GEMMs
+        # the small per-token arrays go up front; the 7.5 GB of hidden states stay in PINNED host memory (required for
+        # the asynchronous copy) and are streamed in chunk by chunk inside the step (skyb200_policy_step_from_host),
+        # overlapping the GEMMs
         d = {k: (v.to(dev, non_blocking=True) if (torch.is_tensor(v) and k != "hidden") else v) for k, v in hb.items()}
         adv, _ = skyrl_b200.compute_grpo_outcome_advantage(d["rewards"], d["mask"], d["uids"])
         out = skyrl_b200.policy_update_step(d["hidden"], weight, d["labels"], d["olp"], adv, cfg,
@@ -438,32 +454,16 @@ def run_ours(args, w):
             ms = float(t.item())
         return ms / steps
 
-    # isolated timing of the dominant kernel family (forward GEMM + epilogue) with CUDA events on the launch stream
-    from skyrl_b200 import _lib
-
-    lib = _lib.load()
-    lp_buf = torch.empty(N, dtype=torch.float32, device=dev)
-    ent_buf = torch.empty(N, dtype=torch.float32, device=dev)
-    lse_buf = torch.empty(N, dtype=torch.float32, device=dev)
-    fws = lib.skyb200_head_forward_workspace(N, H, V, 0)
-    fws_buf = torch.empty(fws, dtype=torch.uint8, device=dev)
-    hid2d = db["hidden"].view(N, H)
-    lab1d = db["labels"].view(N)
-
-    def fwd_only():
-        _lib.check(lib.skyb200_head_forward(_lib.ptr(hid2d), _lib.ptr(weight), _lib.ptr(lab1d), None, _lib.ptr(lp_buf),
-                                            _lib.ptr(ent_buf), _lib.ptr(lse_buf), _lib.ptr(fws_buf), fws, N, H, V,
-                                            TEMPERATURE, 0, _lib.stream_ptr()))
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ms_step = timed(device_step, args.steps, args.warmup, record=True)
-    evs = phase_ms["_ev"]
-    adv_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in evs])) if evs else None
-    upd_ms = float(np.mean([b.elapsed_time(c) for _, b, c in evs])) if evs else None
     clocks = sampler.stop() if rank == 0 else None
-    ms_fwd = timed(fwd_only, max(1, min(args.steps, 3)), 1)
+    evs = phase_ms["_ev"]
+    adv_ms = float(np.mean([a.elapsed_time(b) for a, b, _, _ in evs])) if evs else None
+    upd_ms = float(np.mean([b.elapsed_time(c) for _, b, c, _ in evs])) if evs else None
+    comm_ms = float(np.mean([c.elapsed_time(d) for _, _, c, d in evs])) if evs else None
+    gemm_times = skyrl_b200.step_gemm_times(dev)  # live per-kernel durations of the timed steps
     e2e_steps = max(1, min(args.steps, 3))
     ms_e2e = timed(e2e_step, e2e_steps, 1)
 
@@ -473,7 +473,60 @@ def run_ours(args, w):
     # (+ live-row lists and dead-tile zero fill of the zero-row skipping per chunk)
     launches_per_step = 2 + 2 + 8 * n_chunks
 
+    # ---- multi-GPU evidence: N-GPU numerics + what the collectives cost with the rank skew taken out
+    dp = None
+    if world > 1:
+        out = device_step(False)  # d_weight now holds the all-reduced (mean) gradient of one step
+        red_sum = d_weight.double().sum()
+        red_abs = d_weight.double().abs().sum()
+        red_loss = sdist.all_reduce_packed_stats(out.stats)[skyrl_b200._lib.STAT_FINAL_LOSS].double()
+        adv, _ = skyrl_b200.compute_grpo_outcome_advantage(db["rewards"], db["mask"], db["uids"])
+        loc = skyrl_b200.policy_update_step(db["hidden"], weight, db["labels"], db["olp"], adv, cfg,
+                                            loss_mask=db["mask"], base_log_probs=db["base"], temperature=TEMPERATURE,
+                                            d_weight=d_weight, accumulate_d_weight=False, sync=False)
+        mine = torch.stack([d_weight.double().sum(), loc.stats[skyrl_b200._lib.STAT_FINAL_LOSS].double()])
+        allv = torch.empty(world, 2, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allv, mine)
+        want_sum, want_loss = allv[:, 0].mean(), allv[:, 1].mean()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(3):  # the all-reduce alone, all ranks released together: NCCL time without the rank skew
+            barrier()
+            s, e = ev(), ev()
+            s.record()
+            sdist.all_reduce_d_weight(d_weight)
+            e.record()
+            torch.cuda.synchronize()
+            times.append(s.elapsed_time(e))
+        shard = torch.empty((V // world, H), dtype=torch.float32, device=dev) if V % world == 0 else None
+        rs_times = []
+        for _ in range(3 if shard is not None else 0):
+            barrier()
+            s, e = ev(), ev()
+            s.record()
+            sdist.reduce_scatter_d_weight(d_weight, out=shard)
+            e.record()
+            torch.cuda.synchronize()
+            rs_times.append(s.elapsed_time(e))
+        t = torch.tensor([min(times), min(rs_times) if rs_times else 0.0, upd_ms + adv_ms, comm_ms], device=dev,
+                         dtype=torch.float64)
+        tall = torch.empty(world, 4, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(tall, t)
+        tall = tall.cpu()
+        dp = {
+            # checksum of the reduced gradient == mean of the per-rank checksums; reduced loss == mean of per-rank losses
+            "d_weight_checksum_rel_err": float((red_sum - want_sum).abs() / red_abs.clamp(min=1e-30)),
+            "final_loss_rel_err": float((red_loss - want_loss).abs() / want_loss.abs().clamp(min=1e-30)),
+            "semantics": "mean over ranks of per-rank losses / gradients (worker.py:909-914, SURVEY trap 11)",
+            "allreduce_ms": float(tall[:, 0].max()), "reduce_scatter_ms": float(tall[:, 1].max()) or None,
+            "per_rank_compute_ms": [round(float(x), 1) for x in tall[:, 2]],
+            "per_rank_comm_wait_ms_in_step": [round(float(x), 1) for x in tall[:, 3]],
+        }
+        dp["ok"] = bool(dp["d_weight_checksum_rel_err"] < 1e-5 and dp["final_loss_rel_err"] < 1e-5)
+
     # the library GEMM on the same shape and data, sustained (context for the power-capped regime)
+    hid2d = db["hidden"].view(N, H)
+
     def cublas_same_shape():
         a = hid2d[:chunk]
         out = torch.empty((a.shape[0], V), dtype=torch.bfloat16, device=dev)
@@ -497,46 +550,89 @@ def run_ours(args, w):
     hbm = hbm_kernels(dev, peaks) if rank == 0 else None
     tok_s = world * N / (ms_step * 1e-3)
     tok_s_e2e = world * N / (ms_e2e * 1e-3)
-    flops_fwd_launch = 2.0 * min(chunk, N) * H * V
-    fwd_launch_ms = ms_fwd / n_chunks
-    achieved = flops_fwd_launch / (fwd_launch_ms * 1e-3) / 1e12
     step_tflops_alg = 6.0 * N * H * V / (ms_step * 1e-3) / 1e12
     h2d = sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
+
+    # ---- roofline: the three GEMMs as the step runs them (live CUDA-event durations), the slowest one is `roofline`
+    traffic, traffic_note = measured_traffic(H, V)
+    kernel_names = {
+        "forward": "gemm_sm100_kernel<2,256,6,K-major,K-major,EpiLseStoreRel> (logits tile -> LSE partials + bf16 tile store)",
+        "d_hidden": "gemm_sm100_kernel<2,256,6,K-major,MN-major,EpiStoreBF16> (d_hidden = dS * W)",
+        "d_weight": "gemm_sm100_kernel<2,256,6,MN-major,MN-major,EpiStoreF32> (d_weight += dS^T * hidden, fp32)",
+    }
+    roofline_kernels = {}
+    for kind, t in gemm_times.items():
+        if t["launches"] == 0:
+            continue
+        ms_launch = t["ms"] / t["launches"]
+        flops_launch = 2.0 * N * H * V * args.steps / t["launches"]  # every launch covers one token chunk
+        ach = flops_launch / (ms_launch * 1e-3) / 1e12
+        roofline_kernels[kind] = {"kernel": kernel_names[kind], "bound": "tensor", "achieved": ach,
+                                  "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                                  "traffic": traffic.get(kind), "flops_per_launch": flops_launch,
+                                  "ms_per_launch": ms_launch, "launches": t["launches"],
+                                  "share_of_step": t["ms"] / (ms_step * args.steps)}
+    worst = min(roofline_kernels, key=lambda k: roofline_kernels[k]["frac"]) if roofline_kernels else None
+
+    # ---- other BASELINE configs (2 timed steps each) and the reference's own GPU path on this GPU
+    other = None
+    if args.workload == "c2" and not args.no_other:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_configs
+
+        del db, hid2d, d_weight, weight  # free the config-2 batch (16 GB) before the larger shapes
+        torch.cuda.empty_cache()
+        other = {}
+        for name in bench_configs.DEFAULT_SET:
+            try:
+                other[name] = bench_configs.run_config(name, dev, rank, world, steps=2, warmup=1, peaks=peaks)
+            except Exception as exc:  # noqa: BLE001  (never lose the headline line over a side measurement)
+                other[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.empty_cache()
+    ref_gpu = None
+    if rank == 0 and not args.no_other:
+        from baseline import ref_path
+
+        ref_gpu = ref_path.gpu_path(w, cfg, dev, micro_tokens=min(8192, N), temperature=TEMPERATURE)
 
     if rank == 0:
         threads = os.cpu_count() or 1
         sample = 4096 if V > 100000 else 16384  # ~10-20 s of host work
-        dt, n_tok = cpu_port_step(w, sample, threads)
+        dt, n_tok, kind = cpu_reference_step(w, sample, threads)
         line = {
             "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config_dict(w, world),
             "tokens_per_s_per_gpu": tok_s / world,
-            "phases_ms": {"advantages": adv_ms, "head_fwd+loss+head_bwd": upd_ms, "head_fwd_alone": ms_fwd},
+            "phases_ms": {"advantages": adv_ms, "head_fwd+loss+head_bwd": upd_ms, "collectives(+rank skew)": comm_ms},
             "cublas_same_shape_tflops": cublas_tflops,
             "hbm_kernels": hbm,
             "step_roofline": {"bound": "tensor", "algorithmic_flops_per_token": 6.0 * H * V,
                               "achieved": step_tflops_alg, "peak": peaks["tflops"], "unit": "TFLOP/s",
                               "frac": step_tflops_alg / peaks["tflops"],
                               "note": "6*H*V*N algorithmic flops / step time (fused step: the backward reads the bf16 "
-                                      "logits tile store, 6*H*V*N executed); peak = " + peaks["source"]},
-            "roofline": {"kernel": "gemm_sm100_kernel<2,256,6,K-major,K-major,EpiLsePartials> (head forward)",
-                         "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"],
-                         # dram__bytes_read.sum + dram__bytes_write.sum per full-chunk launch of this kernel with its
-                         # bf16 tile store, from the `ncu --set full` capture in profiles/r01b_gemm_full_metrics.csv
-                         # (5.15 GB read + 2.99 GB written; algorithmic: 1.09 GB weight + 0.07 GB hidden + 2.9 GB store)
-                         "traffic": 8.14e9 if (H, V) == (3584, 152064) else None,
-                         "flops_per_launch": flops_fwd_launch, "ms_per_launch": fwd_launch_ms,
-                         "note": "per-launch = head_forward call / %d chunks (includes the <1%% merge kernel); peak = %s"
-                                 % (n_chunks, peaks["source"])},
-            "cpu_baseline": {"value": n_tok / dt, "unit": "tokens/s", "cores": threads, "kind": "port",
-                             "sample": f"{n_tok} tokens of the same workload, fp32 torch CPU path restated in oracle/"},
+                                      "tile store, 6*H*V*N executed); peak = " + peaks["source"]},
+            "roofline": dict(roofline_kernels[worst], which=worst,
+                             note="slowest of the step's three GEMMs; duration = CUDA events around every launch "
+                                  "inside the timed steps (live, power-capped regime); traffic: " + traffic_note
+                                  + "; peak = " + peaks["source"]) if worst else None,
+            "roofline_kernels": roofline_kernels,
+            "cpu_baseline": {"value": n_tok / dt, "unit": "tokens/s", "cores": threads, "kind": kind,
+                             "sample": f"{n_tok} tokens of the same workload, fp32 torch CPU path of the "
+                                       + ("unmodified reference (baseline/_ref)" if kind == "reference"
+                                          else "oracle restatement")},
+            "ref_gpu_path": ref_gpu,
+            "vs_ref_gpu_path": (tok_s / world / ref_gpu["tokens_per_s"]) if ref_gpu and "tokens_per_s" in ref_gpu else None,
+            "other_configs": other,
             "e2e": {"value": tok_s_e2e, "unit": "tokens/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": 64, "ms_per_step": ms_e2e, "steps": e2e_steps,
-                    "api": "compute_grpo_outcome_advantage + policy_update_step on pinned host tensors (hidden streamed in chunk by chunk inside the step)"},
+                    "api": "compute_grpo_outcome_advantage + policy_update_step on PINNED host tensors (hidden streamed "
+                           "in chunk by chunk inside the step; pageable memory would serialise the copy); d_hidden and "
+                           "log-probs stay on the device for the trunk backward"},
             "gpu_launches": launches_per_step * args.steps,
+            "dp_check": dp,
+            "allreduce_exposed_ms": dp["allreduce_ms"] if dp else None,
             "clocks": clocks,
         }
         print(json.dumps(line))
@@ -551,6 +647,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-other", action="store_true", help="skip other_configs / ref_gpu_path (A/B runs, profiling)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

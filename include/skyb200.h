@@ -365,12 +365,34 @@ size_t skyb200_policy_step_workspace(int64_t B, int64_t A, int64_t n_tokens, int
  */
 int skyb200_policy_step_plan(int64_t B, int64_t A, int64_t n_tokens, int64_t H, int64_t V, int32_t loss_type,
                              int32_t need_grad, int64_t* plan_out);
+/*
+ * Optional inputs of the step (pass NULL for none).
+ *   tis / clip_mask : the off-policy correction of the reference (off_policy_correction_utils.py:173-262) as
+ *     skyb200_off_policy_correction produces it BEFORE the step (it depends only on old / rollout log-probs): `tis`
+ *     [B, A] is the detached per-token importance weight that multiplies the loss; `loss_mask` is then the CORRECTED
+ *     mask and `clip_mask` [B, A] the mask before the correction, which the clip_ratio metric keeps
+ *     (ppo_utils.py:570 vs :579-583).
+ */
+typedef struct {
+    const float* tis;
+    const float* clip_mask;
+    int64_t timing;      /* != 0: bracket every GEMM launch with CUDA timing events (see skyb200_policy_step_timing) */
+    int64_t reserved[5]; /* must be zero */
+} skyb200_step_opts;
 int skyb200_policy_step(const void* hidden, const void* weight, const int64_t* labels, const float* old_log_probs,
                         const float* advantages, const float* loss_mask, const float* base_log_probs,
                         const float* entropy_mask, float* log_probs, float* entropy, void* d_hidden, float* d_weight,
                         int32_t accumulate, float* stats, void* workspace, size_t workspace_bytes, int64_t B, int64_t A,
                         int64_t H, int64_t V, const int32_t* cu_seqlens, int64_t n_tokens, float temperature,
-                        const skyb200_loss_params* params, void* stream);
+                        const skyb200_loss_params* params, const skyb200_step_opts* opts, void* stream);
+
+/*
+ * Per-kernel durations of the steps run with opts->timing since the last call, measured LIVE (CUDA events on the
+ * caller's stream around each GEMM launch, inside the running step - the power-capped regime the step really sees):
+ * out[0..2] = summed ms of the forward / d_hidden / d_weight GEMM launches, out[3..5] = their launch counts.
+ * Synchronises on the last recorded event and clears the record.  Per device (call it on the step's device).
+ */
+int skyb200_policy_step_timing(double* out);
 
 /*
  * Same step with the hidden states resident in HOST memory (pinned for an asynchronous copy): hidden_host [N, H]
@@ -384,7 +406,8 @@ int skyb200_policy_step_from_host(const void* hidden_host, void* hidden_staging,
                                   float* log_probs, float* entropy, void* d_hidden, float* d_weight,
                                   int32_t accumulate, float* stats, void* workspace, size_t workspace_bytes, int64_t B,
                                   int64_t A, int64_t H, int64_t V, const int32_t* cu_seqlens, int64_t n_tokens,
-                                  float temperature, const skyb200_loss_params* params, void* stream);
+                                  float temperature, const skyb200_loss_params* params,
+                                  const skyb200_step_opts* opts, void* stream);
 
 /*
  * logprobs_from_logits (torch_utils.py:115-177) and chunked_entropy_from_logits (:59-111) on materialised

@@ -1,7 +1,9 @@
-"""Load the UNMODIFIED reference hot-path modules from /root/reference (build container only).
+"""Load the UNMODIFIED reference hot-path modules: from /root/reference in the build container, else from the copy
+of the same four files that ``__graft_entry__.build()`` vendors into ``baseline/_ref/`` (git-ignored, travels to the
+GPU box with the repo snapshot - ``baseline/ref_path.py``).
 
-Used by ``oracle/make_golden.py`` and by the CPU tests that cross-check the oracle against the real reference
-when it is present.  Never used on the GPU box (``/root/reference`` does not exist there).
+Used by ``oracle/make_golden.py``, by the CPU tests that cross-check the oracle against the real reference, and by the
+baseline arms of ``bench.py`` (``--impl reference``, ``cpu_baseline``, ``ref_gpu_path``).  Never by the product.
 """
 from __future__ import annotations
 
@@ -11,7 +13,11 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("SKYRL_REF_ROOT", "/root/reference/skyrl-train/skyrl_train")
+_CANDIDATES = ["/root/reference/skyrl-train/skyrl_train",
+               os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref",
+                            "skyrl_train")]
+REF_ROOT = os.environ.get("SKYRL_REF_ROOT") or next(
+    (c for c in _CANDIDATES if os.path.isfile(os.path.join(c, "utils", "ppo_utils.py"))), _CANDIDATES[0])
 
 
 def available() -> bool:

@@ -2,8 +2,10 @@
 config 2, the headline; these are the other named shapes).  One JSON line per config; under torchrun every rank owns
 its own shard (weak scaling) and the packed stats + fp32 lm_head gradient are all-reduced per step, as in bench.py.
 
-    python scripts/bench_configs.py [c3] [c4-dual_clip] [c4-gspo] [c5] [steps=3] [warmup=2]
+    python scripts/bench_configs.py [c1] [c3] [c3-strong] [c4-dual_clip] [c4-gspo] [c5] [steps=3] [warmup=2]
 
+    c1  GRPO + regular loss + KL loss; 64 x 1024 tokens, Qwen2.5-0.5B head (H = 896, V = 151936) - the whole config
+    c3-strong  config 3 at its FIXED size (512 x 8192 tokens) split over the ranks: strong scaling
     c3  PPO: KL-in-reward (k3) -> GAE (gamma 1, lambda 0.95) -> regular loss + KL loss; 64 x 8192 tokens, 7B head
     c4  dual-clip (c = 3, token_mean) or GSPO (sequence_mean); 8 x 32768-token trajectories (lengths 24K-32K),
         Qwen3-32B-shaped head (H = 5120, V = 151936)
@@ -27,7 +29,10 @@ from bench import ClockSampler, make_cfg, make_weight, measured_peaks  # noqa: E
 from skyrl_b200 import dist as sdist  # noqa: E402
 
 SHAPES = {
+    "c1": dict(B=64, A=1024, H=896, V=151936, model="Qwen2.5-0.5B head"),
     "c3": dict(B=64, A=8192, H=3584, V=152064, model="Qwen2.5-7B head"),
+    # the FIXED 512 x 8192 config-3 batch split over the ranks (strong scaling; B is per-rank = 512 / world)
+    "c3-strong": dict(B=512, A=8192, H=3584, V=152064, model="Qwen2.5-7B head", strong=True),
     "c4-dual_clip": dict(B=8, A=32768, H=5120, V=151936, model="Qwen3-32B-shaped head"),
     "c4-gspo": dict(B=8, A=32768, H=5120, V=151936, model="Qwen3-32B-shaped head"),
     "c5": dict(B=64, A=16384, H=3584, V=152064, G=16, model="Qwen2.5-7B head"),
@@ -53,16 +58,19 @@ def _randn_bf16(n, h, gen, dev):
     return out
 
 
-def build(name, dev, rank):
+def build(name, dev, rank, world=1):
     """Returns (step_fn, n_valid_tokens, n_positions, description).  All inputs are resident in HBM."""
     s = SHAPES[name]
     B, A, H, V = s["B"], s["A"], s["H"], s["V"]
+    if s.get("strong"):
+        B = B // world
+    name = "c3" if name == "c3-strong" else name
     gen = torch.Generator(device=dev).manual_seed(1234 + 17 * rank)
     cfg = _cfg(name)
     weight = make_weight(s, dev)
     d_weight = torch.zeros((V, H), dtype=torch.float32, device=dev)
     ar = torch.arange(A, device=dev)[None]
-    if name == "c3":
+    if name in ("c3", "c1"):
         lens = torch.full((B,), A, device=dev)
     elif name.startswith("c4"):
         lens = torch.randint(24 * 1024, A + 1, (B,), generator=gen, device=dev)
@@ -113,6 +121,14 @@ def build(name, dev, rank):
 
         return step, int(mask.sum()), N, f"{B} x {A} tokens, KL-in-reward + GAE + regular loss + KL loss"
     uids = np.array([f"prompt-{rank}-{i // 8}" for i in range(B)])
+    if name == "c1":
+
+        def step():
+            adv, _ = skyrl_b200.compute_grpo_outcome_advantage(rewards, mask, uids)
+            return skyrl_b200.policy_update_step(hidden, weight, labels, olp, adv, cfg, loss_mask=mask,
+                                                 base_log_probs=base, d_weight=d_weight, sync=False)
+
+        return step, int(mask.sum()), N, f"{B} x {A} tokens, GRPO + regular loss + KL loss"
 
     def step():
         adv, _ = skyrl_b200.compute_grpo_outcome_advantage(rewards, mask, uids)
@@ -122,11 +138,71 @@ def build(name, dev, rank):
     return step, int(mask.sum()), N, f"{B} x {A}-token trajectories (lengths 24K-32K), GRPO + {cfg.policy_loss_type}"
 
 
+DEFAULT_SET = ["c1", "c3", "c4-dual_clip", "c4-gspo", "c5", "c3-strong"]
+
+
+def run_config(name, dev, rank, world, steps, warmup, peaks):
+    """Time `steps` fused steps of config `name` (after `warmup`), CUDA events, max over ranks.  Returns the result
+    dict on every rank (values are whole-job aggregates)."""
+    import torch.distributed as dist
+
+    step, n_valid, n_pos, desc = build(name, dev, rank, world)
+
+    def full_step():
+        out = step()
+        if world > 1:
+            sdist.all_reduce_packed_stats(out.stats)
+            sdist.all_reduce_d_weight(out.d_weight)
+        return out
+
+    for _ in range(warmup):
+        full_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        out = full_step()
+    e.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([s.elapsed_time(e) / steps, float(n_valid), float(n_pos)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t[0] = tmax[0]
+    ms, valid, pos = (float(x) for x in t.tolist())
+    sh = SHAPES[name]
+    tflops = 6.0 * sh["H"] * sh["V"] * pos / (ms * 1e-3) / 1e12 / world
+    st = out.stats.tolist()
+    res = {
+        "config": name, "workload": f"{sh['model']} (H={sh['H']}, V={sh['V']}): {desc} per GPU",
+        "n_gpus": world, "scaling": "strong" if sh.get("strong") else "weak", "steps": steps, "warmup": warmup,
+        "ms_per_step": round(ms, 2),
+        "tokens_per_s": round(valid / (ms * 1e-3)), "positions_per_s": round(pos / (ms * 1e-3)),
+        "valid_fraction": round(valid / pos, 4),
+        "step_roofline": {"bound": "tensor", "achieved": round(tflops, 1), "peak": peaks["tflops"],
+                          "unit": "TFLOP/s per GPU", "frac": round(tflops / peaks["tflops"], 4),
+                          "note": "6*H*V per processed position; peak = " + peaks["source"]},
+        "final_loss": st[skyrl_b200._lib.STAT_FINAL_LOSS], "clip_ratio": st[skyrl_b200._lib.STAT_CLIP_RATIO],
+        "clocks": clocks}
+    del step, full_step, out
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     import torch.distributed as dist
 
     kv = dict(a.split("=", 1) for a in sys.argv[1:] if "=" in a)
-    names = [a for a in sys.argv[1:] if "=" not in a] or list(SHAPES)
+    names = [a for a in sys.argv[1:] if "=" not in a] or [n for n in DEFAULT_SET]
     steps, warmup = int(kv.get("steps", 3)), int(kv.get("warmup", 2))
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
@@ -135,55 +211,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     peaks = measured_peaks()
     for name in names:
-        step, n_valid, n_pos, desc = build(name, dev, rank)
-
-        def full_step():
-            out = step()
-            if world > 1:
-                sdist.all_reduce_packed_stats(out.stats)
-                sdist.all_reduce_d_weight(out.d_weight)
-            return out
-
-        for _ in range(warmup):
-            full_step()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        sampler = ClockSampler(dev.index)
+        res = run_config(name, dev, rank, world, steps, warmup, peaks)
         if rank == 0:
-            sampler.start()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(steps):
-            out = full_step()
-        e.record()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        clocks = sampler.stop() if rank == 0 else None
-        t = torch.tensor([s.elapsed_time(e) / steps, float(n_valid), float(n_pos)], dtype=torch.float64, device=dev)
-        if world > 1:
-            tmax = t.clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            t[0] = tmax[0]
-        ms, valid, pos = (float(x) for x in t.tolist())
-        sh = SHAPES[name]
-        tflops = 6.0 * sh["H"] * sh["V"] * pos / (ms * 1e-3) / 1e12 / world
-        if rank == 0:
-            st = out.stats.tolist()
-            print(json.dumps({
-                "config": name, "workload": f"{sh['model']} (H={sh['H']}, V={sh['V']}): {desc} per GPU",
-                "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 2),
-                "tokens_per_s": round(valid / (ms * 1e-3)), "positions_per_s": round(pos / (ms * 1e-3)),
-                "valid_fraction": round(valid / pos, 4),
-                "roofline": {"bound": "tensor", "achieved": round(tflops, 1), "peak": peaks["tflops"],
-                             "unit": "TFLOP/s per GPU", "frac": round(tflops / peaks["tflops"], 4),
-                             "note": "6*H*V per processed position; peak = " + peaks["source"]},
-                "final_loss": st[skyrl_b200._lib.STAT_FINAL_LOSS], "clip_ratio": st[skyrl_b200._lib.STAT_CLIP_RATIO],
-                "clocks": clocks}), flush=True)
-        del step, full_step, out
-        torch.cuda.empty_cache()
+            print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -37,7 +37,8 @@ from .model_wrapper import (  # noqa: F401
     action_log_probs_from_sp_hidden,
     action_log_probs_from_sp_packed_hidden,
 )
-from .policy_update import PolicyUpdateOutput, fused_policy_loss, pack_by_lengths, policy_update_step  # noqa: F401
+from .policy_update import (PolicyUpdateOutput, fused_policy_loss, pack_by_lengths, policy_update_step,  # noqa: F401
+                            step_gemm_times)
 from .registry import (  # noqa: F401
     AdvantageEstimator,
     AdvantageEstimatorRegistry,

@@ -58,6 +58,11 @@ class OpcParams(C.Structure):
     ]
 
 
+class StepOpts(C.Structure):
+    """skyb200_step_opts: optional inputs of the fused step (off-policy correction)."""
+    _fields_ = [("tis", C.c_void_p), ("clip_mask", C.c_void_p), ("timing", C.c_int64), ("reserved", C.c_int64 * 5)]
+
+
 OPC_NMETRICS = 16
 LOSS_KL_COV = 7  # skyb200_policy_loss only (global token selection): not in LOSS_TYPES, the fused step rejects it
 COV_KL, COV_CLIP = 0, 1
@@ -124,9 +129,11 @@ SIGNATURES = {
     "skyb200_policy_step_workspace": (_SZ, [_I64, _I64, _I64, _I64, _I64, _I32, _I32]),
     "skyb200_policy_step_plan": (C.c_int, [_I64, _I64, _I64, _I64, _I64, _I32, _I32, C.POINTER(C.c_int64)]),
     "skyb200_policy_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _SZ, _I64, _I64,
-                                      _I64, _I64, _P, _I64, _F, C.POINTER(LossParams), _P]),
+                                      _I64, _I64, _P, _I64, _F, C.POINTER(LossParams), C.POINTER(StepOpts), _P]),
     "skyb200_policy_step_from_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _P, _SZ,
-                                                _I64, _I64, _I64, _I64, _P, _I64, _F, C.POINTER(LossParams), _P]),
+                                                _I64, _I64, _I64, _I64, _P, _I64, _F, C.POINTER(LossParams),
+                                                C.POINTER(StepOpts), _P]),
+    "skyb200_policy_step_timing": (C.c_int, [C.POINTER(C.c_double)]),
     "skyb200_logits_logprob_entropy": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _I64, _I64, _P]),
     "skyb200_logits_backward": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
     "skyb200_gemm_selftest": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P]),
@@ -178,10 +185,13 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """The current torch stream of ``device`` (default: the current device).  Call it INSIDE the
+    ``torch.cuda.device`` context the kernels are launched in, or pass the device: a stream taken under another
+    current device belongs to that device."""
     import torch
 
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def gemm_debug_record():

@@ -24,7 +24,7 @@ int num_sms() {
 
 }  // namespace skyb200
 
-extern "C" int skyb200_abi_version(void) { return 1; }
+extern "C" int skyb200_abi_version(void) { return 2; }
 
 extern "C" const char* skyb200_last_error(void) { return skyb200::last_error_buffer(); }
 

@@ -96,13 +96,17 @@ __device__ __forceinline__ void bounded_wait(uint64_t* bar, uint32_t parity, Gem
     }
 }
 
-template <int kCtas, int BN, int kStages>
+// Shared memory: [A stages][B stages][epilogue staging: kEpiBytes, 1024-byte aligned][barriers]
+template <int kCtas, int BN, int kStages, uint32_t kEpiBytes = 0>
 struct GemmSmem {
     static constexpr uint32_t kABytes = kBM * kBK * 2;
     static constexpr uint32_t kLoadN = BN / kCtas;
     static constexpr uint32_t kBBytes = kLoadN * kBK * 2;
     static constexpr uint32_t kBarBytes = (2 * kStages + 4) * 8 + 16;
-    static constexpr uint32_t kTotal = 1024 + kStages * (kABytes + kBBytes) + kBarBytes;
+    static constexpr uint32_t kEpiOffset = kStages * (kABytes + kBBytes);
+    static constexpr uint32_t kTotal = 1024 + kStages * (kABytes + kBBytes) + kEpiBytes + kBarBytes;
+    static_assert(kEpiBytes % 1024 == 0, "epilogue staging must keep the 1024-byte swizzle alignment");
+    static_assert(kTotal <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
 };
 
 // Optional device-side compaction of the iteration space (all pointers may be null):
@@ -120,9 +124,10 @@ struct GemmMaps {
 template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
-                  int N, int K, int group_m, int tile_order, uint64_t hint_a, uint64_t hint_b, typename Epi::Params ep,
-                  GemmDebug* dbg, unsigned int* sync_ctr, int sync_every, GemmMaps maps) {
-    using S = GemmSmem<kCtas, BN, kStages>;
+                  int N, int K, int group_m, int tile_order, uint64_t hint_a, uint64_t hint_b,
+                  const __grid_constant__ typename Epi::Params ep, GemmDebug* dbg, unsigned int* sync_ctr,
+                  int sync_every, GemmMaps maps) {
+    using S = GemmSmem<kCtas, BN, kStages, Epi::kSmemBytes>;
     constexpr int TILE_M = kBM * kCtas;
     constexpr uint32_t kTmemCols = 2 * BN;
     static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
@@ -134,7 +139,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * S::kABytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kStages * S::kBBytes);
+    uint8_t* smem_epi = smem + S::kEpiOffset;  // Epi::kSmemBytes of staging for TMA-store epilogues (4 equal warp slices)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + Epi::kSmemBytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tfull_bar = empty_bar + kStages;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -296,6 +302,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
         // ------------------------------------------------------------ epilogue (4 warps, row per thread)
         const int q = warp & 3;  // TMEM lane quarter this warp may access
+        uint8_t* stage_w = smem_epi + q * (Epi::kSmemBytes / 4);
         uint32_t accum = 0, aphase = 0;
         for (int t = cluster_id; t < total_tiles; t += num_clusters) {
             const TileCoord tc = decode_tile(t, num_m_tiles, num_n_tiles, group_m, tile_order);
@@ -304,7 +311,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + accum * BN;
             const int m_tile = maps.m_map ? maps.m_map[tc.m_tile] : tc.m_tile;
             const int row = m_tile * TILE_M + static_cast<int>(cta_rank) * kBM + q * 32 + lane;
-            Epi::template run<BN>(ep, taddr, row, tc.n_tile, M, N);
+            Epi::template run<BN>(ep, taddr, row, tc.n_tile, M, N, stage_w);
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -318,6 +325,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 aphase ^= 1u;
             }
         }
+        Epi::finish();  // TMA-store epilogues: this warp's outstanding bulk stores complete before the CTA exits
     }
 
     ptx::tcgen05_fence_before();
@@ -386,13 +394,15 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float
 
 // C (fp32, row-major, leading dim ldc) = or += accumulator.   Used for dW and for GEMM self-tests.
 struct EpiStoreF32 {
+    static constexpr uint32_t kSmemBytes = 0;
+    __device__ static void finish() {}
     struct Params {
         float* C;
         int64_t ldc;
         int accumulate;
     };
     template <int BN>
-    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N, uint8_t*) {
         const int n0 = n_tile * BN;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -431,11 +441,13 @@ struct EpiStoreF32 {
 
 // Drains the accumulator and discards it (mainloop-only timing in scripts/gemm_tune.py).
 struct EpiNull {
+    static constexpr uint32_t kSmemBytes = 0;
+    __device__ static void finish() {}
     struct Params {
         float* sink;
     };
     template <int BN>
-    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N, uint8_t*) {
         float acc = 0.f;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -451,23 +463,27 @@ struct EpiNull {
 
 // Does not even read the accumulator (isolates the cost of the TMEM drain itself in scripts/gemm_tune.py).
 struct EpiSkip {
+    static constexpr uint32_t kSmemBytes = 0;
+    __device__ static void finish() {}
     struct Params {
         float* sink;
     };
     template <int BN>
-    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N, uint8_t*) {
         if (row == -12345 && p.sink != nullptr) p.sink[0] = static_cast<float>(taddr + n_tile + M + N);
     }
 };
 
 // C (bf16, row-major) = accumulator.   Used for d_hidden.
 struct EpiStoreBF16 {
+    static constexpr uint32_t kSmemBytes = 0;
+    __device__ static void finish() {}
     struct Params {
         __nv_bfloat16* C;
         int64_t ldc;
     };
     template <int BN>
-    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N, uint8_t*) {
         const int n0 = n_tile * BN;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -495,12 +511,6 @@ struct EpiStoreBF16 {
 //   y = acc * scale_log2  (scale_log2 = log2(e) / temperature)
 //   part_m = max_j y_j ; part_s = sum_j 2^(y_j - part_m) ; part_t = sum_j 2^(y_j - part_m) * acc_j
 // and the raw accumulator at the label column (written by the one slab that contains it).
-//
-// kStored (EpiLsePartialsStored): additionally part_sb = sum_j 2^(bf16(acc_j) * scale_log2 - part_m), the same sum
-// over the bf16-ROUNDED logits that go to the tile store.  The backward of the fused step reads that store; with the
-// log-sum-exp of the rounded logits its p = 2^(bf16(z) * scale - lse_b) is exactly softmax(bf16 logits) - a
-// distribution, and the arithmetic the reference differentiates (its lm_head emits bf16 logits) - instead of rounded
-// logits against the exact normaliser, whose probabilities miss 1 by up to 0.25 ulp(bf16) * |z| per element.
 struct LsePartialsParams {
     float scale_log2;
     float* part_m;  // [num_n_tiles][ld]
@@ -509,135 +519,212 @@ struct LsePartialsParams {
     int64_t ld;
     const int64_t* labels;  // [M]
     float* label_acc;       // [M]
-    __nv_bfloat16* logits;  // [M, ld_logits] bf16 copy of the raw accumulators, or nullptr
+    __nv_bfloat16* logits;  // EpiLseStoreRel only: [M, ld_logits] bf16 slab-relative log2-logits (see below)
     int64_t ld_logits;
 };
-struct LsePartialsStoredParams : LsePartialsParams {
-    float* part_sb;  // [num_n_tiles][ld]
-};
 
-template <int BN, bool kStored, class P>
-__device__ __forceinline__ void lse_partials_tile(const P& p, uint32_t taddr, int row, int n_tile, int M, int N) {
-    const int n0 = n_tile * BN;
-    const bool row_ok = row < M;
-    const int lab = row_ok ? static_cast<int>(p.labels[row]) : -1;
-    float m2 = -INFINITY, s = 0.f, tt = 0.f;
-    [[maybe_unused]] float sb = 0.f;
-    uint32_t held[16];
-    __nv_bfloat16* held_dst = nullptr;
+// Plain forward (no backward follows, or the backward recomputes): one pass over the accumulator tile with a running
+// maximum that rescales the sums when it moves.
+struct EpiLsePartials {
+    static constexpr uint32_t kSmemBytes = 0;
+    __device__ static void finish() {}
+    using Params = LsePartialsParams;
+    template <int BN>
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N, uint8_t*) {
+        const int n0 = n_tile * BN;
+        const bool row_ok = row < M;
+        const int lab = row_ok ? static_cast<int>(p.labels[row]) : -1;
+        float m2 = -INFINITY, s = 0.f, tt = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
-        ptx::tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (col0 >= N) continue;  // uniform across the whole warp
-        const int nvalid = min(32, N - col0);
-        float cm = -INFINITY;
-        if (nvalid == 32) {
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            __syncwarp();
+            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            const int col0 = n0 + c * 32;
+            if (col0 >= N) continue;  // uniform across the whole warp
+            const int nvalid = min(32, N - col0);
+            float cm = -INFINITY;
+            if (nvalid == 32) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]));
-        } else {
+                for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]));
+            } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (i < nvalid) cm = fmaxf(cm, __uint_as_float(v[i]));
-        }
-        const float m_new = fmaxf(m2, cm * p.scale_log2);
-        const float corr = ex2_approx(m2 - m_new);  // 0 on the first chunk (m2 = -inf)
-        s *= corr;
-        tt *= corr;
-        if constexpr (kStored) sb *= corr;
-        m2 = m_new;
-        if (nvalid == 32) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float a = __uint_as_float(v[i]);
-                const float e = ex2_approx(fmaf(a, p.scale_log2, -m2));
-                s += e;
-                tt = fmaf(e, a, tt);
-                if constexpr (kStored) {
-                    const float r = __bfloat162float(__float2bfloat16_rn(a));
-                    sb += ex2_approx(fmaf(r, p.scale_log2, -m2));
-                }
+                for (int i = 0; i < 32; ++i)
+                    if (i < nvalid) cm = fmaxf(cm, __uint_as_float(v[i]));
             }
-        } else {
+            const float m_new = fmaxf(m2, cm * p.scale_log2);
+            const float corr = ex2_approx(m2 - m_new);  // 0 on the first chunk (m2 = -inf)
+            s *= corr;
+            tt *= corr;
+            m2 = m_new;
+            if (nvalid == 32) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (i < nvalid) {
+                for (int i = 0; i < 32; ++i) {
                     const float a = __uint_as_float(v[i]);
                     const float e = ex2_approx(fmaf(a, p.scale_log2, -m2));
                     s += e;
                     tt = fmaf(e, a, tt);
-                    if constexpr (kStored) {
-                        const float r = __bfloat162float(__float2bfloat16_rn(a));
-                        sb += ex2_approx(fmaf(r, p.scale_log2, -m2));
-                    }
-                }
-            }
-        }
-        if (lab >= col0 && lab < col0 + nvalid) {
-            float z = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (col0 + i == lab) z = __uint_as_float(v[i]);
-            p.label_acc[row] = z;
-        }
-        if (p.logits != nullptr && row_ok) {
-            __nv_bfloat16* dst = p.logits + static_cast<int64_t>(row) * p.ld_logits + col0;
-            if (nvalid == 32 && (p.ld_logits & 15) == 0 && (reinterpret_cast<uintptr_t>(p.logits) & 31u) == 0) {
-                // Two 32-column chunks are written together as one full 128-byte line (4 x 32 B issued back
-                // to back), so the write-once store never leaves a half-written line behind to be re-filled.
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                if ((c & 1) == 0) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) held[i] = pk[i];
-                    held_dst = dst;
-                } else {
-                    if (held_dst != nullptr) {
-                        st_global_256_stream(held_dst, held[0], held[1], held[2], held[3], held[4], held[5], held[6],
-                                             held[7]);
-                        st_global_256_stream(held_dst + 16, held[8], held[9], held[10], held[11], held[12], held[13],
-                                             held[14], held[15]);
-                        held_dst = nullptr;
-                    }
-                    st_global_256_stream(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
-                    st_global_256_stream(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
                 }
             } else {
-                for (int i = 0; i < nvalid; ++i) dst[i] = __float2bfloat16_rn(__uint_as_float(v[i]));
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i < nvalid) {
+                        const float a = __uint_as_float(v[i]);
+                        const float e = ex2_approx(fmaf(a, p.scale_log2, -m2));
+                        s += e;
+                        tt = fmaf(e, a, tt);
+                    }
+                }
+            }
+            if (lab >= col0 && lab < col0 + nvalid) {
+                float z = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (col0 + i == lab) z = __uint_as_float(v[i]);
+                p.label_acc[row] = z;
             }
         }
-    }
-    if (held_dst != nullptr) {  // odd number of valid 32-column chunks in this tile
-        st_global_256_stream(held_dst, held[0], held[1], held[2], held[3], held[4], held[5], held[6], held[7]);
-        st_global_256_stream(held_dst + 16, held[8], held[9], held[10], held[11], held[12], held[13], held[14],
-                             held[15]);
-    }
-    if (row_ok) {
-        const int64_t o = static_cast<int64_t>(n_tile) * p.ld + row;
-        p.part_m[o] = m2;
-        p.part_s[o] = s;
-        p.part_t[o] = tt;
-        if constexpr (kStored) p.part_sb[o] = sb;
-    }
-}
-
-struct EpiLsePartials {
-    using Params = LsePartialsParams;
-    template <int BN>
-    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
-        lse_partials_tile<BN, false>(p, taddr, row, n_tile, M, N);
+        if (row_ok) {
+            const int64_t o = static_cast<int64_t>(n_tile) * p.ld + row;
+            p.part_m[o] = m2;
+            p.part_s[o] = s;
+            p.part_t[o] = tt;
+        }
     }
 };
-struct EpiLsePartialsStored {
-    using Params = LsePartialsStoredParams;
+
+// Forward of the fused step: the same partials, plus a bf16 copy of the tile for the backward GEMMs (which therefore
+// do not recompute the projection).  What is stored is NOT the raw logit but the SLAB-RELATIVE log2-logit
+//     u_j = acc_j * scale_log2 - part_m            (<= 0, and ~0 exactly where the probability mass is)
+// so that the bf16 rounding error |u| * 2^-9 vanishes on the entries that carry the gradient: the backward forms
+// p_j = 2^(u_j + part_m - lse2) with a relative error of 2^-9 * ln2 * log2(p_max / p_j) - independent of the logit
+// SCALE - whereas rounding the raw logit z costs |z| * 2^-9 on every entry (28 % of p at |z| = 70).  The slab
+// maximum must be known before the first store, so the tile is read from TMEM twice: pass 1 takes the row maximum
+// over the slab, pass 2 exponentiates against it (no running-maximum rescale any more), accumulates the two sums and
+// writes u.  The ex2 argument IS u: the store costs one cvt.bf16x2 per two columns and no extra MUFU.
+//
+// The tile leaves the SM through TMA: each epilogue warp stages 32 rows x 64 columns (4 KB, 128-byte swizzle, two
+// buffers) in shared memory and one lane issues cp.async.bulk.tensor (UTMASTG) - full 128-byte lines written by the
+// copy engine instead of 32 row-strided 32-byte LSU stores per instruction, which cost the forward GEMM 12 % of its
+// tensor-pipe time (profiles/README.md, r02b).  Rows >= M and columns >= N are clipped by the tensor map.
+struct LseStoreParams : LsePartialsParams {
+    CUtensorMap tmap_out;  // bf16 [M, N] with pitch ld_logits, box 64 x 32, SWIZZLE_128B
+};
+struct EpiLseStoreRel {
+    static constexpr uint32_t kSmemBytes = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+    __device__ static void finish() {
+        if ((threadIdx.x & 31) == 0) ptx::bulk_wait_group<0>();
+    }
+    using Params = LseStoreParams;
     template <int BN>
-    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
-        lse_partials_tile<BN, true>(p, taddr, row, n_tile, M, N);
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N, uint8_t* stage) {
+        const int n0 = n_tile * BN;
+        const int lane = threadIdx.x & 31;
+        const bool row_ok = row < M;
+        const int lab = row_ok ? static_cast<int>(p.labels[row]) : -1;
+        // ---- pass 1: slab maximum of the raw accumulators (scale_log2 > 0: the maximum commutes with the scaling)
+        float cm = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            __syncwarp();
+            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            const int col0 = n0 + c * 32;
+            if (col0 >= N) continue;  // uniform across the whole warp
+            const int nvalid = min(32, N - col0);
+            if (nvalid == 32) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(v[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < nvalid) cm = fmaxf(cm, __uint_as_float(v[i]));
+            }
+        }
+        const float m2 = cm * p.scale_log2;
+        // ---- pass 2: sums against the slab maximum + the slab-relative bf16 tile through shared memory and TMA
+        float s = 0.f, tt = 0.f;
+        const uint32_t srow = ptx::smem_u32(stage) + static_cast<uint32_t>(lane) * 128u;
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+#pragma unroll 1
+        for (int c2 = 0; c2 < BN / 64; ++c2) {
+            const int col0 = n0 + c2 * 64;
+            if (col0 >= N) break;  // uniform across the whole warp
+            uint32_t pk[32];  // 64 bf16 of this row
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                __syncwarp();
+                ptx::tmem_ld_32x32b_x32(taddr + c2 * 64 + h * 32, v);
+                ptx::tmem_ld_wait();
+                const int c0 = col0 + h * 32;
+                const int nvalid = min(32, N - c0);  // <= 0: the whole half lies beyond N
+                if (lab >= c0 && lab < c0 + nvalid) {
+                    float z = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c0 + i == lab) z = __uint_as_float(v[i]);
+                    p.label_acc[row] = z;
+                }
+                if (nvalid >= 32) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float a = __uint_as_float(v[i]);
+                        const float u = fmaf(a, p.scale_log2, -m2);
+                        const float e = ex2_approx(u);
+                        s += e;
+                        tt = fmaf(e, a, tt);
+                        v[i] = __float_as_uint(u);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float u = 0.f;  // columns >= N: clipped by the tensor map, never stored
+                        if (i < nvalid) {
+                            const float a = __uint_as_float(v[i]);
+                            u = fmaf(a, p.scale_log2, -m2);
+                            const float e = ex2_approx(u);
+                            s += e;
+                            tt = fmaf(e, a, tt);
+                        }
+                        v[i] = __float_as_uint(u);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    pk[16 * h + i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            }
+            // the buffer about to be rewritten was the source of the store issued two stores ago (one store ago at a
+            // tile start after a ragged tile: wait for all there); only lane 0 issues, so only lane 0 has groups
+            if (lane == 0) {
+                if (c2 == 0)
+                    ptx::bulk_wait_group_read<0>();
+                else
+                    ptx::bulk_wait_group_read<1>();
+            }
+            __syncwarp();
+            const uint32_t sbuf = srow + static_cast<uint32_t>(c2 & 1) * 4096u;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {  // 16-byte chunk j of the 128-byte row goes to slot j ^ (row & 7)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + ((j ^ sw) << 4)), "r"(pk[4 * j]),
+                             "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                             : "memory");
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && row < M) {  // lane 0 holds the warp's first row
+                ptx::tma_store_2d(&p.tmap_out, stage + (c2 & 1) * 4096, col0, row);
+                ptx::bulk_commit_group();
+            }
+        }
+        if (row_ok) {
+            const int64_t o = static_cast<int64_t>(n_tile) * p.ld + row;
+            p.part_m[o] = m2;
+            p.part_s[o] = s;
+            p.part_t[o] = tt;
+        }
     }
 };
 
@@ -646,6 +733,8 @@ struct EpiLsePartialsStored {
 //   p = 2^u
 //   d = inv_T * ( g_lp * 1[j == label] - p * (g_lp + g_ent * (u*ln2 + H)) )
 struct EpiDLogits {
+    static constexpr uint32_t kSmemBytes = 0;
+    __device__ static void finish() {}
     struct Params {
         float scale_log2;
         float inv_temperature;
@@ -658,7 +747,7 @@ struct EpiDLogits {
         int64_t ld;
     };
     template <int BN>
-    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N) {
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N, uint8_t*) {
         const int n0 = n_tile * BN;
         const bool row_ok = row < M;
         float lse2 = 0.f, glp = 0.f, gent = 0.f, H = 0.f;

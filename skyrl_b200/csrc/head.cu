@@ -95,7 +95,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
                        const typename Epi::Params& ep, cudaStream_t stream, int tile_order = 0,
                        uint64_t hint_a = kEvictNormal, uint64_t hint_b = kEvictNormal, int sync_every = 0,
                        const GemmMaps* maps_in = nullptr) {
-    using S = GemmSmem<kCtas, BN, kStages>;
+    using S = GemmSmem<kCtas, BN, kStages, Epi::kSmemBytes>;
     if (M <= 0 || N <= 0 || K <= 0) return SKYB200_OK;
     CUtensorMap ta, tb;
     int rc;
@@ -199,9 +199,10 @@ static int dw_lockstep() { static int v = env_int0("SKYB200_DW_LOCKSTEP", 128); 
 static int dw_group_n() { static int v = env_int("SKYB200_DW_GROUP_N", 14); return v; }
 // skip all-zero d(logits) rows (masked tokens) in the backward GEMMs of the fused step (0 disables)
 static int skip_zero_rows() { static int v = env_int0("SKYB200_SKIP_ZERO_ROWS", 1); return v; }
-// fused step: normalise the backward's probabilities with the log-sum-exp of the bf16-ROUNDED logits it reads from
-// the tile store (softmax(bf16 logits), what the reference differentiates) instead of the exact forward lse
-static int stored_lse() { static int v = env_int0("SKYB200_STORED_LSE", 0); return v; }
+// TIMING EXPERIMENTS ONLY (results are wrong with any bit set): bound what a change could gain before building it.
+//   1 = skip the d(logits) transform pass, 2 = d_weight epilogue stores instead of accumulating (no fp32 re-read),
+//   4 = forward without the bf16 tile store, 8 = skip the d_hidden GEMM, 16 = skip the d_weight GEMM
+static int whatif() { static int v = env_int0("SKYB200_WHATIF", 0); return v; }
 // cap on the resident blocks of the d(logits) transform pass (0 = one block per item)
 static int transform_blocks() { static int v = env_int0("SKYB200_TRANSFORM_BLOCKS", 0); return v; }
 
@@ -274,42 +275,6 @@ __global__ void __launch_bounds__(256) head_merge_kernel(const float* __restrict
     }
 }
 
-// log2-sum-exp of the bf16-rounded logits of the tile store (EpiLsePartialsStored): the slab sums part_sb are taken
-// against the slab maxima part_m of the exact logits, so they merge with the same rescaling as part_s.  Same block
-// layout as head_merge_kernel: 32 rows x 8 slab-splitting warps, fixed-order fold.
-__global__ void __launch_bounds__(256) head_merge_stored_kernel(const float* __restrict__ part_m,
-                                                                const float* __restrict__ part_sb, int64_t ld,
-                                                                int slabs, float* __restrict__ lse2_stored, int rows) {
-    __shared__ float sm[8][kMergeRows], ss[8][kMergeRows];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int r = blockIdx.x * kMergeRows + lane;
-    float m = -INFINITY, sv = 0.f;
-    if (r < rows) {
-#pragma unroll 4
-        for (int sl = w; sl < slabs; sl += 8) {
-            const int64_t o = (int64_t)sl * ld + r;
-            const float pm = __ldcs(part_m + o), ps = __ldcs(part_sb + o);
-            const float nm = fmaxf(m, pm);
-            sv = fmaf(sv, exp2f(m - nm), ps * exp2f(pm - nm));  // m = -inf on the first step: factor 0
-            m = nm;
-        }
-    }
-    sm[w][lane] = m;
-    ss[w][lane] = sv;
-    __syncthreads();
-    if (w != 0 || r >= rows) return;
-    float M = sm[0][lane], S = ss[0][lane];
-#pragma unroll
-    for (int x = 1; x < 8; ++x) {
-        if (x < slabs) {
-            const float nm = fmaxf(M, sm[x][lane]);
-            S = fmaf(S, exp2f(M - nm), ss[x][lane] * exp2f(sm[x][lane] - nm));
-            M = nm;
-        }
-    }
-    lse2_stored[r] = M + log2f(S);
-}
-
 // Vocab-parallel variant: fold the slab partials of ONE vocab shard into per-token (max, sum, weighted sum,
 // label accumulator); the cross-rank combine happens on these 4 numbers per token.
 __global__ void __launch_bounds__(256) head_merge_stats_kernel(const float* __restrict__ part_m,
@@ -347,14 +312,18 @@ __global__ void __launch_bounds__(256) head_combine_stats_kernel(const float4* _
     lse2_out[r] = lse2;
 }
 
-// In-place turn of a stored bf16 logits tile store [rows, ld] into d(logits) (fused step, no recompute):
-//   u = z*scale_log2 - lse2 ; p = 2^u ; d = inv_T * ( g_lp*1[j == label] - p*(g_lp + g_ent*(u*ln2 + H)) )
-// One block row per token; each thread owns 16 consecutive vocab entries (one 32-byte access each way).
+// In-place turn of the bf16 tile store [rows, ld] of the fused step's forward (EpiLseStoreRel: slab-relative
+// log2-logits u) into d(logits):
+//   l = u + (part_m[slab][row] - lse2[row])          log2 of the probability
+//   p = 2^l ; d = inv_T * ( g_lp*1[j == label] - p*(g_lp + g_ent*(l*ln2 + H)) )
+// One block row per token; each thread owns 16 consecutive vocab entries (one 32-byte access each way), which lie in
+// one 256-wide slab.
 __global__ void __launch_bounds__(256)
-dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const float* __restrict__ lse2,
-                         const float* __restrict__ g_lp, const float* __restrict__ g_ent,
-                         const float* __restrict__ g_ent_mask, const float* __restrict__ entropy_raw,
-                         const int64_t* __restrict__ labels, float scale_log2, float inv_T, int rows) {
+dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const float* __restrict__ part_m,
+                         int64_t ld_part, const float* __restrict__ lse2, const float* __restrict__ g_lp,
+                         const float* __restrict__ g_ent, const float* __restrict__ g_ent_mask,
+                         const float* __restrict__ entropy_raw, const int64_t* __restrict__ labels, float inv_T,
+                         int rows) {
     // items = (token row, 4096-wide column block), row-major; a block walks them with a grid stride so the launch can
     // be throttled to a few resident blocks per SM (it runs under the GEMMs of the previous chunk)
     const int cbs = (V + 4095) / 4096;
@@ -363,7 +332,6 @@ dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const
     const int row = (int)(item / cbs);
     const int col0 = ((int)(item % cbs) * 256 + threadIdx.x) * 16;
     if (col0 >= V) continue;
-    const float l2 = lse2[row];
     const float glp = g_lp[row];
     float ge = 0.f, H = 0.f;
     if (g_ent != nullptr) {
@@ -377,6 +345,8 @@ dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const
     const float lab_add = glp * inv_T;
     const bool all_zero = (glp == 0.f && ge == 0.f);
     __nv_bfloat16* ptr = S + static_cast<int64_t>(row) * ld + col0;
+    // reference point of this thread's slab against the row's log-sum-exp
+    const float ref = all_zero ? 0.f : __ldg(part_m + (int64_t)(col0 / kHeadBN) * ld_part + row) - lse2[row];
     if (col0 + 16 <= V && (ld & 15) == 0) {
         uint32_t r[8];
         if (all_zero) {
@@ -388,7 +358,7 @@ dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const
             for (int k = 0; k < 8; ++k) {
                 const __nv_bfloat162 z2 = *reinterpret_cast<const __nv_bfloat162*>(&r[k]);
                 float2 z = __bfloat1622float2(z2);
-                const float u0 = fmaf(z.x, scale_log2, -l2), u1 = fmaf(z.y, scale_log2, -l2);
+                const float u0 = z.x + ref, u1 = z.y + ref;
                 float d0 = ex2_approx(u0) * fmaf(u0, b0, a0);
                 float d1 = ex2_approx(u1) * fmaf(u1, b0, a0);
                 if (col0 + 2 * k == lab) d0 += lab_add;
@@ -401,7 +371,7 @@ dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const
         for (int k = 0; k < 16 && col0 + k < V; ++k) {
             float d = 0.f;
             if (!all_zero) {
-                const float u = fmaf(__bfloat162float(ptr[k]), scale_log2, -l2);
+                const float u = __bfloat162float(ptr[k]) + ref;
                 d = ex2_approx(u) * fmaf(u, b0, a0);
                 if (col0 + k == lab) d += lab_add;
             }
@@ -793,7 +763,6 @@ struct StepPlan {
     // everything below exists twice (parity of the chunk index): the small kernels of chunk c+1 run on the
     // auxiliary stream while the backward GEMMs of chunk c run on the caller's stream
     size_t off_part[2], off_label[2], off_lse2[2], off_entraw[2], off_dlp[2], off_dent[2], off_S[2], off_maps[2];
-    size_t off_partsb[2], off_lse2s[2];  // SKYB200_STORED_LSE: slab sums / log-sum-exp of the stored (bf16) logits
     size_t off_loss, total;
 };
 
@@ -845,9 +814,6 @@ StepPlan plan_step(int64_t B, int64_t A, int64_t N, int64_t H, int64_t V, int lo
         p.off_dent[i] = take((size_t)chunk * 4);
         p.off_S[i] = take(need_grad ? (size_t)chunk * p.ldS * 2 : 0);
         p.off_maps[i] = take(live_maps_ints(chunk) * sizeof(int));
-        const bool stored = need_grad && stored_lse() != 0;
-        p.off_partsb[i] = take(stored ? (size_t)p.slabs * chunk * 4 : 0);
-        p.off_lse2s[i] = take(stored ? (size_t)chunk * 4 : 0);
     }
     // every chunk rounds its loss-partial slots up: 4 spare slots (128 bytes) per chunk
     p.off_loss = take(loss_chunk_ws_bytes(B, N) + (size_t)(N / stride + 2) * 8 * 4 * 4);
@@ -861,7 +827,20 @@ struct StepStreams {
     cudaStream_t copy = nullptr;  // host -> device staging of hidden chunks (policy_step_from_host)
     cudaEvent_t start = nullptr, fwd[2] = {nullptr, nullptr}, mid[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> copied;  // one per chunk, grown on demand
+    // opts->timing: (begin, end) event pairs around every GEMM launch on the caller's stream, accumulated over steps
+    // until skyb200_policy_step_timing() harvests them; tkind[i] = which GEMM pair i brackets
+    std::vector<cudaEvent_t> tev;
+    std::vector<int> tkind;
+    size_t tused = 0;
     bool ok = false;
+    cudaEvent_t timing_event() {  // next unused timing event (nullptr on failure)
+        if (tused == tev.size()) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            tev.push_back(e);
+        }
+        return tev[tused++];
+    }
     bool grow_copied(size_t n) {
         while (copied.size() < n) {
             cudaEvent_t e = nullptr;
@@ -914,8 +893,11 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
                             void* d_hidden, float* d_weight, int32_t accumulate, float* stats, void* workspace,
                             size_t workspace_bytes, int64_t B, int64_t A, int64_t H, int64_t V,
                             const int32_t* cu_seqlens, int64_t n_tokens, float temperature,
-                            const skyb200_loss_params* params, void* stream_) {
+                            const skyb200_loss_params* params, const skyb200_step_opts* opts, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const float* tis = opts ? opts->tis : nullptr;
+    const float* clip_mask = opts ? opts->clip_mask : nullptr;
+    const bool timing = opts != nullptr && opts->timing != 0;
     SKYB200_REQUIRE(hidden && weight && labels && old_log_probs && advantages && log_probs && entropy && stats &&
                         workspace && params,
                     "null pointer");
@@ -952,10 +934,26 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
     const __nv_bfloat16* hid = static_cast<const __nv_bfloat16*>(hidden);
     __nv_bfloat16* dhid = static_cast<__nv_bfloat16*>(d_hidden);
     const bool use_ent_grad = need_grad && params->use_entropy_loss != 0;
-    const bool use_stored_lse = need_grad && stored_lse() != 0;
     const int64_t n_chunks = (N + stride - 1) / stride;
 
     auto fptr = [&](size_t off) { return reinterpret_cast<float*>(wb + off); };
+    // opts->timing: bracket a GEMM launch on the caller's stream with two timing events (kind 0 = forward,
+    // 1 = d_hidden, 2 = d_weight); the pair sees the kernel alone because every stream wait precedes `begin`
+    auto t_begin = [&]() -> int {
+        if (!timing) return SKYB200_OK;
+        cudaEvent_t e = ss->timing_event();
+        if (e == nullptr) return fail(SKYB200_ECUDA, "could not create a timing event");
+        SKYB200_CUDA_CHECK(cudaEventRecord(e, stream));
+        return SKYB200_OK;
+    };
+    auto t_end = [&](int kind) -> int {
+        if (!timing) return SKYB200_OK;
+        cudaEvent_t e = ss->timing_event();
+        if (e == nullptr) return fail(SKYB200_ECUDA, "could not create a timing event");
+        SKYB200_CUDA_CHECK(cudaEventRecord(e, stream));
+        ss->tkind.push_back(kind);
+        return SKYB200_OK;
+    };
 
     // ---- stage A (caller's stream): logits tiles -> online-softmax partials (+ bf16 copy of the tile)
     auto issue_fwd = [&](int64_t ci) -> int {
@@ -963,7 +961,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
         const int64_t t0 = ci * stride;
         const int rows = (int)std::min<int64_t>(stride, N - t0);
         float* part_m = fptr(plan.off_part[p]);
-        EpiLsePartialsStored::Params ep;  // the plain epilogue takes its base-class slice
+        LseStoreParams ep;  // the plain epilogue takes its base-class slice
         ep.scale_log2 = scale_log2;
         ep.part_m = part_m;
         ep.part_s = part_m + (int64_t)plan.slabs * c;
@@ -971,23 +969,28 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
         ep.ld = c;
         ep.labels = labels + t0;
         ep.label_acc = fptr(plan.off_label[p]);
-        ep.logits = need_grad ? reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]) : nullptr;
+        const bool store = need_grad && !(whatif() & 4);
+        ep.logits = store ? reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]) : nullptr;
         ep.ld_logits = plan.ldS;
-        ep.part_sb = use_stored_lse ? fptr(plan.off_partsb[p]) : nullptr;
         // the parity buffers were last read by the auxiliary-stream kernels of chunk ci - 2
         if (ci >= 2) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[p], 0));
         if (hidden_host != nullptr) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->copied[ci], 0));
         SKYB200_CUDA_CHECK(cudaMemsetAsync(ep.label_acc, 0, (size_t)rows * sizeof(float), stream));
         int r;
-        if (use_stored_lse)
-            r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartialsStored>(
+        // TMA store of the tile: [rows, V] bf16 with pitch ldS, 64-column x 32-row boxes (one per epilogue warp)
+        if (store && (r = make_tmap_bf16(&ep.tmap_out, ep.logits, (uint64_t)V, (uint64_t)rows, (uint64_t)plan.ldS, 64, 32)))
+            return r;
+        if ((r = t_begin())) return r;
+        if (store)  // with the backward to follow: slab-relative bf16 tile store for the two backward GEMMs
+            r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLseStoreRel>(
                 hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream, 0, hint_fwd_a(),
                 kEvictNormal, fwd_lockstep());
         else
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
                 hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(),
-                static_cast<const EpiLsePartials::Params&>(ep), stream, 0, hint_fwd_a(), kEvictNormal, fwd_lockstep());
+                static_cast<const LsePartialsParams&>(ep), stream, 0, hint_fwd_a(), kEvictNormal, fwd_lockstep());
         if (r) return r;
+        if ((r = t_end(0))) return r;
         SKYB200_CUDA_CHECK(cudaEventRecord(ss->fwd[p], stream));
         return SKYB200_OK;
     };
@@ -1012,28 +1015,21 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             r = loss_row_logratio(log_probs, old_log_probs, loss_mask, lws, t0 / A, rows / A, A, aux);
             if (r) return r;
         }
-        r = loss_flat_range(log_probs, old_log_probs, advantages, loss_mask, base_log_probs, entropy,
+        r = loss_flat_range(log_probs, old_log_probs, advantages, loss_mask, base_log_probs, entropy, tis, clip_mask,
                             need_grad ? d_lp : nullptr, use_ent_grad ? d_ent : nullptr, lws, B, A, t0,
                             t0 + rows, slot, *params, cu_seqlens, aux);
         if (r) return r;
         if (need_grad) {
-            const float* lse2_bwd = lse2;  // normaliser of the backward's probabilities
-            if (use_stored_lse) {
-                float* lse2s = fptr(plan.off_lse2s[p]);
-                head_merge_stored_kernel<<<(rows + kMergeRows - 1) / kMergeRows, 256, 0, aux>>>(
-                    part_m, fptr(plan.off_partsb[p]), c, plan.slabs, lse2s, rows);
-                r = check_launch("head_merge_stored_kernel");
-                if (r) return r;
-                lse2_bwd = lse2s;
-            }
             const int64_t items = (int64_t)rows * ((V + 4095) / 4096);
             const int64_t cap = transform_blocks() > 0 ? transform_blocks() : items;
-            dlogits_transform_kernel<<<(unsigned)std::min<int64_t>(items, cap), 256, 0, aux>>>(
-                reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]), plan.ldS, (int)V, lse2_bwd, d_lp,
-                use_ent_grad ? d_ent : nullptr, (use_ent_grad && entropy_mask) ? entropy_mask + t0 : nullptr, ent_raw,
-                labels + t0, scale_log2, inv_T, rows);
-            r = check_launch("dlogits_transform_kernel");
-            if (r) return r;
+            if (!(whatif() & 1)) {
+                dlogits_transform_kernel<<<(unsigned)std::min<int64_t>(items, cap), 256, 0, aux>>>(
+                    reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]), plan.ldS, (int)V, part_m, c, lse2, d_lp,
+                    use_ent_grad ? d_ent : nullptr, (use_ent_grad && entropy_mask) ? entropy_mask + t0 : nullptr,
+                    ent_raw, labels + t0, inv_T, rows);
+                r = check_launch("dlogits_transform_kernel");
+                if (r) return r;
+            }
             if (skip_zero_rows()) {
                 const int mt = (int)(c / kTileM), kt = (int)(c / kBK);
                 live_rows_kernel<<<1, 256, (size_t)kt, aux>>>(
@@ -1058,7 +1054,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
         const bool skip = skip_zero_rows() != 0;
         const GemmMaps m_maps = {maps + 2 + mt, maps, nullptr, nullptr};
         const GemmMaps k_maps = {nullptr, nullptr, maps + 2 + 2 * mt, maps + 1};
-        if (dhid != nullptr) {
+        if (dhid != nullptr && !(whatif() & 8)) {
             EpiStoreBF16::Params eh;
             eh.C = dhid + t0 * H;
             eh.ldc = H;
@@ -1068,26 +1064,33 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
                 int rz = check_launch("zero_dead_tiles_kernel");
                 if (rz) return rz;
             }
-            int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
+            int r = t_begin();
+            if (r) return r;
+            r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
                 S, plan.ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, kEvictNormal, kEvictNormal,
                 dh_lockstep(), skip ? &m_maps : nullptr);
             if (r) return r;
+            if ((r = t_end(1))) return r;
         }
-        if (d_weight != nullptr) {
+        if (d_weight != nullptr && !(whatif() & 16)) {
             EpiStoreF32::Params ew;
             ew.C = d_weight;
             ew.ldc = H;
             ew.accumulate = (accumulate != 0 || t0 > 0) ? 1 : 0;
-            int r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
+            if (whatif() & 2) ew.accumulate = 0;
+            int r = t_begin();
+            if (r) return r;
+            r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
                 S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, kEvictNormal,
                 hint_dw_b(), dw_lockstep(), (skip && ew.accumulate) ? &k_maps : nullptr);
             if (r) return r;
+            if ((r = t_end(2))) return r;
         }
         return SKYB200_OK;
     };
 
     // the auxiliary stream starts after everything already queued on the caller's stream (inputs are ready)
-    rc = loss_prepass(loss_mask, lws, B, A, cu_seqlens, stream);
+    rc = loss_prepass(loss_mask, clip_mask, lws, B, A, cu_seqlens, stream);
     if (rc) return rc;
     SKYB200_CUDA_CHECK(cudaEventRecord(ss->start, stream));
     SKYB200_CUDA_CHECK(cudaStreamWaitEvent(aux, ss->start, 0));
@@ -1135,7 +1138,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
     if (n_chunks > 1) SKYB200_CUDA_CHECK(cudaStreamWaitEvent(stream, ss->mid[(n_chunks - 2) & 1], 0));
     const int64_t total_slots =
         slot_of[n_chunks - 1] + loss_chunk_blocks(std::min<int64_t>(stride, N - (n_chunks - 1) * stride));
-    return loss_finalize(lws, total_slots, true, stats, *params, stream);
+    return loss_finalize(lws, total_slots, true, clip_mask != nullptr, stats, *params, stream);
 }
 
 extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const int64_t* labels,
@@ -1144,10 +1147,10 @@ extern "C" int skyb200_policy_step(const void* hidden, const void* weight, const
                                    float* entropy, void* d_hidden, float* d_weight, int32_t accumulate, float* stats,
                                    void* workspace, size_t workspace_bytes, int64_t B, int64_t A, int64_t H, int64_t V,
                                    const int32_t* cu_seqlens, int64_t n_tokens, float temperature,
-                                   const skyb200_loss_params* params, void* stream) {
+                                   const skyb200_loss_params* params, const skyb200_step_opts* opts, void* stream) {
     return policy_step_impl(nullptr, hidden, weight, labels, old_log_probs, advantages, loss_mask, base_log_probs,
                             entropy_mask, log_probs, entropy, d_hidden, d_weight, accumulate, stats, workspace,
-                            workspace_bytes, B, A, H, V, cu_seqlens, n_tokens, temperature, params, stream);
+                            workspace_bytes, B, A, H, V, cu_seqlens, n_tokens, temperature, params, opts, stream);
 }
 
 extern "C" int skyb200_policy_step_from_host(const void* hidden_host, void* hidden_staging, const void* weight,
@@ -1158,11 +1161,31 @@ extern "C" int skyb200_policy_step_from_host(const void* hidden_host, void* hidd
                                              float* stats, void* workspace, size_t workspace_bytes, int64_t B,
                                              int64_t A, int64_t H, int64_t V, const int32_t* cu_seqlens,
                                              int64_t n_tokens, float temperature, const skyb200_loss_params* params,
-                                             void* stream) {
+                                             const skyb200_step_opts* opts, void* stream) {
     SKYB200_REQUIRE(hidden_host && hidden_staging, "null pointer");
     return policy_step_impl(hidden_host, hidden_staging, weight, labels, old_log_probs, advantages, loss_mask,
                             base_log_probs, entropy_mask, log_probs, entropy, d_hidden, d_weight, accumulate, stats,
-                            workspace, workspace_bytes, B, A, H, V, cu_seqlens, n_tokens, temperature, params, stream);
+                            workspace, workspace_bytes, B, A, H, V, cu_seqlens, n_tokens, temperature, params, opts,
+                            stream);
+}
+
+extern "C" int skyb200_policy_step_timing(double* out) {
+    SKYB200_REQUIRE(out != nullptr, "null pointer");
+    StepStreams* ss = step_streams();
+    if (ss == nullptr) return fail(SKYB200_ECUDA, "could not create the auxiliary stream / events");
+    for (int i = 0; i < 6; ++i) out[i] = 0.0;
+    const size_t pairs = ss->tkind.size();
+    if (pairs > 0) SKYB200_CUDA_CHECK(cudaEventSynchronize(ss->tev[2 * pairs - 1]));
+    for (size_t i = 0; i < pairs; ++i) {
+        float ms = 0.f;
+        SKYB200_CUDA_CHECK(cudaEventElapsedTime(&ms, ss->tev[2 * i], ss->tev[2 * i + 1]));
+        const int k = ss->tkind[i];
+        out[k] += ms;
+        out[3 + k] += 1.0;
+    }
+    ss->tkind.clear();
+    ss->tused = 0;
+    return SKYB200_OK;
 }
 
 extern "C" int skyb200_logits_logprob_entropy(const void* logits, int32_t logits_dtype, const int64_t* labels,
@@ -1267,7 +1290,7 @@ extern "C" int skyb200_gemm_bench(const void* A, const void* B, void* C, void* s
         SKYB200_REQUIRE(scratch != nullptr, "epi 3 needs scratch: (3*ceil(N/256)+1)*M floats + M int64 labels");
         const int slabs = (int)num_slabs(N);
         float* part = static_cast<float*>(scratch);
-        EpiLsePartials::Params ep;
+        LseStoreParams ep;
         ep.scale_log2 = 1.4426950408889634f;
         ep.part_m = part;
         ep.part_s = part + (int64_t)slabs * M;
@@ -1275,10 +1298,15 @@ extern "C" int skyb200_gemm_bench(const void* A, const void* B, void* C, void* s
         ep.ld = M;
         ep.label_acc = part + 3 * (int64_t)slabs * M;
         ep.labels = reinterpret_cast<const int64_t*>(ep.label_acc + M);
-        ep.logits = static_cast<__nv_bfloat16*>(C);  // may be NULL
+        ep.logits = static_cast<__nv_bfloat16*>(C);  // NULL: plain forward; else the fused step's forward + tile store
         ep.ld_logits = round_up(N, 64);
+        if (C != nullptr) {
+            if ((rc = make_tmap_bf16(&ep.tmap_out, C, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld_logits, 64, 32))) return rc;
+            return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLseStoreRel>(
+                A, K, B, K, (int)M, (int)N, (int)K, group, ep, stream, order);
+        }
         return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
-            A, K, B, K, (int)M, (int)N, (int)K, group, ep, stream, order);
+            A, K, B, K, (int)M, (int)N, (int)K, group, static_cast<const LsePartialsParams&>(ep), stream, order);
     }
     if (epi == 4) {
         EpiSkip::Params ep{static_cast<float*>(C)};

@@ -416,6 +416,8 @@ struct FlatArgs {
     const float* mask;
     const float* base;
     const float* ent;
+    const float* tis;        // detached per-token weight (off-policy correction) or nullptr
+    const float* clip_mask;  // mask of the clip_ratio metric when it differs from `mask`, or nullptr
     float* d_lp;
     float* d_ent;
     LossChunkWs ws;
@@ -504,11 +506,14 @@ __global__ void __launch_bounds__(kLossThreads) loss_flat_kernel(FlatArgs a) {
                 if (a.mask) m = ldg_stream(reinterpret_cast<const float4*>(a.mask + i));
                 if (a.base) bs = ldg_stream(reinterpret_cast<const float4*>(a.base + i));
                 if (a.ent) en = ldg_stream(reinterpret_cast<const float4*>(a.ent + i));
+                float4 ti = make_float4(1.f, 1.f, 1.f, 1.f), cm = make_float4(-1.f, -1.f, -1.f, -1.f);
+                if (a.tis) ti = ldg_stream(reinterpret_cast<const float4*>(a.tis + i));
+                if (a.clip_mask) cm = ldg_stream(reinterpret_cast<const float4*>(a.clip_mask + i));
                 float4 g;
-                g.x = loss_token<kType>(cx, acc, lp.x, olp.x, adv.x, m.x, bs.x);
-                g.y = loss_token<kType>(cx, acc, lp.y, olp.y, adv.y, m.y, bs.y);
-                g.z = loss_token<kType>(cx, acc, lp.z, olp.z, adv.z, m.z, bs.z);
-                g.w = loss_token<kType>(cx, acc, lp.w, olp.w, adv.w, m.w, bs.w);
+                g.x = loss_token<kType>(cx, acc, lp.x, olp.x, adv.x, m.x, bs.x, ti.x, cm.x);
+                g.y = loss_token<kType>(cx, acc, lp.y, olp.y, adv.y, m.y, bs.y, ti.y, cm.y);
+                g.z = loss_token<kType>(cx, acc, lp.z, olp.z, adv.z, m.z, bs.z, ti.z, cm.z);
+                g.w = loss_token<kType>(cx, acc, lp.w, olp.w, adv.w, m.w, bs.w, ti.w, cm.w);
                 if (a.d_lp) *reinterpret_cast<float4*>(a.d_lp + (i - a.out_base)) = g;
                 if (a.ent) {
                     acc.s_ent = fmaf(en.x, m.x, acc.s_ent);
@@ -528,7 +533,8 @@ __global__ void __launch_bounds__(kLossThreads) loss_flat_kernel(FlatArgs a) {
             if (i < a.t1) {
                 set_row(a.cu ? row_of_token(a.cu, a.B, i) : i / A);
                 const float m = a.mask ? a.mask[i] : 1.f;
-                const float g = loss_token<kType>(cx, acc, a.lp[i], a.olp[i], a.adv[i], m, a.base ? a.base[i] : 0.f);
+                const float g = loss_token<kType>(cx, acc, a.lp[i], a.olp[i], a.adv[i], m, a.base ? a.base[i] : 0.f,
+                                                  a.tis ? a.tis[i] : 1.f, a.clip_mask ? a.clip_mask[i] : -1.f);
                 if (a.d_lp) a.d_lp[i - a.out_base] = g;
                 if (a.ent) {
                     acc.s_ent = fmaf(a.ent[i], m, acc.s_ent);
@@ -557,7 +563,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_flat_kernel(FlatArgs a) {
 }
 
 __global__ void __launch_bounds__(kLossThreads)
-loss_finalize_kernel(LossChunkWs ws, int64_t nslots, int has_entropy, float* __restrict__ stats,
+loss_finalize_kernel(LossChunkWs ws, int64_t nslots, int has_entropy, int has_clip_mask, float* __restrict__ stats,
                      skyb200_loss_params p) {
     __shared__ float sh[34];
     float f_loss = 0.f, f_clip = 0.f, f_kl = 0.f, f_ent = 0.f, f_ratio = 0.f, f_max = -INFINITY, f_min = INFINITY;
@@ -585,7 +591,8 @@ loss_finalize_kernel(LossChunkWs ws, int64_t nslots, int has_entropy, float* __r
         float final_loss = f_loss + f_kl * p.kl_loss_coef;
         if (p.use_entropy_loss && has_entropy) final_loss -= ent_mean * p.entropy_loss_coef;
         stats[SKYB200_STAT_POLICY_LOSS] = f_loss;
-        stats[SKYB200_STAT_CLIP_RATIO] = f_clip * inv_total;
+        // the clip_ratio metric keeps the mask it had BEFORE the off-policy correction (ppo_utils.py:570 vs :579-583)
+        stats[SKYB200_STAT_CLIP_RATIO] = has_clip_mask ? f_clip / fmaxf(ws.total_msum[1], 1.f) : f_clip * inv_total;
         stats[SKYB200_STAT_KL_LOSS] = f_kl;
         stats[SKYB200_STAT_ENTROPY] = ent_mean;
         stats[SKYB200_STAT_FINAL_LOSS] = final_loss;
@@ -599,7 +606,7 @@ loss_finalize_kernel(LossChunkWs ws, int64_t nslots, int has_entropy, float* __r
 
 size_t loss_chunk_ws_bytes(int64_t B, int64_t n_tokens) {
     const int64_t slots = loss_chunk_blocks(n_tokens) + 4 * 64;  // every chunk rounds its block count up
-    return static_cast<size_t>(2 * ((B * 4 + 255) / 256 * 256) + 512 + (slots + B) * kNumPartials * 4 + 512);
+    return static_cast<size_t>(3 * ((B * 4 + 255) / 256 * 256) + 512 + (slots + B) * kNumPartials * 4 + 512);
 }
 int64_t loss_chunk_blocks(int64_t n_tokens) { return (n_tokens + kFlatTile - 1) / kFlatTile; }
 
@@ -609,14 +616,22 @@ void loss_chunk_ws_carve(void* base, int64_t B, int64_t A, LossChunkWs* ws) {
     const size_t rb = static_cast<size_t>((B * 4 + 255) / 256 * 256);
     ws->row_msum = reinterpret_cast<float*>(b);
     ws->row_lw = reinterpret_cast<float*>(b + rb);
-    ws->total_msum = reinterpret_cast<float*>(b + 2 * rb);
-    ws->counters = reinterpret_cast<unsigned int*>(b + 2 * rb + 64);
-    ws->partials = reinterpret_cast<float*>(b + 2 * rb + 256);
+    ws->row_csum = reinterpret_cast<float*>(b + 2 * rb);
+    ws->total_msum = reinterpret_cast<float*>(b + 3 * rb);
+    ws->counters = reinterpret_cast<unsigned int*>(b + 3 * rb + 64);
+    ws->partials = reinterpret_cast<float*>(b + 3 * rb + 256);
 }
 
-int loss_prepass(const float* loss_mask, const LossChunkWs& ws, int64_t B, int64_t A, const int32_t* cu,
-                 cudaStream_t stream) {
+int loss_prepass(const float* loss_mask, const float* clip_mask, const LossChunkWs& ws, int64_t B, int64_t A,
+                 const int32_t* cu, cudaStream_t stream) {
     SKYB200_CUDA_CHECK(cudaMemsetAsync(ws.counters, 0, 16, stream));
+    if (clip_mask != nullptr) {  // sum(clip_mask) -> total_msum[1] (the last block resets the counter)
+        loss_rowstats_kernel<<<(unsigned)B, kLossThreads, 0, stream>>>(nullptr, nullptr, clip_mask, ws.row_csum,
+                                                                       ws.row_lw, ws.total_msum + 1, ws.counters,
+                                                                       (int)B, A, 0, cu);
+        int rc = check_launch("loss_rowstats_kernel(clip mask)");
+        if (rc) return rc;
+    }
     loss_rowstats_kernel<<<(unsigned)B, kLossThreads, 0, stream>>>(nullptr, nullptr, loss_mask, ws.row_msum, ws.row_lw,
                                                                    ws.total_msum, ws.counters, (int)B, A, 0, cu);
     return check_launch("loss_rowstats_kernel(prepass)");
@@ -631,9 +646,9 @@ int loss_row_logratio(const float* lp, const float* olp, const float* loss_mask,
 }
 
 int loss_flat_range(const float* lp, const float* olp, const float* adv, const float* loss_mask, const float* base,
-                    const float* ent, float* d_lp, float* d_ent, const LossChunkWs& ws, int64_t B, int64_t A,
-                    int64_t t0, int64_t t1, int64_t slot0, const skyb200_loss_params& p, const int32_t* cu,
-                    cudaStream_t stream) {
+                    const float* ent, const float* tis, const float* clip_mask, float* d_lp, float* d_ent,
+                    const LossChunkWs& ws, int64_t B, int64_t A, int64_t t0, int64_t t1, int64_t slot0,
+                    const skyb200_loss_params& p, const int32_t* cu, cudaStream_t stream) {
     if (t1 <= t0) return SKYB200_OK;
     FlatArgs a;
     a.cu = cu;
@@ -643,6 +658,8 @@ int loss_flat_range(const float* lp, const float* olp, const float* adv, const f
     a.mask = loss_mask;
     a.base = base;
     a.ent = ent;
+    a.tis = tis;
+    a.clip_mask = clip_mask;
     a.d_lp = d_lp;
     a.d_ent = d_ent;
     a.ws = ws;
@@ -655,7 +672,7 @@ int loss_flat_range(const float* lp, const float* olp, const float* adv, const f
     a.p = p;
     auto al16 = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     a.vec4 = (cu == nullptr) && (A % 4 == 0) && (t0 % 4 == 0) && al16(lp) && al16(olp) && al16(adv) && al16(loss_mask) && al16(base) &&
-             al16(ent) && al16(d_lp) && al16(d_ent);
+             al16(ent) && al16(d_lp) && al16(d_ent) && al16(tis) && al16(clip_mask);
     const unsigned grid = (unsigned)loss_chunk_blocks(t1 - t0);
     if (p.loss_type <= SKYB200_LOSS_GSPO)
         loss_flat_kernel<-2><<<grid, kLossThreads, 0, stream>>>(a);
@@ -664,9 +681,10 @@ int loss_flat_range(const float* lp, const float* olp, const float* adv, const f
     return check_launch("loss_flat_kernel");
 }
 
-int loss_finalize(const LossChunkWs& ws, int64_t nslots, bool has_entropy, float* stats, const skyb200_loss_params& p,
-                  cudaStream_t stream) {
-    loss_finalize_kernel<<<1, kLossThreads, 0, stream>>>(ws, nslots, has_entropy ? 1 : 0, stats, p);
+int loss_finalize(const LossChunkWs& ws, int64_t nslots, bool has_entropy, bool has_clip_mask, float* stats,
+                  const skyb200_loss_params& p, cudaStream_t stream) {
+    loss_finalize_kernel<<<1, kLossThreads, 0, stream>>>(ws, nslots, has_entropy ? 1 : 0, has_clip_mask ? 1 : 0, stats,
+                                                         p);
     return check_launch("loss_finalize_kernel");
 }
 

@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(256) opc_metrics_kernel(const RowOut* __restri
         const float Bf = static_cast<float>(B);
         const double n = static_cast<double>(B) * static_cast<double>(A);
         const double mean = s_x / n;
-        const double var = n > 1.0 ? fmax(s_xx - n * mean * mean, 0.0) / (n - 1.0) : 0.0;  // torch.std: unbiased
+        // torch.std (unbiased): a single element has zero degrees of freedom -> NaN, as the reference reports it
+        const double var = n > 1.0 ? fmax(s_xx - n * mean * mean, 0.0) / (n - 1.0) : nan("");
         out[SKYB200_OPC_IS_RATIO_MEAN] = s_rm / fmaxf(s_m, 1.f);
         out[SKYB200_OPC_IS_RATIO_STD] = static_cast<float>(sqrt(var));
         out[SKYB200_OPC_IS_RATIO_MAX] = mx;

@@ -141,6 +141,34 @@ __device__ __forceinline__ void tma_load_2d_2sm(const void* desc, uint64_t* bar,
         : "memory");
 }
 
+// 2D tiled STORE shared -> global through the tensor map (bulk async-group completion).  The shared tile must have been
+// written by the generic proxy and published with fence_proxy_async() (+ a warp / block sync) before the issue.
+__device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int32_t crd0, int32_t crd1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
+                 : "memory");
+}
+// Same, but global += shared (fp32 add performed at L2): no read-modify-write through the SM.
+__device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* smem_src, int32_t crd0,
+                                                  int32_t crd1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared source (the buffer may be rewritten)
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// wait until at most N of this thread's bulk groups are incomplete (global writes performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 template <int kCtas>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

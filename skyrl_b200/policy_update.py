@@ -21,7 +21,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from .losses import _cfg, _make_params, status_from_packed
+from .losses import _cfg, _make_params, _off_policy_enabled, compute_off_policy_correction, status_from_packed
 
 
 @dataclass
@@ -42,7 +42,8 @@ class _Workspace:
         self.bufs: Dict[tuple, torch.Tensor] = {}
 
     def get(self, key: str, nbytes: int, dev: torch.device) -> torch.Tensor:
-        k = (key, dev.index)
+        # one buffer per (device, stream): two caller streams on one device must not share scratch
+        k = (key, dev.index, torch.cuda.current_stream(dev).cuda_stream)
         b = self.bufs.get(k)
         if b is None or b.numel() < nbytes:
             b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -72,6 +73,8 @@ def policy_update_step(
     sync: bool = True,
     fused: bool = True,
     cu_seqlens: Optional[torch.Tensor] = None,
+    rollout_logprobs: Optional[torch.Tensor] = None,
+    timing: bool = False,
 ) -> PolicyUpdateOutput:
     """``hidden`` [B, A, H] (or [B*A, H]) bf16, ``weight`` [V, H] bf16, ``labels`` [B, A] int64,
     ``old_log_probs`` / ``advantages`` / ``loss_mask`` / ``base_log_probs`` [B, A] fp32.
@@ -95,6 +98,15 @@ def policy_update_step(
     the forward keeping a bf16 copy of its logits tiles in a bounded [chunk, V] store so the backward does not
     recompute the projection (6*H*V executed flop per token).  ``fused=False`` runs the three C-ABI calls
     (``head_forward`` / ``policy_loss`` / ``head_backward``) the autograd path uses (8*H*V, fp32 logits in backward).
+
+    ``rollout_logprobs`` [B, A]: with ``config.off_policy_correction`` set (``tis_ratio_type`` /
+    ``sequence_mask_metric``) the reference's off-policy correction is applied exactly as the registry losses apply
+    it (ppo_utils.py:577-583): TIS weights, outlier-token and sequence masks are computed from ``old_log_probs`` and
+    ``rollout_logprobs`` before the step, the loss uses the corrected mask, ``clip_ratio`` keeps the original one,
+    and the ``is_ratio_*`` / ``tis_*`` / ``*_sequence_mask_*`` metrics are added to the status dict (padded layout).
+
+    ``timing=True`` (fused only) brackets every GEMM launch of the step with CUDA timing events;
+    :func:`step_gemm_times` harvests them (live per-kernel durations, what ``bench.py`` reports as ``roofline``).
     """
     lib = _lib.load()
     from_host = not hidden.is_cuda
@@ -146,6 +158,16 @@ def policy_update_step(
         reduction = "sum"  # Tinker semantics: masked SUM whatever loss_reduction says (ppo_utils.py:892-981)
     if loss_type == "cross_entropy":
         use_kl = use_ent = False  # the SFT path of the worker adds no KL / entropy term (worker.py:810-813)
+    # off-policy correction (TIS weights, outlier / sequence masks): depends only on old / rollout log-probs, so it is
+    # computed before the step; the same rule as the registry losses (losses._registry_loss)
+    tis = clip_mask = None
+    opc_metrics: Dict[str, float] = {}
+    if loss_type not in ("cross_entropy", "importance_sampling") and _off_policy_enabled(config, rollout_logprobs):
+        if packed:
+            raise ValueError("the off-policy correction needs the padded [B, A] layout (it reduces per sequence)")
+        clip_mask = mask if mask is not None else torch.ones_like(olp)
+        tis, opc_metrics, mask = compute_off_policy_correction(olp, f32(rollout_logprobs), mask,
+                                                               _cfg(config, "off_policy_correction"))
     params = _make_params(
         loss_type, reduction, config,
         kl_type=_cfg(config, "kl_estimator_type", "k3"),
@@ -153,9 +175,12 @@ def policy_update_step(
         use_entropy_loss=use_ent, entropy_coef=float(_cfg(config, "entropy_loss_coef", 0.0)),
     )
     T = float(temperature)
-    stream = _lib.stream_ptr()
+    opts = None
+    if clip_mask is not None or timing:
+        opts = _lib.StepOpts(tis=_lib.ptr(tis), clip_mask=_lib.ptr(clip_mask), timing=int(bool(timing)))
     if fused:
         with torch.cuda.device(dev):
+            stream = _lib.stream_ptr(dev)
             logprobs = torch.empty(N, dtype=torch.float32, device=dev)
             ent = torch.empty(N, dtype=torch.float32, device=dev)
             stats = torch.empty(_lib.LOSS_NSTATS, dtype=torch.float32, device=dev)
@@ -177,7 +202,8 @@ def policy_update_step(
             tail = (_lib.ptr(w), _lib.ptr(lab), _lib.ptr(olp), _lib.ptr(adv), _lib.ptr(mask),
                     _lib.ptr(base) if use_kl else None, _lib.ptr(emask), _lib.ptr(logprobs), _lib.ptr(ent),
                     _lib.ptr(d_hidden), _lib.ptr(d_weight) if need_d_weight else None, acc, _lib.ptr(stats),
-                    _lib.ptr(ws), wsb, B, A, H, V, _lib.ptr(cu), N, T, C.byref(params), stream)
+                    _lib.ptr(ws), wsb, B, A, H, V, _lib.ptr(cu), N, T, C.byref(params),
+                    C.byref(opts) if opts is not None else None, stream)
             with _lib.nvtx_range("skyb200/policy_step"):
                 if from_host:
                     h_host, h = h, torch.empty((N, H), dtype=torch.bfloat16, device=dev)
@@ -188,8 +214,10 @@ def policy_update_step(
             if sync:
                 status = status_from_packed(stats.tolist(), use_kl)  # the single host sync of the step
                 status["response_length"] = A
+                for k, v in opc_metrics.items():
+                    status["loss_metrics/" + k] = v
             else:
-                status = {"packed": stats}
+                status = {"packed": stats, **{"loss_metrics/" + k: v for k, v in opc_metrics.items()}}
         if not packed:
             logprobs, ent = logprobs.view(B, A), ent.view(B, A)
         out = PolicyUpdateOutput(status=status, stats=stats, log_probs=logprobs, entropy=ent,
@@ -198,6 +226,7 @@ def policy_update_step(
             out.hidden = h  # the device copy of the streamed-in hidden states
         return out
     with torch.cuda.device(dev):
+        stream = _lib.stream_ptr(dev)
         logprobs = torch.empty(N, dtype=torch.float32, device=dev)
         ent_raw = torch.empty(N, dtype=torch.float32, device=dev)
         lse2 = torch.empty(N, dtype=torch.float32, device=dev)
@@ -220,7 +249,7 @@ def policy_update_step(
             lib.skyb200_policy_loss(_lib.ptr(logprobs), _lib.ptr(olp), _lib.ptr(adv), _lib.ptr(mask),
                                     _lib.ptr(base) if use_kl else None, _lib.ptr(ent), _lib.ptr(d_lp),
                                     _lib.ptr(d_ent), _lib.ptr(stats), _lib.ptr(ws_l), lb, B, A, C.byref(params),
-                                    None, None, stream),
+                                    _lib.ptr(tis), _lib.ptr(clip_mask), stream),
             "skyb200_policy_loss",
         )
         d_hidden = None
@@ -250,10 +279,22 @@ def policy_update_step(
         if sync:
             status = status_from_packed(stats.tolist(), use_kl)  # the single host sync of the step
             status["response_length"] = A
+            for k, v in opc_metrics.items():
+                status["loss_metrics/" + k] = v
         else:
-            status = {"packed": stats}
+            status = {"packed": stats, **{"loss_metrics/" + k: v for k, v in opc_metrics.items()}}
     return PolicyUpdateOutput(status=status, stats=stats, log_probs=logprobs.view(B, A), entropy=ent.view(B, A),
                               d_hidden=d_hidden, d_weight=d_weight if need_d_weight else None)
+
+
+def step_gemm_times(device=None) -> Dict[str, Dict[str, float]]:
+    """Live per-kernel durations of the fused steps run with ``timing=True`` on ``device`` since the last call:
+    ``{"forward" | "d_hidden" | "d_weight": {"ms": summed launch time, "launches": count}}``.  Synchronises."""
+    lib = _lib.load()
+    out = (C.c_double * 6)()
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        _lib.check(lib.skyb200_policy_step_timing(out), "skyb200_policy_step_timing")
+    return {name: {"ms": out[i], "launches": int(out[3 + i])} for i, name in enumerate(("forward", "d_hidden", "d_weight"))}
 
 
 def pack_by_lengths(lengths: torch.Tensor, *tensors: torch.Tensor):
@@ -283,12 +324,12 @@ class _FusedPolicyLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, hidden, weight, labels, old_log_probs, advantages, config, loss_mask, base_log_probs,
-                temperature, entropy_mask, cu_seqlens):
+                temperature, entropy_mask, cu_seqlens, rollout_logprobs=None):
         need_dh, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         out = policy_update_step(hidden.detach(), weight.detach(), labels, old_log_probs, advantages, config,
                                  loss_mask=loss_mask, base_log_probs=base_log_probs, temperature=temperature,
                                  entropy_mask=entropy_mask, need_d_hidden=need_dh, need_d_weight=need_dw,
-                                 sync=False, cu_seqlens=cu_seqlens)
+                                 sync=False, cu_seqlens=cu_seqlens, rollout_logprobs=rollout_logprobs)
         ctx.save_for_backward(out.d_hidden if out.d_hidden is not None else torch.empty(0, device=hidden.device),
                               out.d_weight if out.d_weight is not None else torch.empty(0, device=hidden.device))
         ctx.shapes = (hidden.shape, hidden.dtype, weight.dtype, need_dh, need_dw)
@@ -306,15 +347,16 @@ class _FusedPolicyLossFn(torch.autograd.Function):
             gh = (d_hidden.float() * g).to(h_dtype).view(h_shape)
         if need_dw:
             gw = (d_weight * g).to(w_dtype)
-        return gh, gw, None, None, None, None, None, None, None, None, None
+        return gh, gw, None, None, None, None, None, None, None, None, None, None
 
 
 def fused_policy_loss(hidden, weight, labels, old_log_probs, advantages, config, loss_mask=None,
-                      base_log_probs=None, temperature: float = 1.0, entropy_mask=None, cu_seqlens=None):
+                      base_log_probs=None, temperature: float = 1.0, entropy_mask=None, cu_seqlens=None,
+                      rollout_logprobs=None):
     """Autograd-facing form of the fused step: returns ``(final_loss, stats, log_probs, entropy)`` where
     ``final_loss`` is a 0-d tensor whose ``backward()`` delivers ``d_hidden`` to the trunk and ``weight.grad``.
 
     Equivalent to ``fused_lm_head`` + ``policy_update_loss`` + ``loss.backward()`` (and to the reference's
     worker.py:787-877) but with the 6*H*V executed-flop schedule of :func:`policy_update_step`."""
     return _FusedPolicyLossFn.apply(hidden, weight, labels, old_log_probs, advantages, config, loss_mask,
-                                    base_log_probs, temperature, entropy_mask, cu_seqlens)
+                                    base_log_probs, temperature, entropy_mask, cu_seqlens, rollout_logprobs)

@@ -6,7 +6,7 @@
 
 int main(void) {
     int64_t plan[3];
-    if (skyb200_abi_version() != 1) return 1;
+    if (skyb200_abi_version() != 2) return 1;
     if (skyb200_policy_step_plan(256, 4096, 0, 3584, 152064, SKYB200_LOSS_REGULAR, 1, plan) != 0) return 2;
     size_t ws = skyb200_policy_step_workspace(256, 4096, 0, 3584, 152064, SKYB200_LOSS_REGULAR, 1);
     /* argument validation happens before any CUDA call: a NULL pointer is an error code plus a message */

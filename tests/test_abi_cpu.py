@@ -39,7 +39,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_host_only_entry_points(lib):
-    assert lib.skyb200_abi_version() == 1
+    assert lib.skyb200_abi_version() == 2
     assert lib.skyb200_policy_loss_workspace(256, 4096) >= 256 * 8
     assert lib.skyb200_gae_workspace(512) >= 512 * 24
     fwd = lib.skyb200_head_forward_workspace(1 << 20, 3584, 152064, 0)

@@ -30,6 +30,11 @@ def _worker(rank, world, port, q):
         packed = sdist.all_reduce_packed_stats(stats)
         dw = torch.full((4, 3), float(rank + 1))
         sdist.all_reduce_d_weight(dw)
+        # FSDP semantics: mean reduce-scatter, rank r keeps rows [r * V / world, (r + 1) * V / world)
+        full = torch.arange(12, dtype=torch.float32).view(4, 3) * (rank + 1)
+        shard, _ = sdist.reduce_scatter_d_weight(full)
+        want = (torch.arange(12, dtype=torch.float32).view(4, 3) * 1.5)[2 * rank:2 * rank + 2]
+        assert torch.allclose(shard, want), (shard, want)
         q.put((rank, red, packed.tolist(), dw[0, 0].item()))
     finally:
         dist.destroy_process_group()

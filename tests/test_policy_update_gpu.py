@@ -305,7 +305,9 @@ def test_full_size_config2_sampled_rows_and_checksum_identities():
     base = lp0 + 0.1 * torch.randn((B, A), generator=gen, device=DEV)
     out = skyrl_b200.policy_update_step(hidden, weight, labels, olp, adv, cfg, loss_mask=mask, base_log_probs=base,
                                         temperature=T)
-    assert torch.equal(out.log_probs, lp0)  # the forward does not depend on the loss inputs: bit-identical
+    assert torch.allclose(out.log_probs, lp0, atol=2e-5, rtol=0)  # the forward does not depend on the loss inputs
+    # (last-bit differences only: the forward-only call sums the slab in one online pass, the forward that also
+    # stores the tile for the backward takes the slab maximum first)
     # ---- status vs the oracle on the kernel's log-probs
     ref_final, ref_st = O.loss_assembly(out.log_probs.cpu(), olp.cpu(), adv.cpu(), cfg, mask.cpu(), base.cpu(), None)
     for k in ("final_loss", "policy_loss", "policy_kl", "loss_metrics/clip_ratio"):

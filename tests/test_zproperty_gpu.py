@@ -1,8 +1,8 @@
 """Property tests (hypothesis) of the CUDA path against the oracle: the drawn shapes, group structures, masks and
 special values of the CPU property tests that pin the oracle to the reference (tests/test_oracle_cpu.py), replayed on
-the GPU.  Opt-in (SKYB200_TEST_EXPERIMENTAL=1) until they have run on a B200 once: they were written after the round-1
-GPU budget was spent, and a property test's first run is where tolerances get triaged."""
-import os
+the GPU.  First run on a B200 in round 2 (profiles/r02a_gpu_tests.log) triaged two findings: `is_ratio_std` of a
+single element is NaN in the reference (torch.std) and was 0 here - fixed in offpolicy.cu; a suffix scan's fp32 error
+scales with its largest running magnitude, not with the cancelled value at a position - the floor below."""
 from types import SimpleNamespace as NS
 
 import numpy as np
@@ -13,9 +13,7 @@ import skyrl_b200
 from oracle import policy_oracle as O
 from conftest import assert_close
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SKYB200_TEST_EXPERIMENTAL") != "1",
-                                 reason="opt-in until first run on a B200: SKYB200_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 DEV = "cuda:0"
 
 
@@ -57,11 +55,13 @@ def test_advantages_property():
         if mask.sum() >= 2:
             a_ref, r_ref = O.gae_advantage_return(r, v, mask, gamma, lambd)
             a, ret = skyrl_b200.compute_gae_advantage_return(r.to(DEV), v.to(DEV), m.to(DEV), gamma, lambd)
-            assert_close(ret, r_ref, what="gae returns")
+            # a suffix scan's fp32 rounding error scales with the largest running magnitude of the scan (the
+            # reference's own sequential fp32 sum carries it), not with the possibly cancelled value at a position
+            assert_close(ret, r_ref, floor=max(1.0, float(r_ref.abs().max())), what="gae returns")
             assert_close(a, a_ref, rel=1e-4, what="gae advantages")
             a_ref, r_ref = O.reinforce_pp_advantage(r, mask, gamma)
             a, ret = skyrl_b200.compute_reinforce_plus_plus_outcome_advantage(r.to(DEV), m.to(DEV), gamma=gamma)
-            assert_close(ret, r_ref, what="reinforce++ returns")
+            assert_close(ret, r_ref, floor=max(1.0, float(r_ref.abs().max())), what="reinforce++ returns")
             assert_close(a, a_ref, rel=1e-4, what="reinforce++ advantages")
         lp, base = -torch.rand(B, A, generator=g) * 3, -torch.rand(B, A, generator=g) * 3
         for kind in ("k1", "abs", "k2", "k3"):
