@@ -446,6 +446,15 @@ int skyb200_gemm_selftest(const void* A, const void* B, float* C, int64_t M, int
 int skyb200_gemm_bench(const void* A, const void* B, void* C, void* scratch, int64_t M, int64_t N, int64_t K,
                        int32_t epi, int32_t group, int32_t order, void* stream);
 
+/*
+ * Tuning hook (scripts/bwd_gemm_probe.py): ONE launch of a backward GEMM of the fused step exactly as the step issues
+ * it (operand majors, tile order, L2 hints, lockstep) on caller-provided buffers.  which = 1: d_hidden [rows, H] bf16 =
+ * S [rows, V] * weight [V, H]; which = 2: d_weight [V, H] fp32 (+)= S^T * hidden [rows, H].  S = bf16 d(logits) with
+ * pitch round_up(V, 64).
+ */
+int skyb200_head_gemm_bench(int32_t which, const void* hidden, const void* weight, const void* S, void* d_hidden,
+                            float* d_weight, int32_t accumulate, int64_t rows, int64_t H, int64_t V, void* stream);
+
 /* host pointer to the last GEMM watchdog record (8 uint32: flag, role, which, stage, parity, tile, block, pad) */
 const uint32_t* skyb200_gemm_debug_record(void);
 

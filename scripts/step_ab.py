@@ -31,17 +31,31 @@ def main():
         lens = torch.randint(A // 8, A + 1, (B,), generator=gen, device=dev)
         mask = (torch.arange(A, device=dev)[None] < lens[:, None]).float()
     adv = torch.randn((B, 1), generator=gen, device=dev).expand(B, A).contiguous()
-    olp = -torch.rand((B, A), generator=gen, device=dev) * 12
     cfg = make_cfg()  # regular / token_mean / k3 KL loss: the bench configuration
+    if kv.get("data", "bench") == "bench":
+        # the data of bench.py: old / base log-probs next to the current policy's (near on-policy), so that nearly
+        # every token carries a gradient - operand data matters on a power-capped part
+        with torch.no_grad():
+            lp0 = skyrl_b200.fused_lm_head_logprobs(hidden, weight, labels.view(N)).view(B, A)
+        olp = lp0 + 0.05 * torch.randn((B, A), generator=gen, device=dev)
+        base = lp0 + 0.1 * torch.randn((B, A), generator=gen, device=dev)
+        del lp0
+    else:  # round-1 data: far-off-policy, half of the sequences fully clipped (zero gradient rows)
+        olp = -torch.rand((B, A), generator=gen, device=dev) * 12
+        base = olp
     dw = torch.empty((V, H), dtype=torch.float32, device=dev)
+    timing = kv.get("timing", "1") == "1" and hasattr(skyrl_b200, "step_gemm_times")
 
     def step():
-        return skyrl_b200.policy_update_step(hidden, weight, labels, olp, adv, cfg, loss_mask=mask, base_log_probs=olp,
-                                             d_weight=dw, sync=False)
+        kw = dict(timing=True) if timing else {}
+        return skyrl_b200.policy_update_step(hidden, weight, labels, olp, adv, cfg, loss_mask=mask, base_log_probs=base,
+                                             d_weight=dw, sync=False, **kw)
 
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
+    if timing:
+        skyrl_b200.step_gemm_times(dev)  # drop the warm-up record
     cs = ClockSampler(0)
     cs.start()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -52,7 +66,10 @@ def main():
     torch.cuda.synchronize()
     clocks = cs.stop()
     ms = s.elapsed_time(e) / steps
-    print(json.dumps({"tag": kv.get("tag", ""), "ms_per_step": round(ms, 1), "tok_s": round(N / ms * 1e3),
+    gemm = None
+    if timing:
+        gemm = {k: round(v["ms"] / max(v["launches"], 1), 3) for k, v in skyrl_b200.step_gemm_times(dev).items()}
+    print(json.dumps({"tag": kv.get("tag", ""), "ms_per_step": round(ms, 1), "tok_s": round(N / ms * 1e3), "gemm_ms": gemm,
                       "valid_frac": round(float(mask.mean()), 3), "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")}), flush=True)
 
 

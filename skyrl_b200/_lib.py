@@ -138,6 +138,7 @@ SIGNATURES = {
     "skyb200_logits_backward": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
     "skyb200_gemm_selftest": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P]),
     "skyb200_gemm_bench": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _P]),
+    "skyb200_head_gemm_bench": (C.c_int, [_I32, _P, _P, _P, _P, _P, _I32, _I64, _I64, _I64, _P]),
     "skyb200_gemm_debug_record": (C.POINTER(C.c_uint32), []),
 }
 

@@ -922,7 +922,9 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
     if (rc) return rc;
     StepStreams* ss = step_streams();
     if (ss == nullptr) return fail(SKYB200_ECUDA, "could not create the auxiliary stream / events");
-    cudaStream_t aux = ss->aux;
+    // SKYB200_AUX_SERIAL=1 (experiment): the small kernels run on the caller's stream instead of overlapping the GEMMs
+    static const int aux_serial = env_int0("SKYB200_AUX_SERIAL", 0);
+    cudaStream_t aux = aux_serial ? stream : ss->aux;
 
     char* wb = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     const int64_t c = plan.chunk;        // buffer capacity (rows) of a chunk
@@ -1314,6 +1316,34 @@ extern "C" int skyb200_gemm_bench(const void* A, const void* B, void* C, void* s
                                                                                   group, ep, stream, order);
     }
     return fail(SKYB200_EINVAL, "epi must be 0..4");
+}
+
+// Tuning hook: ONE launch of a backward GEMM of the fused step exactly as the step issues it (operand majors, tile
+// order, L2 hints, lockstep), on caller-provided buffers: which = 1: d_hidden[rows, H] = S[rows, V] * W[V, H];
+// which = 2: d_weight[V, H] (+)= S^T * hidden[rows, H].  S is the bf16 d(logits) store with pitch round_up(V, 64).
+extern "C" int skyb200_head_gemm_bench(int32_t which, const void* hidden, const void* weight, const void* S,
+                                       void* d_hidden, float* d_weight, int32_t accumulate, int64_t rows, int64_t H,
+                                       int64_t V, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SKYB200_REQUIRE(S != nullptr && rows > 0 && H % 8 == 0, "bad arguments");
+    int rc = skyb200_check_device();
+    if (rc) return rc;
+    const int64_t ldS = round_up(V, 64);
+    if (which == 1) {
+        SKYB200_REQUIRE(weight && d_hidden, "null pointer");
+        EpiStoreBF16::Params eh{static_cast<__nv_bfloat16*>(d_hidden), H};
+        return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
+            S, ldS, weight, H, (int)rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, kEvictNormal, kEvictNormal,
+            dh_lockstep(), nullptr);
+    }
+    if (which == 2) {
+        SKYB200_REQUIRE(hidden && d_weight, "null pointer");
+        EpiStoreF32::Params ew{d_weight, H, accumulate};
+        return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
+            S, ldS, hidden, H, (int)V, (int)H, (int)rows, dw_group_n(), ew, stream, 1, kEvictNormal, hint_dw_b(),
+            dw_lockstep(), nullptr);
+    }
+    return fail(SKYB200_EINVAL, "which must be 1 (d_hidden) or 2 (d_weight)");
 }
 
 extern "C" const uint32_t* skyb200_gemm_debug_record(void) {

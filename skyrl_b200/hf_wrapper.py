@@ -11,6 +11,13 @@ Same call signature and return convention as the reference wrapper: ``action_log
 ``output["entropy"]`` is ``[B, S]`` so that the worker's own slice ``[:, -A-1:-1]`` (worker.py:855) keeps working
 (positions outside the response window hold zeros - the worker never reads them).
 
+FSDP: the wrapper reads ``lm_head.weight`` directly instead of calling ``lm_head.forward``.  With FSDP2
+(``fully_shard``) the weight is a ``DTensor``: it is all-gathered with ``full_tensor()`` for the fused head, and autograd
+reduce-scatters the ``d_weight`` the head produces back onto the shards.  With FSDP1 (``FullyShardedDataParallel``)
+a unit's parameters only exist un-sharded inside that unit's own ``forward``; reading the weight from outside would
+see the flat shard, so the wrapper refuses with a clear error unless the weight is whole (``use_orig_params`` views of
+a root-unit lm_head inside the root forward, or ``summon_full_params``).  Tied embeddings follow the same rule.
+
 Padded layout, one trunk per GPU.  A trunk that runs on sample-packed or Ulysses-sliced inputs (both need the
 reference's attention patches around the HF model) calls the matching glue function of :mod:`skyrl_b200.model_wrapper`
 on its own hidden states instead: ``action_log_probs_from_packed_hidden`` / ``_from_sp_hidden`` / ``_from_sp_packed_hidden``.
@@ -24,6 +31,20 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import model_wrapper as _glue
+
+
+def _whole_weight(weight: torch.Tensor, hidden_size: int) -> torch.Tensor:
+    """The un-sharded ``[V, H]`` lm_head weight, or a clear error: the fused head bypasses ``lm_head.forward``, so the
+    FSDP hooks that un-shard a parameter for its own module's forward do not fire for it."""
+    if hasattr(weight, "full_tensor"):      # DTensor (FSDP2 / TP): gather; the backward reduce-scatters d_weight
+        weight = weight.full_tensor()
+    if weight.dim() != 2 or weight.shape[1] != hidden_size or weight.numel() == 0:
+        raise RuntimeError(
+            f"FusedHeadPolicy needs the whole [V, H] lm_head weight but sees a tensor of shape {tuple(weight.shape)} "
+            f"(hidden size {hidden_size}): under FSDP1 a wrapped unit's parameters are only un-sharded inside its own "
+            "forward.  Keep lm_head (and tied embeddings) in the ROOT FSDP unit with use_orig_params=True, use FSDP2 "
+            "(fully_shard: the DTensor weight is gathered here), or call the wrapper under summon_full_params().")
+    return weight
 
 
 class FusedHeadPolicy(nn.Module):
@@ -49,7 +70,7 @@ class FusedHeadPolicy(nn.Module):
         position_ids = attention_mask.long().cumsum(-1) - 1   # model_wrapper.py:272-273
         position_ids.masked_fill_(attention_mask == 0, 1)
         hidden = self._trunk[0](sequences, attention_mask=attention_mask, position_ids=position_ids).last_hidden_state
-        weight = self._head[0].weight
+        weight = _whole_weight(self._head[0].weight, hidden.shape[-1])
         lp, ent = _glue.action_log_probs_from_hidden(hidden, weight, sequences, A, attention_mask, temperature,
                                                      compute_entropy)
         if not return_output:

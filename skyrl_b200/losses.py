@@ -286,7 +286,13 @@ def compute_policy_loss_cispo(log_probs, old_log_probs, advantages, config, loss
 
 
 def cross_entropy_loss(log_probs, old_log_probs, advantages, config, loss_mask=None, rollout_logprobs=None):
-    """SFT negative log-likelihood, masked SUM (Tinker semantics; reference: ppo_utils.py:892-930)."""
+    """SFT negative log-likelihood, masked SUM (Tinker semantics; reference: ppo_utils.py:892-930).
+
+    ``old_log_probs`` and ``advantages`` are ignored, as in the reference, and may be ``None``."""
+    if old_log_probs is None:  # the kernel signature wants the arrays; SFT never reads their values
+        old_log_probs = log_probs.detach()
+    if advantages is None:
+        advantages = log_probs.detach()
     loss, _ = _registry_loss("cross_entropy", log_probs, old_log_probs, advantages, config, loss_mask, None,
                              reduction="sum", want_stats=True)
     return loss, {"clip_ratio": 0.0}

@@ -17,6 +17,32 @@ from . import _lib
 
 _DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1}
 
+# Storages whose logits are still needed by the backward of a grad-requiring entropy node (storage pointer -> count).
+# ``HFModelWrapper.forward`` calls ``logprobs_from_logits(logits, inplace_backward=True)`` AND
+# ``chunked_entropy_from_logits(logits, requires_grad=use_entropy_loss)`` on the SAME buffer (model_wrapper.py:317,
+# 347): if the log-prob node's backward overwrote that buffer with d_logits before the entropy node's backward has
+# read it, the entropy gradient would be silently wrong.  (The reference is safe because its entropy goes through
+# ``log_softmax``, which saves its OUTPUT.)  The log-prob backward therefore falls back to a fresh d_logits buffer while
+# an entropy node on the same storage is pending, and every in-place overwrite bumps the tensor's version counter so
+# that any OTHER consumer that saved the logits gets autograd's "modified by an inplace operation" error, not garbage.
+_PENDING_ENTROPY: dict = {}
+
+
+def _storage_key(t: torch.Tensor) -> int:
+    return t.untyped_storage().data_ptr()
+
+
+def _pending_add(key: int) -> None:
+    _PENDING_ENTROPY[key] = _PENDING_ENTROPY.get(key, 0) + 1
+
+
+def _pending_drop(key: int) -> None:
+    n = _PENDING_ENTROPY.get(key, 0) - 1
+    if n > 0:
+        _PENDING_ENTROPY[key] = n
+    else:
+        _PENDING_ENTROPY.pop(key, None)
+
 
 def _check_logits(logits: torch.Tensor) -> torch.Tensor:
     if not logits.is_cuda:
@@ -47,6 +73,14 @@ class _LogitsLogprobEntropy(torch.autograd.Function):
             )
         ctx.inplace = bool(inplace_backward)
         ctx.has_mask = entropy_mask1d is not None
+        ctx.pending_key = None
+        if want_entropy and ctx.needs_input_grad[0]:
+            import weakref
+
+            ctx.pending_key = _storage_key(logits2d)
+            _pending_add(ctx.pending_key)
+            # a graph that is dropped without running its backward must not leave the entry behind
+            ctx.pending_fin = weakref.finalize(ctx, _pending_drop, ctx.pending_key)
         saved_ent = ent if want_entropy else torch.empty(0, device=dev)
         ctx.save_for_backward(logits2d, labels1d if labels1d is not None else torch.empty(0, device=dev), lse,
                               saved_ent, entropy_mask1d if entropy_mask1d is not None else torch.empty(0, device=dev))
@@ -72,8 +106,12 @@ class _LogitsLogprobEntropy(torch.autograd.Function):
             if ctx.has_mask:
                 g_ent_c = g_ent_c * emask
             g_ent_c = g_ent_c.contiguous()
+        if ctx.pending_key is not None:  # this entropy node has now read the logits
+            ctx.pending_fin.detach()
+            _pending_drop(ctx.pending_key)
+        inplace = ctx.inplace and _PENDING_ENTROPY.get(_storage_key(logits2d), 0) == 0
         with torch.cuda.device(dev):
-            d_logits = logits2d if ctx.inplace else torch.empty_like(logits2d)
+            d_logits = logits2d if inplace else torch.empty_like(logits2d)
             _lib.check(
                 lib.skyb200_logits_backward(_lib.ptr(logits2d), _DTYPE_CODE[logits2d.dtype],
                                             _lib.ptr(labels1d) if labels1d.numel() else None, _lib.ptr(lse),
@@ -81,6 +119,8 @@ class _LogitsLogprobEntropy(torch.autograd.Function):
                                             _lib.ptr(d_logits), N, V, _lib.stream_ptr()),
                 "skyb200_logits_backward",
             )
+        if inplace:  # the raw-pointer write is invisible to autograd: make it visible
+            torch.autograd.graph.increment_version(logits2d)
         return d_logits, None, None, None, None, None
 
 

@@ -31,7 +31,12 @@ def main():
     values = torch.randn(B, A, generator=g).to(dev)
     olp = (-6.0 + 0.3 * torch.randn(B, A, generator=g)).to(dev)
     cfg = O.make_cfg(policy_loss_type="regular", loss_reduction="token_mean", use_kl_loss=False)
-    ok = True
+    failed = []
+
+    def chk(name, cond):
+        if not bool(cond):
+            failed.append(name)
+            print(f"rank {rank}: check failed: {name}", flush=True)
 
     # ---- 1 GPU: the whole batch
     adv_all, _ = skyrl_b200.compute_grpo_outcome_advantage(rewards, mask, uids)
@@ -41,24 +46,59 @@ def main():
     # ---- N GPUs: whole prompt groups per rank, nothing exchanged for the advantages
     rows = torch.tensor(sdist.shard_prompt_groups(uids, [A] * B, world)[rank], device=dev)
     adv, _ = skyrl_b200.compute_grpo_outcome_advantage(rewards[rows], mask[rows], uids[rows.cpu().numpy()])
-    ok = ok and torch.equal(adv, adv_all[rows])
+    chk("c1: torch.equal(adv, adv_all[rows])", torch.equal(adv, adv_all[rows]))
     part = skyrl_b200.policy_update_step(hidden[rows], weight, labels[rows], olp[rows], adv, cfg, loss_mask=mask[rows],
                                          sync=False)
     stats = sdist.all_reduce_packed_stats(part.stats)          # mean of per-rank means
     sdist.all_reduce_d_weight(part.d_weight)                   # mean of per-rank gradients (in place)
     from skyrl_b200 import _lib
 
-    ok = ok and abs(stats[_lib.STAT_FINAL_LOSS].item() - whole.status["final_loss"]) < 1e-5 * max(1.0, abs(whole.status["final_loss"]))
+    chk("c2: abs(stats[_lib.STAT_FINAL_LOSS].item() - whole.status['final", abs(stats[_lib.STAT_FINAL_LOSS].item() - whole.status["final_loss"]) < 1e-5 * max(1.0, abs(whole.status["final_loss"])))
     rel = lambda x, y: float((x.float() - y.float()).norm() / y.float().norm())
-    ok = ok and rel(part.d_weight, whole.d_weight) < 2e-3      # bf16 d_logits are rounded after different 1/n scales
-    ok = ok and rel(part.d_hidden.float() / world, whole.d_hidden[rows].float()) < 2e-3
-    ok = ok and torch.equal(part.log_probs, whole.log_probs[rows])
+    chk("c3: rel(part.d_weight, whole.d_weight) < 2e-3", rel(part.d_weight, whole.d_weight) < 2e-3)      # bf16 d_logits are rounded after different 1/n scales
+    chk("c4: rel(part.d_hidden.float() / world, whole.d_hidden[rows].floa", rel(part.d_hidden.float() / world, whole.d_hidden[rows].float()) < 2e-3)
+    chk("c5: torch.equal(part.log_probs, whole.log_probs[rows])", torch.equal(part.log_probs, whole.log_probs[rows]))
+
+    # ---- ragged masks: the shards hold DIFFERENT token counts, so the mean of per-rank token means is NOT the global
+    # token mean.  The reference's data-parallel semantics are the former (every rank normalises by its local counts,
+    # FSDP averages the gradients: worker.py:909-914, SURVEY trap 11) - assert exactly that, against the oracle.
+    lens = torch.randint(A // 6, A + 1, (B,), generator=g)
+    lens[: B // 4] = A                                          # a few full-length rows: the shards stay unbalanced
+    rmask = (torch.arange(A)[None] < lens[:, None]).float().to(dev)
+    shards = sdist.shard_prompt_groups(uids, [A] * B, world)   # whole prompt groups; same partition on every rank
+    counts = [float(rmask[torch.tensor(r, device=dev)].sum()) for r in shards]
+    chk("c6: len(set(counts)) > 1", len(set(counts)) > 1)                            # the test is only meaningful if the counts differ
+    adv_r, _ = skyrl_b200.compute_grpo_outcome_advantage(rewards, rmask, uids)
+    part = skyrl_b200.policy_update_step(hidden[rows], weight, labels[rows], olp[rows], adv_r[rows], cfg,
+                                         loss_mask=rmask[rows], sync=False)
+    stats = sdist.all_reduce_packed_stats(part.stats)
+    # expected: every shard's own oracle loss (CPU restatement of the reference) on the step's log-probs, averaged
+    local_losses, local_dw = [], []
+    for r in shards:
+        rr = torch.tensor(r, device=dev)
+        loc = skyrl_b200.policy_update_step(hidden[rr], weight, labels[rr], olp[rr], adv_r[rr], cfg,
+                                            loss_mask=rmask[rr])
+        want, _ = O.loss_assembly(loc.log_probs.cpu(), olp[rr].cpu(), adv_r[rr].cpu(), cfg, rmask[rr].cpu(), None,
+                                  loc.entropy.cpu())
+        chk("c7: abs(loc.status['final_loss'] - want.item()) < 1e-5 * max(1.0", abs(loc.status["final_loss"] - want.item()) < 1e-5 * max(1.0, abs(want.item())))
+        local_losses.append(want.item())
+        local_dw.append(loc.d_weight.clone())
+    mean_of_means = sum(local_losses) / world
+    whole_r = skyrl_b200.policy_update_step(hidden, weight, labels, olp, adv_r, cfg, loss_mask=rmask)
+    got = stats[_lib.STAT_FINAL_LOSS].item()
+    chk("c8: abs(got - mean_of_means) < 1e-5 * max(1.0, abs(mean_of_means", abs(got - mean_of_means) < 1e-5 * max(1.0, abs(mean_of_means)))
+    chk("c9: abs(whole_r.status['final_loss'] - mean_of_means) > 1e-4 * a", abs(whole_r.status["final_loss"] - mean_of_means) > 1e-4 * abs(mean_of_means))  # ... and NOT the global mean
+    sdist.all_reduce_d_weight(part.d_weight)
+    chk("c10: rel(part.d_weight, sum(local_dw) / world) < 1e-5", rel(part.d_weight, sum(local_dw) / world) < 1e-5)
+    shard_w, _ = sdist.reduce_scatter_d_weight(sum(local_dw).clone())          # FSDP: mean reduce-scatter
+    per = V // world
+    chk("c11: rel(shard_w, sum(local_dw)[rank * per:(rank + 1) * per]) < 1", rel(shard_w, sum(local_dw)[rank * per:(rank + 1) * per]) < 1e-6)   # every rank fed the same sum
 
     # ---- GAE: rows are local, the whitening statistics are global (3 moments all-reduced)
     a_loc, r_loc = sdist.gae_advantage_sharded(rewards[rows], values[rows], mask[rows], 1.0, 0.95)
-    ok = ok and torch.equal(r_loc, ret_all[rows]) and (a_loc - gae_all[rows]).abs().max().item() < 1e-5
+    chk("c12: torch.equal(r_loc, ret_all[rows]) and (a_loc - gae_all[rows]", torch.equal(r_loc, ret_all[rows]) and (a_loc - gae_all[rows]).abs().max().item() < 1e-5)
 
-    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    flag = torch.tensor([0.0 if failed else 1.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("DP_OK" if flag.item() == 1.0 else "DP_FAIL")

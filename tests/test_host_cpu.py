@@ -468,3 +468,24 @@ def test_registries_mirror_through_a_named_actor_when_ray_is_live(monkeypatch):
     assert "theirs" in fake.actors["test_registry_actor"]._obj.table
     Driver.reset()
     assert Driver._functions == {} and "test_registry_actor" not in fake.actors
+
+
+def test_fused_head_policy_refuses_a_sharded_lm_head_weight():
+    """FusedHeadPolicy reads lm_head.weight without going through lm_head.forward, so FSDP's un-shard hooks do not fire
+    for it: a flat / sharded view must be refused with a clear error, a DTensor-like weight is gathered."""
+    import torch
+
+    from skyrl_b200.hf_wrapper import _whole_weight
+
+    w = torch.zeros(10, 8)
+    assert _whole_weight(w, 8) is w
+    with pytest.raises(RuntimeError, match="FSDP1"):
+        _whole_weight(torch.zeros(40), 8)          # FSDP1 flat shard
+    with pytest.raises(RuntimeError, match="FSDP1"):
+        _whole_weight(torch.zeros(0), 8)           # freed original parameter
+
+    class FakeDTensor:
+        def full_tensor(self):
+            return w
+
+    assert _whole_weight(FakeDTensor(), 8) is w

@@ -37,6 +37,57 @@ def test_match_reference_golden(golden_head):
     assert torch.equal(logits.cpu(), _t(g["logits"])), "non-inplace paths must not touch the logits"
 
 
+@pytest.mark.parametrize("entropy_first", [False, True])
+def test_inplace_logprob_backward_does_not_corrupt_the_entropy_gradient(entropy_first):
+    """HFModelWrapper.forward calls logprobs_from_logits(logits, inplace_backward=True) AND
+    chunked_entropy_from_logits(logits, requires_grad=use_entropy_loss) on the SAME buffer (model_wrapper.py:317, 347).
+    Whichever backward autograd runs first, both gradients must be those of the untouched logits: the log-prob
+    backward only overwrites the buffer once no entropy node still needs it."""
+    g = torch.Generator(device=DEV).manual_seed(3)
+    B, S, V = 2, 7, 1000
+    z0 = torch.randn(B, S, V, device=DEV, generator=g) * 2.0
+    lab = torch.randint(0, V, (B, S), device=DEV, generator=g)
+    am = (torch.rand(B, S, device=DEV, generator=g) > 0.2).float()
+    u, v = torch.randn(B, S, device=DEV, generator=g), torch.randn(B, S, device=DEV, generator=g)
+    zr = z0.clone().requires_grad_(True)
+    lsm = torch.log_softmax(zr, -1)
+    ref = (lsm.gather(-1, lab[..., None]).squeeze(-1) * u).sum() + ((-(lsm.exp() * lsm).sum(-1) * am) * v).sum()
+    ref.backward()
+    z = z0.clone().requires_grad_(True)
+    logits = z * 1.0  # the lm_head output: a non-leaf buffer the in-place backward may overwrite
+    if entropy_first:
+        ent = skyrl_b200.chunked_entropy_from_logits(logits, requires_grad=True, attention_mask=am)
+        lp = skyrl_b200.logprobs_from_logits(logits, lab, inplace_backward=True)
+    else:
+        lp = skyrl_b200.logprobs_from_logits(logits, lab, inplace_backward=True)
+        ent = skyrl_b200.chunked_entropy_from_logits(logits, requires_grad=True, attention_mask=am)
+    ((lp * u).sum() + (ent * v).sum()).backward()
+    assert_close(z.grad, zr.grad, rel=1e-5, floor=0.1)
+    from skyrl_b200 import torch_utils
+
+    assert not torch_utils._PENDING_ENTROPY  # nothing left registered
+    # without a grad-requiring entropy on the buffer the backward IS in place (the reference's memory behaviour)
+    z = z0.clone().requires_grad_(True)
+    logits = z * 1.0
+    before = logits._version
+    (skyrl_b200.logprobs_from_logits(logits, lab, inplace_backward=True) * u).sum().backward()
+    assert logits._version > before  # ... and autograd can see it: the version counter moved
+
+
+def test_cross_entropy_loss_accepts_none_like_the_reference():
+    """ppo_utils.py:892-930 documents old_log_probs / advantages as ignored for SFT; callers pass None."""
+    from types import SimpleNamespace as NS
+
+    g = torch.Generator(device=DEV).manual_seed(4)
+    lp = (-torch.rand(3, 11, device=DEV, generator=g)).requires_grad_(True)
+    mask = (torch.rand(3, 11, device=DEV, generator=g) > 0.3).float()
+    loss, met = skyrl_b200.PolicyLossRegistry.get("cross_entropy")(lp, None, None, NS(loss_reduction="token_mean"),
+                                                                   loss_mask=mask)
+    loss.backward()
+    assert loss.item() == pytest.approx(float((-lp.detach() * mask).sum()), rel=1e-5)
+    assert torch.allclose(lp.grad, -mask) and met == {"clip_ratio": 0.0}
+
+
 def test_uniform_logits_known_answer():  # reference: tests/cpu/utils/test_torch_utils.py:33-55
     ent = skyrl_b200.chunked_entropy_from_logits(torch.zeros(2, 3, 4, device=DEV))
     assert torch.allclose(ent.cpu(), torch.full((2, 3), math.log(4.0)), atol=1e-4)

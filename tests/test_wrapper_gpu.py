@@ -84,3 +84,20 @@ def test_sample_packing_wrapper_matches_unpad_project_pad(A):
     assert rel.item() < 2e-2
     with pytest.raises(ValueError):
         skyrl_b200.action_log_probs_from_packed_hidden(h[:-1], weight.to(DEV), sequences.to(DEV), am.to(DEV), A)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (NCCL sequence-parallel group)")
+def test_sequence_parallel_glue_over_nccl_two_ranks():
+    """SP = 2 equals SP = 1 with the real fused head on two GPUs (the reference's own check:
+    tests/gpu/gpu_ci/test_model_wrapper.py:134-191); windows inside one slice, across both slices, and A = S - 1."""
+    import os
+    import subprocess
+    import sys
+
+    script = os.path.join(os.path.dirname(__file__), "sp_nccl_worker.py")
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29547", script], env=env, capture_output=True,
+                       text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SP_OK" in r.stdout
