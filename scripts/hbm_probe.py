@@ -49,6 +49,18 @@ if __name__ == "__main__":
     us = timed(lambda: None, flush)
     print("calib empty region: %.1f us" % us)
     lib = _lib.load()
+    # GAE on few long rows (config-4 shard: 8 trajectories x 32768 positions): rows are split into one block per tile
+    for (b, a) in ((8, 32768), (64, 8192), (512, 8192)):
+        r, v = torch.randn(b, a, device=dev), torch.randn(b, a, device=dev)
+        m = torch.ones(b, a, device=dev)
+        o1, o2 = torch.empty_like(r), torch.empty_like(r)
+        st4 = torch.zeros(4, device=dev)
+        ws = torch.empty(lib.skyb200_gae_workspace(b), dtype=torch.uint8, device=dev)
+        call = lambda: _lib.check(lib.skyb200_gae_advantage(_lib.ptr(r), _lib.ptr(v), _lib.ptr(m), _lib.MASK_F32,
+                                                            _lib.ptr(o1), _lib.ptr(o2), _lib.ptr(st4), _lib.ptr(ws),
+                                                            ws.numel(), b, a, 1.0, 0.95, _lib.stream_ptr()))
+        us = timed(call, flush)
+        print("gae %d x %d: %.1f us = %.0f GB/s (28 B/position)" % (b, a, us, b * a * 28 / us / 1e3))
     t = torch.zeros(8, 64, device=dev)
     o = torch.zeros(8, 64, device=dev)
     us = timed(lambda: lib.skyb200_approx_kl(_lib.ptr(t), _lib.ptr(t), None, _lib.ptr(o), 512, 3, _lib.stream_ptr()), flush)

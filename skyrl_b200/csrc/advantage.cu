@@ -29,11 +29,19 @@ __global__ void __launch_bounds__(256) row_sum_kernel(const float* __restrict__ 
     float s = 0.f;
     const bool vec = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
     if (vec) {
+        // eight independent 128-bit loads in flight per thread (a 32 KB row is one round): the pass is latency-bound
+        // otherwise - one block per row leaves only ~3.5 blocks per SM for a 512-row batch
         const float4* x4 = reinterpret_cast<const float4*>(x + base);
         const int64_t n4 = A / 4;
-        for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-            const float4 v = ldg_stream(x4 + i);
-            s += (v.x + v.y) + (v.z + v.w);
+        for (int64_t i0 = threadIdx.x; i0 < n4; i0 += 8 * blockDim.x) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t i = i0 + static_cast<int64_t>(u) * blockDim.x;
+                v[u] = (i < n4) ? ldg_stream(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
         }
     } else {
         for (int64_t i = threadIdx.x; i < A; i += blockDim.x) s += x[base + i];
@@ -147,11 +155,27 @@ __device__ __forceinline__ Affine compose_left_of(const Affine& left, const Affi
 //   pass 2 the same 16 positions again with the true carry-in (exactly the sequential recurrence, in fp64)
 //   store  coalesced 128-bit stores of advantages and returns (values come from shared memory), row moments
 // The last block to finish folds the per-row moments in a fixed order (no separate fold launch).
-template <int kMaskType>
+//
+// kSplit: one block per (row, 4096-position tile) instead of one per row - a batch of few long rows (8 trajectories of
+// 32768 positions) otherwise occupies 8 of 148 SMs.  Every block loads its tile and runs pass 1 independently; only
+// the scalar carry travels along the row: the block of tile k waits for the carry tile k + 1 published (a flag in
+// global memory), applies its own 256 composed maps to it and publishes the result BEFORE its pass 2.  Work items are
+// handed out by an atomic ticket in the order "rows ascending, tiles right to left", so the block a waiter depends on
+// always holds an earlier ticket and is running or done: no deadlock whatever the hardware's block order.  The carry
+// arithmetic is the same sequence of fp64 operations as in the row-per-block form: results are bit-identical.
+struct GaeChain {
+    double* carry;        // [B * T] carry leaving tile (row, tile) to its left neighbour
+    unsigned int* flag;   // [B * T] 1 = carry published
+    unsigned int* ticket; // [1]
+    int tiles_per_row;
+};
+
+template <int kMaskType, bool kSplit>
 __global__ void __launch_bounds__(kGaeThreads, 4)
 gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const void* __restrict__ mask,
                 float* __restrict__ adv_raw, float* __restrict__ returns, double* __restrict__ row_stats, int64_t A,
-                float gamma, float lambd, double* __restrict__ moments, unsigned int* __restrict__ counter, int B) {
+                float gamma, float lambd, double* __restrict__ moments, unsigned int* __restrict__ counter, int B,
+                GaeChain chain) {
     __shared__ float s_r[kGaeThreads * kGaePitch + 1];  // rewards -> deltas -> advantages
     __shared__ float s_v[kGaeThreads * kGaePitch + 1];  // values, plus V of the position right of the tile
     __shared__ double s_wmul[kGaeThreads / 32], s_wadd[kGaeThreads / 32];
@@ -159,9 +183,17 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     __shared__ double sh_d[34];
     __shared__ bool is_last;
     pdl_launch_dependents();  // lets the whitening pass get scheduled behind the last blocks of the scan
-    const int row = blockIdx.x;
-    const int64_t base = static_cast<int64_t>(row) * A;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int row = blockIdx.x;
+    int my_tile = 0;
+    if constexpr (kSplit) {
+        __shared__ unsigned int s_ticket;
+        if (tid == 0) s_ticket = atomicAdd(chain.ticket, 1u);
+        __syncthreads();
+        row = static_cast<int>(s_ticket / static_cast<unsigned int>(chain.tiles_per_row));
+        my_tile = chain.tiles_per_row - 1 - static_cast<int>(s_ticket % static_cast<unsigned int>(chain.tiles_per_row));
+    }
+    const int64_t base = static_cast<int64_t>(row) * A;
     const double c = static_cast<double>(gamma) * static_cast<double>(lambd);
     double c16 = 1.0;
 #pragma unroll
@@ -175,7 +207,8 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     double sum_m = 0.0, sum_mx = 0.0, sum_mxx = 0.0;
     if (tid == 0) s_carry = 0.0;
     const int64_t num_tiles = (A + kGaeTile - 1) / kGaeTile;
-    for (int64_t tile = num_tiles - 1; tile >= 0; --tile) {
+    const int64_t tile_hi = kSplit ? my_tile : num_tiles - 1, tile_lo = kSplit ? my_tile : 0;
+    for (int64_t tile = tile_hi; tile >= tile_lo; --tile) {
         const int64_t t0 = tile * kGaeTile;
         __syncthreads();
         float4 mk[4];
@@ -246,6 +279,19 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
             s_wmul[warp] = incl.mul;
             s_wadd[warp] = incl.add;
         }
+        if constexpr (kSplit) {
+            // the carry entering this tile comes from the block of the tile to the right (the rightmost tile starts at 0)
+            if (tid == 0 && tile + 1 < num_tiles) {
+                const int64_t nb = static_cast<int64_t>(row) * chain.tiles_per_row + tile + 1;
+                unsigned int ready = 0u;
+                while (true) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(ready) : "l"(chain.flag + nb));
+                    if (ready != 0u) break;
+                    __nanosleep(64);
+                }
+                s_carry = __ldcg(chain.carry + nb);
+            }
+        }
         __syncthreads();
         double cin = s_carry;  // carry entering this warp = warps to the right applied to the tile carry
         for (int w = kGaeThreads / 32 - 1; w > warp; --w) cin = s_wmul[w] * cin + s_wadd[w];
@@ -253,7 +299,17 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
         const double na = __shfl_down_sync(0xffffffffu, incl.add, 1);
         const double my_cin = (lane == 31) ? cin : (nm * cin + na);
         __syncthreads();
-        if (tid == 0) s_carry = s_wmul[0] * cin + s_wadd[0];  // carry into the next (left) tile
+        if (tid == 0) {
+            s_carry = s_wmul[0] * cin + s_wadd[0];  // carry into the next (left) tile
+            if constexpr (kSplit) {
+                if (tile > 0) {  // publish it before pass 2: the neighbour only needs the scalar
+                    const int64_t me = static_cast<int64_t>(row) * chain.tiles_per_row + tile;
+                    chain.carry[me] = s_carry;
+                    __threadfence();
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(chain.flag + me), "r"(1u) : "memory");
+                }
+            }
+        }
         // pass 2: the recurrence with the true carry-in
         run = my_cin;
 #pragma unroll
@@ -302,18 +358,21 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     sum_m = block_sum(sum_m, sh_d);
     sum_mx = block_sum(sum_mx, sh_d);
     sum_mxx = block_sum(sum_mxx, sh_d);
+    // one partial per block: per row, or per (row, tile) in row-major order when the rows are split
+    const int n_parts = kSplit ? B * chain.tiles_per_row : B;
+    const int part = kSplit ? row * chain.tiles_per_row + my_tile : row;
     if (tid == 0) {
-        row_stats[3 * row + 0] = sum_m;
-        row_stats[3 * row + 1] = sum_mx;
-        row_stats[3 * row + 2] = sum_mxx;
+        row_stats[3 * part + 0] = sum_m;
+        row_stats[3 * part + 1] = sum_mx;
+        row_stats[3 * part + 2] = sum_mxx;
         __threadfence();
-        is_last = (atomicAdd(counter, 1u) == static_cast<unsigned int>(B) - 1u);
+        is_last = (atomicAdd(counter, 1u) == static_cast<unsigned int>(n_parts) - 1u);
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
     double n = 0.0, sx = 0.0, sxx = 0.0;  // same fixed order as fold_moments_kernel
-    for (int i = tid; i < B; i += kGaeThreads) {
+    for (int i = tid; i < n_parts; i += kGaeThreads) {
         n += __ldcg(&row_stats[3 * i + 0]);
         sx += __ldcg(&row_stats[3 * i + 1]);
         sxx += __ldcg(&row_stats[3 * i + 2]);
@@ -737,7 +796,22 @@ extern "C" int skyb200_group_advantage(const float* rewards, const void* respons
     return check_launch("group_broadcast_kernel");
 }
 
-extern "C" size_t skyb200_gae_workspace(int64_t B) { return (size_t)((B * 3 + 6) * sizeof(double) + 512); }
+// Rows are split into one block per 4096-position tile when that is what fills the chip: fewer rows than two blocks
+// per SM, more than one tile, at most kGaeMaxSplit tiles per row.  (With more rows the row-per-block form is faster:
+// 512 x 8192 measured 34.8 us whole-row vs 43.0 us split - a second wave of blocks and the carry hand-off buy nothing
+// once every SM already holds several rows; 8 x 32768 and 64 x 8192 are the shapes that gain.)
+constexpr int kGaeMaxSplit = 32;
+constexpr int64_t kGaeSplitRows = 296;  // 148 SMs x 2
+static int64_t gae_split_tiles(int64_t B, int64_t A) {
+    const int64_t T = (A + kGaeTile - 1) / kGaeTile;
+    return (T > 1 && T <= kGaeMaxSplit && B < kGaeSplitRows) ? T : 1;
+}
+// partial moments (3 doubles per block) + 3 moments + counters, then the carry chain of the split form
+static size_t gae_parts_cap(int64_t B) { return (size_t)std::max<int64_t>(B, std::min<int64_t>(B, kGaeSplitRows) * kGaeMaxSplit); }
+extern "C" size_t skyb200_gae_workspace(int64_t B) {
+    const size_t parts = gae_parts_cap(B);
+    return (parts * 3 + 8) * sizeof(double) + parts * (sizeof(double) + sizeof(unsigned int)) + 1024;
+}
 
 extern "C" int skyb200_gae_scan(const float* rewards, const float* values, const void* response_mask,
                                 int32_t mask_type, float* adv_raw, float* returns, double* moments, void* workspace,
@@ -749,26 +823,49 @@ extern "C" int skyb200_gae_scan(const float* rewards, const float* values, const
     SKYB200_REQUIRE(B > 0 && A > 0 && B < (1ll << 31), "bad shape");
     SKYB200_REQUIRE((reinterpret_cast<uintptr_t>(moments) & 7u) == 0, "moments must be 8-byte aligned");
     if (workspace_bytes < skyb200_gae_workspace(B)) return fail(SKYB200_EWORKSPACE, "gae workspace too small");
-    double* row_stats = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
-    // completion counter of the last-block fold, behind the row stats and the 3 moments of skyb200_gae_advantage
-    unsigned int* counter = reinterpret_cast<unsigned int*>(row_stats + 3 * B + 4);
-    SKYB200_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+    // layout: [3 moments of skyb200_gae_advantage at row_stats + 3 * B][partial moments: 3 * parts doubles, starting
+    // behind them][counter, ticket][carry: parts doubles][flag: parts u32]
+    double* ws0 = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    const size_t parts_cap = gae_parts_cap(B);
+    double* row_stats = ws0 + 3 * B + 4;  // (ws0 .. ws0 + 3B + 3 stays free for the callers' moments slot)
+    unsigned int* counter = reinterpret_cast<unsigned int*>(row_stats + 3 * parts_cap);
+    GaeChain chain;
+    chain.ticket = counter + 1;
+    chain.carry = reinterpret_cast<double*>(counter + 4);
+    chain.flag = reinterpret_cast<unsigned int*>(chain.carry + parts_cap);
+    const int64_t T = gae_split_tiles(B, A);
+    chain.tiles_per_row = (int)T;
+    const bool split = T > 1;
+    if (split) {  // counter + ticket + the flags of this call's B * T tiles in one memset (the carries need none)
+        SKYB200_CUDA_CHECK(cudaMemsetAsync(counter, 0, 16, stream));
+        SKYB200_CUDA_CHECK(cudaMemsetAsync(chain.flag, 0, (size_t)(B * T) * sizeof(unsigned int), stream));
+    } else {
+        SKYB200_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+    }
+    const unsigned grid = (unsigned)(B * T);
+#define SKYB200_GAE_LAUNCH(MT)                                                                                        \
+    if (split)                                                                                                        \
+        gae_scan_kernel<MT, true><<<grid, kGaeThreads, 0, stream>>>(rewards, values, response_mask, adv_raw, returns, \
+                                                                    row_stats, A, gamma, lambd, moments, counter,    \
+                                                                    (int)B, chain);                                   \
+    else                                                                                                              \
+        gae_scan_kernel<MT, false><<<grid, kGaeThreads, 0, stream>>>(rewards, values, response_mask, adv_raw,        \
+                                                                     returns, row_stats, A, gamma, lambd, moments,   \
+                                                                     counter, (int)B, chain);
     switch (mask_type) {
         case SKYB200_MASK_F32:
-            gae_scan_kernel<SKYB200_MASK_F32><<<(unsigned)B, kGaeThreads, 0, stream>>>(
-                rewards, values, response_mask, adv_raw, returns, row_stats, A, gamma, lambd, moments, counter, (int)B);
+            SKYB200_GAE_LAUNCH(SKYB200_MASK_F32)
             break;
         case SKYB200_MASK_I64:
-            gae_scan_kernel<SKYB200_MASK_I64><<<(unsigned)B, kGaeThreads, 0, stream>>>(
-                rewards, values, response_mask, adv_raw, returns, row_stats, A, gamma, lambd, moments, counter, (int)B);
+            SKYB200_GAE_LAUNCH(SKYB200_MASK_I64)
             break;
         case SKYB200_MASK_NONE:
-            gae_scan_kernel<SKYB200_MASK_NONE><<<(unsigned)B, kGaeThreads, 0, stream>>>(
-                rewards, values, response_mask, adv_raw, returns, row_stats, A, gamma, lambd, moments, counter, (int)B);
+            SKYB200_GAE_LAUNCH(SKYB200_MASK_NONE)
             break;
         default:
             return fail(SKYB200_EINVAL, "bad mask_type %d", mask_type);
     }
+#undef SKYB200_GAE_LAUNCH
     return check_launch("gae_scan_kernel");
 }
 

@@ -439,6 +439,61 @@ struct EpiStoreF32 {
     }
 };
 
+// C (fp32 [M, N], pitch in the tensor map) = or += accumulator, through shared memory and TMA: each epilogue warp stages
+// 32 rows x 32 columns (4 KB, 128-byte swizzle, two buffers) and one lane issues cp.async.bulk.tensor (store) or
+// cp.reduce.async.bulk.tensor ... .add (UTMAREDG: the fp32 add is performed at L2 - the SM neither reads the old value
+// nor waits for it).  Used for d_weight: the per-thread read-modify-write of EpiStoreF32 moved 4.4 GB per chunk
+// through the LSU in 32-byte row-strided pieces.  Rows >= M / columns >= N are clipped by the tensor map.
+struct EpiTmaF32 {
+    static constexpr uint32_t kSmemBytes = 4 * 2 * 4096;
+    __device__ static void finish() {
+        if ((threadIdx.x & 31) == 0) ptx::bulk_wait_group<0>();
+    }
+    struct Params {
+        CUtensorMap tmap_out;  // fp32 [M, N], box 32 x 32, SWIZZLE_128B
+        int accumulate;
+    };
+    template <int BN>
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N, uint8_t* stage) {
+        const int n0 = n_tile * BN;
+        const int lane = threadIdx.x & 31;
+        const uint32_t srow = ptx::smem_u32(stage) + static_cast<uint32_t>(lane) * 128u;
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            const int col0 = n0 + c * 32;
+            if (col0 >= N) break;  // uniform across the whole warp
+            uint32_t v[32];
+            __syncwarp();
+            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            if (lane == 0) {  // the buffer about to be rewritten must have been read by its previous bulk operation
+                if (c == 0)
+                    ptx::bulk_wait_group_read<0>();
+                else
+                    ptx::bulk_wait_group_read<1>();
+            }
+            __syncwarp();
+            const uint32_t sbuf = srow + static_cast<uint32_t>(c & 1) * 4096u;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {  // 16-byte chunk j of the 128-byte row goes to slot j ^ (row & 7)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + ((j ^ sw) << 4)), "r"(v[4 * j]),
+                             "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                             : "memory");
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && row < M) {  // lane 0 holds the warp's first row
+                if (p.accumulate)
+                    ptx::tma_reduce_add_2d(&p.tmap_out, stage + (c & 1) * 4096, col0, row);
+                else
+                    ptx::tma_store_2d(&p.tmap_out, stage + (c & 1) * 4096, col0, row);
+                ptx::bulk_commit_group();
+            }
+        }
+    }
+};
+
 // Drains the accumulator and discards it (mainloop-only timing in scripts/gemm_tune.py).
 struct EpiNull {
     static constexpr uint32_t kSmemBytes = 0;

@@ -57,6 +57,23 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t inner, ui
     return SKYB200_OK;
 }
 
+// 2D fp32 tensor map for TMA-store / TMA-reduce epilogues (32 x 32 boxes, 128-byte swizzle)
+static int make_tmap_f32_out(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems) {
+    auto enc = get_encode_fn();
+    if (enc == nullptr) return fail(SKYB200_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return fail(SKYB200_EINVAL, "TMA base not 16B aligned");
+    if ((pitch_elems * 4) % 16 != 0) return fail(SKYB200_EINVAL, "row pitch must be a multiple of 4 fp32");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {pitch_elems * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SKYB200_ECUDA, "cuTensorMapEncodeTiled (fp32 out) failed with CUresult %d", (int)r);
+    return SKYB200_OK;
+}
+
 static GemmDebug* g_dbg_host = nullptr;  // mapped pinned memory
 static GemmDebug* g_dbg_dev = nullptr;
 
@@ -739,11 +756,10 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
         }
         // (3) d_weight[V, H] (+)= dS^T[V, rows] * hidden[rows, H]   (both MN-major)
         if (d_weight != nullptr) {
-            EpiStoreF32::Params ew;
-            ew.C = d_weight;
-            ew.ldc = H;
+            EpiTmaF32::Params ew;
+            if ((rc = make_tmap_f32_out(&ew.tmap_out, d_weight, (uint64_t)H, (uint64_t)V, (uint64_t)H))) return rc;
             ew.accumulate = acc_w ? 1 : 0;
-            rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
+            rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
                 dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, kEvictNormal, kEvictLast,
                 dw_lockstep(), skip ? &k_maps : nullptr);
             if (rc) return rc;
@@ -1075,14 +1091,13 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             if ((r = t_end(1))) return r;
         }
         if (d_weight != nullptr && !(whatif() & 16)) {
-            EpiStoreF32::Params ew;
-            ew.C = d_weight;
-            ew.ldc = H;
+            EpiTmaF32::Params ew;
+            int r = make_tmap_f32_out(&ew.tmap_out, d_weight, (uint64_t)H, (uint64_t)V, (uint64_t)H);
+            if (r) return r;
             ew.accumulate = (accumulate != 0 || t0 > 0) ? 1 : 0;
             if (whatif() & 2) ew.accumulate = 0;
-            int r = t_begin();
-            if (r) return r;
-            r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
+            if ((r = t_begin())) return r;
+            r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
                 S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, kEvictNormal,
                 hint_dw_b(), dw_lockstep(), (skip && ew.accumulate) ? &k_maps : nullptr);
             if (r) return r;
@@ -1338,8 +1353,10 @@ extern "C" int skyb200_head_gemm_bench(int32_t which, const void* hidden, const 
     }
     if (which == 2) {
         SKYB200_REQUIRE(hidden && d_weight, "null pointer");
-        EpiStoreF32::Params ew{d_weight, H, accumulate};
-        return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiStoreF32>(
+        EpiTmaF32::Params ew;
+        if ((rc = make_tmap_f32_out(&ew.tmap_out, d_weight, (uint64_t)H, (uint64_t)V, (uint64_t)H))) return rc;
+        ew.accumulate = accumulate;
+        return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
             S, ldS, hidden, H, (int)V, (int)H, (int)rows, dw_group_n(), ew, stream, 1, kEvictNormal, hint_dw_b(),
             dw_lockstep(), nullptr);
     }

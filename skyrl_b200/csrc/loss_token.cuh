@@ -17,6 +17,19 @@
 #define SKYB200_TOKEN_FN inline
 #endif
 
+// exp() of a clamped argument (|x| <= 20, or <= 10 for the GSPO sequence ratio).  On the device this is
+// ex2.approx(x * log2 e): 2 instructions instead of ~10, relative error <= 2^-22 (ex2.approx) + 2^-24 * |x| * log2 e
+// (rounding of the scaled argument) <= 1.3e-6 at |x| = 20 - inside the 1e-5 tolerance of the loss, its gradient and
+// the ratio / KL metrics, and exact where it matters structurally: exp(0) == 1 (on-policy ratio), and the clip tie
+// s1 == s2 only depends on the ratio lying inside the clip range, not on its last bits.  The token pass is
+// instruction-bound (profiles/README.md r01g), so the two exponentials per token are worth removing.  The host build
+// of this header (tests/test_loss_token_host_cpu.py) keeps libm's expf.
+#ifdef __CUDA_ARCH__
+#define SKYB200_EXPF(x) __expf(x)
+#else
+#define SKYB200_EXPF(x) expf(x)
+#endif
+
 namespace skyb200 {
 
 SKYB200_TOKEN_FN float kl_estimate(float lp, float base, int type, float* dkl_dlp) {
@@ -34,7 +47,7 @@ SKYB200_TOKEN_FN float kl_estimate(float lp, float base, int type, float* dkl_dl
         default: {  // k3
             const float xr = base - lp;
             const float x = fminf(fmaxf(xr, -20.f), 20.f);
-            const float r = expf(x);
+            const float r = SKYB200_EXPF(x);
             const float k = r - x - 1.f;
             const float kc = fminf(fmaxf(k, -10.f), 10.f);
             const bool pass = (xr >= -20.f && xr <= 20.f) && (k >= -10.f && k <= 10.f);
@@ -76,7 +89,7 @@ SKYB200_TOKEN_FN float loss_token(const TokenCtx& cx, LossAcc& acc, float lp, fl
             dr_dlp = cx.seq_ratio * cx.seq_pass;
         } else {
             const float delta = lp - olp;
-            ratio = expf(fminf(fmaxf(delta, -20.f), 20.f));
+            ratio = SKYB200_EXPF(fminf(fmaxf(delta, -20.f), 20.f));
             dr_dlp = (delta >= -20.f && delta <= 20.f) ? ratio : 0.f;
         }
         const float rc = fminf(fmaxf(ratio, cx.lo), cx.hi);
@@ -98,14 +111,14 @@ SKYB200_TOKEN_FN float loss_token(const TokenCtx& cx, LossAcc& acc, float lp, fl
         dl_dlp = dl_dr * dr_dlp;
     } else if (loss_type == SKYB200_LOSS_SAPO) {
         const float delta = lp - olp;
-        ratio = expf(fminf(fmaxf(delta, -20.f), 20.f));
+        ratio = SKYB200_EXPF(fminf(fmaxf(delta, -20.f), 20.f));
         const float dr_dlp = (delta >= -20.f && delta <= 20.f) ? ratio : 0.f;
         const float tau = (adv > 0.f) ? cx.tau_pos : cx.tau_neg;
-        const float sg = 1.f / (1.f + expf(-tau * (ratio - 1.f)));
+        const float sg = 1.f / (1.f + SKYB200_EXPF(-tau * (ratio - 1.f)));
         loss = -(sg * (4.f / tau)) * adv;
         dl_dlp = -adv * 4.f * sg * (1.f - sg) * dr_dlp;
     } else if (loss_type == SKYB200_LOSS_CISPO) {
-        ratio = expf(fminf(fmaxf(lp - olp, -20.f), 20.f));
+        ratio = SKYB200_EXPF(fminf(fmaxf(lp - olp, -20.f), 20.f));
         const float rc = fminf(fmaxf(ratio, cx.lo), cx.hi);  // detached: acts as a per-token weight
         loss = -adv * rc * lp;
         dl_dlp = -adv * rc;
@@ -116,12 +129,12 @@ SKYB200_TOKEN_FN float loss_token(const TokenCtx& cx, LossAcc& acc, float lp, fl
         dl_dlp = -1.f;
     } else if (loss_type == SKYB200_LOSS_KL_COV) {  // `tis` carries the per-token KL weight of the selection
         const float d = lp - olp;
-        ratio = expf(d);
+        ratio = SKYB200_EXPF(d);
         loss = fmaf(tis, fabsf(d), -ratio * adv);
         dl_dlp = fmaf(tis, (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f), -ratio * adv);
         tis = 1.f;
     } else {  // importance sampling: un-clamped ratio, Tinker semantics
-        ratio = expf(lp - olp);
+        ratio = SKYB200_EXPF(lp - olp);
         loss = -ratio * adv;
         dl_dlp = loss;
     }
@@ -139,7 +152,7 @@ SKYB200_TOKEN_FN float loss_token(const TokenCtx& cx, LossAcc& acc, float lp, fl
     if (has_base) {
         if constexpr (kKl == SKYB200_KL_K3) {  // value only: same arithmetic as kl_estimate's k3 branch
             const float x = fminf(fmaxf(base - lp, -20.f), 20.f);
-            const float kl = fminf(fmaxf(expf(x) - x - 1.f, -10.f), 10.f);
+            const float kl = fminf(fmaxf(SKYB200_EXPF(x) - x - 1.f, -10.f), 10.f);
             const float km = cx.has_mask ? kl * m : kl;
             acc.s_kl = fmaf(km * m, cx.kl_scale, acc.s_kl);
         } else {
