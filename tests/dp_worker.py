@@ -56,7 +56,7 @@ def main():
     chk("c2: abs(stats[_lib.STAT_FINAL_LOSS].item() - whole.status['final", abs(stats[_lib.STAT_FINAL_LOSS].item() - whole.status["final_loss"]) < 1e-5 * max(1.0, abs(whole.status["final_loss"])))
     rel = lambda x, y: float((x.float() - y.float()).norm() / y.float().norm())
     chk("c3: rel(part.d_weight, whole.d_weight) < 2e-3", rel(part.d_weight, whole.d_weight) < 2e-3)      # bf16 d_logits are rounded after different 1/n scales
-    chk("c4: rel(part.d_hidden.float() / world, whole.d_hidden[rows].floa", rel(part.d_hidden.float() / world, whole.d_hidden[rows].float()) < 2e-3)
+    chk("c4: rel(part.d_hidden.float() / world, whole.d_hidden[rows].floa", rel(part.d_hidden.float() / world, whole.d_hidden.view(B, A, H)[rows].reshape(-1, H).float()) < 2e-3)
     chk("c5: torch.equal(part.log_probs, whole.log_probs[rows])", torch.equal(part.log_probs, whole.log_probs[rows]))
 
     # ---- ragged masks: the shards hold DIFFERENT token counts, so the mean of per-rank token means is NOT the global
