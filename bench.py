@@ -260,9 +260,13 @@ def hbm_kernels(dev, peaks):
     P = _lib.ptr
     cases = {
         # name: (call, algorithmic bytes per position)
-        "grpo_advantage": (lambda: lib.skyb200_group_advantage(P(rewards), P(mask), _lib.MASK_F32, P(gid), P(gstart),
-                                                               P(grows), P(out1), P(scores), B, A, B // G, 0, 1e-6, st),
-                           12),
+        # uniform groups of 8 (what compute_grpo_outcome_advantage launches for this batch): one cluster launch
+        "grpo_advantage": (lambda: lib.skyb200_group_advantage_uniform(P(rewards), P(mask), _lib.MASK_F32, P(grows),
+                                                                       P(out1), P(scores), B, A, G, 0, 1e-6, st), 12),
+        # the general form (ragged / shuffled groups): row sums, then group statistics + broadcast
+        "grpo_advantage_general_form": (lambda: lib.skyb200_group_advantage(P(rewards), P(mask), _lib.MASK_F32, P(gid),
+                                                                            P(gstart), P(grows), P(out1), P(scores),
+                                                                            B, A, B // G, 0, 1e-6, st), 12),
         "gae_advantage+whiten": (lambda: lib.skyb200_gae_advantage(P(rewards), P(values), P(mask), _lib.MASK_F32,
                                                                    P(out1), P(out2), P(stats), P(gae_ws),
                                                                    gae_ws.numel(), B, A, 1.0, 0.95, st), 28),
@@ -558,7 +562,7 @@ def run_ours(args, w):
     kernel_names = {
         "forward": "gemm_sm100_kernel<2,256,6,K-major,K-major,EpiLseStoreRel> (logits tile -> LSE partials + bf16 tile store)",
         "d_hidden": "gemm_sm100_kernel<2,256,6,K-major,MN-major,EpiStoreBF16> (d_hidden = dS * W)",
-        "d_weight": "gemm_sm100_kernel<2,256,6,MN-major,MN-major,EpiStoreF32> (d_weight += dS^T * hidden, fp32)",
+        "d_weight": "gemm_sm100_kernel<2,256,6,MN-major,MN-major,EpiTmaF32> (d_weight += dS^T * hidden, fp32 TMA reduce-add)",
     }
     roofline_kernels = {}
     for kind, t in gemm_times.items():

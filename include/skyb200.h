@@ -212,6 +212,18 @@ int skyb200_group_advantage(const float* rewards, const void* response_mask, int
                             float epsilon, void* stream);
 
 /*
+ * The same estimators in ONE launch for batches whose prompt groups all have `group_size` rows (the trainer's
+ * n_samples_per_prompt layout): a thread-block cluster per group exchanges the row sums through distributed shared
+ * memory; rewards and mask cross HBM exactly once.  group g owns rows group_rows[g * group_size .. (g + 1) *
+ * group_size).  Shapes outside skyb200_group_advantage_uniform_supported(A, group_size) (A % 4, A <= 32768,
+ * group_size <= 8, or even and <= 16 with A <= 16384) take skyb200_group_advantage.  Pointers 16-byte aligned.
+ */
+int skyb200_group_advantage_uniform_supported(int64_t A, int64_t group_size);
+int skyb200_group_advantage_uniform(const float* rewards, const void* response_mask, int32_t mask_type,
+                                    const int32_t* group_rows, float* out, float* scores_ws, int64_t B, int64_t A,
+                                    int32_t group_size, int32_t mode, float epsilon, void* stream);
+
+/*
  * GAE (compute_gae_advantage_return, ppo_utils.py:1101-1129) + masked_whiten (:163-172).
  * One segment per ROW, no reset on mask (the reference does not reset).
  * rewards, values [B, A] fp32; mask of mask_type; advantages, returns [B, A] fp32 out.

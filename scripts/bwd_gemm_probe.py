@@ -42,7 +42,10 @@ def sustained(fn, seconds=1.5):
 
 
 def main():
-    rows, V, H = (int(x) for x in sys.argv[1:4]) if len(sys.argv) >= 4 else (9472, 152064, 3584)
+    kv = dict(a.split("=", 1) for a in sys.argv[1:] if "=" in a)
+    pos = [a for a in sys.argv[1:] if "=" not in a]
+    rows, V, H = (int(x) for x in pos[:3]) if len(pos) >= 3 else (9472, 152064, 3584)
+    quick = kv.get("quick") == "1"  # A/B mode: realistic d(logits) only, no cuBLAS legs
     lib = _lib.load()
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(0)
@@ -73,7 +76,7 @@ def main():
                 S[r0:r0 + n, :V] = (-gl * p)
 
     out = {}
-    for kind in ("randn", "dlogits", "zeros"):
+    for kind in (("dlogits",) if quick else ("randn", "dlogits", "zeros")):
         fill(kind)
         for name, call in (
             ("d_hidden", lambda: _lib.check(lib.skyb200_head_gemm_bench(1, None, P(weight), P(S), P(d_hidden), None, 0,
@@ -86,6 +89,9 @@ def main():
             d_weight.zero_()
             ms, mhz = sustained(call)
             out[f"{name}[{kind}]"] = (round(flops / ms / 1e9, 1), round(ms, 3), mhz)
+    if quick:
+        print(json.dumps({"tag": kv.get("tag", ""), "tflops_ms_mhz": out}), flush=True)
+        return
     a = hidden
     c = torch.empty(rows, V, dtype=torch.bfloat16, device=dev)
     ms, mhz = sustained(lambda: torch.matmul(a, weight.t(), out=c))

@@ -40,7 +40,7 @@ def kind_of(name):
         return "forward"
     if "EpiStoreBF16" in name:
         return "d_hidden"
-    if "EpiStoreF32" in name:
+    if "EpiTmaF32" in name or "EpiStoreF32" in name:
         return "d_weight"
     return None
 

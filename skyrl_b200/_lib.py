@@ -107,6 +107,8 @@ SIGNATURES = {
     "skyb200_masked_mean": (C.c_int, [_P, _P, _P, _P, _SZ, _I64, _P]),
     "skyb200_approx_kl": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
     "skyb200_group_advantage": (C.c_int, [_P, _P, _I32, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _P]),
+    "skyb200_group_advantage_uniform_supported": (C.c_int, [_I64, _I64]),
+    "skyb200_group_advantage_uniform": (C.c_int, [_P, _P, _I32, _P, _P, _P, _I64, _I64, _I32, _I32, _F, _P]),
     "skyb200_gae_workspace": (_SZ, [_I64]),
     "skyb200_gae_advantage": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _SZ, _I64, _I64, _F, _F, _P]),
     "skyb200_gae_scan": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _SZ, _I64, _I64, _F, _F, _P]),

@@ -74,7 +74,9 @@ def build_group_index(index: Sequence) -> Tuple[np.ndarray, np.ndarray, np.ndarr
 
 
 def _group_advantage(rewards: torch.Tensor, response_mask: torch.Tensor, index, mode: int,
-                     epsilon: float) -> torch.Tensor:
+                     epsilon: float, one_launch: Optional[bool] = None) -> torch.Tensor:
+    """``one_launch``: None = the cluster form whenever the batch allows it, False = always the general two-kernel
+    form, True = raise if the cluster form cannot take the batch (tests pin each path with it)."""
     lib = _lib.load()
     dev = _device_for(rewards)
     B, A = rewards.shape
@@ -89,14 +91,29 @@ def _group_advantage(rewards: torch.Tensor, response_mask: torch.Tensor, index, 
         g_of_row, g_start, g_rows = packed[:B], packed[B:B + ng + 1], packed[B + ng + 1:]
         out = torch.empty((B, A), dtype=torch.float32, device=dev)
         scores = torch.empty(B, dtype=torch.float32, device=dev)
-        _lib.check(
-            lib.skyb200_group_advantage(_lib.ptr(r), _lib.ptr(m), mtype, _lib.ptr(g_of_row), _lib.ptr(g_start),
-                                        _lib.ptr(g_rows), _lib.ptr(out), _lib.ptr(scores), B, A, ng, mode,
-                                        float(epsilon), _lib.stream_ptr()),
-            "skyb200_group_advantage",
-        )
+        sizes = np.diff(gstart)
+        n = int(sizes[0]) if ng > 0 else 0
+        aligned = all(t is None or t.data_ptr() % 16 == 0 for t in (r, m, out))
+        uniform = (ng > 0 and bool((sizes == n).all()) and aligned
+                   and bool(lib.skyb200_group_advantage_uniform_supported(A, n)))
+        if one_launch and not uniform:
+            raise ValueError(f"the one-launch form needs uniform groups and a supported shape (A={A}, sizes={set(sizes.tolist())})")
+        if uniform and one_launch is not False:
+            # every prompt has n samples (the trainer's layout): one launch, a thread-block cluster per group
+            _lib.check(
+                lib.skyb200_group_advantage_uniform(_lib.ptr(r), _lib.ptr(m), mtype, _lib.ptr(g_rows), _lib.ptr(out),
+                                                    _lib.ptr(scores), B, A, n, mode, float(epsilon),
+                                                    _lib.stream_ptr()),
+                "skyb200_group_advantage_uniform",
+            )
+        else:
+            _lib.check(
+                lib.skyb200_group_advantage(_lib.ptr(r), _lib.ptr(m), mtype, _lib.ptr(g_of_row), _lib.ptr(g_start),
+                                            _lib.ptr(g_rows), _lib.ptr(out), _lib.ptr(scores), B, A, ng, mode,
+                                            float(epsilon), _lib.stream_ptr()),
+                "skyb200_group_advantage",
+            )
         if mode == 2:
-            sizes = np.diff(gstart)
             if (sizes == 1).any():
                 for g in np.nonzero(sizes == 1)[0]:
                     logger.warning("Only one response for prompt index %s, setting advantage to 0",

@@ -11,6 +11,12 @@
 
 namespace skyb200 {
 
+__device__ __forceinline__ uint32_t ptx_mapa(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+
 template <int kMaskType>
 __device__ __forceinline__ float mask_at(const void* mask, int64_t i) {
     if constexpr (kMaskType == SKYB200_MASK_F32) return static_cast<const float*>(mask)[i];
@@ -126,6 +132,122 @@ group_broadcast_kernel(const float* __restrict__ scores, const void* __restrict_
         for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x)
             out[base + t] = value * mask_at<kMaskType>(mask, base + t);
     }
+}
+
+// ---- GRPO / RLOO in ONE launch when every prompt group has the same size (the trainer's layout: n samples per
+// prompt): a thread-block CLUSTER per group.  CTA `rank` of the cluster owns kRows rows of its group; every load of
+// the pass (the rewards AND the mask of those rows) is in flight at once, the mask stays in registers, the row sums
+// are exchanged through distributed shared memory (one cluster barrier), and each CTA scales its own mask rows.
+// 12 B per position cross HBM exactly once - no score round trip through global memory, no second launch.
+template <int kMaskType, int kPer>
+__device__ __forceinline__ void load_mask_row(const void* __restrict__ mask, int64_t base, int64_t n4, int T,
+                                              float4 (&m)[kPer]) {
+    if constexpr (kMaskType == SKYB200_MASK_F32) {
+        const float4* m4 = reinterpret_cast<const float4*>(static_cast<const float*>(mask) + base);
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int64_t i = static_cast<int64_t>(u) * T + threadIdx.x;
+            m[u] = (i < n4) ? __ldcs(m4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else if constexpr (kMaskType == SKYB200_MASK_I64) {
+        const longlong2* m2 = reinterpret_cast<const longlong2*>(static_cast<const long long*>(mask) + base);
+        longlong2 a[kPer], b[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int64_t i = static_cast<int64_t>(u) * T + threadIdx.x;
+            a[u] = b[u] = make_longlong2(0, 0);
+            if (i < n4) {
+                a[u] = __ldcs(m2 + 2 * i);
+                b[u] = __ldcs(m2 + 2 * i + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) m[u] = make_float4((float)a[u].x, (float)a[u].y, (float)b[u].x, (float)b[u].y);
+    } else {
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+}
+
+template <int kMaskType, int kRows, int kPer>
+__global__ void __launch_bounds__(512)
+group_cluster_kernel(const float* __restrict__ rewards, const void* __restrict__ mask,
+                     const int32_t* __restrict__ group_rows, float* __restrict__ out, float* __restrict__ scores,
+                     int64_t A, int n, int mode, float eps) {
+    __shared__ float sh[34];
+    __shared__ float my_scores[kRows];  // read by the other CTAs of the cluster
+    __shared__ float my_value[kRows];
+    const int T = blockDim.x;
+    uint32_t csize, rank;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int g = blockIdx.x / csize;
+    const int64_t n4 = A / 4;
+    int rows[kRows];
+    float4 m[kRows][kPer];
+#pragma unroll
+    for (int j = 0; j < kRows; ++j) {
+        rows[j] = group_rows[static_cast<int64_t>(g) * n + rank * kRows + j];
+        const float4* x4 = reinterpret_cast<const float4*>(rewards + static_cast<int64_t>(rows[j]) * A);
+        float4 r[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int64_t i = static_cast<int64_t>(u) * T + threadIdx.x;
+            r[u] = (i < n4) ? ldg_stream(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        load_mask_row<kMaskType, kPer>(mask, static_cast<int64_t>(rows[j]) * A, n4, T, m[j]);
+        float s = 0.f;
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) s += (r[u].x + r[u].y) + (r[u].z + r[u].w);
+        s = block_sum(s, sh);
+        if (threadIdx.x == 0) {
+            my_scores[j] = s;
+            scores[rows[j]] = s;
+        }
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        float sc = 0.f;
+        if (lane < n) {
+            const uint32_t addr = ptx_mapa(static_cast<uint32_t>(__cvta_generic_to_shared(&my_scores[lane % kRows])),
+                                           static_cast<uint32_t>(lane / kRows));
+            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(sc) : "r"(addr) : "memory");
+        }
+        const float nf = static_cast<float>(n);
+        const float mean = warp_sum(sc) / nf;
+        const float d = (lane < n) ? sc - mean : 0.f;
+        const float q = warp_sum(d * d);
+        if (lane < kRows) {
+            const float mine = my_scores[lane];
+            float value;
+            if (mode == 2) {
+                value = (n > 1) ? (mine - mean) * (nf / static_cast<float>(n - 1)) : 0.f;
+            } else if (n == 1) {
+                value = (mode == 0) ? mine / (1.f + eps) : mine;
+            } else if (mode == 1) {
+                value = mine - mean;
+            } else {
+                value = (mine - mean) / (sqrtf(q / static_cast<float>(n - 1)) + eps);
+            }
+            my_value[lane] = value;
+        }
+    }
+    // every remote read of this CTA's scores precedes the peer's arrive; the matching wait is the last instruction
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kRows; ++j) {
+        const float value = my_value[j];
+        float4* o4 = reinterpret_cast<float4*>(out + static_cast<int64_t>(rows[j]) * A);
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int64_t i = static_cast<int64_t>(u) * T + threadIdx.x;
+            if (i < n4)
+                __stcs(o4 + i, make_float4(value * m[j][u].x, value * m[j][u].y, value * m[j][u].z, value * m[j][u].w));
+        }
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------ GAE
@@ -794,6 +916,93 @@ extern "C" int skyb200_group_advantage(const float* rewards, const void* respons
             return fail(SKYB200_EINVAL, "bad mask_type %d", mask_type);
     }
     return check_launch("group_broadcast_kernel");
+}
+
+// Shape gate of the one-launch cluster form (also exported: the host mirror asks before it picks the entry point).
+struct GroupClusterPlan {
+    int cluster, rows_per_cta, per, threads;
+};
+static bool group_cluster_plan(int64_t A, int64_t n, GroupClusterPlan* p) {
+    if (A <= 0 || A % 4 != 0 || A > 32768 || n < 1) return false;
+    int cluster, rows;
+    if (n <= 8) {
+        cluster = (int)n, rows = 1;
+    } else if (n <= 16 && n % 2 == 0) {
+        cluster = (int)(n / 2), rows = 2;
+    } else {
+        return false;
+    }
+    int per = 8, threads = 256;
+    if (A > 8192) threads = 512;
+    if (A > 16384) {
+        if (rows != 1) return false;
+        per = 16;
+    }
+    if (p) *p = {cluster, rows, per, threads};
+    return true;
+}
+extern "C" int skyb200_group_advantage_uniform_supported(int64_t A, int64_t group_size) {
+    return group_cluster_plan(A, group_size, nullptr) ? 1 : 0;
+}
+
+template <int kMaskType, int kRows, int kPer>
+static int launch_group_cluster(const GroupClusterPlan& pl, const float* rewards, const void* mask,
+                                const int32_t* group_rows, float* out, float* scores, int64_t B, int64_t A, int n,
+                                int mode, float eps, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B / n * pl.cluster));
+    cfg.blockDim = dim3((unsigned)pl.threads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)pl.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SKYB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, group_cluster_kernel<kMaskType, kRows, kPer>, rewards, mask, group_rows,
+                                          out, scores, A, n, mode, eps));
+    return SKYB200_OK;
+}
+template <int kMaskType>
+static int dispatch_group_cluster(const GroupClusterPlan& pl, const float* rewards, const void* mask,
+                                  const int32_t* group_rows, float* out, float* scores, int64_t B, int64_t A, int n,
+                                  int mode, float eps, cudaStream_t stream) {
+    if (pl.rows_per_cta == 2)
+        return launch_group_cluster<kMaskType, 2, 8>(pl, rewards, mask, group_rows, out, scores, B, A, n, mode, eps, stream);
+    if (pl.per == 16)
+        return launch_group_cluster<kMaskType, 1, 16>(pl, rewards, mask, group_rows, out, scores, B, A, n, mode, eps, stream);
+    return launch_group_cluster<kMaskType, 1, 8>(pl, rewards, mask, group_rows, out, scores, B, A, n, mode, eps, stream);
+}
+
+extern "C" int skyb200_group_advantage_uniform(const float* rewards, const void* response_mask, int32_t mask_type,
+                                               const int32_t* group_rows, float* out, float* scores_ws, int64_t B,
+                                               int64_t A, int32_t group_size, int32_t mode, float epsilon,
+                                               void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (B == 0 || A == 0) return SKYB200_OK;
+    SKYB200_REQUIRE(rewards && group_rows && out && scores_ws, "null pointer");
+    SKYB200_REQUIRE(mask_type == SKYB200_MASK_NONE || response_mask != nullptr, "mask pointer missing");
+    SKYB200_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (grpo), 1 (grpo no std) or 2 (rloo)");
+    SKYB200_REQUIRE(group_size >= 1 && B % group_size == 0, "B must be a whole number of groups of group_size rows");
+    GroupClusterPlan pl;
+    SKYB200_REQUIRE(group_cluster_plan(A, group_size, &pl),
+                    "shape not supported by the cluster form (ask skyb200_group_advantage_uniform_supported)");
+    SKYB200_REQUIRE(((reinterpret_cast<uintptr_t>(rewards) | reinterpret_cast<uintptr_t>(out) |
+                      reinterpret_cast<uintptr_t>(response_mask)) & 15u) == 0, "pointers must be 16-byte aligned");
+    switch (mask_type) {
+        case SKYB200_MASK_F32:
+            return dispatch_group_cluster<SKYB200_MASK_F32>(pl, rewards, response_mask, group_rows, out, scores_ws, B, A,
+                                                            group_size, mode, epsilon, stream);
+        case SKYB200_MASK_I64:
+            return dispatch_group_cluster<SKYB200_MASK_I64>(pl, rewards, response_mask, group_rows, out, scores_ws, B, A,
+                                                            group_size, mode, epsilon, stream);
+        case SKYB200_MASK_NONE:
+            return dispatch_group_cluster<SKYB200_MASK_NONE>(pl, rewards, response_mask, group_rows, out, scores_ws, B,
+                                                             A, group_size, mode, epsilon, stream);
+        default:
+            return fail(SKYB200_EINVAL, "bad mask_type %d", mask_type);
+    }
 }
 
 // Rows are split into one block per 4096-position tile when that is what fills the chip: fewer rows than two blocks

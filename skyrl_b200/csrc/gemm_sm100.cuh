@@ -452,6 +452,7 @@ struct EpiTmaF32 {
     struct Params {
         CUtensorMap tmap_out;  // fp32 [M, N], box 32 x 32, SWIZZLE_128B
         int accumulate;
+        uint64_t hint;  // L2 eviction policy of the output traffic (kEvictNormal / kEvictFirst)
     };
     template <int BN>
     __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N, uint8_t* stage) {
@@ -485,9 +486,9 @@ struct EpiTmaF32 {
             __syncwarp();
             if (lane == 0 && row < M) {  // lane 0 holds the warp's first row
                 if (p.accumulate)
-                    ptx::tma_reduce_add_2d(&p.tmap_out, stage + (c & 1) * 4096, col0, row);
+                    ptx::tma_reduce_add_2d_hint(&p.tmap_out, stage + (c & 1) * 4096, col0, row, p.hint);
                 else
-                    ptx::tma_store_2d(&p.tmap_out, stage + (c & 1) * 4096, col0, row);
+                    ptx::tma_store_2d_hint(&p.tmap_out, stage + (c & 1) * 4096, col0, row, p.hint);
                 ptx::bulk_commit_group();
             }
         }

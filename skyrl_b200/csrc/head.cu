@@ -206,6 +206,11 @@ static uint64_t hint_of(const char* name, int dflt) {
 }
 static uint64_t hint_fwd_a() { static uint64_t v = hint_of("SKYB200_HINT_FWD_A", 3); return v; }
 static uint64_t hint_dw_b() { static uint64_t v = hint_of("SKYB200_HINT_DW_B", 3); return v; }
+// d_weight GEMM: the d(logits) panels (A) and the fp32 output traffic (C) are each touched once per launch
+static uint64_t hint_dw_a() { static uint64_t v = hint_of("SKYB200_HINT_DW_A", 1); return v; }
+static uint64_t hint_dw_c() { static uint64_t v = hint_of("SKYB200_HINT_DW_C", 1); return v; }
+static uint64_t hint_dh_a() { static uint64_t v = hint_of("SKYB200_HINT_DH_A", 1); return v; }
+static uint64_t hint_dh_b() { static uint64_t v = hint_of("SKYB200_HINT_DH_B", 1); return v; }
 static int env_int0(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v == nullptr || *v == 0) ? dflt : atoi(v);
@@ -750,7 +755,7 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
                 if ((rc = check_launch("zero_dead_tiles_kernel"))) return rc;
             }
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
-                dS, ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, kEvictNormal, kEvictNormal,
+                dS, ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, hint_dh_a(), hint_dh_b(),
                 dh_lockstep(), skip ? &m_maps : nullptr);
             if (rc) return rc;
         }
@@ -759,8 +764,9 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
             EpiTmaF32::Params ew;
             if ((rc = make_tmap_f32_out(&ew.tmap_out, d_weight, (uint64_t)H, (uint64_t)V, (uint64_t)H))) return rc;
             ew.accumulate = acc_w ? 1 : 0;
+            ew.hint = hint_dw_c();
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
-                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, kEvictNormal, kEvictLast,
+                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, hint_dw_a(), hint_dw_b(),
                 dw_lockstep(), skip ? &k_maps : nullptr);
             if (rc) return rc;
         }
@@ -1085,7 +1091,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             int r = t_begin();
             if (r) return r;
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
-                S, plan.ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, kEvictNormal, kEvictNormal,
+                S, plan.ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, hint_dh_a(), hint_dh_b(),
                 dh_lockstep(), skip ? &m_maps : nullptr);
             if (r) return r;
             if ((r = t_end(1))) return r;
@@ -1096,9 +1102,10 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             if (r) return r;
             ew.accumulate = (accumulate != 0 || t0 > 0) ? 1 : 0;
             if (whatif() & 2) ew.accumulate = 0;
+            ew.hint = hint_dw_c();
             if ((r = t_begin())) return r;
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
-                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, kEvictNormal,
+                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, hint_dw_a(),
                 hint_dw_b(), dw_lockstep(), (skip && ew.accumulate) ? &k_maps : nullptr);
             if (r) return r;
             if ((r = t_end(2))) return r;
@@ -1348,7 +1355,7 @@ extern "C" int skyb200_head_gemm_bench(int32_t which, const void* hidden, const 
         SKYB200_REQUIRE(weight && d_hidden, "null pointer");
         EpiStoreBF16::Params eh{static_cast<__nv_bfloat16*>(d_hidden), H};
         return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
-            S, ldS, weight, H, (int)rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, kEvictNormal, kEvictNormal,
+            S, ldS, weight, H, (int)rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, hint_dh_a(), hint_dh_b(),
             dh_lockstep(), nullptr);
     }
     if (which == 2) {
@@ -1356,8 +1363,9 @@ extern "C" int skyb200_head_gemm_bench(int32_t which, const void* hidden, const 
         EpiTmaF32::Params ew;
         if ((rc = make_tmap_f32_out(&ew.tmap_out, d_weight, (uint64_t)H, (uint64_t)V, (uint64_t)H))) return rc;
         ew.accumulate = accumulate;
+        ew.hint = hint_dw_c();
         return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
-            S, ldS, hidden, H, (int)V, (int)H, (int)rows, dw_group_n(), ew, stream, 1, kEvictNormal, hint_dw_b(),
+            S, ldS, hidden, H, (int)V, (int)H, (int)rows, dw_group_n(), ew, stream, 1, hint_dw_a(), hint_dw_b(),
             dw_lockstep(), nullptr);
     }
     return fail(SKYB200_EINVAL, "which must be 1 (d_hidden) or 2 (d_weight)");

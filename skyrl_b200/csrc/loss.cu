@@ -30,6 +30,7 @@ constexpr int kNumPartials = 8;
 struct LossWs {
     float* row_msum;          // [B]
     float* row_lw;            // [B]  GSPO: masked mean of (lp - olp)
+    float* row_scale;         // [B]  1 / max(row mask sum, 1) / B: the per-row normaliser of the token pass
     float* total_msum;        // [1]
     unsigned int* counters;   // [2]
     float* partials;          // [num_blocks][kNumPartials]
@@ -45,12 +46,13 @@ static size_t loss_ws_layout(int64_t B, int64_t A, LossWs* ws, void* base) {
         off += (bytes + 255) / 256 * 256;
         return o;
     };
-    size_t o_rm = take(B * 4), o_lw = take(B * 4), o_tot = take(16), o_cnt = take(16),
+    size_t o_rm = take(B * 4), o_lw = take(B * 4), o_rs = take(B * 4), o_tot = take(16), o_cnt = take(16),
            o_part = take(blocks * kNumPartials * 4), o_tmp = take(148 * 4 * 2 * 4 + 64);
     if (ws != nullptr) {
         char* b = static_cast<char*>(base);
         ws->row_msum = reinterpret_cast<float*>(b + o_rm);
         ws->row_lw = reinterpret_cast<float*>(b + o_lw);
+        ws->row_scale = reinterpret_cast<float*>(b + o_rs);
         ws->total_msum = reinterpret_cast<float*>(b + o_tot);
         ws->counters = reinterpret_cast<unsigned int*>(b + o_cnt);
         ws->partials = reinterpret_cast<float*>(b + o_part);
@@ -64,7 +66,8 @@ __global__ void __launch_bounds__(kLossThreads)
 loss_rowstats_kernel(const float* __restrict__ lp, const float* __restrict__ olp, const float* __restrict__ mask,
                      float* __restrict__ row_msum, float* __restrict__ row_lw, float* __restrict__ total_msum,
                      unsigned int* __restrict__ counter, int B, int64_t A, int need_lw,
-                     const int32_t* __restrict__ cu = nullptr) {
+                     const int32_t* __restrict__ cu = nullptr, float* __restrict__ row_scale = nullptr,
+                     unsigned int* __restrict__ clear = nullptr) {
     __shared__ float sh[34];
     __shared__ bool is_last;
     pdl_launch_dependents();  // the token pass may be scheduled while this pre-pass drains (it waits before reading)
@@ -122,6 +125,8 @@ loss_rowstats_kernel(const float* __restrict__ lp, const float* __restrict__ olp
     if (threadIdx.x == 0) {
         row_msum[row] = ms;
         row_lw[row] = need_lw ? lw / fmaxf(ms, 1.f) : 0.f;
+        if (row_scale != nullptr) row_scale[row] = (1.f / fmaxf(ms, 1.f)) / static_cast<float>(B);
+        if (clear != nullptr && row == 0) *clear = 0u;  // the token pass's "last block" ticket (no memset node)
         is_last = false;
         if (total_msum != nullptr) {
             __threadfence();
@@ -169,7 +174,7 @@ struct TileIn {
     float lp[4], olp[4], adv[4], m[4], bs[4], en[4], ti[4], cm[4];
     int64_t i0;        // flat index of component 0; component u sits at i0 + u * stride
     unsigned ok;       // bit u set = component u is a real position
-    float row_m, row_lw;
+    int row;
 };
 
 __device__ __forceinline__ void ld4(const float* p, int64_t i, float (&dst)[4]) {
@@ -180,13 +185,15 @@ __device__ __forceinline__ void ld4(const float* p, int64_t i, float (&dst)[4]) 
     dst[3] = v.w;
 }
 
-template <bool kVec>
-__device__ __forceinline__ void tile_load(const LossArgs& a, int row, int tile_in_row, bool valid, bool gspo,
-                                          TileIn& d) {
+// Issues the loads of one tile (inputs only: nothing here depends on the pre-pass).  kExtra = the off-policy
+// correction arrays (tis, clip_mask) may be present; without it they cost neither registers nor instructions.
+template <bool kVec, bool kExtra>
+__device__ __forceinline__ void tile_load(const LossArgs& a, int row, int tile_in_row, bool valid, TileIn& d) {
     d.ok = 0u;
     if (!valid) return;
     const int64_t t0 = static_cast<int64_t>(tile_in_row) * kMainTile;
     const int64_t rbase = static_cast<int64_t>(row) * a.A;
+    d.row = row;
     if constexpr (kVec) {
         const int64_t t = t0 + static_cast<int64_t>(threadIdx.x) * 4;
         if (t >= a.A) return;  // consume() skips tiles with ok == 0: nothing else needs a value
@@ -202,15 +209,17 @@ __device__ __forceinline__ void tile_load(const LossArgs& a, int row, int tile_i
         }
         if (a.base) ld4(a.base, i, d.bs);
         if (a.ent) ld4(a.ent, i, d.en);
-        if (a.tis) {
-            ld4(a.tis, i, d.ti);
-        } else {
-            d.ti[0] = d.ti[1] = d.ti[2] = d.ti[3] = 1.f;
-        }
-        if (a.clip_mask) {
-            ld4(a.clip_mask, i, d.cm);
-        } else {
-            d.cm[0] = d.cm[1] = d.cm[2] = d.cm[3] = -1.f;
+        if constexpr (kExtra) {
+            if (a.tis) {
+                ld4(a.tis, i, d.ti);
+            } else {
+                d.ti[0] = d.ti[1] = d.ti[2] = d.ti[3] = 1.f;
+            }
+            if (a.clip_mask) {
+                ld4(a.clip_mask, i, d.cm);
+            } else {
+                d.cm[0] = d.cm[1] = d.cm[2] = d.cm[3] = -1.f;
+            }
         }
         d.ok = 0xFu;
         d.i0 = i;
@@ -236,25 +245,21 @@ __device__ __forceinline__ void tile_load(const LossArgs& a, int row, int tile_i
             }
         }
     }
-    if (d.ok) {
-        d.row_m = __ldcg(&a.ws.row_msum[row]);
-        d.row_lw = gspo ? __ldcg(&a.ws.row_lw[row]) : 0.f;
-    }
 }
 
-// Persistent grid (a few blocks per SM): every block walks 1024-position tiles with a grid stride, two tiles in
-// flight per thread (all loads of both tiles are issued before the first is consumed), one block reduction at the end.
-template <int kInFlight, int kMinBlocks, int kType, int kBase, int kKl, bool kVec>
+// Persistent grid (a few blocks per SM): every block walks 1024-position tiles with a grid stride, kInFlight tiles in
+// flight per thread (all loads of all of them are issued before the first is consumed), one block reduction at the
+// end.  The first round of loads is issued BEFORE the kernel waits for the mask pre-pass (programmatic dependent
+// launch): the pre-pass's tail and this kernel's DRAM latency overlap.
+template <int kInFlight, int kMinBlocks, int kType, int kBase, int kKl, bool kVec, bool kExtra>
 __global__ void __launch_bounds__(kLossThreads, kMinBlocks) loss_main_kernel(LossArgs a) {
     __shared__ float sh[34];
     __shared__ bool is_last;
-    pdl_wait();  // row / total mask sums of the pre-pass are complete and visible
     const int64_t A = a.A;
-    const float total_m = __ldcg(a.ws.total_msum);
     const float Bf = static_cast<float>(a.B);
-    const float inv_total = 1.f / fmaxf(total_m, 1.f);
     const bool gspo = (a.p.loss_type == SKYB200_LOSS_GSPO);
     const bool use_ent_loss = (a.p.use_entropy_loss != 0);
+    const int reduction = a.p.reduction;
 
     LossAcc acc;
     TokenCtx cx;
@@ -271,31 +276,38 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) loss_main_kernel(Los
     cx.tau_neg = a.p.sapo_tau_neg;
     cx.has_mask = (a.mask != nullptr);
     cx.has_base = (a.base != nullptr);
-    cx.d_ent_val = use_ent_loss ? -a.p.entropy_loss_coef * inv_total : 0.f;
+    cx.w_scale = (reduction == SKYB200_REDUCE_SUM) ? 1.f : 1.f / (a.p.max_seq_len * Bf);  // the row-independent forms
+    float total_m = 0.f, inv_total = 0.f;
+
+    // after the pre-pass: global mask sum = fixed-order fold of its row sums (the same in every block)
+    auto after_prepass = [&]() {
+        pdl_wait();
+        float tot = 0.f;
+        for (int i = threadIdx.x; i < a.B; i += blockDim.x) tot += __ldcg(&a.ws.row_msum[i]);
+        total_m = block_sum(tot, sh);
+        inv_total = 1.f / fmaxf(total_m, 1.f);
+        cx.d_ent_val = use_ent_loss ? -a.p.entropy_loss_coef * inv_total : 0.f;
+        if (reduction == SKYB200_REDUCE_TOKEN_MEAN) cx.w_scale = inv_total;
+    };
 
     auto consume = [&](const TileIn& d) {
         if (!d.ok) return;
-        const float inv_row = 1.f / fmaxf(d.row_m, 1.f);
-        if (a.p.reduction == SKYB200_REDUCE_TOKEN_MEAN)
-            cx.w_scale = inv_total;
-        else if (a.p.reduction == SKYB200_REDUCE_SEQUENCE_MEAN)
-            cx.w_scale = inv_row / Bf;
-        else if (a.p.reduction == SKYB200_REDUCE_SUM)
-            cx.w_scale = 1.f;
-        else
-            cx.w_scale = 1.f / (a.p.max_seq_len * Bf);
-        cx.kl_scale = inv_row / Bf;
-        cx.kl_grad_scale = a.p.kl_has_grad ? a.p.kl_loss_coef * cx.kl_scale : 0.f;
+        const float rs = __ldcg(&a.ws.row_scale[d.row]);  // 1 / max(row mask sum, 1) / B
+        if (reduction == SKYB200_REDUCE_SEQUENCE_MEAN) cx.w_scale = rs;
+        cx.kl_scale = rs;
+        cx.kl_grad_scale = a.p.kl_has_grad ? a.p.kl_loss_coef * rs : 0.f;
         if (gspo) {
-            cx.seq_ratio = expf(fminf(d.row_lw, 10.f));
-            cx.seq_pass = (d.row_lw <= 10.f) ? 1.f : 0.f;
+            const float lw = __ldcg(&a.ws.row_lw[d.row]);
+            cx.seq_ratio = expf(fminf(lw, 10.f));
+            cx.seq_pass = (lw <= 10.f) ? 1.f : 0.f;
         }
         float g[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             g[u] = 0.f;
-            if (d.ok >> u & 1u) {
-                g[u] = loss_token<kType, kBase, kKl>(cx, acc, d.lp[u], d.olp[u], d.adv[u], d.m[u], d.bs[u], d.ti[u], d.cm[u]);
+            if (kVec || (d.ok >> u & 1u)) {  // the 128-bit path handles whole float4s: ok is all or nothing
+                g[u] = loss_token<kType, kBase, kKl>(cx, acc, d.lp[u], d.olp[u], d.adv[u], d.m[u], d.bs[u],
+                                                     kExtra ? d.ti[u] : 1.f, kExtra ? d.cm[u] : -1.f);
                 if (a.ent) acc.s_ent = fmaf(d.en[u], d.m[u], acc.s_ent);
             }
         }
@@ -321,11 +333,12 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) loss_main_kernel(Los
     const unsigned tiles_per_row = static_cast<unsigned>((A + kMainTile - 1) / kMainTile);
     const unsigned step_rows = gridDim.x / tiles_per_row, step_tiles = gridDim.x % tiles_per_row;
     unsigned row = blockIdx.x / tiles_per_row, tir = blockIdx.x % tiles_per_row;
+    bool waited = false;
     while (row < static_cast<unsigned>(a.B)) {
         TileIn d[kInFlight];
 #pragma unroll
         for (int u = 0; u < kInFlight; ++u) {
-            tile_load<kVec>(a, static_cast<int>(row), static_cast<int>(tir), row < static_cast<unsigned>(a.B), gspo, d[u]);
+            tile_load<kVec, kExtra>(a, static_cast<int>(row), static_cast<int>(tir), row < static_cast<unsigned>(a.B), d[u]);
             row += step_rows;
             tir += step_tiles;
             if (tir >= tiles_per_row) {
@@ -333,9 +346,14 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) loss_main_kernel(Los
                 ++row;
             }
         }
+        if (!waited) {  // block-uniform
+            after_prepass();
+            waited = true;
+        }
 #pragma unroll
         for (int u = 0; u < kInFlight; ++u) consume(d[u]);
     }
+    if (!waited) after_prepass();
     float s_loss = acc.s_loss, s_clip = acc.s_clip, s_kl = acc.s_kl, s_ent = acc.s_ent, s_ratio = acc.s_ratio;
     float r_max = acc.r_max, r_min = acc.r_min;
 
@@ -860,11 +878,12 @@ extern "C" int skyb200_policy_loss(const float* log_probs, const float* old_log_
     // 256-byte align the workspace base
     char* wbase = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     loss_ws_layout(B, A, &ws, wbase);
-    SKYB200_CUDA_CHECK(cudaMemsetAsync(ws.counters, 0, 16, stream));
+    // no memset node and no global counter in the pre-pass: it writes the per-row mask sums / normalisers and clears
+    // the token pass's ticket; the token pass folds the global mask sum from the row sums itself
     const int need_lw = params->loss_type == SKYB200_LOSS_GSPO;
     loss_rowstats_kernel<<<(unsigned)B, kLossThreads, 0, stream>>>(log_probs, old_log_probs, loss_mask, ws.row_msum,
-                                                                   ws.row_lw, ws.total_msum, ws.counters, (int)B, A,
-                                                                   need_lw);
+                                                                   ws.row_lw, nullptr, ws.counters, (int)B, A,
+                                                                   need_lw, nullptr, ws.row_scale, ws.counters + 1);
     int rc = check_launch("loss_rowstats_kernel");
     if (rc) return rc;
     if (clip_mask != nullptr) {  // sum(clip_mask) -> total_msum[1]
@@ -895,14 +914,20 @@ extern "C" int skyb200_policy_loss(const float* log_probs, const float* old_log_
              al16(base_log_probs) && al16(entropy) && al16(d_log_probs) && al16(d_entropy) && al16(tis) &&
              al16(clip_mask);
     const int64_t tiles = ((A + kLossThreads * 4 - 1) / (kLossThreads * 4)) * B;
+    // 128-bit path: 3 blocks per SM with two tiles (2 x 5 x 16 B per thread) in flight; scalar path: 4 blocks, one tile
+    const int per_sm = a.vec4 ? 3 : 4;
     const unsigned grid = (unsigned)std::max<int64_t>(
-        1, std::min<int64_t>(tiles, std::min<int64_t>((int64_t)num_sms() * 4, (int64_t)kMaxMainGrid)));
+        1, std::min<int64_t>(tiles, std::min<int64_t>((int64_t)num_sms() * per_sm, (int64_t)kMaxMainGrid)));
     // instantiated per loss type x {no base, base with the reference's value-only k3 KL term, base (general)} x
-    // {128-bit path, scalar path}: the pass is instruction-bound, dead branches cost throughput
+    // {128-bit path without / with the off-policy-correction arrays, scalar path}: dead branches cost throughput
     const bool k3_value_only = (params->kl_type == SKYB200_KL_K3) && (params->kl_has_grad == 0);
-#define SKYB200_LOSS_LAUNCH(T, BASE, KL)                                                                           \
-    (a.vec4 ? launch_pdl(loss_main_kernel<1, 4, T, BASE, KL, true>, dim3(grid), dim3(kLossThreads), 0, stream, a)  \
-            : launch_pdl(loss_main_kernel<1, 4, T, BASE, KL, false>, dim3(grid), dim3(kLossThreads), 0, stream, a))
+    const bool extra = (tis != nullptr) || (clip_mask != nullptr);
+#define SKYB200_LOSS_LAUNCH(T, BASE, KL)                                                                                \
+    (a.vec4 ? (extra ? launch_pdl(loss_main_kernel<2, 3, T, BASE, KL, true, true>, dim3(grid), dim3(kLossThreads), 0,   \
+                                  stream, a)                                                                            \
+                     : launch_pdl(loss_main_kernel<2, 3, T, BASE, KL, true, false>, dim3(grid), dim3(kLossThreads), 0,  \
+                                  stream, a))                                                                           \
+            : launch_pdl(loss_main_kernel<1, 4, T, BASE, KL, false, true>, dim3(grid), dim3(kLossThreads), 0, stream, a))
 #define SKYB200_LOSS_CASE(T)                                                            \
     case T:                                                                             \
         if (!base_log_probs)                                                            \

@@ -157,6 +157,23 @@ __device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* 
                  : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
                  : "memory");
 }
+// Both with an L2 eviction policy for the global side (output that this kernel never reads back: evict_first keeps
+// it from displacing the operand panels the other CTAs are about to reuse).
+__device__ __forceinline__ void tma_store_2d_hint(const void* desc, const void* smem_src, int32_t crd0, int32_t crd1,
+                                                  uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d_hint(const void* desc, const void* smem_src, int32_t crd0,
+                                                       int32_t crd1, uint64_t policy) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+        :
+        : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still READ their shared source (the buffer may be rewritten)
 template <int N>

@@ -107,6 +107,37 @@ def test_group_random_vs_oracle(B, A, G):
         assert torch.equal(got.cpu() == 0, want == 0)
 
 
+@pytest.mark.parametrize("B,A,G", [(64, 1024, 8), (48, 1000, 16), (6, 4100, 1), (16, 8192, 8), (8, 32768, 8),
+                                   (32, 12000, 4), (10, 16384, 2), (32, 16384, 16), (21, 8, 7)])
+@pytest.mark.parametrize("int_mask", [False, True])
+def test_group_cluster_form_vs_general_form_and_oracle(B, A, G, int_mask):
+    """Uniform prompt groups take the one-launch thread-block-cluster kernel; the same batch through the general
+    two-kernel form and the oracle must agree (zero pattern bit-exact)."""
+    g = torch.Generator().manual_seed(B * 31 + A + G)
+    uids = np.array([f"uid-{i // G}" for i in range(B)])[torch.randperm(B, generator=g).numpy()]
+    lens = torch.randint(1, A + 1, (B,), generator=g)
+    mask = (torch.arange(A)[None] < lens[:, None])
+    mask = mask.long() if int_mask else mask.float()
+    r = 0.01 * torch.randn(B, A, generator=g)
+    r[torch.arange(B), lens - 1] += (torch.rand(B, generator=g) < 0.5).float()
+    for mode, fn, kw in ((0, O.grpo_advantage, {}), (1, O.grpo_advantage, {"norm_by_std": False}),
+                         (2, O.rloo_advantage, {})):
+        want, _ = fn(r, mask, uids, **kw)
+        one = advantages._group_advantage(r.to(DEV), mask.to(DEV), uids, mode, 1e-6 if mode < 2 else 0.0, one_launch=True)
+        two = advantages._group_advantage(r.to(DEV), mask.to(DEV), uids, mode, 1e-6 if mode < 2 else 0.0, one_launch=False)
+        assert_close(one, want, what=f"cluster form, mode {mode}")
+        assert_close(one, two, what=f"cluster vs general form, mode {mode}")
+        assert torch.equal(one.cpu() == 0, want == 0)
+
+
+def test_group_cluster_form_refuses_ragged_groups():
+    r, m = torch.zeros(3, 8, device=DEV), torch.ones(3, 8, device=DEV)
+    with pytest.raises(ValueError, match="uniform groups"):
+        advantages._group_advantage(r, m, ["a", "a", "b"], 0, 1e-6, one_launch=True)
+    with pytest.raises(ValueError, match="uniform groups"):  # A not a multiple of 4
+        advantages._group_advantage(r[:, :5].contiguous(), m[:, :5].contiguous(), ["a", "b", "c"], 0, 1e-6, one_launch=True)
+
+
 def test_kl_estimators_and_reward_penalty_match_reference_golden(golden_adv):
     g = golden_adv
     lp, base, fm, r = _t(g["lp"]), _t(g["base"]), _t(g["mask_i64"]).float(), _t(g["rewards"])
