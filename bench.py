@@ -401,19 +401,37 @@ def run_ours(args, w):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     phase_ms = {"_ev": []}
 
+    # N > 1: how the lm_head weight gradient is reduced over the data-parallel ranks.
+    #   "scatter"   = fused into the d_weight GEMM: every epilogue piece is averaged straight into its owner's
+    #                 [V / world, H] shard over NVLink peer memory (FSDP's reduce-scatter semantics), no collective
+    #                 after the step; the packed-stats all-reduce doubles as the "all ranks done" barrier;
+    #   "allreduce" = local fp32 [V, H] gradient, then NCCL all-reduce (mean) after the step.
+    scatter = None
+    if world > 1 and args.dw_reduce == "scatter":
+        scatter = sdist.DWeightScatter(V, H, remote=os.environ.get("SKYB200_DWS_REMOTE", "tma"))
+
     def device_step(record):
         """Inputs already resident in HBM."""
         e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        if scatter is not None:
+            scatter.begin()
         e0.record()
         adv, _ = skyrl_b200.compute_grpo_outcome_advantage(db["rewards"], db["mask"], db["uids"])
         e1.record()
-        out = skyrl_b200.policy_update_step(db["hidden"], weight, db["labels"], db["olp"], adv, cfg,
-                                            loss_mask=db["mask"], base_log_probs=db["base"], temperature=TEMPERATURE,
-                                            d_weight=d_weight, accumulate_d_weight=False, sync=False, timing=record)
+        if scatter is not None:
+            out = skyrl_b200.policy_update_step(db["hidden"], weight, db["labels"], db["olp"], adv, cfg,
+                                                loss_mask=db["mask"], base_log_probs=db["base"],
+                                                temperature=TEMPERATURE, dw_scatter=scatter, sync=False, timing=record)
+        else:
+            out = skyrl_b200.policy_update_step(db["hidden"], weight, db["labels"], db["olp"], adv, cfg,
+                                                loss_mask=db["mask"], base_log_probs=db["base"],
+                                                temperature=TEMPERATURE, d_weight=d_weight, accumulate_d_weight=False,
+                                                sync=False, timing=record)
         e2.record()
         if world > 1:
-            sdist.all_reduce_packed_stats(out.stats)
-            sdist.all_reduce_d_weight(out.d_weight)
+            sdist.all_reduce_packed_stats(out.stats)  # (scatter mode: also the barrier that completes the shards)
+            if scatter is None:
+                sdist.all_reduce_d_weight(out.d_weight)
         e3.record()
         if record:
             phase_ms["_ev"].append((e0, e1, e2, e3))
@@ -425,13 +443,17 @@ def run_ours(args, w):
         # the asynchronous copy) and are streamed in chunk by chunk inside the step (skyb200_policy_step_from_host),
         # overlapping the GEMMs
         d = {k: (v.to(dev, non_blocking=True) if (torch.is_tensor(v) and k != "hidden") else v) for k, v in hb.items()}
+        if scatter is not None:
+            scatter.begin()
         adv, _ = skyrl_b200.compute_grpo_outcome_advantage(d["rewards"], d["mask"], d["uids"])
+        kw = dict(dw_scatter=scatter) if scatter is not None else dict(d_weight=d_weight, accumulate_d_weight=False)
         out = skyrl_b200.policy_update_step(d["hidden"], weight, d["labels"], d["olp"], adv, cfg,
                                             loss_mask=d["mask"], base_log_probs=d["base"], temperature=TEMPERATURE,
-                                            d_weight=d_weight, accumulate_d_weight=False, sync=(world == 1))
+                                            sync=(world == 1), **kw)
         if world > 1:
             st = sdist.all_reduce_packed_stats(out.stats)
-            sdist.all_reduce_d_weight(out.d_weight)
+            if scatter is None:
+                sdist.all_reduce_d_weight(out.d_weight)
             return st.tolist()
         return out.status
 
@@ -480,7 +502,19 @@ def run_ours(args, w):
     # ---- multi-GPU evidence: N-GPU numerics + what the collectives cost with the rank skew taken out
     dp = None
     if world > 1:
-        out = device_step(False)  # d_weight now holds the all-reduced (mean) gradient of one step
+        out = device_step(False)  # d_weight (or the shards) now hold the rank-averaged gradient of one step
+        fused_err = None
+        if scatter is not None:
+            # fused reduce-scatter vs NCCL's mean reduce-scatter of the local gradients (computed below)
+            fused_shard = scatter.finish().clone()
+            adv, _ = skyrl_b200.compute_grpo_outcome_advantage(db["rewards"], db["mask"], db["uids"])
+            skyrl_b200.policy_update_step(db["hidden"], weight, db["labels"], db["olp"], adv, cfg, loss_mask=db["mask"],
+                                          base_log_probs=db["base"], temperature=TEMPERATURE, d_weight=d_weight,
+                                          accumulate_d_weight=False, sync=False)
+            want_shard, _ = sdist.reduce_scatter_d_weight(d_weight)
+            fused_err = float((fused_shard.double() - want_shard.double()).norm() / want_shard.double().norm())
+            del fused_shard, want_shard
+            sdist.all_reduce_d_weight(d_weight)  # continue the common check on the all-reduced local gradient
         red_sum = d_weight.double().sum()
         red_abs = d_weight.double().abs().sum()
         red_loss = sdist.all_reduce_packed_stats(out.stats)[skyrl_b200._lib.STAT_FINAL_LOSS].double()
@@ -526,7 +560,11 @@ def run_ours(args, w):
             "per_rank_compute_ms": [round(float(x), 1) for x in tall[:, 2]],
             "per_rank_comm_wait_ms_in_step": [round(float(x), 1) for x in tall[:, 3]],
         }
-        dp["ok"] = bool(dp["d_weight_checksum_rel_err"] < 1e-5 and dp["final_loss_rel_err"] < 1e-5)
+        dp["d_weight_reduction"] = ("fused into the d_weight GEMM epilogue: reduce-scatter over NVLink peer memory "
+                                    "(DWeightScatter)" if scatter is not None else "NCCL all-reduce (mean) after the step")
+        dp["fused_scatter_vs_nccl_reduce_scatter_rel_l2"] = fused_err
+        dp["ok"] = bool(dp["d_weight_checksum_rel_err"] < 1e-5 and dp["final_loss_rel_err"] < 1e-5
+                        and (fused_err is None or fused_err < 1e-5))
 
     # the library GEMM on the same shape and data, sustained (context for the power-capped regime)
     hid2d = db["hidden"].view(N, H)
@@ -636,7 +674,7 @@ def run_ours(args, w):
                            "log-probs stay on the device for the trunk backward"},
             "gpu_launches": launches_per_step * args.steps,
             "dp_check": dp,
-            "allreduce_exposed_ms": dp["allreduce_ms"] if dp else None,
+            "allreduce_exposed_ms": (0.0 if scatter is not None else dp["allreduce_ms"]) if dp else None,
             "clocks": clocks,
         }
         print(json.dumps(line))
@@ -652,6 +690,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-other", action="store_true", help="skip other_configs / ref_gpu_path (A/B runs, profiling)")
+    ap.add_argument("--dw-reduce", default="allreduce", choices=["allreduce", "scatter"],
+                    help="N > 1: NCCL all-reduce of the local d_weight after the step, or the reduce-scatter fused into "
+                         "the d_weight GEMM epilogue over NVLink peer memory")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

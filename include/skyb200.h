@@ -385,11 +385,31 @@ int skyb200_policy_step_plan(int64_t B, int64_t A, int64_t n_tokens, int64_t H, 
  *     mask and `clip_mask` [B, A] the mask before the correction, which the clip_ratio metric keeps
  *     (ppo_utils.py:570 vs :579-583).
  */
+/*
+ *   dw_scatter : fuse the data-parallel reduce-scatter of the lm_head weight gradient into the d_weight GEMM (what
+ *     the reference gets from FSDP after the backward: fsdp_strategy.py:151-153, 214-226 - fp32 reduce, gradients
+ *     averaged over the ranks, every rank keeps its own parameter shard).  shard[r] is rank r's [V / world, H] fp32
+ *     gradient shard AS MAPPED INTO THIS PROCESS (shard[rank] = the local buffer, the others peer memory opened with
+ *     skyb200_ipc_open); every accumulator piece is multiplied by `scale` (1 / world) and added into its owner's shard
+ *     by the GEMM epilogue - TMA reduce-add on a tensor map over the owner's shard, local or peer (NVLink carries the
+ *     reduction to the owner's L2).  The
+ *     `d_weight` argument of the step is then ignored (no [V, H] buffer exists) and nothing is ever overwritten: the
+ *     caller zeroes its shard, synchronises the ranks (so nobody adds into a shard before it is zeroed), runs the step
+ *     on every rank and synchronises again before it reads the shard.  V must be a multiple of 32 * world.
+ */
+typedef struct {
+    int32_t world; /* 2 .. 8 */
+    int32_t rank;
+    float* shard[8];
+    float scale;
+    int32_t remote_red; /* 0: peers' pieces through TMA reduce-add on the peer-mapped shard; 1: fp32 vector reductions */
+} skyb200_dw_scatter;
 typedef struct {
     const float* tis;
     const float* clip_mask;
     int64_t timing;      /* != 0: bracket every GEMM launch with CUDA timing events (see skyb200_policy_step_timing) */
-    int64_t reserved[5]; /* must be zero */
+    const skyb200_dw_scatter* dw_scatter; /* NULL: plain local d_weight */
+    int64_t reserved[4]; /* must be zero */
 } skyb200_step_opts;
 int skyb200_policy_step(const void* hidden, const void* weight, const int64_t* labels, const float* old_log_probs,
                         const float* advantages, const float* loss_mask, const float* base_log_probs,
@@ -405,6 +425,17 @@ int skyb200_policy_step(const void* hidden, const void* weight, const int64_t* l
  * Synchronises on the last recorded event and clears the record.  Per device (call it on the step's device).
  */
 int skyb200_policy_step_timing(double* out);
+
+/*
+ * Peer mapping of a device buffer between the processes of one node (one process per GPU): the owner exports a handle
+ * for a buffer that lies inside a cudaMalloc allocation (a torch tensor does), the other ranks open it.
+ * skyb200_ipc_export: handle_out = 64 bytes (cudaIpcMemHandle_t of the allocation), *offset_out = byte offset of `ptr`
+ * inside it.  skyb200_ipc_open: maps the allocation into this process with peer access enabled and returns
+ * base + offset; skyb200_ipc_close takes the pointer skyb200_ipc_open returned.
+ */
+int skyb200_ipc_export(const void* ptr, void* handle_out, int64_t* offset_out);
+int skyb200_ipc_open(const void* handle, int64_t offset, void** ptr_out);
+int skyb200_ipc_close(void* ptr);
 
 /*
  * Same step with the hidden states resident in HOST memory (pinned for an asynchronous copy): hidden_host [N, H]

@@ -58,9 +58,16 @@ class OpcParams(C.Structure):
     ]
 
 
+class DwScatter(C.Structure):
+    """skyb200_dw_scatter: peer-mapped gradient shards of the fused d_weight GEMM + reduce-scatter."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("shard", C.c_void_p * 8), ("scale", C.c_float),
+                ("remote_red", C.c_int32)]
+
+
 class StepOpts(C.Structure):
-    """skyb200_step_opts: optional inputs of the fused step (off-policy correction)."""
-    _fields_ = [("tis", C.c_void_p), ("clip_mask", C.c_void_p), ("timing", C.c_int64), ("reserved", C.c_int64 * 5)]
+    """skyb200_step_opts: optional inputs of the fused step (off-policy correction, timing, fused reduce-scatter)."""
+    _fields_ = [("tis", C.c_void_p), ("clip_mask", C.c_void_p), ("timing", C.c_int64),
+                ("dw_scatter", C.POINTER(DwScatter)), ("reserved", C.c_int64 * 4)]
 
 
 OPC_NMETRICS = 16
@@ -136,6 +143,9 @@ SIGNATURES = {
                                                 _I64, _I64, _I64, _I64, _P, _I64, _F, C.POINTER(LossParams),
                                                 C.POINTER(StepOpts), _P]),
     "skyb200_policy_step_timing": (C.c_int, [C.POINTER(C.c_double)]),
+    "skyb200_ipc_export": (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
+    "skyb200_ipc_open": (C.c_int, [_P, _I64, C.POINTER(C.c_void_p)]),
+    "skyb200_ipc_close": (C.c_int, [_P]),
     "skyb200_logits_logprob_entropy": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _I64, _I64, _P]),
     "skyb200_logits_backward": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P, _I64, _I64, _P]),
     "skyb200_gemm_selftest": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P]),

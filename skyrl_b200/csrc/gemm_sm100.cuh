@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
                   int N, int K, int group_m, int tile_order, uint64_t hint_a, uint64_t hint_b,
                   const __grid_constant__ typename Epi::Params ep, GemmDebug* dbg, unsigned int* sync_ctr,
-                  int sync_every, GemmMaps maps) {
+                  int sync_every, int sync_slack, GemmMaps maps) {
     using S = GemmSmem<kCtas, BN, kStages, Epi::kSmemBytes>;
     constexpr int TILE_M = kBM * kCtas;
     constexpr uint32_t kTmemCols = 2 * BN;
@@ -191,7 +191,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         {
             const bool issuer = ptx::elect_one();
             uint32_t stage = 0, phase = 0;
-            uint32_t sync_step = 0, sync_epoch = 0;
+            uint32_t sync_step = 0, sync_epoch = 0, pend_epoch = 0, pend_active = 0;
+            bool pending = false;
             for (int t = cluster_id; t < total_tiles; t += num_clusters) {
                 const TileCoord tc = decode_tile(t, num_m_tiles, num_n_tiles, group_m, tile_order);
                 const int m_tile = maps.m_map ? maps.m_map[tc.m_tile] : tc.m_tile;
@@ -208,20 +209,31 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         kidx = __shfl_sync(0xffffffffu, k_window, kb & 31);
                     }
                     // Best-effort lockstep: CTAs that share operand panels through L2 re-align every `sync_every`
-                    // K blocks (bounded wait: a straggler can never dead-lock the others).
-                    if (sync_ctr != nullptr && sync_step++ % static_cast<uint32_t>(sync_every) == 0) {
-                        if (issuer) {
-                            unsigned int* c = sync_ctr + (sync_epoch & 8191u);
-                            atomicAdd(c, 1u);
-                            for (int spin = 0; spin < 400; ++spin) {
-                                unsigned int v;
-                                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c));
-                                if (v >= active_ctas) break;
-                                __nanosleep(50);
-                            }
+                    // K blocks (bounded wait: a straggler can never dead-lock the others).  Split phase: a CTA
+                    // ARRIVES at the epoch counter at the period boundary but only WAITS for the others
+                    // `sync_slack` K blocks later - the drift the CTAs accumulate inside a period is absorbed while
+                    // the producer keeps the ring full, instead of starving the tensor pipe at the barrier.
+                    if (sync_ctr != nullptr) {
+                        const uint32_t ph = sync_step++ % static_cast<uint32_t>(sync_every);
+                        if (ph == 0) {
+                            if (issuer) atomicAdd(sync_ctr + (sync_epoch & 8191u), 1u);
+                            pend_epoch = sync_epoch++;
+                            pend_active = active_ctas;
+                            pending = true;
                         }
-                        ++sync_epoch;
-                        __syncwarp();
+                        if (pending && ph == static_cast<uint32_t>(sync_slack)) {
+                            if (issuer) {
+                                unsigned int* c = sync_ctr + (pend_epoch & 8191u);
+                                for (int spin = 0; spin < 400; ++spin) {
+                                    unsigned int v;
+                                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c));
+                                    if (v >= pend_active) break;
+                                    __nanosleep(50);
+                                }
+                            }
+                            pending = false;
+                            __syncwarp();
+                        }
                     }
                     bounded_wait(&empty_bar[stage], phase ^ 1u, dbg, 0, 0, stage, t);
                     if (issuer) {
@@ -490,6 +502,103 @@ struct EpiTmaF32 {
                 else
                     ptx::tma_store_2d_hint(&p.tmap_out, stage + (c & 1) * 4096, col0, row, p.hint);
                 ptx::bulk_commit_group();
+            }
+        }
+    }
+};
+
+// d_weight GEMM fused with the data-parallel REDUCE-SCATTER of the gradient (FSDP semantics: rank r keeps rows
+// [r * rows_per_rank, (r + 1) * rows_per_rank) of the rank-averaged [M, N] fp32 gradient).  Every accumulator piece
+// (32 rows x 32 columns, staged in shared memory exactly as in EpiTmaF32) is scaled by 1 / world and ADDED straight
+// into its owner's shard while the tensor cores work on the next tile, through TMA reduce-add (UTMAREDG) on a tensor
+// map over the owner's shard - the rank's own buffer or a peer-mapped one: NVLink carries the reduction to the owner's
+// L2, which performs the add.  (remote_red = 1 sends the peers' pieces as 16-byte fp32 vector reductions,
+// red.relaxed.sys.global.add.v4.f32, instead - a warp instruction covers 4 rows x 128 contiguous bytes; measured 14 %
+// slower per launch at 2 ranks, kept as the fallback.)  No full-size local gradient buffer exists and no
+// collective follows the step: the transfer is spread over every chunk's GEMM (1.9 GB per 9472-token chunk at 8 ranks,
+// ~8 % of one NVLink direction), the only cross-rank synchronisation is the caller's zero / done barriers.
+// The order in which the ranks' contributions reach an element is not fixed: results are reproducible to fp32
+// rounding, not bit for bit (callers that need that use the local buffer + NCCL).
+struct EpiF32Scatter {
+    static constexpr uint32_t kSmemBytes = 4 * 2 * 4096;
+    static constexpr int kMaxWorld = 8;
+    __device__ static void finish() {
+        if ((threadIdx.x & 31) == 0) ptx::bulk_wait_group<0>();
+    }
+    struct Params {
+        CUtensorMap tmap[kMaxWorld];  // tmap[r]: rank r's shard, fp32 [rows_per_rank, N], box 32 x 32, SWIZZLE_128B
+        float* shard[kMaxWorld];  // shard[r] = rank r's shard as mapped into this process (peer memory for r != rank)
+        int remote_red;           // 0: peers' pieces through TMA reduce-add as well; 1: red.v4.f32 from the threads
+        int64_t ld;              // row pitch of a shard in elements
+        int rows_per_rank;       // multiple of 32: a warp's 32 rows never straddle two owners
+        int rank, world;
+        float scale;
+        uint64_t hint;
+    };
+    template <int BN>
+    __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N, uint8_t* stage) {
+        const int n0 = n_tile * BN;
+        const int lane = threadIdx.x & 31;
+        const int row0 = row - lane;  // the warp's first row (a multiple of 32)
+        const int owner = row0 / p.rows_per_rank;
+        const int lrow0 = row0 - owner * p.rows_per_rank;  // first row inside the owner's shard
+        const bool local = (owner == p.rank) || (p.remote_red == 0);  // "local" = leaves through TMA reduce-add
+        const uint32_t sbase = ptx::smem_u32(stage);
+        const uint32_t srow = sbase + static_cast<uint32_t>(lane) * 128u;
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        float* const dst = (row0 < M && owner < p.world) ? p.shard[owner] : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            const int col0 = n0 + c * 32;
+            if (col0 >= N) break;  // uniform across the whole warp
+            uint32_t v[32];
+            __syncwarp();
+            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            if (lane == 0) {  // the buffer about to be rewritten must have been read by its previous bulk operation
+                if (c == 0)
+                    ptx::bulk_wait_group_read<0>();
+                else
+                    ptx::bulk_wait_group_read<1>();
+            }
+            __syncwarp();
+            const uint32_t boff = static_cast<uint32_t>(c & 1) * 4096u;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {  // 16-byte chunk j of the 128-byte row goes to slot j ^ (row & 7)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + boff + ((j ^ sw) << 4)),
+                             "f"(__uint_as_float(v[4 * j]) * p.scale), "f"(__uint_as_float(v[4 * j + 1]) * p.scale),
+                             "f"(__uint_as_float(v[4 * j + 2]) * p.scale), "f"(__uint_as_float(v[4 * j + 3]) * p.scale)
+                             : "memory");
+            }
+            if (local) {
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && dst != nullptr) {
+                    ptx::tma_reduce_add_2d_hint(&p.tmap[owner], stage + (c & 1) * 4096, col0, lrow0, p.hint);
+                    ptx::bulk_commit_group();
+                }
+            } else {
+                __syncwarp();
+                if (dst != nullptr) {
+                    const int k = lane & 7;          // 16-byte chunk inside the 128-byte row
+                    const int col = col0 + 4 * k;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int r = 4 * j + (lane >> 3);
+                        float4 q;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                                     : "r"(sbase + boff + static_cast<uint32_t>(r) * 128u +
+                                           ((static_cast<uint32_t>(k) ^ static_cast<uint32_t>(r & 7)) << 4))
+                                     : "memory");
+                        if (row0 + r < M && col < N) {
+                            float* g = dst + static_cast<int64_t>(lrow0 + r) * p.ld + col;
+                            asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(q.x),
+                                         "f"(q.y), "f"(q.z), "f"(q.w)
+                                         : "memory");
+                        }
+                    }
+                }
             }
         }
     }

@@ -106,6 +106,10 @@ static unsigned int* lockstep_counters() {
     return per_dev[dev];
 }
 
+static int env_int0(const char* name, int dflt);
+// split-phase lockstep: K blocks between a CTA's arrival at the epoch counter and its wait for the others
+static int lock_slack() { static int v = env_int0("SKYB200_LOCK_SLACK", 0); return v < 0 ? 0 : v; }
+
 // A: K-major -> [M, K] with pitch lda; MN-major -> [K, M] with pitch lda.  Same for B with N.
 template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
 static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int group_m,
@@ -161,7 +165,8 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
     GemmMaps maps = {nullptr, nullptr, nullptr, nullptr};
     if (maps_in != nullptr) maps = *maps_in;
     SKYB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group_m, tile_order, hint_a, hint_b, ep, dbg,
-                                          sync_ctr, sync_every > 0 ? sync_every : 1, maps));
+                                          sync_ctr, sync_every > 0 ? sync_every : 1,
+                                          std::min(lock_slack(), std::max(sync_every, 1) - 1), maps));
     return SKYB200_OK;
 }
 
@@ -207,8 +212,8 @@ static uint64_t hint_of(const char* name, int dflt) {
 static uint64_t hint_fwd_a() { static uint64_t v = hint_of("SKYB200_HINT_FWD_A", 3); return v; }
 static uint64_t hint_dw_b() { static uint64_t v = hint_of("SKYB200_HINT_DW_B", 3); return v; }
 // d_weight GEMM: the d(logits) panels (A) and the fp32 output traffic (C) are each touched once per launch
-static uint64_t hint_dw_a() { static uint64_t v = hint_of("SKYB200_HINT_DW_A", 1); return v; }
-static uint64_t hint_dw_c() { static uint64_t v = hint_of("SKYB200_HINT_DW_C", 1); return v; }
+static uint64_t hint_dw_a() { static uint64_t v = hint_of("SKYB200_HINT_DW_A", 2); return v; }
+static uint64_t hint_dw_c() { static uint64_t v = hint_of("SKYB200_HINT_DW_C", 2); return v; }
 static uint64_t hint_dh_a() { static uint64_t v = hint_of("SKYB200_HINT_DH_A", 1); return v; }
 static uint64_t hint_dh_b() { static uint64_t v = hint_of("SKYB200_HINT_DH_B", 1); return v; }
 static int env_int0(const char* name, int dflt) {
@@ -218,7 +223,22 @@ static int env_int0(const char* name, int dflt) {
 static int dh_lockstep() { static int v = env_int0("SKYB200_DH_LOCKSTEP", 128); return v; }
 static int fwd_lockstep() { static int v = env_int0("SKYB200_FWD_LOCKSTEP", 0); return v; }
 static int dw_lockstep() { static int v = env_int0("SKYB200_DW_LOCKSTEP", 128); return v; }
-static int dw_group_n() { static int v = env_int("SKYB200_DW_GROUP_N", 14); return v; }
+// d_weight tile order (N-fastest inside groups of `group_n` N tiles): the B panels of a group - group_n x [rows, 256]
+// bf16 of the hidden chunk - must STAY in L2 while the d(logits) panels stream past them once per group.  The whole
+// 7B-head chunk (14 panels, 68 MB) does not: ncu (profiles/r02h) shows it re-read from DRAM once per round of M tiles
+// (13.0 GB read per launch, tensor pipe 80 % active).  Groups are sized to <= 36 MB of B panels and balanced: two
+// groups of 7 for the 7B head (A is then read twice, 5.8 GB, but the 7.9 GB of hidden re-reads are gone); together
+// with evict-first on the streamed A panels and the fp32 output traffic: 8.37 -> 8.08 ms per launch sustained
+// (profiles/r02i_bwd_ab.jsonl).  SKYB200_DW_GROUP_N overrides.
+static int dw_group_n(int64_t rows, int64_t H) {
+    static int forced = env_int0("SKYB200_DW_GROUP_N", 0);
+    if (forced > 0) return forced;
+    const int64_t n_tiles = (H + kHeadBN - 1) / kHeadBN;
+    const int64_t panel = std::max<int64_t>(rows, 1) * kHeadBN * 2;
+    const int64_t gmax = std::max<int64_t>(1, (36ll << 20) / panel);
+    const int64_t groups = (n_tiles + gmax - 1) / gmax;
+    return (int)((n_tiles + groups - 1) / groups);
+}
 // skip all-zero d(logits) rows (masked tokens) in the backward GEMMs of the fused step (0 disables)
 static int skip_zero_rows() { static int v = env_int0("SKYB200_SKIP_ZERO_ROWS", 1); return v; }
 // TIMING EXPERIMENTS ONLY (results are wrong with any bit set): bound what a change could gain before building it.
@@ -766,7 +786,7 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
             ew.accumulate = acc_w ? 1 : 0;
             ew.hint = hint_dw_c();
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
-                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, hint_dw_a(), hint_dw_b(),
+                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H), ew, stream, 1, hint_dw_a(), hint_dw_b(),
                 dw_lockstep(), skip ? &k_maps : nullptr);
             if (rc) return rc;
         }
@@ -937,7 +957,17 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
                     "max_seq_len must be provided for seq_mean_token_sum_norm");
     const int64_t N = cu_seqlens ? n_tokens : B * A;
     SKYB200_REQUIRE(N < (1ll << 31) && V < (1ll << 31) && H < (1ll << 31), "dimension too large");
-    const bool need_grad = (d_hidden != nullptr) || (d_weight != nullptr);
+    const skyb200_dw_scatter* scatter = opts ? opts->dw_scatter : nullptr;
+    if (scatter != nullptr) {
+        SKYB200_REQUIRE(scatter->world >= 2 && scatter->world <= EpiF32Scatter::kMaxWorld && scatter->rank >= 0 &&
+                            scatter->rank < scatter->world,
+                        "dw_scatter: world must be 2..8 and 0 <= rank < world");
+        SKYB200_REQUIRE(V % (32 * scatter->world) == 0, "dw_scatter: V must be a multiple of 32 * world");
+        for (int r = 0; r < scatter->world; ++r)
+            SKYB200_REQUIRE(scatter->shard[r] != nullptr && (reinterpret_cast<uintptr_t>(scatter->shard[r]) & 15u) == 0,
+                            "dw_scatter: every shard pointer must be set and 16-byte aligned");
+    }
+    const bool need_grad = (d_hidden != nullptr) || (d_weight != nullptr) || (scatter != nullptr);
     const StepPlan plan = plan_step(B, A, N, H, V, params->loss_type, need_grad);
     if (workspace_bytes < plan.total) return fail(SKYB200_EWORKSPACE, "policy_step workspace too small");
     int rc = skyb200_check_device();
@@ -1096,7 +1126,31 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             if (r) return r;
             if ((r = t_end(1))) return r;
         }
-        if (d_weight != nullptr && !(whatif() & 16)) {
+        if (scatter != nullptr && !(whatif() & 16)) {
+            // d_weight GEMM + reduce-scatter: every piece goes straight to its owner's shard (see EpiF32Scatter)
+            EpiF32Scatter::Params es;
+            const int64_t rpr = V / scatter->world;
+            int r = 0;
+            for (int q = 0; q < EpiF32Scatter::kMaxWorld; ++q) {
+                es.shard[q] = q < scatter->world ? scatter->shard[q] : nullptr;
+                // (slots beyond world are never indexed; give them a valid descriptor anyway)
+                float* base = es.shard[q] ? es.shard[q] : scatter->shard[scatter->rank];
+                if ((r = make_tmap_f32_out(&es.tmap[q], base, (uint64_t)H, (uint64_t)rpr, (uint64_t)H))) return r;
+            }
+            es.remote_red = scatter->remote_red;
+            es.ld = H;
+            es.rows_per_rank = (int)rpr;
+            es.rank = scatter->rank;
+            es.world = scatter->world;
+            es.scale = scatter->scale;
+            es.hint = hint_dw_c();
+            if ((r = t_begin())) return r;
+            r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiF32Scatter>(
+                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H), es, stream, 1, hint_dw_a(),
+                hint_dw_b(), dw_lockstep(), skip ? &k_maps : nullptr);
+            if (r) return r;
+            if ((r = t_end(2))) return r;
+        } else if (d_weight != nullptr && !(whatif() & 16)) {
             EpiTmaF32::Params ew;
             int r = make_tmap_f32_out(&ew.tmap_out, d_weight, (uint64_t)H, (uint64_t)V, (uint64_t)H);
             if (r) return r;
@@ -1105,7 +1159,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             ew.hint = hint_dw_c();
             if ((r = t_begin())) return r;
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
-                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(), ew, stream, 1, hint_dw_a(),
+                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H), ew, stream, 1, hint_dw_a(),
                 hint_dw_b(), dw_lockstep(), (skip && ew.accumulate) ? &k_maps : nullptr);
             if (r) return r;
             if ((r = t_end(2))) return r;
@@ -1365,7 +1419,7 @@ extern "C" int skyb200_head_gemm_bench(int32_t which, const void* hidden, const 
         ew.accumulate = accumulate;
         ew.hint = hint_dw_c();
         return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
-            S, ldS, hidden, H, (int)V, (int)H, (int)rows, dw_group_n(), ew, stream, 1, hint_dw_a(), hint_dw_b(),
+            S, ldS, hidden, H, (int)V, (int)H, (int)rows, dw_group_n(rows, H), ew, stream, 1, hint_dw_a(), hint_dw_b(),
             dw_lockstep(), nullptr);
     }
     return fail(SKYB200_EINVAL, "which must be 1 (d_hidden) or 2 (d_weight)");
@@ -1374,4 +1428,61 @@ extern "C" int skyb200_head_gemm_bench(int32_t which, const void* hidden, const 
 extern "C" const uint32_t* skyb200_gemm_debug_record(void) {
     debug_record_dev();
     return reinterpret_cast<const uint32_t*>(g_dbg_host);
+}
+
+// ------------------------------------------------------------------------------------------ peer mapping (CUDA IPC)
+extern "C" int skyb200_ipc_export(const void* ptr, void* handle_out, int64_t* offset_out) {
+    SKYB200_REQUIRE(ptr && handle_out && offset_out, "null pointer");
+    int rc = skyb200_check_device();
+    if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static RangeFn range_fn = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) != cudaSuccess) fn = nullptr;
+        return reinterpret_cast<RangeFn>(fn);
+    }();
+    if (range_fn == nullptr) return fail(SKYB200_ECUDA, "cuMemGetAddressRange entry point not available");
+    const CUresult cr = range_fn(&base, &size, reinterpret_cast<CUdeviceptr>(ptr));
+    if (cr != CUDA_SUCCESS) return fail(SKYB200_ECUDA, "cuMemGetAddressRange failed with CUresult %d", (int)cr);
+    cudaIpcMemHandle_t h;
+    SKYB200_CUDA_CHECK(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+    memcpy(handle_out, &h, sizeof(h));
+    *offset_out = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(ptr) - base);
+    return SKYB200_OK;
+}
+
+namespace {
+std::mutex g_ipc_mu;
+std::vector<std::pair<void*, void*>> g_ipc_open;  // (pointer handed out, base returned by cudaIpcOpenMemHandle)
+}  // namespace
+
+extern "C" int skyb200_ipc_open(const void* handle, int64_t offset, void** ptr_out) {
+    SKYB200_REQUIRE(handle && ptr_out && offset >= 0, "bad arguments");
+    int rc = skyb200_check_device();
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* base = nullptr;
+    SKYB200_CUDA_CHECK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr_out = static_cast<char*>(base) + offset;
+    std::lock_guard<std::mutex> lk(g_ipc_mu);
+    g_ipc_open.emplace_back(*ptr_out, base);
+    return SKYB200_OK;
+}
+
+extern "C" int skyb200_ipc_close(void* ptr) {
+    std::lock_guard<std::mutex> lk(g_ipc_mu);
+    for (size_t i = 0; i < g_ipc_open.size(); ++i) {
+        if (g_ipc_open[i].first == ptr) {
+            void* base = g_ipc_open[i].second;
+            g_ipc_open.erase(g_ipc_open.begin() + i);
+            SKYB200_CUDA_CHECK(cudaIpcCloseMemHandle(base));
+            return SKYB200_OK;
+        }
+    }
+    return fail(SKYB200_EINVAL, "skyb200_ipc_close: pointer was not returned by skyb200_ipc_open");
 }

@@ -146,6 +146,98 @@ def reduce_scatter_d_weight(d_weight: torch.Tensor, out: Optional[torch.Tensor] 
     return out, None
 
 
+class DWeightScatter:
+    """Peer-mapped gradient shards for the fused ``d_weight`` GEMM + reduce-scatter (``policy_update_step(...,
+    dw_scatter=...)``): what FSDP's post-backward reduce-scatter gives the reference (fsdp_strategy.py:151-153,
+    214-226 - fp32, averaged over the data-parallel ranks, rank r keeps rows ``[r V / world, (r + 1) V / world)``),
+    produced by the GEMM epilogue itself over NVLink instead of by a collective after the step.
+
+    Construction is collective over ``group`` (one process per GPU on one node): every rank allocates its
+    ``[V / world, H]`` fp32 shard, exports a CUDA IPC handle and opens the other ranks' shards.
+
+    Per optimizer step::
+
+        sc.begin()                      # zero my shard; barrier: nobody adds into a shard before it is zeroed
+        policy_update_step(..., dw_scatter=sc)   # any number of micro-batches: contributions accumulate
+        sc.finish()                     # barrier: every rank's kernels are done -> sc.shard is complete
+
+    Both barriers are one-element NCCL all-reduces in stream order (no host sync).  The sum order of the ranks'
+    contributions is not fixed, so results are reproducible to fp32 rounding only; ``reduce_scatter_d_weight`` on a
+    local gradient is the bit-reproducible alternative.
+    """
+
+    def __init__(self, V: int, H: int, group=None, device: Optional[torch.device] = None, remote: str = "tma"):
+        """``remote``: how the peers' pieces travel - ``"tma"`` (TMA reduce-add on a tensor map over the peer-mapped
+        shard) or ``"red"`` (16-byte fp32 vector reductions issued by the epilogue threads; the fallback)."""
+        import ctypes as C
+
+        from . import _lib
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("DWeightScatter needs an initialised torch.distributed process group")
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if not 2 <= self.world <= 8:
+            raise ValueError(f"DWeightScatter supports 2..8 ranks of one node, got {self.world}")
+        if V % (32 * self.world) != 0:
+            raise ValueError(f"V ({V}) must be a multiple of 32 * world ({32 * self.world})")
+        self.shape = (V, H)
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            self.shard = torch.zeros((V // self.world, H), dtype=torch.float32, device=self.device)
+            self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+            handle = (C.c_ubyte * 64)()
+            off = C.c_int64(0)
+            _lib.check(lib.skyb200_ipc_export(_lib.ptr(self.shard), handle, C.byref(off)), "skyb200_ipc_export")
+            mine = (bytes(handle), int(off.value))
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=group)
+            self._opened = []
+            self.c_struct = _lib.DwScatter()
+            self.c_struct.world, self.c_struct.rank = self.world, self.rank
+            self.c_struct.scale = 1.0 / self.world
+            if remote not in ("tma", "red"):
+                raise ValueError("remote must be 'tma' or 'red'")
+            self.c_struct.remote_red = 1 if remote == "red" else 0
+            for r, (h, o) in enumerate(everyone):
+                if r == self.rank:
+                    self.c_struct.shard[r] = self.shard.data_ptr()
+                    continue
+                p = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                _lib.check(lib.skyb200_ipc_open(buf, o, C.byref(p)), "skyb200_ipc_open")
+                self._opened.append(p.value)
+                self.c_struct.shard[r] = p.value
+        self._barrier()
+
+    def _barrier(self):
+        dist.all_reduce(self._flag, op=dist.ReduceOp.SUM, group=self.group)
+
+    def begin(self):
+        """Zero this rank's shard, then a stream-ordered barrier (no peer adds into it before the zero)."""
+        self.shard.zero_()
+        self._barrier()
+
+    def finish(self) -> torch.Tensor:
+        """Stream-ordered barrier after the last step: all ranks' kernels (and their NVLink reductions) are done."""
+        self._barrier()
+        return self.shard
+
+    def close(self):
+        from . import _lib
+
+        if getattr(self, "_opened", None):
+            torch.cuda.synchronize(self.device)
+            self._barrier()  # nobody is still adding into a shard that is about to be unmapped / freed
+            torch.cuda.synchronize(self.device)
+            lib = _lib.load()
+            with torch.cuda.device(self.device):
+                for p in self._opened:
+                    lib.skyb200_ipc_close(p)
+            self._opened = []
+
+
 def gae_advantage_sharded(token_level_rewards, values, response_mask, gamma: float, lambd: float, group=None):
     """GAE on this rank's rows with GLOBAL whitening statistics (3 doubles all-reduced).
 

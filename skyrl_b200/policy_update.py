@@ -75,6 +75,7 @@ def policy_update_step(
     cu_seqlens: Optional[torch.Tensor] = None,
     rollout_logprobs: Optional[torch.Tensor] = None,
     timing: bool = False,
+    dw_scatter=None,
 ) -> PolicyUpdateOutput:
     """``hidden`` [B, A, H] (or [B*A, H]) bf16, ``weight`` [V, H] bf16, ``labels`` [B, A] int64,
     ``old_log_probs`` / ``advantages`` / ``loss_mask`` / ``base_log_probs`` [B, A] fp32.
@@ -104,6 +105,11 @@ def policy_update_step(
     it (ppo_utils.py:577-583): TIS weights, outlier-token and sequence masks are computed from ``old_log_probs`` and
     ``rollout_logprobs`` before the step, the loss uses the corrected mask, ``clip_ratio`` keeps the original one,
     and the ``is_ratio_*`` / ``tis_*`` / ``*_sequence_mask_*`` metrics are added to the status dict (padded layout).
+
+    ``dw_scatter`` (a :class:`skyrl_b200.dist.DWeightScatter`, fused only): the data-parallel reduce-scatter of the
+    lm_head weight gradient is fused into the ``d_weight`` GEMM - every rank's contributions are averaged straight into
+    the owners' ``[V / world, H]`` shards over NVLink while the tensor cores run, no ``[V, H]`` buffer and no
+    collective after the step (``out.d_weight`` is None; read ``dw_scatter.shard`` after ``dw_scatter.finish()``).
 
     ``timing=True`` (fused only) brackets every GEMM launch of the step with CUDA timing events;
     :func:`step_gemm_times` harvests them (live per-kernel durations, what ``bench.py`` reports as ``roofline``).
@@ -176,15 +182,22 @@ def policy_update_step(
     )
     T = float(temperature)
     opts = None
-    if clip_mask is not None or timing:
+    if clip_mask is not None or timing or dw_scatter is not None:
         opts = _lib.StepOpts(tis=_lib.ptr(tis), clip_mask=_lib.ptr(clip_mask), timing=int(bool(timing)))
+        if dw_scatter is not None:
+            if not fused:
+                raise ValueError("dw_scatter (fused reduce-scatter of d_weight) needs fused=True")
+            if tuple(dw_scatter.shape) != (V, H):
+                raise ValueError(f"dw_scatter was built for a {tuple(dw_scatter.shape)} weight, this head is {(V, H)}")
+            opts.dw_scatter = C.pointer(dw_scatter.c_struct)
+            need_d_weight = False  # no local [V, H] gradient: the shards are the output
     if fused:
         with torch.cuda.device(dev):
             stream = _lib.stream_ptr(dev)
             logprobs = torch.empty(N, dtype=torch.float32, device=dev)
             ent = torch.empty(N, dtype=torch.float32, device=dev)
             stats = torch.empty(_lib.LOSS_NSTATS, dtype=torch.float32, device=dev)
-            need_grad = need_d_hidden or need_d_weight
+            need_grad = need_d_hidden or need_d_weight or dw_scatter is not None
             d_hidden = torch.empty((N, H), dtype=torch.bfloat16, device=dev) if need_d_hidden else None
             acc = 0
             if need_d_weight:

@@ -514,6 +514,26 @@ def test_data_parallel_step_over_nccl_two_ranks():
     assert "DP_OK" in r.stdout
 
 
+@pytest.mark.parametrize("remote", ["red", "tma"])
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (NCCL data-parallel group)")
+def test_fused_dweight_reduce_scatter_over_nccl_two_ranks(remote):
+    """The d_weight GEMM whose epilogue reduce-scatters the gradient over NVLink peer memory (TMA reduce-add for the
+    rank's own rows, fp32 vector reductions on the peers' shards) == NCCL's mean reduce-scatter of the local
+    gradients: single chunk, several chunks with masked rows, accumulated micro-batches, repeated optimizer steps."""
+    import os
+    import subprocess
+    import sys
+
+    script = os.path.join(os.path.dirname(__file__), "dws_worker.py")
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+               SKYB200_TEST_DWS_REMOTE=remote)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29543", script], env=env, capture_output=True,
+                       text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DWS_OK" in r.stdout
+
+
 @pytest.mark.parametrize("dead", [0, 1, 2])
 def test_gspo_chunk_whose_every_row_is_dead(dead):
     """GSPO clips whole sequences: a sequence whose ratio left the clip range on the side its advantage clips carries
