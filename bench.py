@@ -227,7 +227,7 @@ def run_reference(args, w):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-def hbm_kernels(dev, peaks):
+def hbm_kernels(dev, peaks, B=512, flush_l2=True):
     """The memory-bound kernels of the path (K2 advantages, KL-in-reward, K3 loss) through the C ABI on the
     config-3 batch shape (512 x 8192 = 4.19 M positions, 50-117 MB per call): algorithmic bytes / CUDA-event time,
     L2 flushed before every timed call, median of 15.  Reported against the measured HBM copy bandwidth."""
@@ -236,7 +236,7 @@ def hbm_kernels(dev, peaks):
     from skyrl_b200 import _lib
 
     lib = _lib.load()
-    B, A, G = 512, 8192, 8
+    A, G = 8192, 8
     n = B * A
     g = torch.Generator(device=dev).manual_seed(7)
     f = lambda: torch.randn((B, A), generator=g, device=dev)
@@ -279,23 +279,30 @@ def hbm_kernels(dev, peaks):
     }
     # L2 flush = streaming READ of 3x the 126 MB L2 (a write flush would leave ~100 MB of dirty lines whose write-back
     # lands inside the timed region of a 50-100 MB kernel)
-    flush = torch.zeros(96 << 20, dtype=torch.int32, device=dev)
+    flush = torch.zeros((96 << 20) if flush_l2 else 1, dtype=torch.int32, device=dev)
     res = {}
-    for name, (call, bpt) in cases.items():
-        for _ in range(3):
-            _lib.check(call(), name)
-        times = []
-        for _ in range(15):
+    def queued_times(fn, reps=15, skip=3):
+        """Device time of `fn` between two CUDA events, `reps` times, WITHOUT a host sync in between: the stream is
+        kept full (the L2 flush in front of every call takes ~70 us of GPU time, the host needs ~25 us per round), so
+        the events bracket what the call costs inside an asynchronously enqueued training step - kernels plus the gaps
+        between them - and not the host's launch latency after an idle GPU."""
+        evs = []
+        for _ in range(reps + skip):
             flush.sum()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            rc = call()
+            fn()
             e.record()
-            _lib.check(rc, name)
-            torch.cuda.synchronize()
-            times.append(s.elapsed_time(e))
-        times.sort()
-        ms = times[len(times) // 2]
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        t = sorted(s.elapsed_time(e) for s, e in evs[skip:])
+        return t[len(t) // 2]
+
+    res["_timer_floor_us"] = round(queued_times(lambda: None) * 1e3, 2)
+    for name, (call, bpt) in cases.items():
+        for _ in range(3):
+            _lib.check(call(), name)
+        ms = queued_times(lambda: _lib.check(call(), name))
         gbs = n * bpt / (ms * 1e-3) / 1e9
         res[name] = {"us": round(ms * 1e3, 1), "bytes_per_position": bpt, "achieved_gbs": round(gbs, 1),
                      "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)}
@@ -303,26 +310,18 @@ def hbm_kernels(dev, peaks):
     # method (the kernels above move 50-117 MB: launch ramp and tail are a visible share of 20-40 us)
     try:
         a, b, c = rewards, values, out1
-        times = []
-        for it in range(18):
-            flush.sum()
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            torch.add(a, b, out=c)
-            e.record()
-            torch.cuda.synchronize()
-            if it >= 3:
-                times.append(s.elapsed_time(e))
-        times.sort()
-        ms = times[len(times) // 2]
+        ms = queued_times(lambda: torch.add(a, b, out=c))
         gbs = n * 12 / (ms * 1e-3) / 1e9
         res["_calibration_torch_add"] = {"us": round(ms * 1e3, 1), "bytes_per_position": 12,
                                          "achieved_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm"], 3)}
     except Exception as exc:  # noqa: BLE001  (context only: never fail the bench over it)
         res["_calibration_torch_add"] = {"error": str(exc)[:200]}
-    res["_note"] = ("512 x 8192 positions (config-3 shape), fp32 mask, L2 flushed (384 MB streamed through it) before each "
-                    "timed call, median of 15, "
-                    "CUDA events; hbm peak %.1f GB/s (%s)" % (peaks["hbm"], peaks["source"].split(" (")[0]))
+    res["_note"] = ("%d x 8192 positions%s, fp32 mask, %s, median of 15, CUDA events in a stream that is kept full (no host sync between "
+                    "rounds; `_timer_floor_us` = an empty region measured the same way); hbm peak %.1f GB/s (%s)"
+                    % (B, " (config-3 shape)" if B == 512 else " (%dx the config-3 batch)" % (B // 512),
+                       "L2 flushed (384 MB streamed through it) before each timed call" if flush_l2 else
+                       "no flush: every array (%d MB) exceeds what L2 keeps of it" % (n * 4 >> 20),
+                       peaks["hbm"], peaks["source"].split(" (")[0]))
     return res
 
 
@@ -590,6 +589,8 @@ def run_ours(args, w):
 
     cublas_tflops = cublas_same_shape() if rank == 0 else None
     hbm = hbm_kernels(dev, peaks) if rank == 0 else None
+    # the same kernels on 4x the batch: launch ramp / tail and the 2.6 us timer floor no longer dominate
+    hbm4 = hbm_kernels(dev, peaks, B=2048) if rank == 0 else None
     tok_s = world * N / (ms_step * 1e-3)
     tok_s_e2e = world * N / (ms_e2e * 1e-3)
     step_tflops_alg = 6.0 * N * H * V / (ms_step * 1e-3) / 1e12
@@ -650,6 +651,7 @@ def run_ours(args, w):
             "phases_ms": {"advantages": adv_ms, "head_fwd+loss+head_bwd": upd_ms, "collectives(+rank skew)": comm_ms},
             "cublas_same_shape_tflops": cublas_tflops,
             "hbm_kernels": hbm,
+            "hbm_kernels_4x_batch": hbm4,
             "step_roofline": {"bound": "tensor", "algorithmic_flops_per_token": 6.0 * H * V,
                               "achieved": step_tflops_alg, "peak": peaks["tflops"], "unit": "TFLOP/s",
                               "frac": step_tflops_alg / peaks["tflops"],

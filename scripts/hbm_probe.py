@@ -33,6 +33,11 @@ if __name__ == "__main__":
     res = bench.hbm_kernels(dev, bench.measured_peaks())
     for k, v in res.items():
         print(k, json.dumps(v) if isinstance(v, dict) else v)
+    if "quick" not in sys.argv:
+        for k, v in bench.hbm_kernels(dev, bench.measured_peaks(), B=2048).items():
+            print("4x", k, json.dumps(v) if isinstance(v, dict) else v)
+    if "quick" in sys.argv:
+        sys.exit(0)
     flush = torch.zeros(96 << 20, dtype=torch.int32, device=dev)
     B, A = 512, 8192
     x = torch.randn(B, A, device=dev)

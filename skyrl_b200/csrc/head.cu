@@ -230,14 +230,33 @@ static int dw_lockstep() { static int v = env_int0("SKYB200_DW_LOCKSTEP", 128); 
 // groups of 7 for the 7B head (A is then read twice, 5.8 GB, but the 7.9 GB of hidden re-reads are gone); together
 // with evict-first on the streamed A panels and the fp32 output traffic: 8.37 -> 8.08 ms per launch sustained
 // (profiles/r02i_bwd_ab.jsonl).  SKYB200_DW_GROUP_N overrides.
-static int dw_group_n(int64_t rows, int64_t H) {
+static int dw_group_n(int64_t rows, int64_t H, int64_t V) {
     static int forced = env_int0("SKYB200_DW_GROUP_N", 0);
     if (forced > 0) return forced;
-    const int64_t n_tiles = (H + kHeadBN - 1) / kHeadBN;
-    const int64_t panel = std::max<int64_t>(rows, 1) * kHeadBN * 2;
-    const int64_t gmax = std::max<int64_t>(1, (36ll << 20) / panel);
-    const int64_t groups = (n_tiles + gmax - 1) / gmax;
-    return (int)((n_tiles + groups - 1) / groups);
+    // DRAM-traffic model per launch, minimised over the group size g (n_groups = ceil(n_tiles / g)):
+    //   A (dS, rows x V bf16) is streamed once per group;
+    //   B: a group whose panels fit (<= 36 MB) is read once; one that does not is re-read once per round of
+    //      74 / g concurrently resident M tiles.
+    // 7B head, 9472-row chunk: g = 14 -> 10.5 GB (measured 10.9 + the reduce), g = 7 -> 5.9 GB.  A GSPO chunk of one
+    // 32768-token sequence on the 32B-shaped head (B = 335 MB, no group fits): g = 10 -> 47 GB vs 64 GB for g = 20.
+    const int64_t n_tiles = (H + kHeadBN - 1) / kHeadBN, m_tiles = (V + kTileM - 1) / kTileM;
+    const double panel = (double)std::max<int64_t>(rows, 1) * kHeadBN * 2;
+    const double a_bytes = (double)rows * (double)V * 2.0;
+    double best = -1.0;
+    int best_g = (int)n_tiles;
+    for (int64_t g = 1; g <= n_tiles; ++g) {
+        const int64_t groups = (n_tiles + g - 1) / g;
+        if ((n_tiles + groups - 1) / groups != g) continue;  // only balanced group sizes
+        const bool fits = g * panel <= (double)(36ll << 20);
+        const double b_bytes = fits ? (double)n_tiles * panel
+                                    : (double)groups * (double)m_tiles * (double)(g * g) * panel / 74.0;
+        const double t = a_bytes * (double)groups + b_bytes;
+        if (best < 0.0 || t < best) {
+            best = t;
+            best_g = (int)g;
+        }
+    }
+    return best_g;
 }
 // skip all-zero d(logits) rows (masked tokens) in the backward GEMMs of the fused step (0 disables)
 static int skip_zero_rows() { static int v = env_int0("SKYB200_SKIP_ZERO_ROWS", 1); return v; }
@@ -247,6 +266,7 @@ static int skip_zero_rows() { static int v = env_int0("SKYB200_SKIP_ZERO_ROWS", 
 static int whatif() { static int v = env_int0("SKYB200_WHATIF", 0); return v; }
 // cap on the resident blocks of the d(logits) transform pass (0 = one block per item)
 static int transform_blocks() { static int v = env_int0("SKYB200_TRANSFORM_BLOCKS", 0); return v; }
+static int transform_evict() { static int v = env_int0("SKYB200_TRANSFORM_EVICT", 0); return v; }
 
 
 static int64_t num_slabs(int64_t V) { return (V + kHeadBN - 1) / kHeadBN; }
@@ -365,7 +385,7 @@ dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const
                          int64_t ld_part, const float* __restrict__ lse2, const float* __restrict__ g_lp,
                          const float* __restrict__ g_ent, const float* __restrict__ g_ent_mask,
                          const float* __restrict__ entropy_raw, const int64_t* __restrict__ labels, float inv_T,
-                         int rows) {
+                         int rows, int store_evict_first) {
     // items = (token row, 4096-wide column block), row-major; a block walks them with a grid stride so the launch can
     // be throttled to a few resident blocks per SM (it runs under the GEMMs of the previous chunk)
     const int cbs = (V + 4095) / 4096;
@@ -408,7 +428,12 @@ dlogits_transform_kernel(__nv_bfloat16* __restrict__ S, int64_t ld, int V, const
                 r[k] = pack_bf16x2(d0, d1);
             }
         }
-        st_global_256(ptr, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);  // re-read by the two GEMMs next
+        // re-read by the two GEMMs next - but 2.9 GB per chunk never survive in L2 until then: evict-first keeps the
+        // pass from displacing the operand panels of the GEMMs it runs under (SKYB200_TRANSFORM_EVICT, A/B in r02m)
+        if (store_evict_first)
+            st_global_256_stream(ptr, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+        else
+            st_global_256(ptr, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
     } else {
         for (int k = 0; k < 16 && col0 + k < V; ++k) {
             float d = 0.f;
@@ -786,7 +811,7 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
             ew.accumulate = acc_w ? 1 : 0;
             ew.hint = hint_dw_c();
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
-                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H), ew, stream, 1, hint_dw_a(), hint_dw_b(),
+                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H, V), ew, stream, 1, hint_dw_a(), hint_dw_b(),
                 dw_lockstep(), skip ? &k_maps : nullptr);
             if (rc) return rc;
         }
@@ -1080,7 +1105,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
                 dlogits_transform_kernel<<<(unsigned)std::min<int64_t>(items, cap), 256, 0, aux>>>(
                     reinterpret_cast<__nv_bfloat16*>(wb + plan.off_S[p]), plan.ldS, (int)V, part_m, c, lse2, d_lp,
                     use_ent_grad ? d_ent : nullptr, (use_ent_grad && entropy_mask) ? entropy_mask + t0 : nullptr,
-                    ent_raw, labels + t0, inv_T, rows);
+                    ent_raw, labels + t0, inv_T, rows, transform_evict());
                 r = check_launch("dlogits_transform_kernel");
                 if (r) return r;
             }
@@ -1146,7 +1171,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             es.hint = hint_dw_c();
             if ((r = t_begin())) return r;
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiF32Scatter>(
-                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H), es, stream, 1, hint_dw_a(),
+                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H, V), es, stream, 1, hint_dw_a(),
                 hint_dw_b(), dw_lockstep(), skip ? &k_maps : nullptr);
             if (r) return r;
             if ((r = t_end(2))) return r;
@@ -1159,7 +1184,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             ew.hint = hint_dw_c();
             if ((r = t_begin())) return r;
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
-                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H), ew, stream, 1, hint_dw_a(),
+                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H, V), ew, stream, 1, hint_dw_a(),
                 hint_dw_b(), dw_lockstep(), (skip && ew.accumulate) ? &k_maps : nullptr);
             if (r) return r;
             if ((r = t_end(2))) return r;
@@ -1419,7 +1444,7 @@ extern "C" int skyb200_head_gemm_bench(int32_t which, const void* hidden, const 
         ew.accumulate = accumulate;
         ew.hint = hint_dw_c();
         return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
-            S, ldS, hidden, H, (int)V, (int)H, (int)rows, dw_group_n(rows, H), ew, stream, 1, hint_dw_a(), hint_dw_b(),
+            S, ldS, hidden, H, (int)V, (int)H, (int)rows, dw_group_n(rows, H, V), ew, stream, 1, hint_dw_a(), hint_dw_b(),
             dw_lockstep(), nullptr);
     }
     return fail(SKYB200_EINVAL, "which must be 1 (d_hidden) or 2 (d_weight)");

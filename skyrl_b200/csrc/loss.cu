@@ -333,27 +333,54 @@ __global__ void __launch_bounds__(kLossThreads, kMinBlocks) loss_main_kernel(Los
     const unsigned tiles_per_row = static_cast<unsigned>((A + kMainTile - 1) / kMainTile);
     const unsigned step_rows = gridDim.x / tiles_per_row, step_tiles = gridDim.x % tiles_per_row;
     unsigned row = blockIdx.x / tiles_per_row, tir = blockIdx.x % tiles_per_row;
-    bool waited = false;
-    while (row < static_cast<unsigned>(a.B)) {
-        TileIn d[kInFlight];
+    auto advance = [&]() {
+        row += step_rows;
+        tir += step_tiles;
+        if (tir >= tiles_per_row) {
+            tir -= tiles_per_row;
+            ++row;
+        }
+    };
+    if constexpr (kInFlight == 2) {
+        // Rolling two-buffer pipeline: while one tile is consumed the other one's loads (and, right after the consume,
+        // the reload of the buffer just freed) are in flight - the DRAM latency of a round of loads is hidden behind
+        // the arithmetic of the other tile instead of being paid once per round.
+        TileIn d[2];
+        bool live[2];
 #pragma unroll
-        for (int u = 0; u < kInFlight; ++u) {
-            tile_load<kVec, kExtra>(a, static_cast<int>(row), static_cast<int>(tir), row < static_cast<unsigned>(a.B), d[u]);
-            row += step_rows;
-            tir += step_tiles;
-            if (tir >= tiles_per_row) {
-                tir -= tiles_per_row;
-                ++row;
+        for (int u = 0; u < 2; ++u) {
+            live[u] = row < static_cast<unsigned>(a.B);  // block-uniform
+            tile_load<kVec, kExtra>(a, static_cast<int>(row), static_cast<int>(tir), live[u], d[u]);
+            advance();
+        }
+        after_prepass();
+        while (live[0] || live[1]) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (live[u]) consume(d[u]);
+                live[u] = row < static_cast<unsigned>(a.B);
+                tile_load<kVec, kExtra>(a, static_cast<int>(row), static_cast<int>(tir), live[u], d[u]);
+                advance();
             }
         }
-        if (!waited) {  // block-uniform
-            after_prepass();
-            waited = true;
-        }
+    } else {
+        bool waited = false;
+        while (row < static_cast<unsigned>(a.B)) {
+            TileIn d[kInFlight];
 #pragma unroll
-        for (int u = 0; u < kInFlight; ++u) consume(d[u]);
+            for (int u = 0; u < kInFlight; ++u) {
+                tile_load<kVec, kExtra>(a, static_cast<int>(row), static_cast<int>(tir), row < static_cast<unsigned>(a.B), d[u]);
+                advance();
+            }
+            if (!waited) {  // block-uniform
+                after_prepass();
+                waited = true;
+            }
+#pragma unroll
+            for (int u = 0; u < kInFlight; ++u) consume(d[u]);
+        }
+        if (!waited) after_prepass();
     }
-    if (!waited) after_prepass();
     float s_loss = acc.s_loss, s_clip = acc.s_clip, s_kl = acc.s_kl, s_ent = acc.s_ent, s_ratio = acc.s_ratio;
     float r_max = acc.r_max, r_min = acc.r_min;
 
