@@ -490,6 +490,13 @@ int skyb200_gemm_bench(const void* A, const void* B, void* C, void* scratch, int
                        int32_t epi, int32_t group, int32_t order, void* stream);
 
 /*
+ * Host-only: the N-group size of the d_weight GEMM's tile order for a chunk of `rows` tokens (the hidden-chunk panels of
+ * one group must stay L2-resident while the d(logits) panels stream past; minimises a DRAM-traffic model, see
+ * csrc/head.cu dw_group_n).  SKYB200_DW_GROUP_N overrides.
+ */
+int skyb200_dw_group_plan(int64_t rows, int64_t H, int64_t V);
+
+/*
  * Tuning hook (scripts/bwd_gemm_probe.py): ONE launch of a backward GEMM of the fused step exactly as the step issues
  * it (operand majors, tile order, L2 hints, lockstep) on caller-provided buffers.  which = 1: d_hidden [rows, H] bf16 =
  * S [rows, V] * weight [V, H]; which = 2: d_weight [V, H] fp32 (+)= S^T * hidden [rows, H].  S = bf16 d(logits) with

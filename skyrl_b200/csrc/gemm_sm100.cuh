@@ -62,6 +62,15 @@ __device__ __forceinline__ void tma_load_2d_hint(const void* desc, uint64_t* bar
     }
 }
 
+// L2 prefetch of one TMA box (no shared-memory destination, no barrier): issued a few K blocks ahead of the load so
+// that the load itself finds its lines in L2 - the 6-stage ring covers ~2 us, an L2 hit but not a DRAM miss under load.
+__device__ __forceinline__ void tma_prefetch_2d_hint(const void* desc, int32_t crd0, int32_t crd1, uint64_t policy) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile.L2::cache_hint [%0, {%1, %2}], %3;"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(desc)), "r"(crd0), "r"(crd1), "l"(policy)
+                 : "memory");
+}
+
 // Debug record written to mapped host memory when a barrier wait times out (so a protocol bug shows up
 // as a failed launch with a readable reason instead of a hung GPU).
 struct GemmDebug {
@@ -126,7 +135,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
                   int N, int K, int group_m, int tile_order, uint64_t hint_a, uint64_t hint_b,
                   const __grid_constant__ typename Epi::Params ep, GemmDebug* dbg, unsigned int* sync_ctr,
-                  int sync_every, int sync_slack, GemmMaps maps) {
+                  int sync_every, int sync_slack, int prefetch_kb, GemmMaps maps) {
     using S = GemmSmem<kCtas, BN, kStages, Epi::kSmemBytes>;
     constexpr int TILE_M = kBM * kCtas;
     constexpr uint32_t kTmemCols = 2 * BN;
@@ -199,14 +208,43 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const int m0 = m_tile * TILE_M + static_cast<int>(cta_rank) * kBM;
                 const int n0 = tc.n_tile * BN + static_cast<int>(cta_rank * S::kLoadN);
                 int k_window = 0;  // lane l holds k_map[32 * (kb / 32) + l]: one coalesced load per 32 K blocks
+                int k_window_next = 0;  // ... and k_map[32 * (kb / 32 + 1) + l] (indices of the blocks to prefetch)
                 // CTAs that are resident at this tile iteration (the last iteration may be partial)
                 const uint32_t active_ctas =
                     (t - cluster_id + num_clusters <= total_tiles ? num_clusters : total_tiles % num_clusters) * kCtas;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     int kidx = kb;
                     if (maps.k_map != nullptr) {
-                        if ((kb & 31) == 0) k_window = (kb + lane < num_kb) ? maps.k_map[kb + lane] : 0;
+                        if ((kb & 31) == 0) {
+                            k_window = (kb + lane < num_kb) ? maps.k_map[kb + lane] : 0;
+                            if (prefetch_kb > 0) k_window_next = (kb + 32 + lane < num_kb) ? maps.k_map[kb + 32 + lane] : 0;
+                        }
                         kidx = __shfl_sync(0xffffffffu, k_window, kb & 31);
+                    }
+                    if (prefetch_kb > 0 && kb + prefetch_kb < num_kb) {  // warp-uniform
+                        int pidx = kb + prefetch_kb;
+                        if (maps.k_map != nullptr) {
+                            const int w = (kb & 31) + prefetch_kb;  // prefetch_kb <= 32
+                            const int cur = __shfl_sync(0xffffffffu, k_window, w & 31);
+                            const int nxt = __shfl_sync(0xffffffffu, k_window_next, w & 31);
+                            pidx = (w < 32) ? cur : nxt;
+                        }
+                        if (issuer) {
+                            const int kp = pidx * kBK;
+                            if constexpr (kAMn) {
+#pragma unroll
+                                for (int j = 0; j < kBM / 64; ++j) tma_prefetch_2d_hint(&tmap_a, m0 + j * 64, kp, hint_a);
+                            } else {
+                                tma_prefetch_2d_hint(&tmap_a, kp, m0, hint_a);
+                            }
+                            if constexpr (kBMn) {
+#pragma unroll
+                                for (int j = 0; j < static_cast<int>(S::kLoadN) / 64; ++j)
+                                    tma_prefetch_2d_hint(&tmap_b, n0 + j * 64, kp, hint_b);
+                            } else {
+                                tma_prefetch_2d_hint(&tmap_b, kp, n0, hint_b);
+                            }
+                        }
                     }
                     // Best-effort lockstep: CTAs that share operand panels through L2 re-align every `sync_every`
                     // K blocks (bounded wait: a straggler can never dead-lock the others).  Split phase: a CTA

@@ -115,7 +115,7 @@ template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
 static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int group_m,
                        const typename Epi::Params& ep, cudaStream_t stream, int tile_order = 0,
                        uint64_t hint_a = kEvictNormal, uint64_t hint_b = kEvictNormal, int sync_every = 0,
-                       const GemmMaps* maps_in = nullptr) {
+                       const GemmMaps* maps_in = nullptr, int prefetch_kb = 0) {
     using S = GemmSmem<kCtas, BN, kStages, Epi::kSmemBytes>;
     if (M <= 0 || N <= 0 || K <= 0) return SKYB200_OK;
     CUtensorMap ta, tb;
@@ -166,7 +166,8 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
     if (maps_in != nullptr) maps = *maps_in;
     SKYB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group_m, tile_order, hint_a, hint_b, ep, dbg,
                                           sync_ctr, sync_every > 0 ? sync_every : 1,
-                                          std::min(lock_slack(), std::max(sync_every, 1) - 1), maps));
+                                          std::min(lock_slack(), std::max(sync_every, 1) - 1),
+                                          std::max(0, std::min(prefetch_kb, 32)), maps));
     return SKYB200_OK;
 }
 
@@ -223,6 +224,10 @@ static int env_int0(const char* name, int dflt) {
 static int dh_lockstep() { static int v = env_int0("SKYB200_DH_LOCKSTEP", 128); return v; }
 static int fwd_lockstep() { static int v = env_int0("SKYB200_FWD_LOCKSTEP", 0); return v; }
 static int dw_lockstep() { static int v = env_int0("SKYB200_DW_LOCKSTEP", 128); return v; }
+// L2 prefetch distance of the TMA producer in K blocks (0 = off, <= 32)
+static int fwd_prefetch() { static int v = env_int0("SKYB200_FWD_PREFETCH", 0); return v; }
+static int dh_prefetch() { static int v = env_int0("SKYB200_DH_PREFETCH", 0); return v; }
+static int dw_prefetch() { static int v = env_int0("SKYB200_DW_PREFETCH", 0); return v; }
 // d_weight tile order (N-fastest inside groups of `group_n` N tiles): the B panels of a group - group_n x [rows, 256]
 // bf16 of the hidden chunk - must STAY in L2 while the d(logits) panels stream past them once per group.  The whole
 // 7B-head chunk (14 panels, 68 MB) does not: ncu (profiles/r02h) shows it re-read from DRAM once per round of M tiles
@@ -801,7 +806,7 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
             }
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
                 dS, ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, hint_dh_a(), hint_dh_b(),
-                dh_lockstep(), skip ? &m_maps : nullptr);
+                dh_lockstep(), skip ? &m_maps : nullptr, dh_prefetch());
             if (rc) return rc;
         }
         // (3) d_weight[V, H] (+)= dS^T[V, rows] * hidden[rows, H]   (both MN-major)
@@ -812,7 +817,7 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
             ew.hint = hint_dw_c();
             rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
                 dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H, V), ew, stream, 1, hint_dw_a(), hint_dw_b(),
-                dw_lockstep(), skip ? &k_maps : nullptr);
+                dw_lockstep(), skip ? &k_maps : nullptr, dw_prefetch());
             if (rc) return rc;
         }
     }
@@ -1063,11 +1068,12 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
         if (store)  // with the backward to follow: slab-relative bf16 tile store for the two backward GEMMs
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLseStoreRel>(
                 hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream, 0, hint_fwd_a(),
-                kEvictNormal, fwd_lockstep());
+                kEvictNormal, fwd_lockstep(), nullptr, fwd_prefetch());
         else
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
                 hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(),
-                static_cast<const LsePartialsParams&>(ep), stream, 0, hint_fwd_a(), kEvictNormal, fwd_lockstep());
+                static_cast<const LsePartialsParams&>(ep), stream, 0, hint_fwd_a(), kEvictNormal, fwd_lockstep(), nullptr,
+                fwd_prefetch());
         if (r) return r;
         if ((r = t_end(0))) return r;
         SKYB200_CUDA_CHECK(cudaEventRecord(ss->fwd[p], stream));
@@ -1147,7 +1153,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             if (r) return r;
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
                 S, plan.ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, hint_dh_a(), hint_dh_b(),
-                dh_lockstep(), skip ? &m_maps : nullptr);
+                dh_lockstep(), skip ? &m_maps : nullptr, dh_prefetch());
             if (r) return r;
             if ((r = t_end(1))) return r;
         }
@@ -1172,7 +1178,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             if ((r = t_begin())) return r;
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiF32Scatter>(
                 S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H, V), es, stream, 1, hint_dw_a(),
-                hint_dw_b(), dw_lockstep(), skip ? &k_maps : nullptr);
+                hint_dw_b(), dw_lockstep(), skip ? &k_maps : nullptr, dw_prefetch());
             if (r) return r;
             if ((r = t_end(2))) return r;
         } else if (d_weight != nullptr && !(whatif() & 16)) {
@@ -1185,7 +1191,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             if ((r = t_begin())) return r;
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
                 S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H, V), ew, stream, 1, hint_dw_a(),
-                hint_dw_b(), dw_lockstep(), (skip && ew.accumulate) ? &k_maps : nullptr);
+                hint_dw_b(), dw_lockstep(), (skip && ew.accumulate) ? &k_maps : nullptr, dw_prefetch());
             if (r) return r;
             if ((r = t_end(2))) return r;
         }
@@ -1419,6 +1425,8 @@ extern "C" int skyb200_gemm_bench(const void* A, const void* B, void* C, void* s
     return fail(SKYB200_EINVAL, "epi must be 0..4");
 }
 
+extern "C" int skyb200_dw_group_plan(int64_t rows, int64_t H, int64_t V) { return dw_group_n(rows, H, V); }
+
 // Tuning hook: ONE launch of a backward GEMM of the fused step exactly as the step issues it (operand majors, tile
 // order, L2 hints, lockstep), on caller-provided buffers: which = 1: d_hidden[rows, H] = S[rows, V] * W[V, H];
 // which = 2: d_weight[V, H] (+)= S^T * hidden[rows, H].  S is the bf16 d(logits) store with pitch round_up(V, 64).
@@ -1435,7 +1443,7 @@ extern "C" int skyb200_head_gemm_bench(int32_t which, const void* hidden, const 
         EpiStoreBF16::Params eh{static_cast<__nv_bfloat16*>(d_hidden), H};
         return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
             S, ldS, weight, H, (int)rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, hint_dh_a(), hint_dh_b(),
-            dh_lockstep(), nullptr);
+            dh_lockstep(), nullptr, dh_prefetch());
     }
     if (which == 2) {
         SKYB200_REQUIRE(hidden && d_weight, "null pointer");
@@ -1445,7 +1453,7 @@ extern "C" int skyb200_head_gemm_bench(int32_t which, const void* hidden, const 
         ew.hint = hint_dw_c();
         return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
             S, ldS, hidden, H, (int)V, (int)H, (int)rows, dw_group_n(rows, H, V), ew, stream, 1, hint_dw_a(), hint_dw_b(),
-            dw_lockstep(), nullptr);
+            dw_lockstep(), nullptr, dw_prefetch());
     }
     return fail(SKYB200_EINVAL, "which must be 1 (d_hidden) or 2 (d_weight)");
 }

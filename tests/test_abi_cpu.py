@@ -77,6 +77,23 @@ def test_fused_step_chunk_plan(lib):
     assert _plan(lib, 64, 1, H, V, "regular", n_tokens=500000)[2] == -(-500000 // 9472)
 
 
+def test_d_weight_tile_groups_fit_l2(lib):
+    """Host-only: the N-group size of the d_weight GEMM.  A group's hidden-chunk panels (group x rows x 256 bf16) stay
+    under 36 MB whenever that is cheaper than re-reading them once per round of M tiles; groups are balanced."""
+    V = 152064
+    assert lib.skyb200_dw_group_plan(9472, 3584, V) == 7        # 7B head: two groups of 7 (34 MB each), not 14 (68 MB)
+    assert lib.skyb200_dw_group_plan(9472, 896, 151936) == 4    # 0.5B head: all 4 N tiles fit (19 MB)
+    assert lib.skyb200_dw_group_plan(9472, 5120, 151936) == 7   # 32B-shaped head: 7 / 7 / 6
+    assert lib.skyb200_dw_group_plan(32768, 5120, 151936) == 10  # one 32768-token GSPO sequence: nothing fits, 2 x 10
+    assert lib.skyb200_dw_group_plan(4352, 3584, V) == 14       # a short last chunk: the whole hidden chunk fits
+    for rows in (1, 300, 5000, 9472, 18944, 70000):
+        for H in (64, 256, 896, 3584, 5120, 8192):
+            g = lib.skyb200_dw_group_plan(rows, H, V)
+            n = -(-H // 256)
+            groups = -(-n // g)
+            assert 1 <= g <= n and -(-n // groups) == g, (rows, H, g)
+
+
 def test_loss_params_layout_matches_header():
     assert ctypes.sizeof(_lib.LossParams) == 6 * 4 + 8 * 4
 
