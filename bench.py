@@ -51,7 +51,7 @@ WORKLOADS = {
     # name: (B, A, H, V, group)
     "c2": dict(B=256, A=4096, H=3584, V=152064, G=8, model="Qwen2.5-7B head"),
     "c1": dict(B=64, A=1024, H=896, V=151936, G=8, model="Qwen2.5-0.5B head"),
-    "c2s": dict(B=8, A=4096, H=3584, V=152064, G=8, model="Qwen2.5-7B head (8-sequence slice, profiling)"),
+    "c2s": dict(B=16, A=4096, H=3584, V=152064, G=8, model="Qwen2.5-7B head (16-sequence slice = 3 full chunks + a tail, profiling)"),
     "tiny": dict(B=16, A=256, H=256, V=4096, G=8, model="tiny"),
 }
 METRIC = "policy-update tokens/sec/GPU (loss head+adv+loss fwd/bwd)"
@@ -492,8 +492,17 @@ def run_ours(args, w):
     e2e_steps = max(1, min(args.steps, 3))
     ms_e2e = timed(e2e_step, e2e_steps, 1)
 
-    chunk = 37 * 256
-    n_chunks = (N + chunk - 1) // chunk
+    # the token chunk and the tile widths the library runs this shape with (host-only planning calls)
+    import ctypes
+
+    from skyrl_b200 import _lib
+
+    lib = _lib.load()
+    plan = (ctypes.c_int64 * 3)()
+    _lib.check(lib.skyb200_policy_step_plan(B, A, 0, H, V, _lib.LOSS_TYPES["regular"], 1, plan), "skyb200_policy_step_plan")
+    chunk, n_chunks = int(plan[0]), int(plan[2])
+    tiles = (ctypes.c_int32 * 4)()
+    _lib.check(lib.skyb200_head_tile_plan(min(chunk, N), H, V, tiles), "skyb200_head_tile_plan")
     # GRPO (2) + loss pre-pass + finalize (2) + per chunk: fwd GEMM, merge, loss, d_logits transform, dH GEMM, dW GEMM
     # (+ live-row lists and dead-tile zero fill of the zero-row skipping per chunk)
     launches_per_step = 2 + 2 + 8 * n_chunks
@@ -600,8 +609,9 @@ def run_ours(args, w):
     traffic, traffic_note = measured_traffic(H, V)
     kernel_names = {
         "forward": "gemm_sm100_kernel<2,256,6,K-major,K-major,EpiLseStoreRel> (logits tile -> LSE partials + bf16 tile store)",
-        "d_hidden": "gemm_sm100_kernel<2,256,6,K-major,MN-major,EpiStoreBF16> (d_hidden = dS * W)",
-        "d_weight": "gemm_sm100_kernel<2,256,6,MN-major,MN-major,EpiTmaF32> (d_weight += dS^T * hidden, fp32 TMA reduce-add)",
+        "d_hidden": f"gemm_sm100_kernel<2,{tiles[1]},{6 if tiles[1] == 256 else 4},K-major,MN-major,EpiStoreBF16> (d_hidden = dS * W)",
+        "d_weight": f"gemm_sm100_kernel<2,{tiles[2]},{6 if tiles[2] == 256 else 4},MN-major,MN-major,EpiTmaF32> "
+                    "(d_weight += dS^T * hidden, fp32 TMA reduce-add)",
     }
     roofline_kernels = {}
     for kind, t in gemm_times.items():
@@ -647,6 +657,9 @@ def run_ours(args, w):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config_dict(w, world),
+            "chunk_plan": {"tokens_per_chunk": chunk, "chunks_per_step": n_chunks,
+                           "tile_columns": {"forward": tiles[0], "d_hidden": tiles[1], "d_weight": tiles[2]},
+                           "d_weight_n_group": tiles[3]},
             "tokens_per_s_per_gpu": tok_s / world,
             "phases_ms": {"advantages": adv_ms, "head_fwd+loss+head_bwd": upd_ms, "collectives(+rank skew)": comm_ms},
             "cublas_same_shape_tflops": cublas_tflops,

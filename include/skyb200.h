@@ -497,6 +497,15 @@ int skyb200_gemm_bench(const void* A, const void* B, void* C, void* scratch, int
 int skyb200_dw_group_plan(int64_t rows, int64_t H, int64_t V);
 
 /*
+ * Host-only: the tile widths (columns of one CTA pair's 256-row tile) the three GEMMs of a `rows`-token chunk run with:
+ * bn_out[0] = forward (always 256: two accumulators, the epilogue of a tile runs under the next tile's mainloop),
+ * bn_out[1] = d_hidden, bn_out[2] = d_weight - 512 (one accumulator in all 512 tensor-memory columns, 25 % fewer
+ * operand bytes per flop) unless tile quantisation on the 74 CTA pairs costs more than that gains, or SKYB200_WIDE
+ * disables it; bn_out[3] = the N-group size of the d_weight tile order in tiles of that width.
+ */
+int skyb200_head_tile_plan(int64_t rows, int64_t H, int64_t V, int32_t* bn_out);
+
+/*
  * Tuning hook (scripts/bwd_gemm_probe.py): ONE launch of a backward GEMM of the fused step exactly as the step issues
  * it (operand majors, tile order, L2 hints, lockstep) on caller-provided buffers.  which = 1: d_hidden [rows, H] bf16 =
  * S [rows, V] * weight [V, H]; which = 2: d_weight [V, H] fp32 (+)= S^T * hidden [rows, H].  S = bf16 d(logits) with

@@ -89,6 +89,11 @@ def main():
             d_weight.zero_()
             ms, mhz = sustained(call)
             out[f"{name}[{kind}]"] = (round(flops / ms / 1e9, 1), round(ms, 3), mhz)
+        if kind == "dlogits":  # full-size spot check of the form that just ran (the last call was a plain store)
+            rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-300))
+            out["err_d_weight_rows"] = rel(d_weight[-300:], S[:, V - 300:V].float().t() @ hidden.float())
+            _lib.check(lib.skyb200_head_gemm_bench(1, None, P(weight), P(S), P(d_hidden), None, 0, rows, H, V, st))
+            out["err_d_hidden_rows"] = rel(d_hidden[-300:].float(), S[-300:, :V].float() @ weight.float())
     if quick:
         print(json.dumps({"tag": kv.get("tag", ""), "tflops_ms_mhz": out}), flush=True)
         return

@@ -144,6 +144,7 @@ SIGNATURES = {
                                                 C.POINTER(StepOpts), _P]),
     "skyb200_policy_step_timing": (C.c_int, [C.POINTER(C.c_double)]),
     "skyb200_dw_group_plan": (C.c_int, [_I64, _I64, _I64]),
+    "skyb200_head_tile_plan": (C.c_int, [_I64, _I64, _I64, C.POINTER(C.c_int32)]),
     "skyb200_ipc_export": (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
     "skyb200_ipc_open": (C.c_int, [_P, _I64, C.POINTER(C.c_void_p)]),
     "skyb200_ipc_close": (C.c_int, [_P]),

@@ -7,6 +7,13 @@
 // (thread i <-> accumulator row i) through tcgen05.ld.  kCtas == 2 pairs two SMs on one 256-row tile
 // (cta_group::2): each CTA loads its own 128 A rows and half of the B tile.
 //
+// BN == 512 is the WIDE form for deep-K GEMMs: one 256 x 512 tile per CTA pair fills all 512 TMEM columns (a single
+// accumulator: the epilogue no longer overlaps the next tile's mainloop, which costs nothing when a tile spends
+// hundreds of K blocks in the mainloop) and every K block issues two N = 256 MMA groups against the same A stage.
+// Operand bytes fetched per flop fall by 25 % ((256 + 512) / (2 * 256 * 512) vs (256 + 256) / (2 * 256 * 256)): the
+// 256 x 256 form needs ~12 TB/s of L2 -> SM traffic at 1.5 PFLOP/s, which is what the chip delivers at best
+// (profiles/README.md, r02o: all three GEMMs move 80.7 GB per launch and none finishes under 6.4 ms at any clock).
+//
 // Either operand may be K-major (rows of K contiguous elements) or MN-major (stored [K, MN] with MN
 // contiguous); the backward GEMMs of the fused LM head use the MN-major forms so no transposed copies of
 // the weight / hidden / dlogits matrices are ever made.
@@ -62,15 +69,6 @@ __device__ __forceinline__ void tma_load_2d_hint(const void* desc, uint64_t* bar
     }
 }
 
-// L2 prefetch of one TMA box (no shared-memory destination, no barrier): issued a few K blocks ahead of the load so
-// that the load itself finds its lines in L2 - the 6-stage ring covers ~2 us, an L2 hit but not a DRAM miss under load.
-__device__ __forceinline__ void tma_prefetch_2d_hint(const void* desc, int32_t crd0, int32_t crd1, uint64_t policy) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile.L2::cache_hint [%0, {%1, %2}], %3;"
-                 :
-                 : "l"(reinterpret_cast<uint64_t>(desc)), "r"(crd0), "r"(crd1), "l"(policy)
-                 : "memory");
-}
-
 // Debug record written to mapped host memory when a barrier wait times out (so a protocol bug shows up
 // as a failed launch with a readable reason instead of a hung GPU).
 struct GemmDebug {
@@ -105,6 +103,18 @@ __device__ __forceinline__ void bounded_wait(uint64_t* bar, uint32_t parity, Gem
     }
 }
 
+// Tile geometry.  A tile of BN columns is computed as kHalves MMA groups of kMmaN <= 256 columns (the UMMA limit); the
+// B stage of a CTA is kHalves sub-blocks of kSubN rows, sub-block h = columns h * kMmaN + cta_rank * kSubN + [0, kSubN)
+// of the tile.  BN <= 256: two accumulator buffers (epilogue of tile t under the mainloop of tile t + 1); BN == 512: one.
+template <int kCtas, int BN>
+struct GemmTile {
+    static constexpr int kMmaN = BN > 256 ? 256 : BN;
+    static constexpr int kHalves = BN / kMmaN;
+    static constexpr int kAcc = BN > 256 ? 1 : 2;
+    static constexpr int kSubN = kMmaN / kCtas;
+    static constexpr uint32_t kSubBytes = kSubN * kBK * 2;
+};
+
 // Shared memory: [A stages][B stages][epilogue staging: kEpiBytes, 1024-byte aligned][barriers]
 template <int kCtas, int BN, int kStages, uint32_t kEpiBytes = 0>
 struct GemmSmem {
@@ -135,11 +145,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
                   int N, int K, int group_m, int tile_order, uint64_t hint_a, uint64_t hint_b,
                   const __grid_constant__ typename Epi::Params ep, GemmDebug* dbg, unsigned int* sync_ctr,
-                  int sync_every, int sync_slack, int prefetch_kb, GemmMaps maps) {
+                  int sync_every, int sync_slack, GemmMaps maps) {
     using S = GemmSmem<kCtas, BN, kStages, Epi::kSmemBytes>;
+    using T = GemmTile<kCtas, BN>;
     constexpr int TILE_M = kBM * kCtas;
-    constexpr uint32_t kTmemCols = 2 * BN;
-    static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
+    constexpr int kMmaN = T::kMmaN, kHalves = T::kHalves, kAcc = T::kAcc, kSubN = T::kSubN;
+    constexpr uint32_t kSubBytes = T::kSubBytes;
+    constexpr uint32_t kTmemCols = kAcc * BN;
+    static_assert(BN == 128 || BN == 256 || BN == 512, "BN must be 128, 256 or 512");
     static_assert(kTmemCols <= 512, "TMEM overflow");
 
     extern __shared__ uint8_t smem_raw[];
@@ -206,45 +219,16 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const TileCoord tc = decode_tile(t, num_m_tiles, num_n_tiles, group_m, tile_order);
                 const int m_tile = maps.m_map ? maps.m_map[tc.m_tile] : tc.m_tile;
                 const int m0 = m_tile * TILE_M + static_cast<int>(cta_rank) * kBM;
-                const int n0 = tc.n_tile * BN + static_cast<int>(cta_rank * S::kLoadN);
+                const int n0 = tc.n_tile * BN + static_cast<int>(cta_rank) * kSubN;
                 int k_window = 0;  // lane l holds k_map[32 * (kb / 32) + l]: one coalesced load per 32 K blocks
-                int k_window_next = 0;  // ... and k_map[32 * (kb / 32 + 1) + l] (indices of the blocks to prefetch)
                 // CTAs that are resident at this tile iteration (the last iteration may be partial)
                 const uint32_t active_ctas =
                     (t - cluster_id + num_clusters <= total_tiles ? num_clusters : total_tiles % num_clusters) * kCtas;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     int kidx = kb;
                     if (maps.k_map != nullptr) {
-                        if ((kb & 31) == 0) {
-                            k_window = (kb + lane < num_kb) ? maps.k_map[kb + lane] : 0;
-                            if (prefetch_kb > 0) k_window_next = (kb + 32 + lane < num_kb) ? maps.k_map[kb + 32 + lane] : 0;
-                        }
+                        if ((kb & 31) == 0) k_window = (kb + lane < num_kb) ? maps.k_map[kb + lane] : 0;
                         kidx = __shfl_sync(0xffffffffu, k_window, kb & 31);
-                    }
-                    if (prefetch_kb > 0 && kb + prefetch_kb < num_kb) {  // warp-uniform
-                        int pidx = kb + prefetch_kb;
-                        if (maps.k_map != nullptr) {
-                            const int w = (kb & 31) + prefetch_kb;  // prefetch_kb <= 32
-                            const int cur = __shfl_sync(0xffffffffu, k_window, w & 31);
-                            const int nxt = __shfl_sync(0xffffffffu, k_window_next, w & 31);
-                            pidx = (w < 32) ? cur : nxt;
-                        }
-                        if (issuer) {
-                            const int kp = pidx * kBK;
-                            if constexpr (kAMn) {
-#pragma unroll
-                                for (int j = 0; j < kBM / 64; ++j) tma_prefetch_2d_hint(&tmap_a, m0 + j * 64, kp, hint_a);
-                            } else {
-                                tma_prefetch_2d_hint(&tmap_a, kp, m0, hint_a);
-                            }
-                            if constexpr (kBMn) {
-#pragma unroll
-                                for (int j = 0; j < static_cast<int>(S::kLoadN) / 64; ++j)
-                                    tma_prefetch_2d_hint(&tmap_b, n0 + j * 64, kp, hint_b);
-                            } else {
-                                tma_prefetch_2d_hint(&tmap_b, kp, n0, hint_b);
-                            }
-                        }
                     }
                     // Best-effort lockstep: CTAs that share operand panels through L2 re-align every `sync_every`
                     // K blocks (bounded wait: a straggler can never dead-lock the others).  Split phase: a CTA
@@ -289,13 +273,18 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     } else {
                         tma_load_2d_hint<kCtas>(&tmap_a, &full_bar[stage], a_dst, k0, m0, hint_a);
                     }
-                    if constexpr (kBMn) {
 #pragma unroll
-                        for (int j = 0; j < static_cast<int>(S::kLoadN) / 64; ++j) {
-                            tma_load_2d_hint<kCtas>(&tmap_b, &full_bar[stage], b_dst + j * 8192, n0 + j * 64, k0, hint_b);
+                    for (int h = 0; h < kHalves; ++h) {
+                        if constexpr (kBMn) {
+#pragma unroll
+                            for (int j = 0; j < kSubN / 64; ++j) {
+                                tma_load_2d_hint<kCtas>(&tmap_b, &full_bar[stage], b_dst + h * kSubBytes + j * 8192,
+                                                        n0 + h * kMmaN + j * 64, k0, hint_b);
+                            }
+                        } else {
+                            tma_load_2d_hint<kCtas>(&tmap_b, &full_bar[stage], b_dst + h * kSubBytes, k0, n0 + h * kMmaN,
+                                                    hint_b);
                         }
-                    } else {
-                        tma_load_2d_hint<kCtas>(&tmap_b, &full_bar[stage], b_dst, k0, n0, hint_b);
                     }
                     }  // issuer
                     __syncwarp();
@@ -312,7 +301,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // the same elected lane issues every tcgen05.mma and tcgen05.commit.
         if (cta_rank == 0) {
             const bool issuer = ptx::elect_one();
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(TILE_M, BN, kAMn ? 1u : 0u, kBMn ? 1u : 0u);
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(TILE_M, kMmaN, kAMn ? 1u : 0u, kBMn ? 1u : 0u);
             // K-major: 8-row groups are 1024 B apart, K advances 32 B inside the swizzle atom.
             // MN-major: 64-element MN groups are one [64 x 64] box (8192 B) apart, 8-row K groups 1024 B.
             constexpr uint32_t a_lbo = kAMn ? 8192u : 16u, a_sbo = 1024u, a_kstep = kAMn ? 2048u : 32u;
@@ -331,8 +320,12 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                         for (int j = 0; j < kBK / kUmmaK; ++j) {
                             const uint64_t da = ptx::make_smem_desc_sw128(a_addr + j * a_kstep, a_lbo, a_sbo);
-                            const uint64_t db = ptx::make_smem_desc_sw128(b_addr + j * b_kstep, b_lbo, b_sbo);
-                            ptx::umma_bf16<kCtas>(tmem_d, da, db, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+#pragma unroll
+                            for (int h = 0; h < kHalves; ++h) {  // the MMA groups of one K step share the A operand
+                                const uint64_t db =
+                                    ptx::make_smem_desc_sw128(b_addr + h * kSubBytes + j * b_kstep, b_lbo, b_sbo);
+                                ptx::umma_bf16<kCtas>(tmem_d + h * kMmaN, da, db, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                            }
                         }
                         ptx::umma_commit<kCtas>(&empty_bar[stage]);
                         if (kb == num_kb - 1) ptx::umma_commit<kCtas>(&tfull_bar[accum]);
@@ -343,7 +336,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         phase ^= 1u;
                     }
                 }
-                if (++accum == 2) {
+                if (++accum == kAcc) {
                     accum = 0;
                     aphase ^= 1u;
                 }
@@ -370,7 +363,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 else
                     ptx::mbar_arrive(&tempty_bar[accum]);
             }
-            if (++accum == 2) {
+            if (++accum == kAcc) {
                 accum = 0;
                 aphase ^= 1u;
             }
@@ -504,42 +497,56 @@ struct EpiTmaF32 {
         int accumulate;
         uint64_t hint;  // L2 eviction policy of the output traffic (kEvictNormal / kEvictFirst)
     };
+    // One 32 x 32 piece: registers -> swizzled staging buffer -> bulk store / reduce-add.
+    __device__ static __forceinline__ void emit(const Params& p, const uint32_t (&v)[32], uint8_t* stage, uint32_t srow,
+                                                uint32_t sw, int c, int col0, int row, int M, int lane) {
+        if (lane == 0) {  // the buffer about to be rewritten must have been read by its previous bulk operation
+            if (c == 0)
+                ptx::bulk_wait_group_read<0>();
+            else
+                ptx::bulk_wait_group_read<1>();
+        }
+        __syncwarp();
+        const uint32_t sbuf = srow + static_cast<uint32_t>(c & 1) * 4096u;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {  // 16-byte chunk j of the 128-byte row goes to slot j ^ (row & 7)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + ((j ^ sw) << 4)), "r"(v[4 * j]),
+                         "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                         : "memory");
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && row < M) {  // lane 0 holds the warp's first row
+            if (p.accumulate)
+                ptx::tma_reduce_add_2d_hint(&p.tmap_out, stage + (c & 1) * 4096, col0, row, p.hint);
+            else
+                ptx::tma_store_2d_hint(&p.tmap_out, stage + (c & 1) * 4096, col0, row, p.hint);
+            ptx::bulk_commit_group();
+        }
+    }
+    // Software-pipelined over pairs of pieces: the tcgen05.ld of piece c + 1 is in flight while piece c is staged and
+    // handed to the copy engine (with the wide tiles the epilogue is no longer hidden behind the next tile's mainloop).
     template <int BN>
     __device__ static void run(const Params& p, uint32_t taddr, int row, int n_tile, int M, int N, uint8_t* stage) {
         const int n0 = n_tile * BN;
         const int lane = threadIdx.x & 31;
         const uint32_t srow = ptx::smem_u32(stage) + static_cast<uint32_t>(lane) * 128u;
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        const int pieces = min(BN / 32, (N - n0 + 31) / 32);  // uniform across the whole warp; >= 1
+        uint32_t va[32], vb[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32b_x32(taddr, va);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            const int col0 = n0 + c * 32;
-            if (col0 >= N) break;  // uniform across the whole warp
-            uint32_t v[32];
-            __syncwarp();
-            ptx::tmem_ld_32x32b_x32(taddr + c * 32, v);
+        for (int c = 0; c < pieces; c += 2) {
             ptx::tmem_ld_wait();
-            if (lane == 0) {  // the buffer about to be rewritten must have been read by its previous bulk operation
-                if (c == 0)
-                    ptx::bulk_wait_group_read<0>();
-                else
-                    ptx::bulk_wait_group_read<1>();
-            }
             __syncwarp();
-            const uint32_t sbuf = srow + static_cast<uint32_t>(c & 1) * 4096u;
-#pragma unroll
-            for (uint32_t j = 0; j < 8; ++j) {  // 16-byte chunk j of the 128-byte row goes to slot j ^ (row & 7)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbuf + ((j ^ sw) << 4)), "r"(v[4 * j]),
-                             "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                             : "memory");
-            }
-            ptx::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0 && row < M) {  // lane 0 holds the warp's first row
-                if (p.accumulate)
-                    ptx::tma_reduce_add_2d_hint(&p.tmap_out, stage + (c & 1) * 4096, col0, row, p.hint);
-                else
-                    ptx::tma_store_2d_hint(&p.tmap_out, stage + (c & 1) * 4096, col0, row, p.hint);
-                ptx::bulk_commit_group();
+            if (c + 1 < pieces) ptx::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
+            emit(p, va, stage, srow, sw, c, n0 + c * 32, row, M, lane);
+            if (c + 1 < pieces) {
+                ptx::tmem_ld_wait();
+                __syncwarp();
+                if (c + 2 < pieces) ptx::tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
+                emit(p, vb, stage, srow, sw, c + 1, n0 + (c + 1) * 32, row, M, lane);
             }
         }
     }

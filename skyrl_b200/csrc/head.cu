@@ -115,7 +115,7 @@ template <int kCtas, int BN, int kStages, bool kAMn, bool kBMn, class Epi>
 static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int group_m,
                        const typename Epi::Params& ep, cudaStream_t stream, int tile_order = 0,
                        uint64_t hint_a = kEvictNormal, uint64_t hint_b = kEvictNormal, int sync_every = 0,
-                       const GemmMaps* maps_in = nullptr, int prefetch_kb = 0) {
+                       const GemmMaps* maps_in = nullptr) {
     using S = GemmSmem<kCtas, BN, kStages, Epi::kSmemBytes>;
     if (M <= 0 || N <= 0 || K <= 0) return SKYB200_OK;
     CUtensorMap ta, tb;
@@ -128,7 +128,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
     if (kBMn)
         rc = make_tmap_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64);
     else
-        rc = make_tmap_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, S::kLoadN);
+        rc = make_tmap_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, GemmTile<kCtas, BN>::kSubN);
     if (rc) return rc;
 
     auto kern = gemm_sm100_kernel<kCtas, BN, kStages, kAMn, kBMn, Epi>;
@@ -166,8 +166,7 @@ static int launch_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, i
     if (maps_in != nullptr) maps = *maps_in;
     SKYB200_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, group_m, tile_order, hint_a, hint_b, ep, dbg,
                                           sync_ctr, sync_every > 0 ? sync_every : 1,
-                                          std::min(lock_slack(), std::max(sync_every, 1) - 1),
-                                          std::max(0, std::min(prefetch_kb, 32)), maps));
+                                          std::min(lock_slack(), std::max(sync_every, 1) - 1), maps));
     return SKYB200_OK;
 }
 
@@ -182,9 +181,13 @@ constexpr int kTileM = kBM * kHeadCtas;
 // Token chunk = 37 pair-tiles: 37 * n_tiles is a multiple of the 74 resident CTA pairs, so every GEMM of the
 // chunk runs in whole waves on the 148 SMs.
 static int env_int(const char* name, int dflt);
-// 37 pair-tiles = 9472 tokens; SKYB200_CHUNK_TILES overrides (multiples of 37 keep whole waves)
+// 37 pair-tiles = 9472 tokens; SKYB200_CHUNK_TILES overrides (multiples of 37 keep whole waves).  With the wide
+// (256 x 512) backward tiles the d_hidden GEMM has half as many tiles per token row, so whole waves need 74 pair-tiles
+// = 18944 tokens (74 * ceil(H / 512) tiles); the deeper d_weight reduction (296 K blocks per tile) also halves the
+// share of its now un-overlapped epilogue and the fp32 read-modify-write traffic per token.
+static int wide_mask();
 static int64_t default_chunk() {
-    static int64_t v = (int64_t)env_int("SKYB200_CHUNK_TILES", 37) * kTileM;
+    static int64_t v = (int64_t)env_int("SKYB200_CHUNK_TILES", wide_mask() ? 74 : 37) * kTileM;
     return v;
 }
 #define kDefaultChunk default_chunk()
@@ -224,10 +227,6 @@ static int env_int0(const char* name, int dflt) {
 static int dh_lockstep() { static int v = env_int0("SKYB200_DH_LOCKSTEP", 128); return v; }
 static int fwd_lockstep() { static int v = env_int0("SKYB200_FWD_LOCKSTEP", 0); return v; }
 static int dw_lockstep() { static int v = env_int0("SKYB200_DW_LOCKSTEP", 128); return v; }
-// L2 prefetch distance of the TMA producer in K blocks (0 = off, <= 32)
-static int fwd_prefetch() { static int v = env_int0("SKYB200_FWD_PREFETCH", 0); return v; }
-static int dh_prefetch() { static int v = env_int0("SKYB200_DH_PREFETCH", 0); return v; }
-static int dw_prefetch() { static int v = env_int0("SKYB200_DW_PREFETCH", 0); return v; }
 // d_weight tile order (N-fastest inside groups of `group_n` N tiles): the B panels of a group - group_n x [rows, 256]
 // bf16 of the hidden chunk - must STAY in L2 while the d(logits) panels stream past them once per group.  The whole
 // 7B-head chunk (14 panels, 68 MB) does not: ncu (profiles/r02h) shows it re-read from DRAM once per round of M tiles
@@ -235,7 +234,7 @@ static int dw_prefetch() { static int v = env_int0("SKYB200_DW_PREFETCH", 0); re
 // groups of 7 for the 7B head (A is then read twice, 5.8 GB, but the 7.9 GB of hidden re-reads are gone); together
 // with evict-first on the streamed A panels and the fp32 output traffic: 8.37 -> 8.08 ms per launch sustained
 // (profiles/r02i_bwd_ab.jsonl).  SKYB200_DW_GROUP_N overrides.
-static int dw_group_n(int64_t rows, int64_t H, int64_t V) {
+static int dw_group_n(int64_t rows, int64_t H, int64_t V, int bn = kHeadBN) {
     static int forced = env_int0("SKYB200_DW_GROUP_N", 0);
     if (forced > 0) return forced;
     // DRAM-traffic model per launch, minimised over the group size g (n_groups = ceil(n_tiles / g)):
@@ -244,8 +243,8 @@ static int dw_group_n(int64_t rows, int64_t H, int64_t V) {
     //      74 / g concurrently resident M tiles.
     // 7B head, 9472-row chunk: g = 14 -> 10.5 GB (measured 10.9 + the reduce), g = 7 -> 5.9 GB.  A GSPO chunk of one
     // 32768-token sequence on the 32B-shaped head (B = 335 MB, no group fits): g = 10 -> 47 GB vs 64 GB for g = 20.
-    const int64_t n_tiles = (H + kHeadBN - 1) / kHeadBN, m_tiles = (V + kTileM - 1) / kTileM;
-    const double panel = (double)std::max<int64_t>(rows, 1) * kHeadBN * 2;
+    const int64_t n_tiles = (H + bn - 1) / bn, m_tiles = (V + kTileM - 1) / kTileM;
+    const double panel = (double)std::max<int64_t>(rows, 1) * bn * 2;
     const double a_bytes = (double)rows * (double)V * 2.0;
     double best = -1.0;
     int best_g = (int)n_tiles;
@@ -272,6 +271,59 @@ static int whatif() { static int v = env_int0("SKYB200_WHATIF", 0); return v; }
 // cap on the resident blocks of the d(logits) transform pass (0 = one block per item)
 static int transform_blocks() { static int v = env_int0("SKYB200_TRANSFORM_BLOCKS", 0); return v; }
 static int transform_evict() { static int v = env_int0("SKYB200_TRANSFORM_EVICT", 0); return v; }
+
+
+// ------------------------------------------------------------------------------------------ backward GEMM dispatch
+
+// Wide tiles (gemm_sm100.cuh, BN == 512) for the two deep-K backward GEMMs: 25 % fewer operand bytes per flop.  Measured
+// (profiles/r02q_*, one B200, alternating processes): d_hidden 1228 -> 1406 TFLOP/s sustained, d_weight (accumulating)
+// 1199 -> 1361, the fused step of config 2 2880 -> 2680 ms with every GEMM then at the power-capped tensor peak.
+// SKYB200_WIDE: bit 1 = d_hidden, bit 2 = d_weight (default both), bit 4 = even where tile quantisation says otherwise;
+// 0 = the 256 x 256 tiles everywhere.
+constexpr int kWideBN = 512;
+constexpr int kWideStages = 4;
+static int wide_mask() { static int v = env_int0("SKYB200_WIDE", 3); return v; }
+static int dh_group_m_wide() { static int v = env_int("SKYB200_DH_GROUP_M_WIDE", 11); return v; }
+
+// fraction of the machine a [m_tiles x ceil(n / bn)] tile grid keeps busy: whole waves of 74 CTA pairs x useful columns
+static double tile_grid_efficiency(int64_t m_tiles, int64_t n, int bn) {
+    const int64_t n_tiles = (n + bn - 1) / bn, tiles = m_tiles * n_tiles, pairs = std::max(1, num_sms() / kHeadCtas);
+    if (tiles <= 0) return 0.0;
+    const int64_t waves = (tiles + pairs - 1) / pairs;
+    return ((double)tiles / (double)(waves * pairs)) * ((double)n / (double)(n_tiles * bn));
+}
+// The wide form is worth +13..15 % at equal tile-grid efficiency and still +8 % at 0.875 of it (a 37-tile chunk of the 7B
+// head: 259 tiles = 3.5 waves): take it unless quantisation gives back more than that.
+static bool use_wide(int bit, int64_t m_tiles, int64_t n) {
+    if (!(wide_mask() & bit)) return false;
+    if (wide_mask() & 4) return true;
+    return tile_grid_efficiency(m_tiles, n, kWideBN) >= 0.85 * tile_grid_efficiency(m_tiles, n, kHeadBN);
+}
+
+// d_hidden[rows, H] (bf16) = S[rows, V] * W[V, H]      (A K-major, B MN-major)
+static int launch_d_hidden(const void* S, int64_t ldS, const void* weight, int rows, int64_t H, int64_t V,
+                           const EpiStoreBF16::Params& eh, cudaStream_t stream, const GemmMaps* maps) {
+    if (use_wide(1, (rows + kTileM - 1) / kTileM, H))
+        return launch_gemm<kHeadCtas, kWideBN, kWideStages, false, true, EpiStoreBF16>(
+            S, ldS, weight, H, rows, (int)H, (int)V, dh_group_m_wide(), eh, stream, 0, hint_dh_a(), hint_dh_b(),
+            dh_lockstep(), maps);
+    return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
+        S, ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, hint_dh_a(), hint_dh_b(), dh_lockstep(),
+        maps);
+}
+
+// d_weight[V, H] (fp32) (+)= S^T[V, rows] * hidden[rows, H]   (both MN-major); Epi = EpiTmaF32 or EpiF32Scatter
+template <class Epi>
+static int launch_d_weight(const void* S, int64_t ldS, const void* hidden, int rows, int64_t H, int64_t V,
+                           const typename Epi::Params& ew, cudaStream_t stream, const GemmMaps* maps) {
+    if (use_wide(2, (V + kTileM - 1) / kTileM, H))
+        return launch_gemm<kHeadCtas, kWideBN, kWideStages, true, true, Epi>(
+            S, ldS, hidden, H, (int)V, (int)H, rows, dw_group_n(rows, H, V, kWideBN), ew, stream, 1, hint_dw_a(),
+            hint_dw_b(), dw_lockstep(), maps);
+    return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, Epi>(
+        S, ldS, hidden, H, (int)V, (int)H, rows, dw_group_n(rows, H, V), ew, stream, 1, hint_dw_a(), hint_dw_b(),
+        dw_lockstep(), maps);
+}
 
 
 static int64_t num_slabs(int64_t V) { return (V + kHeadBN - 1) / kHeadBN; }
@@ -804,9 +856,7 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
                 zero_dead_tiles_kernel<<<zgrid, 256, 0, stream>>>(eh.C, H, (int)H, rows, maps + 2);
                 if ((rc = check_launch("zero_dead_tiles_kernel"))) return rc;
             }
-            rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
-                dS, ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, hint_dh_a(), hint_dh_b(),
-                dh_lockstep(), skip ? &m_maps : nullptr, dh_prefetch());
+            rc = launch_d_hidden(dS, ldS, weight, rows, H, V, eh, stream, skip ? &m_maps : nullptr);
             if (rc) return rc;
         }
         // (3) d_weight[V, H] (+)= dS^T[V, rows] * hidden[rows, H]   (both MN-major)
@@ -815,9 +865,7 @@ extern "C" int skyb200_head_backward(const void* hidden, const void* weight, con
             if ((rc = make_tmap_f32_out(&ew.tmap_out, d_weight, (uint64_t)H, (uint64_t)V, (uint64_t)H))) return rc;
             ew.accumulate = acc_w ? 1 : 0;
             ew.hint = hint_dw_c();
-            rc = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
-                dS, ldS, hid + r0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H, V), ew, stream, 1, hint_dw_a(), hint_dw_b(),
-                dw_lockstep(), skip ? &k_maps : nullptr, dw_prefetch());
+            rc = launch_d_weight<EpiTmaF32>(dS, ldS, hid + r0 * H, rows, H, V, ew, stream, skip ? &k_maps : nullptr);
             if (rc) return rc;
         }
     }
@@ -847,16 +895,15 @@ StepPlan plan_step(int64_t B, int64_t A, int64_t N, int64_t H, int64_t V, int lo
         // whole sequences per chunk: k * A tokens in buffers of round_up(k * A, 256) rows.  The padded response
         // length A is whatever the longest response of the batch was, so it need not be a multiple of the tile
         // height: the chunk START is then not tile-aligned (every consumer takes a plain row offset) and the last
-        // tile of a chunk is partial.  k (up to ~2 default chunks) is chosen so that the d_hidden GEMM of a chunk
+        // tile of a chunk is partial.  k (up to ~1.5 default chunks) is chosen so that the d_hidden GEMM of a chunk
         // fills whole waves of the resident CTA pairs as well as possible.
-        const int64_t clusters = std::max(1, num_sms() / kHeadCtas);
-        const int64_t n_tiles_h = (H + kHeadBN - 1) / kHeadBN;
         int64_t best_k = 1;
         double best_eff = -1.0;
-        for (int64_t k = 1; k * A <= std::max<int64_t>(A, 2 * kDefaultChunk); ++k) {
-            const int64_t tiles = ((k * A + kTileM - 1) / kTileM) * n_tiles_h;
-            const double eff = (double)(k * A) * (double)n_tiles_h /
-                               ((double)kTileM * (double)(((tiles + clusters - 1) / clusters) * clusters));
+        for (int64_t k = 1; k * A <= std::max<int64_t>(A, kDefaultChunk + kDefaultChunk / 2); ++k) {
+            const int64_t mt = (k * A + kTileM - 1) / kTileM;
+            const bool wide = use_wide(1, mt, H);  // the form launch_d_hidden will pick for this chunk
+            const double eff = tile_grid_efficiency(mt, H, wide ? kWideBN : kHeadBN) * (double)(k * A) /
+                               (double)(mt * kTileM) * (wide ? 1.12 : 1.0);
             if (eff > best_eff + 1e-9) {
                 best_eff = eff;
                 best_k = k;
@@ -1068,12 +1115,11 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
         if (store)  // with the backward to follow: slab-relative bf16 tile store for the two backward GEMMs
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLseStoreRel>(
                 hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(), ep, stream, 0, hint_fwd_a(),
-                kEvictNormal, fwd_lockstep(), nullptr, fwd_prefetch());
+                kEvictNormal, fwd_lockstep());
         else
             r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, false, EpiLsePartials>(
                 hid + t0 * H, H, weight, H, rows, (int)V, (int)H, fwd_group_m(),
-                static_cast<const LsePartialsParams&>(ep), stream, 0, hint_fwd_a(), kEvictNormal, fwd_lockstep(), nullptr,
-                fwd_prefetch());
+                static_cast<const LsePartialsParams&>(ep), stream, 0, hint_fwd_a(), kEvictNormal, fwd_lockstep());
         if (r) return r;
         if ((r = t_end(0))) return r;
         SKYB200_CUDA_CHECK(cudaEventRecord(ss->fwd[p], stream));
@@ -1151,9 +1197,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             }
             int r = t_begin();
             if (r) return r;
-            r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
-                S, plan.ldS, weight, H, rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, hint_dh_a(), hint_dh_b(),
-                dh_lockstep(), skip ? &m_maps : nullptr, dh_prefetch());
+            r = launch_d_hidden(S, plan.ldS, weight, rows, H, V, eh, stream, skip ? &m_maps : nullptr);
             if (r) return r;
             if ((r = t_end(1))) return r;
         }
@@ -1176,9 +1220,7 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             es.scale = scatter->scale;
             es.hint = hint_dw_c();
             if ((r = t_begin())) return r;
-            r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiF32Scatter>(
-                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H, V), es, stream, 1, hint_dw_a(),
-                hint_dw_b(), dw_lockstep(), skip ? &k_maps : nullptr, dw_prefetch());
+            r = launch_d_weight<EpiF32Scatter>(S, plan.ldS, hid + t0 * H, rows, H, V, es, stream, skip ? &k_maps : nullptr);
             if (r) return r;
             if ((r = t_end(2))) return r;
         } else if (d_weight != nullptr && !(whatif() & 16)) {
@@ -1189,9 +1231,8 @@ static int policy_step_impl(const void* hidden_host, const void* hidden, const v
             if (whatif() & 2) ew.accumulate = 0;
             ew.hint = hint_dw_c();
             if ((r = t_begin())) return r;
-            r = launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
-                S, plan.ldS, hid + t0 * H, H, (int)V, (int)H, rows, dw_group_n(rows, H, V), ew, stream, 1, hint_dw_a(),
-                hint_dw_b(), dw_lockstep(), (skip && ew.accumulate) ? &k_maps : nullptr, dw_prefetch());
+            r = launch_d_weight<EpiTmaF32>(S, plan.ldS, hid + t0 * H, rows, H, V, ew, stream,
+                                           (skip && ew.accumulate) ? &k_maps : nullptr);
             if (r) return r;
             if ((r = t_end(2))) return r;
         }
@@ -1367,6 +1408,8 @@ extern "C" int skyb200_gemm_selftest(const void* A, const void* B, float* C, int
         return selftest_dispatch<1, 128, 6>(A, B, C, (int)M, (int)N, (int)K, a_mn, b_mn, accumulate, stream);
     if (ctas == 2 && bn == 256)
         return selftest_dispatch<2, 256, 6>(A, B, C, (int)M, (int)N, (int)K, a_mn, b_mn, accumulate, stream);
+    if (ctas == 2 && bn == 512)
+        return selftest_dispatch<2, 512, 4>(A, B, C, (int)M, (int)N, (int)K, a_mn, b_mn, accumulate, stream);
     if (ctas == 2 && bn == 128)
         return selftest_dispatch<2, 128, 6>(A, B, C, (int)M, (int)N, (int)K, a_mn, b_mn, accumulate, stream);
     return fail(SKYB200_EINVAL, "unsupported selftest configuration ctas=%d bn=%d", ctas, bn);
@@ -1427,6 +1470,16 @@ extern "C" int skyb200_gemm_bench(const void* A, const void* B, void* C, void* s
 
 extern "C" int skyb200_dw_group_plan(int64_t rows, int64_t H, int64_t V) { return dw_group_n(rows, H, V); }
 
+extern "C" int skyb200_head_tile_plan(int64_t rows, int64_t H, int64_t V, int32_t* bn_out) {
+    SKYB200_REQUIRE(bn_out != nullptr, "null pointer");
+    SKYB200_REQUIRE(rows > 0 && H > 0 && V > 0, "bad shape");
+    bn_out[0] = kHeadBN;
+    bn_out[1] = use_wide(1, (rows + kTileM - 1) / kTileM, H) ? kWideBN : kHeadBN;
+    bn_out[2] = use_wide(2, (V + kTileM - 1) / kTileM, H) ? kWideBN : kHeadBN;
+    bn_out[3] = dw_group_n(rows, H, V, bn_out[2]);
+    return SKYB200_OK;
+}
+
 // Tuning hook: ONE launch of a backward GEMM of the fused step exactly as the step issues it (operand majors, tile
 // order, L2 hints, lockstep), on caller-provided buffers: which = 1: d_hidden[rows, H] = S[rows, V] * W[V, H];
 // which = 2: d_weight[V, H] (+)= S^T * hidden[rows, H].  S is the bf16 d(logits) store with pitch round_up(V, 64).
@@ -1441,9 +1494,7 @@ extern "C" int skyb200_head_gemm_bench(int32_t which, const void* hidden, const 
     if (which == 1) {
         SKYB200_REQUIRE(weight && d_hidden, "null pointer");
         EpiStoreBF16::Params eh{static_cast<__nv_bfloat16*>(d_hidden), H};
-        return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, false, true, EpiStoreBF16>(
-            S, ldS, weight, H, (int)rows, (int)H, (int)V, dh_group_m(), eh, stream, 0, hint_dh_a(), hint_dh_b(),
-            dh_lockstep(), nullptr, dh_prefetch());
+        return launch_d_hidden(S, ldS, weight, (int)rows, H, V, eh, stream, nullptr);
     }
     if (which == 2) {
         SKYB200_REQUIRE(hidden && d_weight, "null pointer");
@@ -1451,9 +1502,7 @@ extern "C" int skyb200_head_gemm_bench(int32_t which, const void* hidden, const 
         if ((rc = make_tmap_f32_out(&ew.tmap_out, d_weight, (uint64_t)H, (uint64_t)V, (uint64_t)H))) return rc;
         ew.accumulate = accumulate;
         ew.hint = hint_dw_c();
-        return launch_gemm<kHeadCtas, kHeadBN, kHeadStages, true, true, EpiTmaF32>(
-            S, ldS, hidden, H, (int)V, (int)H, (int)rows, dw_group_n(rows, H, V), ew, stream, 1, hint_dw_a(), hint_dw_b(),
-            dw_lockstep(), nullptr, dw_prefetch());
+        return launch_d_weight<EpiTmaF32>(S, ldS, hidden, (int)rows, H, V, ew, stream, nullptr);
     }
     return fail(SKYB200_EINVAL, "which must be 1 (d_hidden) or 2 (d_weight)");
 }

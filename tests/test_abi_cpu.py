@@ -47,7 +47,7 @@ def test_host_only_entry_points(lib):
     # bounded scratch: independent of N once N exceeds one chunk, and far below N*V*2 bytes (= 319 GB)
     assert fwd == lib.skyb200_head_forward_workspace(1 << 22, 3584, 152064, 0)
     assert bwd == lib.skyb200_head_backward_workspace(1 << 22, 3584, 152064, 0)
-    assert bwd < 4 * 2**30 and fwd < 2**30
+    assert bwd < 7 * 2**30 and fwd < 2**30
 
 
 def _plan(lib, B, A, H, V, loss, n_tokens=0, need_grad=1):
@@ -61,7 +61,7 @@ def test_fused_step_chunk_plan(lib):
     """Host-only planning of the fused step: bounded scratch for every loss and any padded response length."""
     H, V = 3584, 152064
     cap, stride, n, ws = _plan(lib, 256, 4096, H, V, "regular")
-    assert (cap, stride, n) == (9472, 9472, 111) and ws < 7 * 2**30            # 37 pair-tiles, 2 x 2.9 GB store
+    assert (cap, stride, n) == (18944, 18944, 56) and ws < 13 * 2**30          # 74 pair-tiles, 2 x 5.8 GB store
     assert _plan(lib, 1024, 4096, H, V, "regular")[3] - ws < 2**20             # independent of the batch size
     assert _plan(lib, 4, 100, H, V, "dual_clip")[:3] == (512, 512, 1)          # a batch smaller than one chunk
     # GSPO: whole sequences per chunk; the chunk count covers the batch exactly
@@ -69,12 +69,12 @@ def test_fused_step_chunk_plan(lib):
         cap, stride, n, ws = _plan(lib, B, A, H, V, "gspo")
         assert stride % A == 0 and cap % 256 == 0 and stride <= cap < stride + 256, (B, A, cap, stride)
         assert n == -(-B * A // stride)
-        assert cap <= max(2 * 9472, -(-A // 256) * 256), (B, A, cap)             # ~2 default chunks, or one sequence
+        assert cap <= max(18944 * 3 // 2, -(-A // 256) * 256), (B, A, cap)       # ~1.5 default chunks, or one sequence
         assert ws < 2 * cap * (V + 64) * 2 + 2 * cap * (3 * 595 + 6) * 4 + (B + n) * 64 + 2**22, (B, A, ws)
     # a response length that shares no factor with the 256-row tile used to need lcm(A, 256) = 1 M tokens (611 GB)
-    assert _plan(lib, 256, 3917, H, V, "gspo")[3] < 12 * 2**30
+    assert _plan(lib, 256, 3917, H, V, "gspo")[3] < 18 * 2**30
     # the packed layout plans over n_tokens
-    assert _plan(lib, 64, 1, H, V, "regular", n_tokens=500000)[2] == -(-500000 // 9472)
+    assert _plan(lib, 64, 1, H, V, "regular", n_tokens=500000)[2] == -(-500000 // 18944)
 
 
 def test_d_weight_tile_groups_fit_l2(lib):
@@ -92,6 +92,30 @@ def test_d_weight_tile_groups_fit_l2(lib):
             n = -(-H // 256)
             groups = -(-n // g)
             assert 1 <= g <= n and -(-n // groups) == g, (rows, H, g)
+
+
+def _tiles(lib, rows, H, V):
+    out = (ctypes.c_int32 * 4)()
+    assert lib.skyb200_head_tile_plan(rows, H, V, out) == 0
+    return list(out)
+
+
+def test_backward_gemm_tile_widths(lib):
+    """Host-only: which GEMMs of a chunk run on the wide 256 x 512 tiles.  The forward never does (its epilogue needs the
+    second accumulator); the backward GEMMs do unless tile quantisation on the 74 CTA pairs costs more than the 25 %
+    of operand traffic the wide form saves."""
+    V = 152064
+    assert _tiles(lib, 18944, 3584, V) == [256, 512, 512, 7]    # the default chunk: 74 x 7 tiles = 7 whole waves
+    assert _tiles(lib, 9472, 3584, V)[:3] == [256, 512, 512]    # 37 x 7 = 259 tiles = 3.5 waves: still ahead (measured)
+    assert _tiles(lib, 6656, 3584, V)[1] == 256                 # config 2's last chunk: 182 tiles would idle 18 % of 3 waves
+    assert _tiles(lib, 18944, 896, 151936)[:3] == [256, 512, 512]  # 0.5B head: 896 = 1.75 wide tiles = 3.5 narrow ones
+    assert _tiles(lib, 18944, 256, V)[1:3] == [256, 256]        # half of every wide tile would be padding
+    assert _tiles(lib, 32768, 5120, 151936)[:3] == [256, 512, 512]  # one GSPO sequence on the 32B-shaped head
+    for rows in (1, 300, 5000, 9472, 18944, 70000):
+        for H in (64, 256, 896, 3584, 5120, 8192):
+            t = _tiles(lib, rows, H, V)
+            n = -(-H // t[2])
+            assert t[0] == 256 and t[1] in (256, 512) and t[2] in (256, 512) and 1 <= t[3] <= n, (rows, H, t)
 
 
 def test_loss_params_layout_matches_header():
@@ -132,6 +156,6 @@ def test_header_is_plain_c_and_a_c_program_links_the_library(lib, tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
     out = r.stdout.split(maxsplit=5)
-    assert out[:3] == ["9472", "9472", "111"] and int(out[3]) > 5 * 2**30 and out[4] == "1"
+    assert out[:3] == ["18944", "18944", "56"] and int(out[3]) > 10 * 2**30 and out[4] == "1"
     assert "null pointer" in out[5]
 

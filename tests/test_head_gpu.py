@@ -25,6 +25,11 @@ def _rel_l2(a, b):
 @pytest.mark.parametrize("cfg", [
     (1, 128, 0, 0, 256, 384, 256), (1, 256, 0, 0, 200, 300, 136), (2, 256, 0, 0, 1000, 1288, 328),
     (2, 256, 0, 1, 512, 512, 256), (2, 256, 1, 1, 1000, 904, 200), (1, 256, 1, 0, 256, 512, 256),
+    # wide 256 x 512 tiles (one accumulator in all 512 TMEM columns, two MMA groups per K step): a ragged last tile whose
+    # second half holds 8 columns, every operand-major combination, N below one half (second half entirely out of
+    # bounds), and 90 tiles on the 74 CTA pairs (the single accumulator's barrier phases across tiles)
+    (2, 512, 0, 0, 1000, 1288, 328), (2, 512, 0, 1, 512, 1024, 256), (2, 512, 1, 1, 1000, 904, 200),
+    (2, 512, 1, 0, 304, 200, 136), (2, 512, 0, 1, 2560, 4608, 192), (2, 512, 1, 1, 2560, 4608, 192),
 ])
 def test_gemm_mainloop_all_operand_layouts(cfg):
     ctas, bn, a_mn, b_mn, M, N, K = cfg

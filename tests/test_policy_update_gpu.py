@@ -71,8 +71,8 @@ def test_step_matches_oracle(kw, fused, shape):
 
 
 def test_fused_step_multi_chunk_entropy_mask_and_accumulate():
-    """Several chunks (ragged last one), an entropy mask, entropy gradient and d_weight accumulation."""
-    B, A, H, V, T = 3, 4096, 64, 1024, 1.0
+    """Several chunks (24576 tokens = 18944 + a ragged one), an entropy mask, entropy gradient and d_weight accumulation."""
+    B, A, H, V, T = 6, 4096, 64, 1024, 1.0
     g, hidden, weight, labels, mask = _batch(B, A, H, V, 5)
     emask = (torch.rand(B, A, generator=g) > 0.1).float()
     cfg = O.make_cfg(policy_loss_type="regular", loss_reduction="sequence_mean", use_kl_loss=True,
@@ -172,8 +172,15 @@ def test_packed_ragged_layout_equals_padded_reference(kw):
 
 
 def test_gspo_fused_step_row_aligned_multi_chunk():
-    """GSPO needs whole sequences per chunk: 7 x 4096 tokens -> chunks of 4 and 3 sequences (skyb200_policy_step_plan)."""
+    """GSPO needs whole sequences per chunk: 7 x 4096 tokens -> two chunks of whole sequences (skyb200_policy_step_plan)."""
+    import ctypes
+
+    from skyrl_b200 import _lib
+
     B, A, H, V, T = 7, 4096, 64, 512, 1.0
+    plan = (ctypes.c_int64 * 3)()
+    _lib.load().skyb200_policy_step_plan(B, A, 0, H, V, _lib.LOSS_TYPES["gspo"], 1, plan)
+    assert plan[1] % A == 0 and plan[2] == 2, list(plan)
     g, hidden, weight, labels, mask = _batch(B, A, H, V, 21)
     cfg = O.make_cfg(policy_loss_type="gspo", loss_reduction="sequence_mean", use_kl_loss=False,
                      eps_clip_low=0.02, eps_clip_high=0.02)
@@ -254,7 +261,7 @@ def test_degenerate_shapes(shape, fused):
 def test_host_resident_hidden_streams_in_and_matches_device_path():
     """policy_step_from_host: hidden states in pinned host memory are copied chunk by chunk ahead of the GEMMs; every
     output must be bit-identical to the step on device-resident hidden states (same kernels, same order)."""
-    B, A, H, V, T = 3, 4096, 64, 1024, 0.9  # 12288 tokens = two chunks, the second ragged
+    B, A, H, V, T = 5, 4096, 64, 1024, 0.9  # 20480 tokens = two chunks, the second ragged
     g, hidden, weight, labels, mask = _batch(B, A, H, V, 11)
     cfg = O.make_cfg(policy_loss_type="regular", loss_reduction="token_mean", use_kl_loss=True)
     olp = -torch.rand(B, A, generator=g) * 3
@@ -340,3 +347,29 @@ def test_zero_row_skipping_is_bit_identical(tmp_path):
     dead = a["mask"].reshape(-1) == 0
     assert dead.sum() > 10000 and torch.all(b["d_hidden"][dead] == 0) and torch.all(b["ag_d_hidden"][dead] == 0)
     assert b["d_hidden"][~dead].abs().sum() > 0
+
+
+def test_wide_backward_tiles_equal_narrow(tmp_path):
+    """The 256 x 512 backward tiles (gemm_sm100.cuh, BN == 512: one accumulator in all 512 TMEM columns, two MMA groups
+    per K step) against the 256 x 256 ones on a head that is ragged in every tile dimension, in two processes with the
+    same chunking: every element accumulates the same K blocks in the same order, so the gradients must agree to fp32
+    rounding of the cross-chunk d_weight sums - in the fused step (dense and masked batch, fresh and accumulating
+    d_weight) and in the autograd head backward."""
+    import os
+    import subprocess
+    import sys
+
+    worker = os.path.join(os.path.dirname(__file__), "wide_worker.py")
+    res = {}
+    for flag in ("0", "7"):
+        path = str(tmp_path / f"wide{flag}.pt")
+        env = dict(os.environ, SKYB200_WIDE=flag, SKYB200_CHUNK_TILES="37")
+        r = subprocess.run([sys.executable, worker, path], env=env, capture_output=True, text=True, timeout=280)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        res[flag] = torch.load(path)
+    a, b = res["0"], res["7"]
+    assert torch.equal(a["log_probs"], b["log_probs"]) and a["status"] == b["status"]
+    for k in ("d_hidden", "d_hidden2", "ag_d_hidden", "d_weight", "d_weight2", "ag_d_weight"):
+        x, y = a[k].double(), b[k].double()
+        assert x.abs().sum() > 0
+        assert float((x - y).norm() / x.norm()) < 1e-6, k

@@ -285,12 +285,13 @@ def test_sharded_gae_equals_the_batch_gae():
 @pytest.mark.parametrize("A", [1000, 1001])
 def test_gspo_fused_step_with_a_response_length_off_the_tile_grid(A):
     """The padded response length is whatever the longest response of the batch was.  GSPO chunks are whole
-    sequences, so with A % 256 != 0 the chunks start off the 256-row tile grid (here 18 sequences per chunk: token
-    offsets 18000 / 18018, 36000 / 36036) and end in a partial tile; A = 1001 also takes the scalar paths."""
+    sequences, so with A % 256 != 0 the chunks start off the 256-row tile grid (here three chunks of whole sequences,
+    the later ones at token offsets that are no multiple of 256) and end in a partial tile; A = 1001 also takes the
+    scalar paths."""
     from skyrl_b200 import _lib
     import ctypes
 
-    B, H, V, T = 40, 64, 512, 1.0
+    B, H, V, T = 60, 64, 512, 1.0
     plan = (ctypes.c_int64 * 3)()
     _lib.load().skyb200_policy_step_plan(B, A, 0, H, V, _lib.LOSS_TYPES["gspo"], 1, plan)
     assert plan[1] % A == 0 and plan[1] % 256 != 0 and plan[2] >= 3, list(plan)
