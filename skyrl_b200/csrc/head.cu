@@ -283,7 +283,7 @@ static int transform_evict() { static int v = env_int0("SKYB200_TRANSFORM_EVICT"
 constexpr int kWideBN = 512;
 constexpr int kWideStages = 4;
 static int wide_mask() { static int v = env_int0("SKYB200_WIDE", 3); return v; }
-static int dh_group_m_wide() { static int v = env_int("SKYB200_DH_GROUP_M_WIDE", 11); return v; }
+static int dh_group_m_wide() { static int v = env_int("SKYB200_DH_GROUP_M_WIDE", 7); return v; }
 
 // fraction of the machine a [m_tiles x ceil(n / bn)] tile grid keeps busy: whole waves of 74 CTA pairs x useful columns
 static double tile_grid_efficiency(int64_t m_tiles, int64_t n, int bn) {
