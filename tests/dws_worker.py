@@ -32,7 +32,9 @@ def main():
     rel = lambda x, y: float((x.double() - y.double()).norm() / y.double().norm().clamp(min=1e-30))
     cfg = O.make_cfg(policy_loss_type="regular", loss_reduction="token_mean", use_kl_loss=False)
     for case, (B, A, H, V, ragged) in enumerate([(4, 300, 128, 2048, False), (6, 4000, 256, 4096, True),
-                                                 (3, 10000, 64, 64 * world * 5, True)]):
+                                                 (3, 10000, 64, 64 * world * 5, True),
+                                                 # H = 1024, 64 row tiles: the d_weight GEMM takes the wide 256 x 512 tiles
+                                                 (2, 3000, 1024, 16384, True)]):
         g = torch.Generator().manual_seed(100 + 7 * case + rank)      # different data on every rank
         hidden = torch.randn(B, A, H, generator=g).bfloat16().to(dev)
         gw = torch.Generator().manual_seed(55 + case)                 # the same weight on every rank
