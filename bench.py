@@ -503,9 +503,10 @@ def run_ours(args, w):
     chunk, n_chunks = int(plan[0]), int(plan[2])
     tiles = (ctypes.c_int32 * 4)()
     _lib.check(lib.skyb200_head_tile_plan(min(chunk, N), H, V, tiles), "skyb200_head_tile_plan")
-    # GRPO (2) + loss pre-pass + finalize (2) + per chunk: fwd GEMM, merge, loss, d_logits transform, dH GEMM, dW GEMM
-    # (+ live-row lists and dead-tile zero fill of the zero-row skipping per chunk)
-    launches_per_step = 2 + 2 + 8 * n_chunks
+    # GRPO (1: the cluster kernel, uniform prompt groups) + loss pre-pass + finalize (2) + per chunk: fwd GEMM, merge,
+    # loss, d_logits transform, dH GEMM, dW GEMM, live-row lists and dead-tile zero fill of the zero-row skipping
+    # (profiles/r02t_launches_c2_step.csv: 450 launches between the pre-pass and the finalize of one step)
+    launches_per_step = 1 + 2 + 8 * n_chunks
 
     # ---- multi-GPU evidence: N-GPU numerics + what the collectives cost with the rank skew taken out
     dp = None
