@@ -97,7 +97,9 @@ def policy_update_step(
 
     ``fused=True`` (default) runs ``skyb200_policy_step``: per token chunk forward GEMM -> loss -> backward GEMMs,
     the forward keeping a bf16 copy of its logits tiles in a bounded [chunk, V] store so the backward does not
-    recompute the projection (6*H*V executed flop per token).  ``fused=False`` runs the three C-ABI calls
+    recompute the projection (6*H*V executed flop per token).  The store is double-buffered: 2 x 18944 tokens x V bf16 =
+    11.5 GB of grow-only scratch for a 152k vocabulary (``SKYB200_CHUNK_TILES=37`` halves it at the cost of whole waves
+    for the wide backward tiles, ``skyb200_policy_step_workspace`` reports the exact size).  ``fused=False`` runs the three C-ABI calls
     (``head_forward`` / ``policy_loss`` / ``head_backward``) the autograd path uses (8*H*V, fp32 logits in backward).
 
     ``rollout_logprobs`` [B, A]: with ``config.off_policy_correction`` set (``tis_ratio_type`` /
