@@ -2,7 +2,7 @@
 config 2, the headline; these are the other named shapes).  One JSON line per config; under torchrun every rank owns
 its own shard (weak scaling) and the packed stats + fp32 lm_head gradient are all-reduced per step, as in bench.py.
 
-    python scripts/bench_configs.py [c1] [c3] [c3-strong] [c4-dual_clip] [c4-gspo] [c5] [steps=3] [warmup=2]
+    python scripts/bench_configs.py [c1] [c3] [c3-strong] [c4-dual_clip] [c4-gspo] [c5] [c5-sharded] [steps=3] [warmup=2]
 
     c1  GRPO + regular loss + KL loss; 64 x 1024 tokens, Qwen2.5-0.5B head (H = 896, V = 151936) - the whole config
     c3-strong  config 3 at its FIXED size (512 x 8192 tokens) split over the ranks: strong scaling
@@ -10,6 +10,9 @@ its own shard (weak scaling) and the packed stats + fp32 lm_head gradient are al
     c4  dual-clip (c = 3, token_mean) or GSPO (sequence_mean); 8 x 32768-token trajectories (lengths 24K-32K),
         Qwen3-32B-shaped head (H = 5120, V = 151936)
     c5  RLOO (group 16) + entropy bonus; 64 ragged responses of 128-16K tokens, PACKED layout, 7B head
+    c5-sharded  ONE global batch of 64 x world such responses (the same on every rank), whole prompt groups dealt to
+        the ranks by dist.shard_prompt_groups (longest-processing-time first on the groups' valid tokens); reports the
+        ranks' token counts next to what the reference's contiguous row split (dispatch.py:186-205) would give
 
 `tokens_per_s` counts loss-masked (valid) tokens, `positions_per_s` every position the head processes; the roofline
 fraction is 6*H*V flop per processed position against the measured sustained bf16 peak (zero-row skipping makes
@@ -36,6 +39,7 @@ SHAPES = {
     "c4-dual_clip": dict(B=8, A=32768, H=5120, V=151936, model="Qwen3-32B-shaped head"),
     "c4-gspo": dict(B=8, A=32768, H=5120, V=151936, model="Qwen3-32B-shaped head"),
     "c5": dict(B=64, A=16384, H=3584, V=152064, G=16, model="Qwen2.5-7B head"),
+    "c5-sharded": dict(B=64, A=16384, H=3584, V=152064, G=16, model="Qwen2.5-7B head", sharded=True),
 }
 
 
@@ -46,7 +50,7 @@ def _cfg(name):
     elif name == "c4-gspo":
         cfg.policy_loss_type, cfg.loss_reduction, cfg.use_kl_loss = "gspo", "sequence_mean", False
         cfg.eps_clip_low, cfg.eps_clip_high = 3e-4, 4e-4
-    elif name == "c5":
+    elif name.startswith("c5"):
         cfg.use_kl_loss, cfg.use_entropy_loss, cfg.entropy_loss_coef = False, True, 0.01
     return cfg
 
@@ -65,6 +69,7 @@ def build(name, dev, rank, world=1):
     if s.get("strong"):
         B = B // world
     name = "c3" if name == "c3-strong" else name
+    shard_note = ""
     gen = torch.Generator(device=dev).manual_seed(1234 + 17 * rank)
     cfg = _cfg(name)
     weight = make_weight(s, dev)
@@ -74,6 +79,20 @@ def build(name, dev, rank, world=1):
         lens = torch.full((B,), A, device=dev)
     elif name.startswith("c4"):
         lens = torch.randint(24 * 1024, A + 1, (B,), generator=gen, device=dev)
+    elif s.get("sharded"):
+        # the GLOBAL ragged batch, identical on every rank; this rank keeps the rows the sharder deals to it
+        gg = torch.Generator().manual_seed(97531)
+        lens_g = torch.randint(128, A + 1, (B * world,), generator=gg)
+        uids_g = np.array([f"prompt-{i // s['G']}" for i in range(B * world)])
+        shards = sdist.shard_prompt_groups(uids_g, lens_g.tolist(), world)
+        per_rank = [int(lens_g[r].sum()) for r in shards]
+        contiguous = [int(c.sum()) for c in lens_g.chunk(world)]
+        imb = lambda v: max(v) / (sum(v) / len(v))
+        shard_note = (f"; shard of a global batch of {B * world}: valid tokens per rank {per_rank} (max / mean "
+                      f"{imb(per_rank):.3f}; the reference's contiguous split: {contiguous}, {imb(contiguous):.3f})")
+        rows = shards[rank]
+        lens, B, name = lens_g[rows].to(dev), len(rows), "c5"
+        shard_uids = uids_g[rows]
     else:
         lens = torch.randint(128, A + 1, (B,), generator=gen, device=dev)
     mask = (ar < lens[:, None]).float()
@@ -83,7 +102,7 @@ def build(name, dev, rank, world=1):
     noise = lambda ref, sd: ref + sd * torch.randn(ref.shape, generator=gen, device=dev)
 
     if name == "c5":
-        uids = np.array([f"prompt-{rank}-{i // s['G']}" for i in range(B)])
+        uids = shard_uids if s.get("sharded") else np.array([f"prompt-{rank}-{i // s['G']}" for i in range(B)])
         cu, (maskp,) = skyrl_b200.pack_by_lengths(lens, mask)
         N = int(cu[-1])
         hidden, labels = _randn_bf16(N, H, gen, dev), torch.randint(0, V, (N,), generator=gen, device=dev)
@@ -99,7 +118,8 @@ def build(name, dev, rank, world=1):
             return skyrl_b200.policy_update_step(hidden, weight, labels, olp, advp, cfg, loss_mask=maskp,
                                                  d_weight=d_weight, sync=False, cu_seqlens=cu)
 
-        return step, int(maskp.sum()), N, f"{B} ragged responses (128-16K tokens, {N} packed), RLOO group {s['G']}"
+        return (step, int(maskp.sum()), N,
+                f"{B} ragged responses (128-16K tokens, {N} packed), RLOO group {s['G']}" + shard_note)
 
     N = B * A
     hidden, labels = _randn_bf16(N, H, gen, dev), torch.randint(0, V, (B, A), generator=gen, device=dev)
