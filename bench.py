@@ -23,7 +23,8 @@ Besides the contract keys the line carries
   `cpu_baseline`      the UNMODIFIED reference (baseline/_ref, kind "reference") on this box's host cores;
   `ref_gpu_path`      the UNMODIFIED reference's own GPU path (cuBLAS lm_head + flash-attn Triton CE + chunked entropy +
                       registry loss) on this GPU, and `vs_ref_gpu_path` = value / that;
-  `other_configs`     BASELINE configs 1, 3, 4 (dual-clip, GSPO), 5 and the fixed-size config-3 split (strong scaling);
+  `other_configs`     BASELINE configs 1, 3, 4 (dual-clip, GSPO), 5 (per-rank batches, and one global ragged batch dealt
+                      to the ranks by the prompt-group sharder) and the fixed-size config-3 split (strong scaling);
   `e2e`, `gpu_launches`, `clocks`; for N > 1 also `dp_check`, `allreduce_exposed_ms`, `per_rank_step_ms`.
 
 `--impl reference` times the reference's own CPU implementation of the path (baseline/ref_path.py drives the

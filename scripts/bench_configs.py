@@ -158,7 +158,7 @@ def build(name, dev, rank, world=1):
     return step, int(mask.sum()), N, f"{B} x {A}-token trajectories (lengths 24K-32K), GRPO + {cfg.policy_loss_type}"
 
 
-DEFAULT_SET = ["c1", "c3", "c4-dual_clip", "c4-gspo", "c5", "c3-strong"]
+DEFAULT_SET = ["c1", "c3", "c4-dual_clip", "c4-gspo", "c5", "c5-sharded", "c3-strong"]
 
 
 def run_config(name, dev, rank, world, steps, warmup, peaks):
